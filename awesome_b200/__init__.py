@@ -1,0 +1,12 @@
+"""awesome_b200 -- B200-native shape-prior fitting path of jp-schneider/awesome.
+
+Drop-in names for the reference's YAML configs (``prior_model_type`` / ``optimizer_type``):
+``awesome_b200.ConvexNextNet``, ``awesome_b200.ConvexNet``, ``awesome_b200.PathConnectedNet``,
+``awesome_b200.real_nvp_path_connected_net``, ``awesome_b200.FusedAdam``, ``awesome_b200.FusedAdamax``.
+All arithmetic runs in ``csrc/libawb.so`` (hand-written sm_100a CUDA); there is no CPU fallback.
+"""
+from .core import GridSpecHost, Prior, iou_counts, target_counts  # noqa: F401
+from .fit import LossConfig, OptimConfig, PriorFitter  # noqa: F401
+from .model import ConvexNet, ConvexNextNet  # noqa: F401
+
+__version__ = "0.1.0"

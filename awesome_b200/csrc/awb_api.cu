@@ -1,0 +1,264 @@
+// extern "C" entry points of libawb.so (declared in include/awb.h) and the host-side
+// bookkeeping behind them: handle, parameter-arena layout, workspace carving, error state.
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "awb_internal.cuh"
+
+namespace awb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return AWB_ERR_CUDA;
+}
+
+static Layout make_layout(const awb_desc& d) {
+  Layout L = {};
+  L.C = d.C; L.h = d.h; L.L = d.L; L.F = d.F; L.m = d.m;
+  L.ld = (int)round_up(d.h + d.C + 1, 8);
+  L.P_icnn = (int64_t)d.h * d.C + d.h + (int64_t)d.L * ((int64_t)d.h * d.h + d.h + (int64_t)d.h * d.C) + d.h + 1 + d.C;
+  L.off_icnn = 0;
+  L.per_flow = 2 * ((int64_t)d.m * d.C + d.m + (int64_t)d.C * d.m + d.C) + 2 * d.C;
+  if (d.kind == AWB_KIND_FLOW_ICNN) {
+    // module registration order of PathConnectedNet: convex_net, flow_net, linear
+    L.off_flow = L.P_icnn;
+    L.P_flow = L.per_flow * d.F;
+    L.off_lin = L.off_flow + L.P_flow;
+    L.P = L.off_lin + 2 * d.C;
+  } else {
+    L.off_flow = L.P_icnn; L.P_flow = 0; L.off_lin = L.P_icnn; L.P = L.P_icnn;
+  }
+  L.aug_in = 0;
+  L.aug_layer = 4 * (int64_t)d.h;
+  L.aug_out = L.aug_layer + (int64_t)d.L * d.h * L.ld;
+  L.G = L.aug_out + L.ld;
+  return L;
+}
+
+static int64_t align256(int64_t b) { return round_up(b, 256); }
+
+Workspace carve(const awb_prior* h, int64_t N, bool training, void* base) {
+  const Layout& L = h->lay;
+  const int64_t O = h->desc.n_objects;
+  const int S = n_splits(N);
+  char* p = (char*)base;
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) { char* r = p ? p + off : nullptr; off += align256(bytes); return r; };
+  Workspace w = {};
+  w.waug = (float*)take(4 * O * L.G);
+  w.part = (float*)take(training ? 4 * (int64_t)S * O * L.G : 0);
+  w.lossp = (float*)take(4 * (int64_t)S * O);
+  w.fpart = (float*)take(training ? 4 * (int64_t)S * O * (L.P_flow + 2 * L.C) : 0);
+  w.X = (float*)take(4 * O * N * 4);
+  w.dX = (float*)take(training ? 4 * O * N * 4 : 0);
+  w.ZA = (float*)take(4 * O * (L.L + 1) * N * L.ld);
+  w.D = (float*)take(training ? 4 * O * 2 * N * L.ld : 0);
+  w.logits = (float*)take(4 * O * N);
+  w.tc = nullptr;
+  w.bytes = off;
+  return w;
+}
+
+}  // namespace awb
+
+using namespace awb;
+
+extern "C" {
+
+const char* awb_version(void) { return "awb 0.1 (sm_100a)"; }
+const char* awb_last_error(void) { return g_err; }
+
+int awb_prior_create(const awb_desc* d, awb_handle* out) {
+  if (!d || !out) { set_error("null argument"); return AWB_ERR_INVALID; }
+  if (d->kind != AWB_KIND_ICNN && d->kind != AWB_KIND_FLOW_ICNN) { set_error("unknown prior kind %d", d->kind); return AWB_ERR_INVALID; }
+  if (d->C < 2 || d->C > 3) { set_error("C must be 2 or 3, got %d", d->C); return AWB_ERR_UNSUPPORTED; }
+  if (d->h < 8 || d->h > 256) { set_error("h must be in [8,256], got %d", d->h); return AWB_ERR_UNSUPPORTED; }
+  if (d->L < 0 || d->L > 8) { set_error("L must be in [0,8], got %d", d->L); return AWB_ERR_UNSUPPORTED; }
+  if (d->n_objects < 1 || d->n_objects > 16) { set_error("n_objects must be in [1,16], got %d", d->n_objects); return AWB_ERR_UNSUPPORTED; }
+  if (d->kind == AWB_KIND_FLOW_ICNN && (d->F < 1 || d->F > 64 || d->m < 1 || d->m > 32)) {
+    set_error("flow needs 1<=F<=64 and 1<=m<=32, got F=%d m=%d", d->F, d->m);
+    return AWB_ERR_UNSUPPORTED;
+  }
+  if (d->precision != AWB_PREC_FP32 && d->precision != AWB_PREC_F16) { set_error("unknown precision %d", d->precision); return AWB_ERR_INVALID; }
+  awb_prior* h = new awb_prior();
+  h->desc = *d;
+  if (d->kind == AWB_KIND_ICNN) { h->desc.F = 0; h->desc.m = 0; }
+  h->lay = make_layout(h->desc);
+  h->fc_set = false;
+  h->d_map = nullptr; h->d_clamp = nullptr; h->d_group = nullptr;
+  const Layout& L = h->lay;
+  // arena (state_dict order) -> augmented index; clamp mask; optimizer groups
+  std::vector<int32_t> map(L.P_icnn);
+  std::vector<uint8_t> clamp(L.P, 0), group(L.P, 1);
+  int64_t i = 0;
+  const int hh = L.h, C = L.C, ld = L.ld;
+  for (int j = 0; j < hh; j++) for (int c = 0; c < C; c++) map[i++] = (int32_t)(L.aug_in + j * 4 + c);  // input.weight
+  for (int j = 0; j < hh; j++) map[i++] = (int32_t)(L.aug_in + j * 4 + 3);                               // input.bias
+  for (int l = 0; l < L.L; l++) {
+    int64_t base = L.aug_layer + (int64_t)l * hh * ld;
+    for (int j = 0; j < hh; j++) for (int k = 0; k < hh; k++) { clamp[L.off_icnn + i] = 1; map[i++] = (int32_t)(base + (int64_t)j * ld + k); }  // ln.weight
+    for (int j = 0; j < hh; j++) map[i++] = (int32_t)(base + (int64_t)j * ld + hh + C);                  // ln.bias
+    for (int j = 0; j < hh; j++) for (int c = 0; c < C; c++) map[i++] = (int32_t)(base + (int64_t)j * ld + hh + c);  // skp.weight
+  }
+  for (int k = 0; k < hh; k++) { clamp[L.off_icnn + i] = 1; map[i++] = (int32_t)(L.aug_out + k); }       // out.ln.weight
+  map[i++] = (int32_t)(L.aug_out + hh + C);                                                             // out.ln.bias
+  for (int c = 0; c < C; c++) map[i++] = (int32_t)(L.aug_out + hh + c);                                  // out.skp.weight
+  if (i != L.P_icnn) { set_error("internal: layout mismatch"); delete h; return AWB_ERR_INVALID; }
+  for (int64_t k = L.off_flow; k < L.off_flow + L.P_flow; k++) group[k] = 0;
+  for (int64_t k = L.off_lin; k < L.P; k++) group[k] = 2;
+  cudaError_t e;
+  if ((e = cudaGetDevice(&h->device)) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_map, sizeof(int32_t) * L.P_icnn)) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_clamp, L.P)) != cudaSuccess || (e = cudaMalloc(&h->d_group, L.P)) != cudaSuccess ||
+      (e = cudaMemcpy(h->d_map, map.data(), sizeof(int32_t) * L.P_icnn, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(h->d_clamp, clamp.data(), L.P, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(h->d_group, group.data(), L.P, cudaMemcpyHostToDevice)) != cudaSuccess) {
+    cudaFree(h->d_map); cudaFree(h->d_clamp); cudaFree(h->d_group);
+    delete h;
+    return cuda_fail(e, "awb_prior_create");
+  }
+  *out = h;
+  return AWB_OK;
+}
+
+int awb_prior_destroy(awb_handle h) {
+  if (!h) return AWB_OK;
+  cudaFree(h->d_map); cudaFree(h->d_clamp); cudaFree(h->d_group);
+  delete h;
+  return AWB_OK;
+}
+
+int64_t awb_prior_param_count(awb_handle h) { return h ? h->lay.P : -1; }
+
+int64_t awb_prior_workspace_bytes(awb_handle h, int64_t n_pixels, int32_t training) {
+  if (!h || n_pixels < 1) return -1;
+  return carve(h, n_pixels, training != 0, nullptr).bytes;
+}
+
+int64_t awb_opt_state_bytes(awb_handle h) {
+  if (!h) return -1;
+  int64_t n = h->lay.P * h->desc.n_objects;
+  return round_up(2 * n * 4, 256) + round_up((int64_t)sizeof(OptScal) * h->desc.n_objects, 256);
+}
+
+int awb_prior_set_flow_consts(awb_handle h, const float* nmin, const float* nmax, float new_min, float new_max,
+                              const uint8_t* masks) {
+  if (!h || !nmin || !nmax || !masks) { set_error("null argument"); return AWB_ERR_INVALID; }
+  if (h->desc.kind != AWB_KIND_FLOW_ICNN) { set_error("not a flow prior"); return AWB_ERR_INVALID; }
+  for (int c = 0; c < h->lay.C; c++) { h->fc.nmin[c] = nmin[c]; h->fc.nmax[c] = nmax[c]; }
+  h->fc.new_min = new_min; h->fc.new_max = new_max;
+  memcpy(h->fc.masks, masks, (size_t)h->lay.F * h->lay.C);
+  h->fc_set = true;
+  return AWB_OK;
+}
+
+static int check_common(awb_handle h, const awb_grid_spec* g, void* ws, size_t ws_bytes, bool training, int64_t* N) {
+  if (!h || !g || !ws) { set_error("null argument"); return AWB_ERR_INVALID; }
+  if (g->B < 1 || g->H < 1 || g->W < 1) { set_error("empty grid %dx%dx%d", g->B, g->H, g->W); return AWB_ERR_INVALID; }
+  if (g->mode == AWB_GRID_EXPLICIT && !g->grid) { set_error("explicit grid needs a pointer"); return AWB_ERR_INVALID; }
+  if (g->mode < 0 || g->mode > 2) { set_error("unknown grid mode %d", g->mode); return AWB_ERR_INVALID; }
+  *N = (int64_t)g->B * g->H * g->W;
+  if (*N > (int64_t)1 << 30) { set_error("too many pixel rows"); return AWB_ERR_UNSUPPORTED; }
+  int64_t need = carve(h, *N, training, nullptr).bytes;
+  if ((int64_t)ws_bytes < need) { set_error("workspace too small: %lld < %lld", (long long)ws_bytes, (long long)need); return AWB_ERR_WORKSPACE; }
+  if (h->desc.kind == AWB_KIND_FLOW_ICNN && !h->fc_set) { set_error("awb_prior_set_flow_consts not called"); return AWB_ERR_INVALID; }
+  return AWB_OK;
+}
+
+int awb_prior_forward(awb_handle h, const float* params, const awb_grid_spec* g, float* logits, float* deformed,
+                      int32_t training, void* ws, size_t ws_bytes, void* stream) {
+  int64_t N;
+  int rc = check_common(h, g, ws, ws_bytes, training != 0, &N);
+  if (rc) return rc;
+  if (!params) { set_error("null params"); return AWB_ERR_INVALID; }
+  Workspace w = carve(h, N, training != 0, ws);
+  return simt_forward(h, params, g, logits, deformed, training != 0, w, (cudaStream_t)stream);
+}
+
+int awb_prior_backward(awb_handle h, const float* params, const awb_grid_spec* g, const float* dlogits, float* grads,
+                       float* dgrid, void* ws, size_t ws_bytes, void* stream) {
+  int64_t N;
+  int rc = check_common(h, g, ws, ws_bytes, true, &N);
+  if (rc) return rc;
+  if (!params || !dlogits || !grads) { set_error("null argument"); return AWB_ERR_INVALID; }
+  if (dgrid && (h->desc.kind != AWB_KIND_ICNN || h->desc.n_objects != 1)) {
+    set_error("dgrid is only provided for single-object ICNN priors");
+    return AWB_ERR_UNSUPPORTED;
+  }
+  Workspace w = carve(h, N, true, ws);
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = simt_backward(h, params, g, nullptr, nullptr, dlogits, dgrid != nullptr, w, st);
+  if (rc) return rc;
+  rc = simt_reduce_grads(h, grads, w, N, st);
+  if (rc) return rc;
+  if (dgrid) rc = simt_dgrid(h, g, dgrid, w, st);
+  return rc;
+}
+
+int awb_prior_fit_step(awb_handle h, float* params, void* opt_state, const awb_grid_spec* g, const float* target,
+                       const awb_loss_spec* loss, const awb_opt_hyper* hy, float* loss_out, void* ws, size_t ws_bytes,
+                       void* stream) {
+  int64_t N;
+  int rc = check_common(h, g, ws, ws_bytes, true, &N);
+  if (rc) return rc;
+  if (!params || !opt_state || !target || !loss || !hy) { set_error("null argument"); return AWB_ERR_INVALID; }
+  Workspace w = carve(h, N, true, ws);
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = simt_forward(h, params, g, nullptr, nullptr, true, w, st);
+  if (rc) return rc;
+  rc = simt_backward(h, params, g, target, loss, nullptr, false, w, st);
+  if (rc) return rc;
+  return simt_reduce_opt(h, params, opt_state, hy, loss_out, w, N, st);
+}
+
+int awb_optim_step(awb_handle h, float* params, const float* grads, void* opt_state, const awb_opt_hyper* hy,
+                   void* stream) {
+  if (!h || !params || !grads || !opt_state || !hy) { set_error("null argument"); return AWB_ERR_INVALID; }
+  return optim_step(h, params, grads, opt_state, hy, (cudaStream_t)stream);
+}
+
+int awb_prior_enforce_convexity(awb_handle h, float* params, void* stream) {
+  if (!h || !params) { set_error("null argument"); return AWB_ERR_INVALID; }
+  return clamp_only(h, params, (cudaStream_t)stream);
+}
+
+int awb_opt_state_init(awb_handle h, void* opt_state, const double* lr, void* stream) {
+  if (!h || !opt_state || !lr) { set_error("null argument"); return AWB_ERR_INVALID; }
+  return opt_state_init(h, opt_state, lr, (cudaStream_t)stream);
+}
+
+int awb_opt_read_scalars(awb_handle h, const void* opt_state, int32_t obj, awb_opt_scalars* out, void* stream) {
+  if (!h || !opt_state || !out || obj < 0 || obj >= h->desc.n_objects) { set_error("bad argument"); return AWB_ERR_INVALID; }
+  int64_t n = h->lay.P * h->desc.n_objects;
+  const OptScal* sc = (const OptScal*)((const char*)opt_state + round_up(2 * n * 4, 256)) + obj;
+  OptScal s;
+  AWB_CUDA(cudaMemcpyAsync(&s, sc, sizeof(s), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  AWB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  out->step = s.step; out->num_bad = s.num_bad; out->nonfinite = s.nonfinite; out->pad = 0;
+  for (int g = 0; g < AWB_MAX_GROUPS; g++) out->lr[g] = s.lr[g];
+  out->best = s.best; out->last_loss = s.last_loss; out->pad2 = 0.f;
+  return AWB_OK;
+}
+
+int awb_prior_actnorm_init(awb_handle h, float* params, const awb_grid_spec* g, void* ws, size_t ws_bytes,
+                           void* stream) {
+  int64_t N;
+  int rc = check_common(h, g, ws, ws_bytes, false, &N);
+  if (rc) return rc;
+  if (h->desc.kind != AWB_KIND_FLOW_ICNN) { set_error("not a flow prior"); return AWB_ERR_INVALID; }
+  Workspace w = carve(h, N, false, ws);
+  return flow_actnorm_init(h, params, g, w, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,148 @@
+// Internal declarations shared by the translation units of libawb.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/awb.h"
+
+namespace awb {
+
+constexpr int kMaxSplits = 148;  // pixel ranges for cross-pixel reductions = one per SM
+constexpr int kMaxObjects = 64;
+
+// Per-object layout of the parameter arena (state_dict order) and of the "augmented"
+// weight space the kernels consume.
+//
+// Augmented formulation: every hidden activation row is stored as
+//   ZA[n] = [ z (h) | x (C) | 1 | 0-pad ]           (ld = round_up(h+C+1, 8) floats)
+// and every SkipBlock as one matrix  Waug[h][ld] = [ ln.weight | skp.weight | ln.bias | 0 ],
+// so that  z_{i+1} = relu(ZA_i * Waug^T),  dZA_i = delta * Waug  (its x-columns are the
+// coordinate gradient) and  dWaug = delta^T * ZA_i  (dW, dS, db in one contraction).
+struct Layout {
+  int C, h, L, F, m, ld;
+  int64_t P;         // trainable parameters per object
+  int64_t off_icnn;  // arena offset of input.weight
+  int64_t P_icnn;
+  int64_t off_flow;  // arena offset of flows.0.s.net.0.weight
+  int64_t P_flow;    // F * per_flow
+  int64_t per_flow;  // 2*(m*C + m + C*m + C) + 2*C
+  int64_t off_lin;   // arena offset of linear.weight [C], linear.bias [C]
+  // augmented space
+  int64_t G;         // 4*h + L*h*ld + ld
+  int64_t aug_in;    // [h][4]: (w_x, w_y, w_t, bias)
+  int64_t aug_layer; // + i*h*ld, i < L
+  int64_t aug_out;   // [ld]: (w_o | s_o | b_o | 0)
+};
+
+struct OptScal {  // per object, device resident
+  double lr[AWB_MAX_GROUPS];
+  double best;
+  int32_t step;
+  int32_t num_bad;
+  int32_t nonfinite;
+  int32_t pad;
+  float last_loss;
+  float pad2;
+};
+
+struct FlowConsts {
+  float nmin[4], nmax[4];
+  float new_min, new_max;
+  uint8_t masks[64 * 4];  // [F][C]
+};
+
+}  // namespace awb
+
+struct awb_prior {
+  awb_desc desc;
+  awb::Layout lay;
+  int32_t* d_map;     // [P_icnn] arena-local index -> augmented index
+  uint8_t* d_clamp;   // [P] 1 where enforce_convexity clamps
+  uint8_t* d_group;   // [P] optimizer group: 0 flow_net, 1 convex_net, 2 linear
+  awb::FlowConsts fc;
+  bool fc_set;
+  int device;
+};
+
+namespace awb {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+#define AWB_CUDA(expr)                                    \
+  do {                                                    \
+    cudaError_t _e = (expr);                              \
+    if (_e != cudaSuccess) return awb::cuda_fail(_e, #expr); \
+  } while (0)
+
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+inline int n_splits(int64_t n) {
+  int64_t s = (n + 255) / 256;
+  return (int)(s < kMaxSplits ? (s < 1 ? 1 : s) : kMaxSplits);
+}
+inline int64_t split_chunk(int64_t n) { return round_up((n + n_splits(n) - 1) / n_splits(n), 8); }
+
+// Workspace carving (all regions 256-byte aligned).
+struct Workspace {
+  float* waug;    // [O][G]
+  float* part;    // [S][O][G]
+  float* lossp;   // [S][O]
+  float* fpart;   // [S][O][P_flow + 2C]   (flow + linear gradient partials)
+  float* X;       // [O][N][4]   deformed coordinates fed to the ICNN (x, y, t, 1)
+  float* dX;      // [O][N][4]
+  float* ZA;      // [O][L+1][N][ld]
+  float* D;       // [O][2][N][ld]
+  float* logits;  // [O][N]
+  void* tc;       // tensor-core path scratch
+  int64_t bytes;
+};
+Workspace carve(const awb_prior* h, int64_t N, bool training, void* base);
+
+// ---- launchers implemented in awb_simt.cu ----
+struct GridDev {
+  int mode, B, H, W, C;
+  float t0, t_step;
+  const float* grid;
+};
+int simt_forward(const awb_prior* h, const float* params, const awb_grid_spec* g, float* logits_out,
+                 float* deformed, bool training, const Workspace& ws, cudaStream_t st);
+// loss != nullptr: fit mode (dy from loss); else dy = dlogits.
+int simt_backward(const awb_prior* h, const float* params, const awb_grid_spec* g, const float* target,
+                  const awb_loss_spec* loss, const float* dlogits, bool need_dx, const Workspace& ws,
+                  cudaStream_t st);
+int simt_reduce_opt(const awb_prior* h, float* params, void* opt_state, const awb_opt_hyper* hy,
+                    float* loss_out, const Workspace& ws, int64_t N, cudaStream_t st);
+int simt_reduce_grads(const awb_prior* h, float* grads, const Workspace& ws, int64_t N, cudaStream_t st);
+int simt_dgrid(const awb_prior* h, const awb_grid_spec* g, float* dgrid, const Workspace& ws, cudaStream_t st);
+int optim_step(const awb_prior* h, float* params, const float* grads, void* opt_state,
+               const awb_opt_hyper* hy, cudaStream_t st);
+int clamp_only(const awb_prior* h, float* params, cudaStream_t st);
+int opt_state_init(const awb_prior* h, void* opt_state, const double* lr, cudaStream_t st);
+
+// ---- flows, implemented in awb_flow.cu ----
+int flow_forward(const awb_prior* h, const float* params, const awb_grid_spec* g, const Workspace& ws,
+                 float* deformed, cudaStream_t st);
+int flow_backward(const awb_prior* h, const float* params, const awb_grid_spec* g, const Workspace& ws,
+                  cudaStream_t st);
+int flow_actnorm_init(const awb_prior* h, float* params, const awb_grid_spec* g, const Workspace& ws,
+                      cudaStream_t st);
+
+// Pixel coordinate of row n, channel c.  torch.linspace semantics for
+// AWB_GRID_LINSPACE: step = 1/(n-1); first half start+i*step, second half end-(n-1-i)*step.
+__device__ __forceinline__ float lin01(int i, int n) {
+  if (n <= 1) return 0.f;
+  float step = 1.0f / (float)(n - 1);
+  return (i < n / 2) ? (float)i * step : 1.0f - (float)(n - 1 - i) * step;
+}
+__device__ __forceinline__ float coord(const GridDev& g, int64_t n, int c) {
+  int64_t hw = (int64_t)g.H * g.W;
+  int b = (int)(n / hw);
+  int r = (int)(n - (int64_t)b * hw);
+  int i = r / g.W, j = r - i * g.W;
+  if (g.mode == AWB_GRID_EXPLICIT) return g.grid[((int64_t)b * g.C + c) * hw + r];
+  if (c == 2) return g.t0 + (float)b * g.t_step;
+  if (g.mode == AWB_GRID_LINSPACE) return c == 0 ? lin01(j, g.W) : lin01(i, g.H);
+  return c == 0 ? (float)j / (float)g.W : (float)i / (float)g.H;
+}
+
+}  // namespace awb

@@ -1,0 +1,208 @@
+"""The fused fit loop: the body of the reference's per-frame hot loops
+(``awesome/model/path_connected_net.py:939-953``, ``:364-379``; how-to notebooks cell 9)
+as one native call per step, replayed through CUDA graphs so the host never touches a step.
+
+``forward -> sigmoid -> loss -> backward -> optimizer.step -> enforce_convexity ->
+lr_scheduler.step(loss)`` all happen inside ``awb_prior_fit_step``; the loss history stays on
+the device and is read back once per fit (the reference syncs three times per step)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Union
+
+import torch
+
+from . import _lib as L
+from .core import GridSpecHost, Prior, target_counts
+
+
+@dataclass
+class LossConfig:
+    """Which per-pixel loss the fit minimises.
+
+    kind "mse": ``UnariesWeightedLoss(SE("mean"), mode=...)`` on ``sigmoid(y)``
+    (``path_connected_net.py:768``; modes of ``unaries_weighted_loss.py:35-69``).
+    kind "fgbg_se" / "fgbg_bce_logits": the how-to notebooks' fg/bg-weighted means.
+    """
+    kind: str = "mse"
+    mode: str = "none"        # none | ratio | sssdms | equal   (kind == "mse")
+    ratio: float = 1.0
+    fg_weight: float = 0.4    # fgbg_* kinds
+
+    def to_specs(self, target: torch.Tensor) -> List[L.LossSpec]:
+        """target ``[O,N]``.  Folds 1/N, class weights and fg/bg means into two coefficients per object."""
+        O, N = target.shape
+        specs = []
+        if self.kind == "mse":
+            if self.mode == "none":
+                return [L.LossSpec(L.AWB_LOSS_SE_SIGMOID, L.AWB_CLS_UNARY_LT_HALF, 1.0 / N, 1.0 / N) for _ in range(O)]
+            cnt = target_counts(target, L.AWB_CLS_UNARY_LT_HALF).cpu()
+            for o in range(O):
+                fg, bg = float(cnt[o, 0]), float(cnt[o, 1])
+                cc = torch.tensor(bg, dtype=torch.float32) / torch.tensor(fg, dtype=torch.float32)
+                if self.mode == "ratio":
+                    w = (cc - 1) * self.ratio + 1
+                elif self.mode == "sssdms":
+                    w = torch.round(cc / 10) + 1
+                elif self.mode == "equal":
+                    w = cc
+                else:
+                    raise ValueError(f"Mode {self.mode} is not supported")
+                specs.append(L.LossSpec(L.AWB_LOSS_SE_SIGMOID, L.AWB_CLS_UNARY_LT_HALF, float(w) / N, 1.0 / N))
+            return specs
+        if self.kind in ("fgbg_se", "fgbg_bce_logits"):
+            cnt = target_counts(target, L.AWB_CLS_NOT_ONE).cpu()
+            k = L.AWB_LOSS_SE_SIGMOID if self.kind == "fgbg_se" else L.AWB_LOSS_BCE_LOGITS
+            for o in range(O):
+                fg, bg = float(cnt[o, 0]), float(cnt[o, 1])
+                specs.append(L.LossSpec(k, L.AWB_CLS_NOT_ONE, self.fg_weight / max(fg, 1.0),
+                                        (1.0 - self.fg_weight) / max(bg, 1.0)))
+            return specs
+        raise ValueError(f"unknown loss kind {self.kind!r}")
+
+
+@dataclass
+class OptimConfig:
+    """``torch.optim.Adam`` / ``Adamax`` hyper-parameters with the reference's parameter groups
+    (0 flow_net, 1 convex_net, 2 linear; ``path_connected_net.py:923-929``) and the optional
+    ``ReduceLROnPlateau(patience=200, factor=0.5)`` stepped on the loss every iteration (``:932-953``)."""
+    kind: str = "adam"
+    lr: Union[float, Sequence[float]] = 1e-3
+    betas: Sequence[float] = (0.9, 0.999)
+    eps: float = 1e-8
+    weight_decay: Union[float, Sequence[float]] = 0.0
+    plateau: bool = False
+    patience: int = 200
+    factor: float = 0.5
+    threshold: float = 1e-4
+    min_lr: float = 0.0
+    plateau_eps: float = 1e-8
+
+    def _per_group(self, v) -> List[float]:
+        if isinstance(v, (int, float)):
+            return [float(v)] * L.AWB_MAX_GROUPS
+        v = list(v) + [0.0] * L.AWB_MAX_GROUPS
+        return [float(x) for x in v[:L.AWB_MAX_GROUPS]]
+
+    def lrs(self) -> List[float]:
+        return self._per_group(self.lr)
+
+    def to_c(self) -> L.OptHyper:
+        kind = {"adam": L.AWB_OPT_ADAM, "adamax": L.AWB_OPT_ADAMAX}[self.kind.lower()]
+        wd = (C.c_float * L.AWB_MAX_GROUPS)(*self._per_group(self.weight_decay))
+        return L.OptHyper(kind, self.betas[0], self.betas[1], self.eps, wd, int(self.plateau), self.patience,
+                          self.factor, self.threshold, self.min_lr, self.plateau_eps)
+
+
+class PriorFitter:
+    """Fits ``prior`` (a native handle) to ``target`` on ``grid`` in place on ``params``.
+
+    params ``[O,P]`` fp32 CUDA (the module's arena), target ``[O,N]`` fp32 CUDA.
+    ``run(steps)`` replays CUDA graphs of ``steps_per_graph`` fused steps.
+    """
+
+    def __init__(self, prior: Prior, params: torch.Tensor, grid: GridSpecHost, target: torch.Tensor,
+                 loss: LossConfig, optim: OptimConfig, steps_per_graph: int = 25, use_graph: bool = True):
+        L.require_cuda()
+        self.prior, self.params, self.grid = prior, params, grid
+        self.device = params.device
+        O = prior.n_objects
+        self.target = target.detach().reshape(O, -1).contiguous().float()
+        if self.target.shape[1] != grid.n_pixels:
+            raise ValueError(f"target has {self.target.shape[1]} pixels per object, grid has {grid.n_pixels}")
+        if params.numel() != O * prior.n_params or params.dtype != torch.float32 or not params.is_contiguous():
+            raise ValueError("params must be a contiguous fp32 [O,P] arena")
+        self.lib = prior.lib
+        with torch.cuda.device(self.device):
+            self.ws = prior.new_workspace(grid.n_pixels, True, self.device)
+            self.opt_state = torch.empty(prior.opt_state_bytes(), dtype=torch.uint8, device=self.device)
+            self._specs_list = loss.to_specs(self.target)
+        self._specs = (L.LossSpec * O)(*self._specs_list)
+        self._hyper = optim.to_c()
+        self._gs = grid.to_c()
+        self.optim = optim
+        self.K = max(1, int(steps_per_graph))
+        self.use_graph = use_graph
+        self._ring = torch.zeros((self.K, O), dtype=torch.float32, device=self.device)
+        self._graph = None
+        self.steps_done = 0
+        self.reset_optimizer()
+
+    def reset_optimizer(self) -> None:
+        """Fresh optimizer + scheduler, as the reference creates per frame (``path_connected_net.py:923-933``)."""
+        lrs = (C.c_double * L.AWB_MAX_GROUPS)(*self.optim.lrs())
+        with torch.cuda.device(self.device):
+            L.check(self.lib.awb_opt_state_init(self.prior.handle, self.opt_state.data_ptr(), lrs, L.stream_ptr()))
+        self.steps_done = 0
+
+    def set_target(self, target: torch.Tensor, loss: Optional[LossConfig] = None) -> None:
+        """New unaries for the same shapes (next frame): reuses workspace, graph and state buffers."""
+        self.target.copy_(target.detach().reshape(self.target.shape))
+        if loss is not None:
+            with torch.cuda.device(self.device):
+                specs = loss.to_specs(self.target)
+            changed = any((a.kind, a.cls_rule, a.coef_fg, a.coef_bg) != (b.kind, b.cls_rule, b.coef_fg, b.coef_bg)
+                          for a, b in zip(specs, self._specs_list))
+            if changed:
+                self._specs_list = specs
+                self._specs = (L.LossSpec * len(specs))(*specs)
+                self._graph = None      # coefficients are baked into the captured launches
+
+    def _step(self, k: int) -> None:
+        loss_ptr = self._ring.data_ptr() + 4 * k * self.prior.n_objects
+        L.check(self.lib.awb_prior_fit_step(self.prior.handle, self.params.data_ptr(), self.opt_state.data_ptr(),
+                                            C.byref(self._gs), self.target.data_ptr(), self._specs,
+                                            C.byref(self._hyper), loss_ptr, self.ws.data_ptr(), self.ws.numel(),
+                                            L.stream_ptr()))
+
+    def _capture(self) -> None:
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self._step(0)          # warm-up outside capture (module load, lazy init)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        # the warm-up step must not count: restore by re-running from a snapshot
+        with torch.cuda.graph(g, stream=s):
+            for k in range(self.K):
+                self._step(k)
+        self._graph = g
+
+    def run(self, steps: int, record: bool = True) -> Optional[torch.Tensor]:
+        """Run ``steps`` fused fit steps.  Returns the device loss history ``[steps,O]`` (no sync)."""
+        hist = torch.empty((steps, self.prior.n_objects), dtype=torch.float32, device=self.device) if record else None
+        done = 0
+        with torch.cuda.device(self.device):
+            if self.use_graph and steps >= self.K and self._graph is None:
+                snap_p, snap_o = self.params.clone(), self.opt_state.clone()
+                self._capture()
+                self.params.copy_(snap_p)
+                self.opt_state.copy_(snap_o)
+            while self.use_graph and self._graph is not None and steps - done >= self.K:
+                self._graph.replay()
+                if record:
+                    hist[done:done + self.K].copy_(self._ring)
+                done += self.K
+            while done < steps:
+                self._step(0)
+                if record:
+                    hist[done].copy_(self._ring[0])
+                done += 1
+        self.steps_done += steps
+        return hist
+
+    def scalars(self, obj: int = 0) -> L.OptScalars:
+        """Synchronises and returns step / lr / plateau / non-finite flag of one object."""
+        out = L.OptScalars()
+        with torch.cuda.device(self.device):
+            L.check(self.lib.awb_opt_read_scalars(self.prior.handle, self.opt_state.data_ptr(), obj, C.byref(out),
+                                                  L.stream_ptr()))
+        return out
+
+    def raise_if_nonfinite(self) -> None:
+        """Reference behaviour: ``ValueError("Loss is nan or inf!")`` (``path_connected_net.py:232,374,456,702``)."""
+        for o in range(self.prior.n_objects):
+            if self.scalars(o).nonfinite:
+                raise ValueError("Loss is nan or inf!")

@@ -1,0 +1,188 @@
+/*
+ * awb.h -- C-ABI of the B200-native shape-prior fitting library (libawb.so).
+ *
+ * Drop-in boundary for AWESOME's prior-fit hot path.  The
+ * reference is pure Python/PyTorch and has no FFI of its own; each entry point
+ * below states the reference interface it replaces (paths relative to the
+ * reference checkout).  The Python host side (awesome_b200/) binds these with
+ * ctypes and mirrors the reference's module / optimizer / loss API on top.
+ *
+ * Conventions
+ *  - every function returns an int status: 0 ok, <0 error; awb_last_error()
+ *    returns a thread-local message.  No exceptions, no abort().
+ *  - all pointers named d_* / params / grads / target / workspace are DEVICE pointers to
+ *    fp32 unless stated; the library borrows them for the duration of the call
+ *    and never frees or retains them (torch's caching allocator stays the owner).
+ *  - all work is enqueued on the given cudaStream_t (passed as void*) and is
+ *    asynchronous; calls are capturable into CUDA graphs.
+ *  - a non-finite loss never traps a kernel: it skips the parameter update of
+ *    that step and raises a sticky device flag (awb_opt_read_scalars).
+ *  - pixel rows are ordered (b, h, w) row-major, exactly like the reference's
+ *    pixelize() (awesome/util/pixelize.py:30-32).
+ */
+#ifndef AWB_H_
+#define AWB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AWB_OK 0
+#define AWB_ERR_INVALID (-1)
+#define AWB_ERR_UNSUPPORTED (-2)
+#define AWB_ERR_CUDA (-3)
+#define AWB_ERR_WORKSPACE (-4)
+
+/* prior kinds */
+#define AWB_KIND_ICNN 0      /* ConvexNextNet / ConvexNet: awesome/model/convex_net.py:177-220 */
+#define AWB_KIND_FLOW_ICNN 1 /* PathConnectedNet(RealNVP o ConvexNextNet): awesome/model/path_connected_net.py:53-85 */
+
+/* arithmetic of the hidden-layer contractions */
+#define AWB_PREC_FP32 0 /* CUDA-core fp32, bit-level comparable with the reference */
+#define AWB_PREC_F16 1  /* tcgen05 kind::f16 operands, fp32 accumulation in TMEM */
+
+/* coordinate grid conventions */
+#define AWB_GRID_EXPLICIT 0 /* caller-provided [B,C,H,W] fp32 */
+#define AWB_GRID_LINSPACE 1 /* x=linspace(0,1,W)[j], y=linspace(0,1,H)[i]: awesome/dataset/transformator.py:50-60 */
+#define AWB_GRID_INDEX 2    /* x=j/W, y=i/H: notebooks/how_to/convexity.ipynb cell 7 */
+
+/* per-pixel loss kinds */
+#define AWB_LOSS_SE_SIGMOID 0 /* (t - sigmoid(y))^2: awesome/measures/se.py:21-23 on WrapperModule.process_prior_output */
+#define AWB_LOSS_BCE_LOGITS 1 /* BCEWithLogitsLoss: notebooks/how_to/path-connectedness.ipynb cell 9 */
+#define AWB_CLS_UNARY_LT_HALF 0 /* fg = target < 0.5: awesome/measures/unaries_weighted_loss.py:35-69 */
+#define AWB_CLS_NOT_ONE 1       /* fg = target != 1: how-to notebooks, cell 9 */
+
+#define AWB_OPT_ADAM 0
+#define AWB_OPT_ADAMAX 1
+#define AWB_MAX_GROUPS 4
+
+typedef struct awb_prior* awb_handle;
+
+typedef struct awb_desc {
+  int32_t kind;      /* AWB_KIND_* */
+  int32_t C;         /* coordinate channels: 2 (x,y) or 3 (x,y,t) */
+  int32_t h;         /* ICNN hidden width (n_hidden, default 130) */
+  int32_t L;         /* number of SkipBlocks (n_hidden_layers) */
+  int32_t F;         /* number of RealNVP flows (0 for AWB_KIND_ICNN) */
+  int32_t m;         /* flow MLP hidden width */
+  int32_t flow_tanh; /* 1: output_fn == "tanh" */
+  int32_t n_objects; /* O independent priors fitted in one grouped launch (multi-object) */
+  int32_t precision; /* AWB_PREC_* */
+} awb_desc;
+
+typedef struct awb_grid_spec {
+  int32_t mode;      /* AWB_GRID_* */
+  int32_t B, H, W;   /* frames, height, width; N = B*H*W pixel rows */
+  float t0, t_step;  /* C==3 and generated grid: t of frame b = t0 + b*t_step */
+  const float* grid; /* AWB_GRID_EXPLICIT: device [B,C,H,W] */
+} awb_grid_spec;
+
+/* loss = sum_n coef(t_n) * l(y_n, t_n); coef = fg(t_n) ? coef_fg : coef_bg.  The caller folds
+ * any 1/N, class weights (ratio / sssdms / equal) or fg/bg means into the two coefficients. */
+typedef struct awb_loss_spec {
+  int32_t kind;     /* AWB_LOSS_* */
+  int32_t cls_rule; /* AWB_CLS_* */
+  float coef_fg, coef_bg;
+} awb_loss_spec;
+
+typedef struct awb_opt_hyper {
+  int32_t kind; /* AWB_OPT_*: torch.optim.Adam / Adamax single-tensor arithmetic */
+  float beta1, beta2, eps;
+  float weight_decay[AWB_MAX_GROUPS]; /* per parameter group: 0 flow_net, 1 convex_net, 2 linear */
+  /* ReduceLROnPlateau(mode=min, rel threshold) stepped on the loss every iteration
+   * (awesome/model/path_connected_net.py:932-933,953); disabled when plateau_enabled == 0 */
+  int32_t plateau_enabled;
+  int32_t patience;
+  float factor, threshold, min_lr, plateau_eps;
+} awb_opt_hyper;
+
+/* host-readable copy of the per-object optimizer scalars */
+typedef struct awb_opt_scalars {
+  int32_t step;      /* optimizer steps taken */
+  int32_t num_bad;   /* plateau counter */
+  int32_t nonfinite; /* sticky: a step saw a NaN/Inf loss (update skipped) */
+  int32_t pad;
+  double lr[AWB_MAX_GROUPS];
+  double best;
+  float last_loss;
+  float pad2;
+} awb_opt_scalars;
+
+const char* awb_version(void);
+const char* awb_last_error(void);
+
+/* Replaces the constructor prior_model_type(**prior_model_args)
+ * (awesome/run/awesome_runner.py:222-236; ConvexNextNet.__init__ convex_net.py:178-201;
+ * net_factory.real_nvp_path_connected_net net_factory.py:124-176). */
+int awb_prior_create(const awb_desc* desc, awb_handle* out);
+int awb_prior_destroy(awb_handle h);
+
+/* Number of trainable fp32 parameters per object, in state_dict order. */
+int64_t awb_prior_param_count(awb_handle h);
+/* Bytes of scratch the caller must provide for n_pixels rows (all objects). */
+int64_t awb_prior_workspace_bytes(awb_handle h, int64_t n_pixels, int32_t training);
+int64_t awb_opt_state_bytes(awb_handle h);
+
+/* MinMax buffers of NormNet (awesome/transforms/min_max.py:28-32, net_factory.py:159-165)
+ * and the coupling masks [F*C] (net_factory.py:86-99); flow priors only. */
+int awb_prior_set_flow_consts(awb_handle h, const float* norm_min, const float* norm_max,
+                              float new_min, float new_max, const uint8_t* masks);
+
+/* forward(grid) -> raw logits [O][N]  (ConvexNextNet.forward convex_net.py:205-214;
+ * PathConnectedNet.forward path_connected_net.py:79-85).  Leaves activations in the
+ * workspace for awb_prior_backward when training != 0.  deformed (optional, [O][N][C])
+ * receives get_deformation() (path_connected_net.py:125-129). */
+int awb_prior_forward(awb_handle h, const float* params, const awb_grid_spec* grid, float* logits,
+                      float* deformed, int32_t training, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* autograd backward of forward(): dlogits [O][N] -> grads [O][P] (overwritten), optional
+ * dgrid [B,C,H,W] (ICNN, single object; model_input_requires_grad configs).  Must follow
+ * awb_prior_forward(training=1) on the same workspace. */
+int awb_prior_backward(awb_handle h, const float* params, const awb_grid_spec* grid,
+                       const float* dlogits, float* grads, float* dgrid, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* One fused fit step = the body of the reference's hot loops
+ * (path_connected_net.py:939-953, :364-379; notebooks/how_to/convexity.ipynb cell 9):
+ * forward, sigmoid/loss, backward, cross-pixel gradient reduction, Adam/Adamax (+L2),
+ * enforce_convexity clamp (convex_net.py:151-154,216-220), ReduceLROnPlateau.step(loss).
+ * target [O][N]; loss/lr per object; loss_out (optional) device [O]. */
+int awb_prior_fit_step(awb_handle h, float* params, void* opt_state, const awb_grid_spec* grid,
+                       const float* target, const awb_loss_spec* loss, const awb_opt_hyper* hyper,
+                       float* loss_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* torch.optim.Adam/Adamax(...).step() + enforce_convexity on caller-provided grads [O][P]
+ * (agent loop: awesome/agent/torch_agent.py:489-492 + awesome_runner.py:294-297). */
+int awb_optim_step(awb_handle h, float* params, const float* grads, void* opt_state,
+                   const awb_opt_hyper* hyper, void* stream);
+/* enforce_convexity() alone (convex_net.py:216-220). */
+int awb_prior_enforce_convexity(awb_handle h, float* params, void* stream);
+
+/* Optimizer / plateau state (fresh optimizer per frame: path_connected_net.py:923-933). */
+int awb_opt_state_init(awb_handle h, void* opt_state, const double* lr_per_group, void* stream);
+/* synchronises the stream and copies the scalars of object obj to the host. */
+int awb_opt_read_scalars(awb_handle h, const void* opt_state, int32_t obj, awb_opt_scalars* out,
+                         void* stream);
+
+/* ActNorm data-dependent init (normflows ActNorm.forward, first call): sets s,t of every
+ * ActNorm from the pixel statistics of this grid, flow by flow. */
+int awb_prior_actnorm_init(awb_handle h, float* params, const awb_grid_spec* grid, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+/* counts[O][4] (int64 device): {fg&fg, pred_fg, target_fg, n} for masks thresholded at 0.5 with
+ * fg = value < 0.5 (MIOU(average="binary", invert=True): awesome/measures/miou.py:29-48;
+ * in-loop check path_connected_net.py:964-982). pred_is_logit: threshold logits at 0. */
+int awb_mask_iou_counts(const float* pred, const float* target, int64_t n_pixels, int32_t n_objects,
+                        int32_t pred_is_logit, long long* counts, void* stream);
+/* target statistics for the weighted losses: counts[O][2] = {fg, bg} under cls_rule. */
+int awb_target_counts(const float* target, int64_t n_pixels, int32_t n_objects, int32_t cls_rule,
+                      long long* counts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AWB_H_ */
