@@ -6,7 +6,8 @@ Drop-in names for the reference's YAML configs (``prior_model_type`` / ``optimiz
 All arithmetic runs in ``csrc/libawb.so`` (hand-written sm_100a CUDA); there is no CPU fallback.
 """
 from .core import GridSpecHost, Prior, iou_counts, target_counts  # noqa: F401
-from .fit import LossConfig, OptimConfig, PriorFitter  # noqa: F401
-from .model import ConvexNet, ConvexNextNet  # noqa: F401
+from .fit import FlowIdentityFitter, LossConfig, OptimConfig, PriorFitter  # noqa: F401
+from .model import (ConvexNet, ConvexNextNet, MinMax, NormNet, PathConnectedNet, PixelizeNet, get_norm,  # noqa: F401
+                    init_realnvp, real_nvp_path_connected_net)
 
 __version__ = "0.1.0"

@@ -51,7 +51,7 @@ class OptHyper(C.Structure):
                 ("weight_decay", C.c_float * AWB_MAX_GROUPS),
                 ("plateau_enabled", C.c_int32), ("patience", C.c_int32),
                 ("factor", C.c_float), ("threshold", C.c_float), ("min_lr", C.c_float),
-                ("plateau_eps", C.c_float)]
+                ("plateau_eps", C.c_float), ("active_groups", C.c_int32)]
 
 
 class OptScalars(C.Structure):
@@ -76,13 +76,20 @@ SYMBOLS = [
     ("awb_prior_backward", C.c_int, [_P, _P, C.POINTER(GridSpec), _P, _P, _P, _P, C.c_size_t, _P]),
     ("awb_prior_fit_step", C.c_int, [_P, _P, _P, C.POINTER(GridSpec), _P, C.POINTER(LossSpec),
                                      C.POINTER(OptHyper), _P, _P, C.c_size_t, _P]),
+    ("awb_flow_identity_step", C.c_int, [_P, _P, _P, C.POINTER(GridSpec), C.POINTER(OptHyper), _P, _P,
+                                         C.c_size_t, _P]),
     ("awb_optim_step", C.c_int, [_P, _P, _P, _P, C.POINTER(OptHyper), _P]),
     ("awb_prior_enforce_convexity", C.c_int, [_P, _P, _P]),
     ("awb_opt_state_init", C.c_int, [_P, _P, C.POINTER(C.c_double), _P]),
     ("awb_opt_read_scalars", C.c_int, [_P, _P, C.c_int32, C.POINTER(OptScalars), _P]),
     ("awb_prior_actnorm_init", C.c_int, [_P, _P, C.POINTER(GridSpec), _P, C.c_size_t, _P]),
     ("awb_mask_iou_counts", C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
-    ("awb_target_counts", C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
+    ("awb_target_counts", C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
+    ("awb_profile_enable", C.c_int, [C.c_int32]),
+    ("awb_profile_classes", C.c_int, []),
+    ("awb_profile_class_name", C.c_char_p, [C.c_int32]),
+    ("awb_profile_read", C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+    ("awb_launch_count", C.c_longlong, []),
 ]
 
 _lib: Optional[C.CDLL] = None

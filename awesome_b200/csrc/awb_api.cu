@@ -65,6 +65,8 @@ Workspace carve(const awb_prior* h, int64_t N, bool training, void* base) {
   w.ZA = (float*)take(4 * O * (L.L + 1) * N * L.ld);
   w.D = (float*)take(training ? 4 * O * 2 * N * L.ld : 0);
   w.logits = (float*)take(4 * O * N);
+  w.flowz = (float*)take(training ? 4 * O * N * (int64_t)L.F * L.C : 0);
+  if (!training || L.F == 0) w.flowz = nullptr;
   w.tc = nullptr;
   w.bytes = off;
   return w;
@@ -220,6 +222,26 @@ int awb_prior_fit_step(awb_handle h, float* params, void* opt_state, const awb_g
   rc = simt_backward(h, params, g, target, loss, nullptr, false, w, st);
   if (rc) return rc;
   return simt_reduce_opt(h, params, opt_state, hy, loss_out, w, N, st);
+}
+
+int awb_flow_identity_step(awb_handle h, float* params, void* opt_state, const awb_grid_spec* g,
+                           const awb_opt_hyper* hy, float* loss_out, void* ws, size_t ws_bytes, void* stream) {
+  int64_t N;
+  int rc = check_common(h, g, ws, ws_bytes, true, &N);
+  if (rc) return rc;
+  if (!params || !opt_state || !hy) { set_error("null argument"); return AWB_ERR_INVALID; }
+  if (h->desc.kind != AWB_KIND_FLOW_ICNN) { set_error("not a flow prior"); return AWB_ERR_INVALID; }
+  Workspace w = carve(h, N, true, ws);
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = flow_forward(h, params, g, w, nullptr, st, /*use_linear=*/false);
+  if (rc) return rc;
+  rc = flow_identity_loss(h, g, w, st);
+  if (rc) return rc;
+  rc = flow_backward(h, params, g, w, st, /*use_linear=*/false);
+  if (rc) return rc;
+  awb_opt_hyper hh = *hy;
+  hh.active_groups = 1;   // flow_net only
+  return simt_reduce_opt(h, params, opt_state, &hh, loss_out, w, N, st);
 }
 
 int awb_optim_step(awb_handle h, float* params, const float* grads, void* opt_state, const awb_opt_hyper* hy,

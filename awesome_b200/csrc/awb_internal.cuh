@@ -93,10 +93,23 @@ struct Workspace {
   float* ZA;      // [O][L+1][N][ld]
   float* D;       // [O][2][N][ld]
   float* logits;  // [O][N]
+  float* flowz;   // [O][N][F*C] inputs of every coupling (training, flow priors)
   void* tc;       // tensor-core path scratch
   int64_t bytes;
 };
 Workspace carve(const awb_prior* h, int64_t N, bool training, void* base);
+
+// ---- per-kernel-class timing (CUDA events on the launch stream) and launch counting ----
+enum { PK_PACK = 0, PK_INPUT, PK_GEMM_FWD, PK_OUT_LOSS, PK_GEMM_WGRAD, PK_GEMM_DGRAD, PK_IN_BWD, PK_OPT,
+       PK_FLOW_FWD, PK_FLOW_BWD, PK_TC_FUSED, PK_MISC, PK_COUNT };
+void prof_begin(int cls, cudaStream_t st);
+void prof_end(int cls, cudaStream_t st);
+#define AWB_LAUNCH(cls, st, ...)  \
+  do {                            \
+    awb::prof_begin(cls, st);     \
+    __VA_ARGS__;                  \
+    awb::prof_end(cls, st);       \
+  } while (0)
 
 // ---- launchers implemented in awb_simt.cu ----
 struct GridDev {
@@ -121,9 +134,10 @@ int opt_state_init(const awb_prior* h, void* opt_state, const double* lr, cudaSt
 
 // ---- flows, implemented in awb_flow.cu ----
 int flow_forward(const awb_prior* h, const float* params, const awb_grid_spec* g, const Workspace& ws,
-                 float* deformed, cudaStream_t st);
+                 float* deformed, cudaStream_t st, bool use_linear = true);
+int flow_identity_loss(const awb_prior* h, const awb_grid_spec* g, const Workspace& ws, cudaStream_t st);
 int flow_backward(const awb_prior* h, const float* params, const awb_grid_spec* g, const Workspace& ws,
-                  cudaStream_t st);
+                  cudaStream_t st, bool use_linear = true);
 int flow_actnorm_init(const awb_prior* h, float* params, const awb_grid_spec* g, const Workspace& ws,
                       cudaStream_t st);
 

@@ -470,6 +470,7 @@ __global__ void __launch_bounds__(256) k_reduce_opt(OptP a) {
   }
   int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= a.P) return;
+  if (a.hy.active_groups && !((a.hy.active_groups >> a.group[i]) & 1)) return;   // not owned by this optimizer
   float g;
   if (a.grads) {
     g = a.grads[(int64_t)o * a.P + i];
@@ -574,8 +575,8 @@ int simt_forward(const awb_prior* h, const float* params, const awb_grid_spec* g
   const int O = h->desc.n_objects;
   const int64_t N = (int64_t)g->B * g->H * g->W;
   AWB_CUDA(cudaMemsetAsync(ws.waug, 0, sizeof(float) * O * L.G, st));
-  k_pack<<<dim3((unsigned)((L.P_icnn + 255) / 256), O), 256, 0, st>>>(params, ws.waug, h->d_map, (int)L.P_icnn,
-                                                                       L.P, L.off_icnn, L.G);
+  AWB_LAUNCH(PK_PACK, st, k_pack<<<dim3((unsigned)((L.P_icnn + 255) / 256), O), 256, 0, st>>>(params, ws.waug, h->d_map, (int)L.P_icnn,
+                                                                       L.P, L.off_icnn, L.G));
   int x_ready = 0;
   if (h->desc.kind == AWB_KIND_FLOW_ICNN) {
     int rc = flow_forward(h, params, g, ws, deformed, st);
@@ -584,8 +585,8 @@ int simt_forward(const awb_prior* h, const float* params, const awb_grid_spec* g
   }
   const int64_t sLayer = N * L.ld;            // one ZA layer
   const int64_t sZAobj = (L.L + 1) * sLayer;  // all layers of an object
-  k_input<<<dim3((unsigned)((N + 63) / 64), O), 256, 0, st>>>(to_dev(g, L.C), x_ready, ws.X, ws.waug, ws.ZA, N,
-                                                              L.h, L.C, L.ld, L.G, L.aug_in, sZAobj);
+  AWB_LAUNCH(PK_INPUT, st, k_input<<<dim3((unsigned)((N + 63) / 64), O), 256, 0, st>>>(to_dev(g, L.C), x_ready, ws.X, ws.waug, ws.ZA, N,
+                                                              L.h, L.C, L.ld, L.G, L.aug_in, sZAobj));
   for (int i = 0; i < L.L; i++) {
     GemmP p = {};
     p.A = ws.ZA + i * sLayer; p.sA = sZAobj; p.lda = L.ld;
@@ -594,7 +595,7 @@ int simt_forward(const awb_prior* h, const float* params, const awb_grid_spec* g
     p.M = N; p.N = L.h; p.K = L.ld;
     p.E0 = p.A; p.sE0 = sZAobj;
     p.h = L.h; p.C = L.C;
-    k_gemm<0><<<dim3((unsigned)((N + 127) / 128), 1, O), 256, 0, st>>>(p);
+    AWB_LAUNCH(PK_GEMM_FWD, st, k_gemm<0><<<dim3((unsigned)((N + 127) / 128), 1, O), 256, 0, st>>>(p));
   }
   if (!training) {
     OutP q = {};
@@ -603,8 +604,8 @@ int simt_forward(const awb_prior* h, const float* params, const awb_grid_spec* g
     q.logits = logits_out; q.train = 0; q.N = N; q.chunk = split_chunk(N);
     q.h = L.h; q.C = L.C; q.ld = L.ld; q.O = O;
     size_t smem = (8 * L.ld + 8) * sizeof(float);
-    if (L.ld <= 160) k_out<5><<<dim3(n_splits(N), O), 256, smem, st>>>(q);
-    else k_out<9><<<dim3(n_splits(N), O), 256, smem, st>>>(q);
+    if (L.ld <= 160) AWB_LAUNCH(PK_OUT_LOSS, st, k_out<5><<<dim3(n_splits(N), O), 256, smem, st>>>(q));
+    else AWB_LAUNCH(PK_OUT_LOSS, st, k_out<9><<<dim3(n_splits(N), O), 256, smem, st>>>(q));
   } else if (logits_out) {
     // training forward: logits are produced by the same kernel that starts the backward
     OutP q = {};
@@ -613,8 +614,8 @@ int simt_forward(const awb_prior* h, const float* params, const awb_grid_spec* g
     q.logits = logits_out; q.train = 0; q.N = N; q.chunk = split_chunk(N);
     q.h = L.h; q.C = L.C; q.ld = L.ld; q.O = O;
     size_t smem = (8 * L.ld + 8) * sizeof(float);
-    if (L.ld <= 160) k_out<5><<<dim3(n_splits(N), O), 256, smem, st>>>(q);
-    else k_out<9><<<dim3(n_splits(N), O), 256, smem, st>>>(q);
+    if (L.ld <= 160) AWB_LAUNCH(PK_OUT_LOSS, st, k_out<5><<<dim3(n_splits(N), O), 256, smem, st>>>(q));
+    else AWB_LAUNCH(PK_OUT_LOSS, st, k_out<9><<<dim3(n_splits(N), O), 256, smem, st>>>(q));
   }
   AWB_CUDA(cudaGetLastError());
   return AWB_OK;
@@ -644,8 +645,8 @@ int simt_backward(const awb_prior* h, const float* params, const awb_grid_spec* 
   q.part = ws.part; q.sSplit = sSplit; q.lossp = ws.lossp;
   q.N = N; q.chunk = chunk; q.h = L.h; q.C = L.C; q.ld = L.ld; q.O = O;
   size_t smem = (8 * L.ld + 8) * sizeof(float);
-  if (L.ld <= 160) k_out<5><<<dim3(S, O), 256, smem, st>>>(q);
-  else k_out<9><<<dim3(S, O), 256, smem, st>>>(q);
+  if (L.ld <= 160) AWB_LAUNCH(PK_OUT_LOSS, st, k_out<5><<<dim3(S, O), 256, smem, st>>>(q));
+  else AWB_LAUNCH(PK_OUT_LOSS, st, k_out<9><<<dim3(S, O), 256, smem, st>>>(q));
 
   for (int i = L.L; i >= 1; i--) {
     const float* delta = ws.D + (i & 1) * sLayer;
@@ -659,7 +660,7 @@ int simt_backward(const awb_prior* h, const float* params, const awb_grid_spec* 
       p.Cout = ws.part + L.aug_layer + (int64_t)(i - 1) * L.h * L.ld; p.sC = L.G; p.ldc = L.ld;
       p.M = L.h; p.N = L.ld; p.K = (int)N;
       p.h = L.h; p.C = L.C; p.k_chunk = chunk; p.sSplit = sSplit;
-      k_gemm<2><<<dim3(S, 1, O), 256, 0, st>>>(p);
+      AWB_LAUNCH(PK_GEMM_WGRAD, st, k_gemm<2><<<dim3(S, 1, O), 256, 0, st>>>(p));
     }
     {  // data gradient + relu backward
       GemmP p = {};
@@ -670,13 +671,13 @@ int simt_backward(const awb_prior* h, const float* params, const awb_grid_spec* 
       p.E0 = za_prev; p.sE0 = sZAobj;
       p.E1 = need_dx ? ws.dX : nullptr; p.sE1 = N * 4;
       p.h = L.h; p.C = L.C;
-      k_gemm<1><<<dim3((unsigned)((N + 127) / 128), 1, O), 256, 0, st>>>(p);
+      AWB_LAUNCH(PK_GEMM_DGRAD, st, k_gemm<1><<<dim3((unsigned)((N + 127) / 128), 1, O), 256, 0, st>>>(p));
     }
   }
-  k_in_wgrad<<<dim3(S, O), 256, 0, st>>>(ws.D, sDobj, ws.X, ws.part, sSplit, L.G, L.aug_in, N, chunk, L.h, L.ld);
+  AWB_LAUNCH(PK_IN_BWD, st, k_in_wgrad<<<dim3(S, O), 256, 0, st>>>(ws.D, sDobj, ws.X, ws.part, sSplit, L.G, L.aug_in, N, chunk, L.h, L.ld));
   if (need_dx)
-    k_in_dgrad<<<dim3((unsigned)((N + 7) / 8), O), 256, 0, st>>>(ws.D, sDobj, ws.waug, L.G, L.aug_in, ws.dX, N,
-                                                                 L.h, L.ld);
+    AWB_LAUNCH(PK_IN_BWD, st, k_in_dgrad<<<dim3((unsigned)((N + 7) / 8), O), 256, 0, st>>>(ws.D, sDobj, ws.waug, L.G, L.aug_in, ws.dX, N,
+                                                                 L.h, L.ld));
   AWB_CUDA(cudaGetLastError());
   if (h->desc.kind == AWB_KIND_FLOW_ICNN) {
     int rc = flow_backward(h, params, g, ws, st);
@@ -701,8 +702,8 @@ int simt_reduce_opt(const awb_prior* h, float* params, void* opt_state, const aw
   a.map = h->d_map; a.clamp = h->d_clamp; a.group = h->d_group;
   a.P = L.P; a.off_icnn = L.off_icnn; a.P_icnn = L.P_icnn; a.off_flow = L.off_flow; a.G = L.G;
   a.O = O; a.hy = *hy; a.loss_out = loss_out;
-  k_reduce_opt<<<dim3((unsigned)((L.P + 255) / 256), O), 256, 0, st>>>(a);
-  k_step_end<<<1, O, 0, st>>>(a.scal, *hy, n_groups_of(h), 1);
+  AWB_LAUNCH(PK_OPT, st, k_reduce_opt<<<dim3((unsigned)((L.P + 255) / 256), O), 256, 0, st>>>(a));
+  AWB_LAUNCH(PK_OPT, st, k_step_end<<<1, O, 0, st>>>(a.scal, *hy, n_groups_of(h), 1));
   AWB_CUDA(cudaGetLastError());
   return AWB_OK;
 }
@@ -711,16 +712,16 @@ int simt_reduce_grads(const awb_prior* h, float* grads, const Workspace& ws, int
   const Layout& L = h->lay;
   const int O = h->desc.n_objects;
   int64_t PF = L.P_flow + 2 * L.C;
-  k_reduce_grads<<<dim3((unsigned)((L.P + 255) / 256), O), 256, 0, st>>>(
+  AWB_LAUNCH(PK_OPT, st, k_reduce_grads<<<dim3((unsigned)((L.P + 255) / 256), O), 256, 0, st>>>(
       grads, ws.part, (int64_t)O * L.G, n_splits(N), ws.fpart, (int64_t)O * PF, h->d_map, L.P, L.off_icnn,
-      L.P_icnn, L.off_flow, PF, L.G);
+      L.P_icnn, L.off_flow, PF, L.G));
   AWB_CUDA(cudaGetLastError());
   return AWB_OK;
 }
 
 int simt_dgrid(const awb_prior* h, const awb_grid_spec* g, float* dgrid, const Workspace& ws, cudaStream_t st) {
   const int64_t N = (int64_t)g->B * g->H * g->W;
-  k_dgrid<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(ws.dX, dgrid, N, (int64_t)g->H * g->W, h->lay.C);
+  AWB_LAUNCH(PK_MISC, st, k_dgrid<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(ws.dX, dgrid, N, (int64_t)g->H * g->W, h->lay.C));
   AWB_CUDA(cudaGetLastError());
   return AWB_OK;
 }
@@ -736,14 +737,14 @@ int optim_step(const awb_prior* h, float* params, const float* grads, void* opt_
   a.map = h->d_map; a.clamp = h->d_clamp; a.group = h->d_group;
   a.P = L.P; a.off_icnn = L.off_icnn; a.P_icnn = L.P_icnn; a.off_flow = L.off_flow; a.G = L.G;
   a.O = O; a.hy = *hy;
-  k_reduce_opt<<<dim3((unsigned)((L.P + 255) / 256), O), 256, 0, st>>>(a);
-  k_step_end<<<1, O, 0, st>>>(a.scal, *hy, n_groups_of(h), 0);
+  AWB_LAUNCH(PK_OPT, st, k_reduce_opt<<<dim3((unsigned)((L.P + 255) / 256), O), 256, 0, st>>>(a));
+  AWB_LAUNCH(PK_OPT, st, k_step_end<<<1, O, 0, st>>>(a.scal, *hy, n_groups_of(h), 0));
   AWB_CUDA(cudaGetLastError());
   return AWB_OK;
 }
 
 int clamp_only(const awb_prior* h, float* params, cudaStream_t st) {
-  k_clamp<<<dim3((unsigned)((h->lay.P + 255) / 256), h->desc.n_objects), 256, 0, st>>>(params, h->d_clamp, h->lay.P);
+  AWB_LAUNCH(PK_OPT, st, k_clamp<<<dim3((unsigned)((h->lay.P + 255) / 256), h->desc.n_objects), 256, 0, st>>>(params, h->d_clamp, h->lay.P));
   AWB_CUDA(cudaGetLastError());
   return AWB_OK;
 }
@@ -753,7 +754,7 @@ int opt_state_init(const awb_prior* h, void* opt_state, const double* lr, cudaSt
   float* m; float* v; OptScal* sc;
   opt_ptrs(h, opt_state, &m, &v, &sc);
   AWB_CUDA(cudaMemsetAsync(opt_state, 0, 2 * n * sizeof(float), st));
-  k_opt_init<<<1, 64, 0, st>>>(sc, lr[0], lr[1], lr[2], lr[3], h->desc.n_objects);
+  AWB_LAUNCH(PK_MISC, st, k_opt_init<<<1, 64, 0, st>>>(sc, lr[0], lr[1], lr[2], lr[3], h->desc.n_objects));
   AWB_CUDA(cudaGetLastError());
   return AWB_OK;
 }

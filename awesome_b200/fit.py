@@ -92,7 +92,7 @@ class OptimConfig:
         kind = {"adam": L.AWB_OPT_ADAM, "adamax": L.AWB_OPT_ADAMAX}[self.kind.lower()]
         wd = (C.c_float * L.AWB_MAX_GROUPS)(*self._per_group(self.weight_decay))
         return L.OptHyper(kind, self.betas[0], self.betas[1], self.eps, wd, int(self.plateau), self.patience,
-                          self.factor, self.threshold, self.min_lr, self.plateau_eps)
+                          self.factor, self.threshold, self.min_lr, self.plateau_eps, 0)
 
 
 class PriorFitter:
@@ -206,3 +206,33 @@ class PriorFitter:
         for o in range(self.prior.n_objects):
             if self.scalars(o).nonfinite:
                 raise ValueError("Loss is nan or inf!")
+
+
+class FlowIdentityFitter(PriorFitter):
+    """``PathConnectedNet.learn_flow_identity`` (``path_connected_net.py:155-250``) as fused steps:
+    flow-only forward (no 1x1 conv), SE("mean") against the input grid, Adamax on the flow group."""
+
+    def __init__(self, prior: Prior, params: torch.Tensor, grid: GridSpecHost, optim: OptimConfig,
+                 steps_per_graph: int = 25, use_graph: bool = True):
+        L.require_cuda()
+        self.prior, self.params, self.grid = prior, params, grid
+        self.device = params.device
+        self.lib = prior.lib
+        with torch.cuda.device(self.device):
+            self.ws = prior.new_workspace(grid.n_pixels, True, self.device)
+            self.opt_state = torch.empty(prior.opt_state_bytes(), dtype=torch.uint8, device=self.device)
+        self._hyper = optim.to_c()
+        self._gs = grid.to_c()
+        self.optim = optim
+        self.K = max(1, int(steps_per_graph))
+        self.use_graph = use_graph
+        self._ring = torch.zeros((self.K, prior.n_objects), dtype=torch.float32, device=self.device)
+        self._graph = None
+        self.steps_done = 0
+        self.reset_optimizer()
+
+    def _step(self, k: int) -> None:
+        loss_ptr = self._ring.data_ptr() + 4 * k * self.prior.n_objects
+        L.check(self.lib.awb_flow_identity_step(self.prior.handle, self.params.data_ptr(), self.opt_state.data_ptr(),
+                                                C.byref(self._gs), C.byref(self._hyper), loss_ptr,
+                                                self.ws.data_ptr(), self.ws.numel(), L.stream_ptr()))

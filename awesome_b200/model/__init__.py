@@ -1,1 +1,3 @@
 from .convex_net import ConvexNet, ConvexNextNet, OutBlock, SkipBlock  # noqa: F401
+from .path_connected_net import (MinMax, NormNet, PathConnectedNet, PixelizeNet, RealNVP, get_norm,  # noqa: F401
+                                 init_realnvp, real_nvp_path_connected_net, realnvp_masks)

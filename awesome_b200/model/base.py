@@ -103,16 +103,29 @@ class ArenaPriorModule(nn.Module):
         self._arena = arena
 
     def _ensure_flat(self) -> torch.Tensor:
-        a = self._arena
-        ok = a is not None
+        """The parameters as one contiguous fp32 vector.  When they already sit back to back in
+        memory (e.g. this module's tensors are views into a parent module's arena) the arena is
+        re-derived as a view; otherwise they are copied into a fresh arena and re-pointed."""
+        params = self._arena_params()
+        first = params[0]
+        off, ok = first.data_ptr(), first.dtype == torch.float32
+        for p in params:
+            if p.data_ptr() != off or p.device != first.device or p.dtype != torch.float32:
+                ok = False
+                break
+            off += p.numel() * 4
+        n = sum(p.numel() for p in params)
         if ok:
-            off = a.data_ptr()
-            for p in self._arena_params():
-                if p.data_ptr() != off or p.device != a.device or p.dtype != torch.float32:
+            try:
+                if first.untyped_storage().nbytes() - first.storage_offset() * 4 < n * 4:
                     ok = False
-                    break
-                off += p.numel() * 4
-        if not ok:
+            except Exception:
+                ok = False
+        if ok:
+            a = self._arena
+            if a is None or a.data_ptr() != first.data_ptr() or a.numel() != n:
+                self._arena = torch.as_strided(first.detach(), (n,), (1,), first.storage_offset())
+        else:
             self._flatten_()
         return self._arena
 

@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Benchmark of the prior-fit hot path (BASELINE.json metric: prior-fit pixel-samples/sec, fwd+bwd+step).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|f16]
+
+Workload (config.workload): BASELINE configs[1] -- the convexity prior ``ConvexNextNet(h=130, L=2, C=2)``
+fitted per frame on a synthetic FBMS-shaped 640x480 frame (unaries = soft UNet-like blob), loss
+``UnariesWeightedLoss(SE)`` = MSE(sigmoid(y), unaries), Adam lr 1e-3, enforce_convexity every step.
+One "step" = one fused fit step (forward + loss + backward + gradient reduction + Adam + clamp) over
+one frame = 307 200 pixel-samples per GPU.  With N GPUs every rank fits its own frame (frames are
+independent: no data-path collective; weak scaling); value = N * 307200 * K / max-over-ranks time.
+
+Prints ONE JSON line (see the task contract): value (inputs resident in HBM, device-timed with CUDA
+events), e2e (same metric through the public fit API with the step's unaries coming from pinned host
+memory and the step's loss read back, copies inside the timed region), roofline (dominant kernel,
+timed live with CUDA events on the launch stream), cpu_baseline (the oracle port on the host cores,
+rank 0, bounded sample), clocks, gpu_launches.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 480, 640
+N_PIX = H * W
+HID, LAYERS, CH = 130, 2, 2
+MAC_FWD = CH * HID + LAYERS * (HID * HID + CH * HID) + HID + CH        # 34 712
+FLOP_PER_PX_STEP = 6 * MAC_FWD                                          # 208 272
+GEMM_FLOP_PER_PX_LAUNCH = 2 * HID * (HID + CH + 1)                      # one hidden-layer contraction launch
+WORKLOAD = "convexity ICNN prior fit per frame, synthetic FBMS-shaped 640x480 frame (BASELINE configs[1])"
+
+
+def synth_unaries(seed: int, t: float = 0.0):
+    """Soft UNet-like unaries in (0,1): blob on a Lissajous path with breathing axes."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, H), torch.linspace(0, 1, W), indexing="ij")
+    cx, cy = 0.5 + 0.2 * torch.sin(torch.tensor(2.0 * t)), 0.5 + 0.15 * torch.sin(torch.tensor(3.0 * t + 0.5))
+    rx, ry = 0.22 * (1 + 0.2 * torch.sin(torch.tensor(5.0 * t))), 0.28 * (1 + 0.2 * torch.cos(torch.tensor(4.0 * t)))
+    sdf = torch.sqrt(((xx - cx) / rx) ** 2 + ((yy - cy) / ry) ** 2) - 1
+    return torch.sigmoid((sdf + 0.05 * torch.randn(H, W, generator=g)) / 0.08).float()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_oracle_throughput(steps: int, warmup: int, budget_s: float = 60.0):
+    """The reference's CPU implementation of one fit step, restated by the oracle port (same ATen ops as the
+    reference modules), on all host cores.  Each step is a bounded sample of the workload: a horizontal band
+    of the 640x480 frame sized so that warmup+steps finish within ``budget_s``."""
+    import torch
+    from oracle import prior_oracle as O
+    torch.manual_seed(42)
+    lin = torch.nn.Linear  # reference initialisation order (ConvexNextNet.__init__)
+    p = {}
+    l = lin(CH, HID); p["input.weight"], p["input.bias"] = l.weight.detach(), l.bias.detach()
+    for i in range(LAYERS):
+        l = lin(HID, HID); p[f"skip.{i}.ln.weight"], p[f"skip.{i}.ln.bias"] = l.weight.detach(), l.bias.detach()
+        p[f"skip.{i}.skp.weight"] = lin(CH, HID, bias=False).weight.detach()
+    l = lin(HID, 1); p["out.ln.weight"], p["out.ln.bias"] = l.weight.detach(), l.bias.detach()
+    p["out.skp.weight"] = lin(CH, 1, bias=False).weight.detach()
+    p = O.clone_params(p)
+    rows_full = O.pixelize(O.grid_linspace(H, W)[None])
+    un_full = synth_unaries(42).reshape(-1)
+    # calibrate on 1/16 of the frame
+    n_cal = N_PIX // 16
+    t0 = time.perf_counter()
+    O.fit_icnn(O.clone_params(p), rows_full[:n_cal], un_full[:n_cal], steps=1, optimizer="adam", lr=1e-3)
+    t_cal = time.perf_counter() - t0
+    per_px = t_cal / n_cal
+    frac = 1.0
+    while frac > 1 / 64 and per_px * N_PIX * frac * (steps + warmup) > budget_s:
+        frac /= 2
+    n = int(N_PIX * frac)
+    rows, un = rows_full[:n].contiguous(), un_full[:n].contiguous()
+    O.fit_icnn(p, rows, un, steps=max(1, warmup), optimizer="adam", lr=1e-3)
+    t0 = time.perf_counter()
+    O.fit_icnn(p, rows, un, steps=steps, optimizer="adam", lr=1e-3)
+    dt = time.perf_counter() - t0
+    cores = torch.get_num_threads()
+    sample = f"{steps} fit steps on the first {n} of {N_PIX} pixel rows of the frame ({frac:g} frame), torch CPU fp32, " \
+             f"{cores} threads (os.cpu_count()={os.cpu_count()})"
+    return n * steps / dt, dt / steps * 1e3, cores, sample
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    thr, ms, cores, sample = cpu_oracle_throughput(args.steps, args.warmup, budget_s=120.0)
+    line = {
+        "impl": "reference", "metric": "prior-fit pixel-samples/sec (fwd+bwd+step)", "value": thr,
+        "unit": "pixel-samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "prior": f"ConvexNextNet(h={HID},L={LAYERS},C={CH})",
+                                        "loss": "MSE(sigmoid(y), unaries)", "optimizer": "Adam lr=1e-3"},
+        "cpu_baseline": {"value": thr, "unit": "pixel-samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": thr, "unit": "pixel-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("AWB_BENCH_PRECISION", "fp32"), choices=["fp32", "f16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    entry.build()
+    import awesome_b200 as A
+    from awesome_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    warmup = max(3, args.warmup)
+
+    # ---- the fit: one frame per rank (frames are independent units; rank r owns frames r, r+N, ...)
+    torch.manual_seed(42 + rank)
+    model = A.ConvexNextNet(n_hidden=HID, in_features=CH, n_hidden_layers=LAYERS, precision=args.precision).to(dev)
+    unaries_host = synth_unaries(42 + rank, t=0.1 * rank).pin_memory()
+    unaries = unaries_host.to(dev, non_blocking=True)
+    grid = A.GridSpecHost("linspace", 1, H, W)
+    fitter = model.make_fitter(grid, unaries, A.LossConfig("mse"), A.OptimConfig("adam", lr=1e-3), use_graph=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-timed K steps, inputs resident in HBM
+    fitter.run(warmup, record=False)
+    barrier()
+    launches0 = lib.awb_launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    fitter.run(args.steps, record=False)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = lib.awb_launch_count() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+
+    # ---- end to end through the public API: the step's unaries arrive from pinned host memory, loss read back
+    e2e_warm = 3
+    t_e2e = 0.0
+    for i in range(e2e_warm + args.steps):
+        if i == e2e_warm:
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        fitter.target.copy_(unaries_host.reshape(1, -1), non_blocking=True)      # H2D, 4*N_PIX bytes
+        loss_host = fitter.run(1)[0].cpu()                                        # D2H of the step's loss
+    e1.record()
+    barrier()
+    t_e2e = e0.elapsed_time(e1)
+    fitter.raise_if_nonfinite()
+
+    # ---- roofline of the dominant kernel: hidden-layer contraction launches, timed live with CUDA events
+    n_cls = lib.awb_profile_classes()
+    lib.awb_profile_enable(1)
+    fitter.run(6, record=False)
+    tot = (C.c_double * n_cls)()
+    cnt = (C.c_int32 * n_cls)()
+    _lib.check(lib.awb_profile_read(tot, cnt))
+    lib.awb_profile_enable(0)
+    names = [lib.awb_profile_class_name(i).decode() for i in range(n_cls)]
+    per_class = {names[i]: {"ms_per_launch": tot[i] / cnt[i], "launches_per_step": cnt[i] / 6.0,
+                            "ms_per_step": tot[i] / 6.0} for i in range(n_cls) if cnt[i] > 0}
+    step_ms_prof = sum(v["ms_per_step"] for v in per_class.values())
+    pk, pk_src = peaks()
+
+    if world > 1:
+        t = torch.tensor([ms_total, t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, t_e2e = float(t[0]), float(t[1])
+        ln = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
+        launches = int(ln[0])
+
+    if rank == 0:
+        units = world * N_PIX * args.steps
+        value = units / (ms_total * 1e-3)
+        e2e_val = units / (t_e2e * 1e-3)
+        if args.precision == "f16" and "tc_fused" in per_class:
+            dom, dom_flop = "tc_fused", FLOP_PER_PX_STEP * N_PIX
+            peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+            note = "fused fit kernel: all layer contractions of one step; peak = sustained cuBLAS bf16"
+        else:
+            gemm = [k for k in ("gemm_fwd", "gemm_wgrad", "gemm_dgrad") if k in per_class]
+            dom = max(gemm, key=lambda k: per_class[k]["ms_per_step"])
+            dom_flop = GEMM_FLOP_PER_PX_LAUNCH * N_PIX
+            peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+            note = ("fp32 CUDA-core contraction (exact-parity path); reported against the sustained cuBLAS bf16 "
+                    "tensor peak the north star names")
+        ach = dom_flop / (per_class[dom]["ms_per_launch"] * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": ach / peak_tf, "traffic": None, "peak_source": pk_src,
+                    "ms_per_launch": per_class[dom]["ms_per_launch"],
+                    "share_of_step": per_class[dom]["ms_per_step"] / step_ms_prof,
+                    "whole_step_tflops": FLOP_PER_PX_STEP * N_PIX / (ms_total / args.steps * 1e-3) / 1e12,
+                    "note": note, "per_class_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in per_class.items()}}
+        cpu = None
+        if not args.no_cpu_baseline:
+            thr, ms_cpu, cores, sample = cpu_oracle_throughput(steps=8, warmup=1, budget_s=20.0)
+            cpu = {"value": thr, "unit": "pixel-samples/s", "cores": cores, "kind": "port", "sample": sample,
+                   "ms_per_step_sample": ms_cpu}
+        line = {
+            "metric": "prior-fit pixel-samples/sec (fwd+bwd+step)", "value": value, "unit": "pixel-samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "f16 operands / f32 accumulate", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "prior": f"ConvexNextNet(h={HID},L={LAYERS},C={CH})",
+                       "loss": "MSE(sigmoid(y), unaries)", "optimizer": "Adam lr=1e-3 + enforce_convexity",
+                       "pixels_per_step_per_gpu": N_PIX, "precision": args.precision,
+                       "l2": "per-step working set (activations, deltas, partials) ~0.85 GB > 126 MB L2: no flush needed"
+                       if args.precision == "fp32" else "see DESIGN.md",
+                       "frames_per_s_at_400_steps_per_frame": value / N_PIX / 400.0,
+                       "frames_per_s_at_4000_steps_per_frame": value / N_PIX / 4000.0},
+            "e2e": {"value": e2e_val, "unit": "pixel-samples/s", "h2d_bytes_per_step": 4 * N_PIX,
+                    "d2h_bytes_per_step": 4, "ms_per_step": t_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
+                       "samples": clocks["samples"]},
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "final_loss": float(loss_host),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

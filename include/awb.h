@@ -97,6 +97,7 @@ typedef struct awb_opt_hyper {
   int32_t plateau_enabled;
   int32_t patience;
   float factor, threshold, min_lr, plateau_eps;
+  int32_t active_groups; /* bitmask of groups this optimizer owns; 0 = all (learn_flow_identity owns only flow_net) */
 } awb_opt_hyper;
 
 /* host-readable copy of the per-object optimizer scalars */
@@ -155,6 +156,13 @@ int awb_prior_fit_step(awb_handle h, float* params, void* opt_state, const awb_g
                        const float* target, const awb_loss_spec* loss, const awb_opt_hyper* hyper,
                        float* loss_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* One step of PathConnectedNet.learn_flow_identity (path_connected_net.py:155-250): the NormNet-wrapped
+ * flow alone (no 1x1 conv) is regressed onto its own input grid with SE("mean"); only the flow_net
+ * group is updated (hyper->active_groups is forced to the flow group). */
+int awb_flow_identity_step(awb_handle h, float* params, void* opt_state, const awb_grid_spec* grid,
+                           const awb_opt_hyper* hyper, float* loss_out, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 /* torch.optim.Adam/Adamax(...).step() + enforce_convexity on caller-provided grads [O][P]
  * (agent loop: awesome/agent/torch_agent.py:489-492 + awesome_runner.py:294-297). */
 int awb_optim_step(awb_handle h, float* params, const float* grads, void* opt_state,
@@ -181,6 +189,15 @@ int awb_mask_iou_counts(const float* pred, const float* target, int64_t n_pixels
 /* target statistics for the weighted losses: counts[O][2] = {fg, bg} under cls_rule. */
 int awb_target_counts(const float* target, int64_t n_pixels, int32_t n_objects, int32_t cls_rule,
                       long long* counts, void* stream);
+
+/* Measurement hooks (bench.py): CUDA-event timing per kernel class on the launch stream, and the number
+ * of kernels this library has launched.  awb_profile_read synchronises the device and returns, for each
+ * of awb_profile_classes() classes, the summed duration [ms] and the number of timed launches. */
+int awb_profile_enable(int32_t on);
+int awb_profile_classes(void);
+const char* awb_profile_class_name(int32_t cls);
+int awb_profile_read(double* total_ms, int32_t* counts);
+long long awb_launch_count(void);
 
 #ifdef __cplusplus
 }
