@@ -147,11 +147,12 @@ class Prior:
         L.check(self.lib.awb_prior_enforce_convexity(self._h, params.data_ptr(), L.stream_ptr()))
 
 
-def iou_counts(pred: torch.Tensor, target: torch.Tensor, pred_is_logit: bool) -> torch.Tensor:
-    """``[O,4]`` int64 counts {intersection, pred_fg, target_fg, n}; fg = value <= 0.5."""
+def iou_counts(pred: torch.Tensor, target: torch.Tensor, pred_is_logit: bool, n_objects: int = 1) -> torch.Tensor:
+    """``[O,4]`` int64 counts {intersection, pred_fg, target_fg, n}; fg = value <= 0.5.
+    Inputs hold ``n_objects`` masks back to back (any shape)."""
     L.require_cuda()
     lib = L.load()
-    O = pred.shape[0] if pred.dim() == 2 else 1
+    O = n_objects
     p = pred.detach().reshape(O, -1).contiguous().float()
     t = target.detach().reshape(O, -1).contiguous().float()
     counts = torch.empty((O, 4), dtype=torch.int64, device=p.device)
@@ -160,12 +161,12 @@ def iou_counts(pred: torch.Tensor, target: torch.Tensor, pred_is_logit: bool) ->
     return counts
 
 
-def target_counts(target: torch.Tensor, cls_rule: int) -> torch.Tensor:
-    """``[O,2]`` int64 counts {fg, bg} of the target under ``cls_rule``."""
+def target_counts(target: torch.Tensor, cls_rule: int, n_objects: int = 1) -> torch.Tensor:
+    """``[O,2]`` int64 counts {fg, bg} of the target under ``cls_rule`` (``n_objects`` targets back to back)."""
     L.require_cuda()
     lib = L.load()
     t = target.detach()
-    O = t.shape[0] if t.dim() == 2 else 1
+    O = n_objects
     t = t.reshape(O, -1).contiguous().float()
     counts = torch.empty((O, 2), dtype=torch.int64, device=t.device)
     L.check(lib.awb_target_counts(t.data_ptr(), t.shape[1], O, cls_rule, counts.data_ptr(), L.stream_ptr()))

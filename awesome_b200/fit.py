@@ -37,7 +37,7 @@ class LossConfig:
         if self.kind == "mse":
             if self.mode == "none":
                 return [L.LossSpec(L.AWB_LOSS_SE_SIGMOID, L.AWB_CLS_UNARY_LT_HALF, 1.0 / N, 1.0 / N) for _ in range(O)]
-            cnt = target_counts(target, L.AWB_CLS_UNARY_LT_HALF).cpu()
+            cnt = target_counts(target, L.AWB_CLS_UNARY_LT_HALF, O).cpu()
             for o in range(O):
                 fg, bg = float(cnt[o, 0]), float(cnt[o, 1])
                 cc = torch.tensor(bg, dtype=torch.float32) / torch.tensor(fg, dtype=torch.float32)
@@ -52,7 +52,7 @@ class LossConfig:
                 specs.append(L.LossSpec(L.AWB_LOSS_SE_SIGMOID, L.AWB_CLS_UNARY_LT_HALF, float(w) / N, 1.0 / N))
             return specs
         if self.kind in ("fgbg_se", "fgbg_bce_logits"):
-            cnt = target_counts(target, L.AWB_CLS_NOT_ONE).cpu()
+            cnt = target_counts(target, L.AWB_CLS_NOT_ONE, O).cpu()
             k = L.AWB_LOSS_SE_SIGMOID if self.kind == "fgbg_se" else L.AWB_LOSS_BCE_LOGITS
             for o in range(O):
                 fg, bg = float(cnt[o, 0]), float(cnt[o, 1])

