@@ -85,6 +85,8 @@ SYMBOLS = [
     ("awb_prior_actnorm_init", C.c_int, [_P, _P, C.POINTER(GridSpec), _P, C.c_size_t, _P]),
     ("awb_mask_iou_counts", C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
     ("awb_target_counts", C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
+    ("awb_debug_umma_probe", C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _P]),
     ("awb_profile_enable", C.c_int, [C.c_int32]),
     ("awb_profile_classes", C.c_int, []),
     ("awb_profile_class_name", C.c_char_p, [C.c_int32]),

@@ -190,6 +190,13 @@ int awb_mask_iou_counts(const float* pred, const float* target, int64_t n_pixels
 int awb_target_counts(const float* target, int64_t n_pixels, int32_t n_objects, int32_t cls_rule,
                       long long* counts, void* stream);
 
+/* Test hook: one CTA computes D[128][N] = A * B with tcgen05.mma (kind::f16, fp32 accumulate in TMEM) from raw
+ * shared-memory tile images and caller-supplied descriptor fields {start offset, LBO, SBO, start advance per
+ * K=16 step} (bytes).  Pins the operand-layout conventions of the tensor path against a plain matmul. */
+int awb_debug_umma_probe(const void* a_bytes, int32_t a_size, const void* b_bytes, int32_t b_size, float* D,
+                         int32_t N, int32_t K, int32_t a_mn_major, int32_t b_mn_major, const uint32_t* a_desc4,
+                         const uint32_t* b_desc4, void* stream);
+
 /* Measurement hooks (bench.py): CUDA-event timing per kernel class on the launch stream, and the number
  * of kernels this library has launched.  awb_profile_read synchronises the device and returns, for each
  * of awb_profile_classes() classes, the summed duration [ms] and the number of timed launches. */
