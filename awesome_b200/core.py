@@ -132,6 +132,14 @@ class Prior:
                                            int(training), ws.data_ptr(), ws.numel(), L.stream_ptr()))
         return logits, deformed
 
+    def forward_tensor_path(self, params: torch.Tensor, grid: GridSpecHost, ws: torch.Tensor) -> torch.Tensor:
+        """Logits through the tcgen05 forward (fp16 operands, fp32 accumulate); f16 handles only."""
+        logits = torch.empty((self.n_objects, grid.n_pixels), dtype=torch.float32, device=params.device)
+        gs = grid.to_c()
+        L.check(self.lib.awb_prior_forward(self._h, params.data_ptr(), C.byref(gs), logits.data_ptr(), None, 2,
+                                           ws.data_ptr(), ws.numel(), L.stream_ptr()))
+        return logits
+
     def backward(self, params: torch.Tensor, grid: GridSpecHost, dlogits: torch.Tensor, ws: torch.Tensor,
                  want_dgrid: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
         grads = torch.empty((self.n_objects, self.n_params), dtype=torch.float32, device=params.device)

@@ -67,7 +67,7 @@ Workspace carve(const awb_prior* h, int64_t N, bool training, void* base) {
   w.logits = (float*)take(4 * O * N);
   w.flowz = (float*)take(training ? 4 * O * N * (int64_t)L.F * L.C : 0);
   if (!training || L.F == 0) w.flowz = nullptr;
-  w.tc = nullptr;
+  w.tc = (h->desc.precision == AWB_PREC_F16 && tc_supported(h)) ? (void*)take(O * (int64_t)tc_image_bytes(L.L)) : nullptr;
   w.bytes = off;
   return w;
 }
@@ -98,7 +98,7 @@ int awb_prior_create(const awb_desc* d, awb_handle* out) {
   if (d->kind == AWB_KIND_ICNN) { h->desc.F = 0; h->desc.m = 0; }
   h->lay = make_layout(h->desc);
   h->fc_set = false;
-  h->d_map = nullptr; h->d_clamp = nullptr; h->d_group = nullptr;
+  h->d_map = nullptr; h->d_clamp = nullptr; h->d_group = nullptr; h->d_tcmap = nullptr;
   const Layout& L = h->lay;
   // arena (state_dict order) -> augmented index; clamp mask; optimizer groups
   std::vector<int32_t> map(L.P_icnn);
@@ -130,13 +130,28 @@ int awb_prior_create(const awb_desc* d, awb_handle* out) {
     delete h;
     return cuda_fail(e, "awb_prior_create");
   }
+  if (tc_supported(h)) {
+    std::vector<int32_t> tmap(tc_map_elems(L.L));
+    tc_build_map_host(L, tmap.data());
+    if ((e = cudaMalloc(&h->d_tcmap, sizeof(int32_t) * tmap.size())) != cudaSuccess ||
+        (e = cudaMemcpy(h->d_tcmap, tmap.data(), sizeof(int32_t) * tmap.size(), cudaMemcpyHostToDevice)) != cudaSuccess) {
+      cudaFree(h->d_map); cudaFree(h->d_clamp); cudaFree(h->d_group); cudaFree(h->d_tcmap);
+      delete h;
+      return cuda_fail(e, "awb_prior_create (tensor path)");
+    }
+  } else if (d->precision == AWB_PREC_F16) {
+    cudaFree(h->d_map); cudaFree(h->d_clamp); cudaFree(h->d_group);
+    delete h;
+    set_error("precision f16 (tcgen05 path) supports ICNN priors with h=130 and L in {1,2}; use fp32 for this shape");
+    return AWB_ERR_UNSUPPORTED;
+  }
   *out = h;
   return AWB_OK;
 }
 
 int awb_prior_destroy(awb_handle h) {
   if (!h) return AWB_OK;
-  cudaFree(h->d_map); cudaFree(h->d_clamp); cudaFree(h->d_group);
+  cudaFree(h->d_map); cudaFree(h->d_clamp); cudaFree(h->d_group); cudaFree(h->d_tcmap);
   delete h;
   return AWB_OK;
 }
@@ -185,6 +200,10 @@ int awb_prior_forward(awb_handle h, const float* params, const awb_grid_spec* g,
   if (rc) return rc;
   if (!params) { set_error("null params"); return AWB_ERR_INVALID; }
   Workspace w = carve(h, N, training != 0, ws);
+  if (training == 2) {   // fast tensor-path logits (fp16 operands); the default forward stays exact fp32
+    if (h->desc.precision != AWB_PREC_F16) { set_error("tensor-path forward needs an f16 handle"); return AWB_ERR_INVALID; }
+    return tc_fit_forward_backward(h, params, g, nullptr, nullptr, logits, 0, w, nullptr, (cudaStream_t)stream);
+  }
   return simt_forward(h, params, g, logits, deformed, training != 0, w, (cudaStream_t)stream);
 }
 
@@ -217,6 +236,12 @@ int awb_prior_fit_step(awb_handle h, float* params, void* opt_state, const awb_g
   if (!params || !opt_state || !target || !loss || !hy) { set_error("null argument"); return AWB_ERR_INVALID; }
   Workspace w = carve(h, N, true, ws);
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->desc.precision == AWB_PREC_F16) {
+    int n_part = 0;
+    rc = tc_fit_forward_backward(h, params, g, target, loss, nullptr, 1, w, &n_part, st);
+    if (rc) return rc;
+    return simt_reduce_opt(h, params, opt_state, hy, loss_out, w, N, st, n_part);
+  }
   rc = simt_forward(h, params, g, nullptr, nullptr, true, w, st);
   if (rc) return rc;
   rc = simt_backward(h, params, g, target, loss, nullptr, false, w, st);

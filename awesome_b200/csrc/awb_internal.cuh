@@ -60,6 +60,7 @@ struct awb_prior {
   int32_t* d_map;     // [P_icnn] arena-local index -> augmented index
   uint8_t* d_clamp;   // [P] 1 where enforce_convexity clamps
   uint8_t* d_group;   // [P] optimizer group: 0 flow_net, 1 convex_net, 2 linear
+  int32_t* d_tcmap;   // tensor path: weight-image element -> arena index (or -1), null when unsupported
   awb::FlowConsts fc;
   bool fc_set;
   int device;
@@ -124,13 +125,23 @@ int simt_backward(const awb_prior* h, const float* params, const awb_grid_spec* 
                   const awb_loss_spec* loss, const float* dlogits, bool need_dx, const Workspace& ws,
                   cudaStream_t st);
 int simt_reduce_opt(const awb_prior* h, float* params, void* opt_state, const awb_opt_hyper* hy,
-                    float* loss_out, const Workspace& ws, int64_t N, cudaStream_t st);
+                    float* loss_out, const Workspace& ws, int64_t N, cudaStream_t st, int n_partials = -1);
 int simt_reduce_grads(const awb_prior* h, float* grads, const Workspace& ws, int64_t N, cudaStream_t st);
 int simt_dgrid(const awb_prior* h, const awb_grid_spec* g, float* dgrid, const Workspace& ws, cudaStream_t st);
 int optim_step(const awb_prior* h, float* params, const float* grads, void* opt_state,
                const awb_opt_hyper* hy, cudaStream_t st);
 int clamp_only(const awb_prior* h, float* params, cudaStream_t st);
 int opt_state_init(const awb_prior* h, void* opt_state, const double* lr, cudaStream_t st);
+
+// ---- tensor path (tcgen05), implemented in awb_tc_fit.cu ----
+int tc_supported(const awb_prior* h);
+int tc_image_bytes(int L);
+int tc_map_elems(int L);
+void tc_build_map_host(const Layout& Ly, int32_t* map);   // map has tc_map_elems(L) entries
+// mode 0: forward only (logits), mode 1: forward + loss + backward partials (part / lossp, *n_splits_out CTAs)
+int tc_fit_forward_backward(const awb_prior* h, const float* params, const awb_grid_spec* g, const float* target,
+                            const awb_loss_spec* loss, float* logits, int mode, const Workspace& ws,
+                            int* n_splits_out, cudaStream_t st);
 
 // ---- flows, implemented in awb_flow.cu ----
 int flow_forward(const awb_prior* h, const float* params, const awb_grid_spec* g, const Workspace& ws,

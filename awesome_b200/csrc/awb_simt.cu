@@ -689,13 +689,13 @@ int simt_backward(const awb_prior* h, const float* params, const awb_grid_spec* 
 static int n_groups_of(const awb_prior* h) { return h->desc.kind == AWB_KIND_FLOW_ICNN ? 3 : 3; }
 
 int simt_reduce_opt(const awb_prior* h, float* params, void* opt_state, const awb_opt_hyper* hy,
-                    float* loss_out, const Workspace& ws, int64_t N, cudaStream_t st) {
+                    float* loss_out, const Workspace& ws, int64_t N, cudaStream_t st, int n_partials) {
   const Layout& L = h->lay;
   const int O = h->desc.n_objects;
   OptP a = {};
   a.params = params;
   opt_ptrs(h, opt_state, &a.m, &a.v, &a.scal);
-  a.part = ws.part; a.sSplit = (int64_t)O * L.G; a.S = n_splits(N);
+  a.part = ws.part; a.sSplit = (int64_t)O * L.G; a.S = n_partials > 0 ? n_partials : n_splits(N);
   a.PF = L.P_flow + 2 * L.C;
   a.fpart = ws.fpart; a.sFSplit = (int64_t)O * a.PF;
   a.lossp = ws.lossp; a.grads = nullptr;

@@ -1,0 +1,528 @@
+// Fused ICNN fit step on the Blackwell tensor path (AWB_PREC_F16): ONE persistent kernel does, per
+// 128-pixel tile, coordinate generation -> input layer -> L hidden layers -> output layer + sigmoid +
+// loss -> full backward (data gradients and weight gradients), with
+//   * every layer contraction (forward, dgrad, wgrad) on tcgen05.mma kind::f16 (fp16 operands, fp32
+//     accumulation in TMEM), M = 128 pixels, N = K = 144 (130 hidden + skip/bias augmentation + pad);
+//   * bias and skip connection folded into the contraction through the augmented K columns (x, 1);
+//   * weights staged once per CTA in shared memory by TMA bulk copies (cp.async.bulk + mbarrier);
+//   * activations never leaving the SM: TMEM -> registers (relu / relu-backward / loss) -> fp16
+//     shared-memory operand tiles of the next contraction;
+//   * weight gradients accumulated across all tiles of the CTA in TMEM (dW never touches HBM until
+//     the single per-CTA partial write at the end); the 130 = 128 + 2 remainder rows/columns are
+//     covered by two N=16 side contractions plus a handful of per-thread corner sums;
+//   * loss / corner sums reduced with registers + one shared-memory pass (no atomics).
+// The cross-CTA reduction + Adam/Adamax + clamp + plateau run in k_reduce_opt (awb_simt.cu).
+//
+// Shared-memory operand tiles use the SWIZZLE_NONE interleaved layout of awb_tc.cuh with 17 stored
+// column chunks (136 columns); the 18th chunk of a K = 144 walk is redirected to a shared zero chunk
+// through the per-instruction LBO field, and as an MN-major N = 144 operand it reads whatever follows
+// (those accumulator columns, 136..143, are never read).  See DESIGN.md "tensor path".
+#include <math.h>
+
+#include <vector>
+
+#include "awb_internal.cuh"
+#include "awb_tc.cuh"
+
+namespace awb {
+
+namespace {
+constexpr int H_ = 130, LD_ = 136, NPAD = 144;
+constexpr int TILE_B = 17 * 2048;   // [17 chunks][128 rows][8 fp16]
+constexpr int W_B = 17 * 2304;      // [17 chunks][144 rows][8 fp16]
+constexpr int WIN_B = 2 * 2304;     // [2 chunks][144 rows][8 fp16]   input layer (K = 16)
+constexpr int TX_B = 2 * 2048;      // [2 chunks][128 rows][8 fp16]   (x, y, (t), 1, 0...)
+constexpr int ZERO_B = 2304;
+constexpr int VEC_B = NPAD * 4;     // fp32 (w_o | s_o | b_o | 0)
+constexpr int NTHREADS = 288;       // 8 epilogue warps + 1 issuer warp
+__host__ __device__ constexpr int img_bytes(int L) { return L * W_B + WIN_B + VEC_B; }
+__host__ __device__ constexpr int smem_bytes(int L) {
+  return (L + 2) * TILE_B + img_bytes(L) + TX_B + ZERO_B + 1024 + 64;
+}
+}  // namespace
+
+int tc_image_bytes(int L) { return (int)round_up(img_bytes(L), 256); }
+
+// ------------------------------------------------------------------ weight image (fp32 arena -> fp16 UMMA tiles)
+__global__ void k_pack_tc(const float* __restrict__ params, uint8_t* __restrict__ img, const int32_t* __restrict__ tcmap,
+                          int n_elems, int L, int64_t P, int64_t img_stride) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int o = blockIdx.y;
+  if (i >= n_elems) return;
+  int32_t src = tcmap[i];
+  float v = src >= 0 ? params[(int64_t)o * P + src] : 0.f;
+  const int n_half = (L * W_B + WIN_B) / 2;
+  uint8_t* base = img + (int64_t)o * img_stride;
+  if (i < n_half) reinterpret_cast<__half*>(base)[i] = __float2half_rn(v);
+  else reinterpret_cast<float*>(base + 2 * n_half)[i - n_half] = v;
+}
+
+struct TcP {
+  GridDev g;
+  const uint8_t* img; int64_t img_stride;
+  const float* target;
+  awb_loss_spec loss[16];
+  float scale[16];
+  float* part; int64_t sSplit, G, aug_in, aug_layer, aug_out;
+  float* lossp; int O;
+  float* logits;
+  int64_t N; int n_tiles; int mode;
+};
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void st16(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; i++) { float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+// accumulator columns of this thread's half: half 0 -> [0,72), half 1 -> [72,136)
+__device__ __forceinline__ void load_acc(uint32_t taddr, int half, float* v) {
+  const uint32_t a = taddr + (half ? 72 : 0);
+  tc::tmem_ld16(a, v); tc::tmem_ld16(a + 16, v + 16); tc::tmem_ld16(a + 32, v + 32); tc::tmem_ld16(a + 48, v + 48);
+  if (!half) tc::tmem_ld8(a + 64, v + 64);
+  tc::tmem_ld_wait();
+}
+
+template <int L, int C>
+__global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int NT = L + 2;
+  constexpr int IMG = img_bytes(L);
+  constexpr int NC = 12 * L + 15;                 // per-thread corner / scalar accumulators
+  uint8_t* tiles = smem;                          // ZT[0..L-1], ZL, DT
+  uint8_t* simg = smem + NT * TILE_B;             // W_1..W_L | WIN | vec
+  uint8_t* stx = simg + IMG;
+  uint8_t* szero = stx + TX_B;
+  float* xchg = reinterpret_cast<float*>(szero + ZERO_B);          // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(szero + ZERO_B + 1024);
+  uint64_t* bar_e2m = bars;        // epilogue -> issuer (256 arrivals)
+  uint64_t* bar_m2e = bars + 1;    // tcgen05.commit -> epilogue
+  uint64_t* bar_w = bars + 2;      // weight image landed (TMA tx bytes)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  const float* wo = reinterpret_cast<const float*>(simg + L * W_B + WIN_B);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.y;
+  const bool issuer_warp = warp == 8;
+
+  // ---- one-time setup
+  if (threadIdx.x == 0) { tc::mbar_init(bar_e2m, 256); tc::mbar_init(bar_m2e, 1); tc::mbar_init(bar_w, 1); tc::mbar_fence_init(); }
+  for (int i = threadIdx.x * 16; i < ZERO_B; i += NTHREADS * 16) *reinterpret_cast<uint4*>(szero + i) = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  if (issuer_warp) {
+    tc::tmem_alloc<512>(tmem_slot);
+    if (lane == 0) {
+      const uint8_t* src = p.img + (int64_t)o * p.img_stride;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar_w)), "r"((uint32_t)IMG) : "memory");
+      for (int off = 0; off < IMG; off += 16384) {
+        uint32_t sz = IMG - off < 16384 ? IMG - off : 16384;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(tc::smem_u32(simg + off)), "l"(src + off), "r"(sz), "r"(tc::smem_u32(bar_w)) : "memory");
+      }
+    }
+  }
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+  tc::mbar_wait(bar_w, 0);
+
+  constexpr uint32_t T_ACC = 0;
+  auto T_DW = [](int i) { return (uint32_t)(144 * i); };                       // i = 1..L
+  auto T_PB = [](int i) { return (uint32_t)(144 * (L + 1) + 16 * (i - 1)); };  // i = 1..L
+  constexpr uint32_t T_GIN = 144 * (L + 1) + 16 * L, T_GO = T_GIN + 16;
+  static_assert(T_GO + 16 <= 512, "TMEM budget");
+
+  auto tile_ptr = [&](int t) { return tiles + t * TILE_B; };       // t < L: ZT[t]; L: ZL; L+1: DT
+  auto dbuf = [&](int i) { return tile_ptr(((L - i) & 1) ? L : L + 1); };      // delta_i lives in DT / ZL alternately
+
+  const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const bool fit = p.mode != 0;
+  constexpr int NSTAGE_FIT = 2 * L + 2, NSTAGE_FWD = L + 1;
+
+  if (issuer_warp) {
+    // =========================================================== MMA issuer (one elected lane)
+    if (lane == 0) {
+      uint32_t ph = 0;
+      const uint32_t zero_a = tc::smem_u32(szero);
+      const uint32_t a_tx = tc::smem_u32(stx), a_win = tc::smem_u32(simg + L * W_B);
+      auto w_addr = [&](int i) { return tc::smem_u32(simg + (i - 1) * W_B); };
+      auto t_addr = [&](uint8_t* t) { return tc::smem_u32(t); };
+      // K-major A (R=128) x K-major/MN-major B (R=144) over K = 144 (9 steps), N = 144
+      auto mma_k144 = [&](uint32_t dcol, uint32_t a, uint32_t b, bool b_mn) {
+        const uint32_t idesc = tc::make_idesc(128, 144, 0, b_mn ? 1 : 0);
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+          uint32_t as = a + k * 4096;
+          uint64_t ad = tc::make_desc(as, k == 8 ? zero_a - as : 2048, 128);
+          uint64_t bd;
+          if (b_mn) bd = tc::make_desc(b + k * 256, 128, 2304);
+          else { uint32_t bs = b + k * 4608; bd = tc::make_desc(bs, k == 8 ? zero_a - bs : 2304, 128); }
+          tc::umma_f16(tbase + dcol, ad, bd, idesc, k > 0);
+        }
+      };
+      // MN-major A window [0,128) x MN-major B, K = 128 pixels (8 steps)
+      auto mma_px = [&](uint32_t dcol, uint32_t a, uint32_t b, int N, bool acc) {
+        const uint32_t idesc = tc::make_idesc(128, N, 1, 1);
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          tc::umma_f16(tbase + dcol, tc::make_desc(a + k * 256, 128, 2048), tc::make_desc(b + k * 256, 128, 2048), idesc,
+                       (acc || k > 0) ? 1u : 0u);
+      };
+      for (int it = 0; it < n_my; it++) {
+        const bool acc = it > 0;
+        const int nstage = fit ? NSTAGE_FIT : NSTAGE_FWD;
+        for (int s = 0; s < nstage; s++) {
+          tc::mbar_wait(bar_e2m, ph); ph ^= 1;
+          tc::fence_after_sync();
+          if (s == 0) {
+            // input layer: ACC = TX[128x16] * WIN^T
+            tc::umma_f16(tbase + T_ACC, tc::make_desc(a_tx, 2048, 128), tc::make_desc(a_win, 2304, 128),
+                         tc::make_idesc(128, 144, 0, 0), 0);
+            tc::umma_commit(bar_m2e);
+          } else if (s <= L) {
+            mma_k144(T_ACC, t_addr(tile_ptr(s - 1)), w_addr(s), false);          // forward layer s
+            tc::umma_commit(bar_m2e);
+          } else {
+            const int i = L - (s - (L + 1));                                      // delta_i was just written
+            if (i >= 1) {
+              const uint32_t d = t_addr(dbuf(i)), zprev = t_addr(tile_ptr(i - 1));
+              mma_k144(T_ACC, d, w_addr(i), true);                                // dgrad_i: ACC = delta_i * W_i
+              if (i == L) mma_px(T_GO, t_addr(tile_ptr(L)), d + 16 * 2048, 16, acc);   // z_L^T * [d128 d129 dy ..]
+              tc::umma_commit(bar_m2e);
+              mma_px(T_DW(i), d, zprev, 144, acc);                                // wgrad_i main rows 0..127
+              mma_px(T_PB(i), zprev, d + 16 * 2048, 16, acc);                     // wgrad_i rows 128,129 (transposed)
+            } else {
+              mma_px(T_GIN, t_addr(dbuf(0)), a_tx, 16, acc);                      // input-layer wgrad
+              tc::umma_commit(bar_m2e);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // =========================================================== epilogue warps (256 threads)
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
+    const int nch = half ? 8 : 9;                 // stored chunks handled by this thread
+    const int ch0 = half ? 9 : 0;
+    uint32_t ph = 0;
+    float cacc[NC];
+#pragma unroll
+    for (int i = 0; i < NC; i++) cacc[i] = 0.f;
+    const awb_loss_spec ls = p.loss[o];
+    const float S = p.scale[o];
+    float v[72];
+
+    for (int it = 0; it < n_my; it++) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int64_t n = (int64_t)tile * 128 + row;
+      const bool live = n < p.N;
+      const int64_t nn = live ? n : p.N - 1;
+      const float x0 = coord(p.g, nn, 0), x1 = coord(p.g, nn, 1), x2 = C > 2 ? coord(p.g, nn, 2) : 0.f;
+      // aug values of chunk 16 columns 130..135
+      const float a2 = x0, a3 = x1, a4 = C > 2 ? x2 : 1.f, a5 = C > 2 ? 1.f : 0.f;
+      float tgt = 0.f;
+      if (fit && live) tgt = p.target[(int64_t)o * p.N + n];
+
+      // ---- stage 0: TX = (x, 1, 0..)
+      if (half == 0) {
+        st16(stx + row * 16, pack2(x0, x1), pack2(C > 2 ? x2 : 1.f, C > 2 ? 1.f : 0.f), 0u, 0u);
+        st16(stx + 2048 + row * 16, 0u, 0u, 0u, 0u);
+      }
+      tc::fence_async_smem();
+      tc::fence_before_sync();
+      tc::mbar_arrive(bar_e2m);
+
+      // ---- stages 1..L: hidden forward epilogues (ACC -> relu -> ZT[s-1])
+#pragma unroll
+      for (int s = 1; s <= L; s++) {
+        tc::mbar_wait(bar_m2e, ph); ph ^= 1;
+        tc::fence_after_sync();
+        load_acc(tlane + T_ACC, half, v);
+        uint8_t* dst = tile_ptr(s - 1) + ch0 * 2048 + row * 16;
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+          if (i < nch) {
+            float e[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) e[j] = fmaxf(v[8 * i + j], 0.f);
+            if (half && i == 7) { e[2] = a2; e[3] = a3; e[4] = a4; e[5] = a5; e[6] = 0.f; e[7] = 0.f; }
+            st16(dst + i * 2048, pack2(e[0], e[1]), pack2(e[2], e[3]), pack2(e[4], e[5]), pack2(e[6], e[7]));
+          }
+        }
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        tc::mbar_arrive(bar_e2m);
+      }
+
+      // ---- stage L+1: last hidden activation, output layer, loss, delta_L
+      tc::mbar_wait(bar_m2e, ph); ph ^= 1;
+      tc::fence_after_sync();
+      load_acc(tlane + T_ACC, half, v);
+      float dot = 0.f;
+      {
+        const int nz = half ? 58 : 72;                    // real z columns of this half
+        const float* w = wo + (half ? 72 : 0);
+#pragma unroll
+        for (int j = 0; j < 72; j++) {
+          if (j < nz) { v[j] = fmaxf(v[j], 0.f); dot = fmaf(v[j], w[j], dot); }
+        }
+        if (half) {
+          dot = fmaf(x0, wo[H_], dot); dot = fmaf(x1, wo[H_ + 1], dot);
+          if (C > 2) dot = fmaf(x2, wo[H_ + 2], dot);
+          dot += wo[H_ + C];
+        }
+      }
+      xchg[half * 128 + row] = dot;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float y = xchg[row] + xchg[128 + row];
+      if (!fit) {
+        if (half == 0 && live && p.logits) p.logits[(int64_t)o * p.N + n] = y;
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // xchg reuse by the next tile
+        continue;
+      }
+      float dys = 0.f;
+      if (live) {
+        const bool fg = ls.cls_rule == AWB_CLS_UNARY_LT_HALF ? (tgt < 0.5f) : (tgt != 1.0f);
+        const float coef = fg ? ls.coef_fg : ls.coef_bg;
+        const float sg = 1.f / (1.f + expf(-y));
+        float l, dl;
+        if (ls.kind == AWB_LOSS_SE_SIGMOID) { float d = tgt - sg; l = d * d; dl = -2.f * d * sg * (1.f - sg); }
+        else { l = fmaxf(y, 0.f) - y * tgt + log1pf(expf(-fabsf(y))); dl = sg - tgt; }
+        dys = coef * dl * S;
+        if (half == 0) {
+          cacc[NC - 1] += coef * l;                                   // loss
+          cacc[NC - 2] += dys;                                        // d b_o
+          cacc[NC - 5] += dys * x0; cacc[NC - 4] += dys * x1;          // d s_o
+          if (C > 2) cacc[NC - 3] += dys * x2;
+        }
+      }
+      if (p.logits && half == 0 && live) p.logits[(int64_t)o * p.N + n] = y;
+      {
+        uint8_t* zl = tile_ptr(L) + ch0 * 2048 + row * 16;
+        uint8_t* dl = dbuf(L) + ch0 * 2048 + row * 16;
+        const float* w = wo + (half ? 72 : 0);
+        float d128 = 0.f, d129 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+          if (i < nch) {
+            float e[8], d[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) { e[j] = v[8 * i + j]; d[j] = e[j] > 0.f ? dys * w[8 * i + j] : 0.f; }
+            if (half && i == 7) {
+#pragma unroll
+              for (int j = 2; j < 8; j++) { e[j] = 0.f; d[j] = 0.f; }
+              d[2] = dys; d128 = d[0]; d129 = d[1];
+              cacc[12 * L + 8] += e[0] * dys; cacc[12 * L + 9] += e[1] * dys;     // d w_o[128], [129]
+            }
+            st16(zl + i * 2048, pack2(e[0], e[1]), pack2(e[2], e[3]), pack2(e[4], e[5]), pack2(e[6], e[7]));
+            st16(dl + i * 2048, pack2(d[0], d[1]), pack2(d[2], d[3]), pack2(d[4], d[5]), pack2(d[6], d[7]));
+          }
+        }
+        if (half) {   // corner of dW_L: delta_L[128..129] x ZT[L-1][128..133]
+          float cz[8];
+          unpack8(*reinterpret_cast<const uint4*>(tile_ptr(L - 1) + 16 * 2048 + row * 16), cz);
+#pragma unroll
+          for (int b = 0; b < 6; b++) { cacc[12 * (L - 1) + b] += d128 * cz[b]; cacc[12 * (L - 1) + 6 + b] += d129 * cz[b]; }
+        }
+      }
+      tc::fence_async_smem();
+      tc::fence_before_sync();
+      tc::mbar_arrive(bar_e2m);
+
+      // ---- stages L+2 .. 2L+1: backward hidden epilogues: ACC = dZA_{i-1} -> delta_{i-1}
+#pragma unroll
+      for (int i = L; i >= 1; i--) {
+        tc::mbar_wait(bar_m2e, ph); ph ^= 1;
+        tc::fence_after_sync();
+        load_acc(tlane + T_ACC, half, v);
+        const uint8_t* zsrc = tile_ptr(i - 1) + ch0 * 2048 + row * 16;
+        uint8_t* dst = dbuf(i - 1) + ch0 * 2048 + row * 16;
+        float d128 = 0.f, d129 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 9; c++) {
+          if (c < nch) {
+            float zz[8], d[8];
+            unpack8(*reinterpret_cast<const uint4*>(zsrc + c * 2048), zz);
+#pragma unroll
+            for (int j = 0; j < 8; j++) d[j] = zz[j] > 0.f ? v[8 * c + j] : 0.f;
+            if (half && c == 7) {
+#pragma unroll
+              for (int j = 2; j < 8; j++) d[j] = 0.f;
+              d128 = d[0]; d129 = d[1];
+            }
+            st16(dst + c * 2048, pack2(d[0], d[1]), pack2(d[2], d[3]), pack2(d[4], d[5]), pack2(d[6], d[7]));
+          }
+        }
+        if (half) {
+          if (i - 1 >= 1) {   // corner of dW_{i-1}
+            float cz[8];
+            unpack8(*reinterpret_cast<const uint4*>(tile_ptr(i - 2) + 16 * 2048 + row * 16), cz);
+#pragma unroll
+            for (int b = 0; b < 6; b++) { cacc[12 * (i - 2) + b] += d128 * cz[b]; cacc[12 * (i - 2) + 6 + b] += d129 * cz[b]; }
+          } else {            // corner of the input layer: delta_0[128..129] x (x, y, t, 1)
+            cacc[12 * L + 0] += d128 * x0; cacc[12 * L + 1] += d128 * x1; cacc[12 * L + 2] += d128 * x2; cacc[12 * L + 3] += d128;
+            cacc[12 * L + 4] += d129 * x0; cacc[12 * L + 5] += d129 * x1; cacc[12 * L + 6] += d129 * x2; cacc[12 * L + 7] += d129;
+          }
+        }
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        tc::mbar_arrive(bar_e2m);
+      }
+      // ---- input-layer wgrad issued; its commit frees TX / tiles for the next tile
+      tc::mbar_wait(bar_m2e, ph); ph ^= 1;
+      tc::fence_after_sync();
+    }
+
+    // =========================================================== per-CTA partial write-out
+    if (fit) {
+      const float inv = 1.f / S;
+      float* out = p.part + (int64_t)blockIdx.x * p.sSplit + (int64_t)o * p.G;
+#pragma unroll
+      for (int i = 1; i <= L; i++) {
+        load_acc(tlane + T_DW(i), half, v);
+        float* dst = out + p.aug_layer + (int64_t)(i - 1) * H_ * LD_ + (int64_t)row * LD_ + (half ? 72 : 0);
+        const int nv = half ? 64 : 72;
+#pragma unroll
+        for (int j = 0; j < 72; j++) if (j < nv) dst[j] = v[j] * inv;
+        if (half == 0) {
+          float pb[8];
+          tc::tmem_ld8(tlane + T_PB(i), pb);
+          tc::tmem_ld_wait();
+          float* l = out + p.aug_layer + (int64_t)(i - 1) * H_ * LD_;
+          l[(int64_t)128 * LD_ + row] = pb[0] * inv;
+          l[(int64_t)129 * LD_ + row] = pb[1] * inv;
+        }
+      }
+      if (half == 0) {
+        float g8[8];
+        tc::tmem_ld8(tlane + T_GIN, g8);
+        tc::tmem_ld_wait();
+        float* gi = out + p.aug_in + row * 4;
+        gi[0] = g8[0] * inv; gi[1] = g8[1] * inv;
+        if (C > 2) { gi[2] = g8[2] * inv; gi[3] = g8[3] * inv; } else { gi[2] = 0.f; gi[3] = g8[2] * inv; }
+        tc::tmem_ld8(tlane + T_GO, g8);
+        tc::tmem_ld_wait();
+        out[p.aug_out + row] = g8[2] * inv;
+      }
+      // corner sums: fixed-order reduction over the 256 epilogue threads through shared memory
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float* red = reinterpret_cast<float*>(tiles);       // [NC][256], tiles are dead now
+      const int et = threadIdx.x;                         // 0..255
+#pragma unroll
+      for (int i = 0; i < NC; i++) red[i * 256 + et] = cacc[i];
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (et < NC) {
+        float a = 0.f;
+        for (int t = 0; t < 256; t++) a += red[et * 256 + t];
+        if (et == NC - 1) {
+          p.lossp[blockIdx.x * p.O + o] = a;
+        } else if (et < 12 * L) {
+          const int li = et / 12, r = (et % 12) / 6, b = et % 6;
+          if (b < 3 + C) out[p.aug_layer + (int64_t)li * H_ * LD_ + (int64_t)(128 + r) * LD_ + 128 + b] = a * inv;
+        } else if (et < 12 * L + 8) {
+          const int r = (et - 12 * L) / 4, c = (et - 12 * L) % 4;
+          out[p.aug_in + (128 + r) * 4 + c] = a * inv;
+        } else if (et < 12 * L + 10) {
+          out[p.aug_out + 128 + (et - 12 * L - 8)] = a * inv;
+        } else if (et < NC - 2) {
+          const int c = et - (NC - 5);
+          if (c < C) out[p.aug_out + H_ + c] = a * inv;
+        } else {   // NC - 2
+          out[p.aug_out + H_ + C] = a * inv;
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (issuer_warp) tc::tmem_dealloc<512>(tbase);
+}
+
+// ======================================================================= host launcher
+int tc_supported(const awb_prior* h) {
+  return h->desc.kind == AWB_KIND_ICNN && h->lay.h == H_ && (h->lay.L == 1 || h->lay.L == 2) && h->lay.ld == LD_;
+}
+
+int tc_map_elems(int L) { return (L * W_B + WIN_B) / 2 + NPAD; }
+
+// image element index -> arena index (or -1)
+void tc_build_map_host(const Layout& Ly, int32_t* map) {
+  const int L = Ly.L, C = Ly.C;
+  const int n_half = (L * W_B + WIN_B) / 2;
+  for (int i = 0; i < n_half + NPAD; i++) map[i] = -1;
+  // arena order (state_dict): input.weight [h][C], input.bias [h], {ln.weight [h][h], ln.bias [h], skp.weight [h][C]} x L,
+  // out.ln.weight [h], out.ln.bias, out.skp.weight [C]
+  int64_t a = Ly.off_icnn;
+  auto w_elem = [&](int l, int j, int k) { return l * (W_B / 2) + (k / 8) * (NPAD * 8) + j * 8 + (k % 8); };
+  auto win_elem = [&](int j, int k) { return L * (W_B / 2) + (k / 8) * (NPAD * 8) + j * 8 + (k % 8); };
+  for (int j = 0; j < H_; j++) for (int c = 0; c < C; c++) map[win_elem(j, c)] = (int32_t)a++;
+  for (int j = 0; j < H_; j++) map[win_elem(j, C)] = (int32_t)a++;
+  for (int l = 0; l < L; l++) {
+    for (int j = 0; j < H_; j++) for (int k = 0; k < H_; k++) map[w_elem(l, j, k)] = (int32_t)a++;
+    for (int j = 0; j < H_; j++) map[w_elem(l, j, H_ + C)] = (int32_t)a++;
+    for (int j = 0; j < H_; j++) for (int c = 0; c < C; c++) map[w_elem(l, j, H_ + c)] = (int32_t)a++;
+  }
+  for (int k = 0; k < H_; k++) map[n_half + k] = (int32_t)a++;
+  map[n_half + H_ + C] = (int32_t)a++;
+  for (int c = 0; c < C; c++) map[n_half + H_ + c] = (int32_t)a++;
+}
+
+int tc_fit_forward_backward(const awb_prior* h, const float* params, const awb_grid_spec* g, const float* target,
+                            const awb_loss_spec* loss, float* logits, int mode, const Workspace& ws, int* n_splits_out,
+                            cudaStream_t st) {
+  const Layout& Ly = h->lay;
+  const int O = h->desc.n_objects, L = Ly.L, C = Ly.C;
+  const int64_t N = (int64_t)g->B * g->H * g->W;
+  if (!tc_supported(h)) { set_error("precision f16 supports ICNN priors with h=130, L in {1,2}"); return AWB_ERR_UNSUPPORTED; }
+  const int n_tiles = (int)((N + 127) / 128);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  const int grid = n_tiles < sms ? n_tiles : sms;
+  if (grid > kMaxSplits) { set_error("internal: grid exceeds split capacity"); return AWB_ERR_INVALID; }
+  const int64_t img_stride = tc_image_bytes(L);
+  const int n_elems = (L * W_B + WIN_B) / 2 + NPAD;
+  AWB_LAUNCH(PK_PACK, st, k_pack_tc<<<dim3((n_elems + 255) / 256, O), 256, 0, st>>>(params, (uint8_t*)ws.tc, h->d_tcmap, n_elems,
+                                                                                    L, Ly.P, img_stride));
+  TcP p = {};
+  p.g.mode = g->mode; p.g.B = g->B; p.g.H = g->H; p.g.W = g->W; p.g.C = C; p.g.t0 = g->t0; p.g.t_step = g->t_step; p.g.grid = g->grid;
+  p.img = (const uint8_t*)ws.tc; p.img_stride = img_stride;
+  p.target = target;
+  for (int o = 0; o < O && o < 16; o++) {
+    if (loss) {
+      p.loss[o] = loss[o];
+      float mx = fmaxf(fabsf(loss[o].coef_fg), fabsf(loss[o].coef_bg));
+      p.scale[o] = mx > 0.f ? exp2f(rintf(log2f(64.f / mx))) : 1.f;   // keeps fp16 deltas in range (loss scaling)
+    } else {
+      p.scale[o] = 1.f;
+    }
+  }
+  p.part = ws.part; p.sSplit = (int64_t)O * Ly.G; p.G = Ly.G; p.aug_in = Ly.aug_in; p.aug_layer = Ly.aug_layer; p.aug_out = Ly.aug_out;
+  p.lossp = ws.lossp; p.O = O; p.logits = logits; p.N = N; p.n_tiles = n_tiles; p.mode = mode;
+  const size_t smem = smem_bytes(L);
+  dim3 gd(grid, O);
+#define AWB_TC_LAUNCH(LL, CC)                                                                                      \
+  do {                                                                                                             \
+    AWB_CUDA(cudaFuncSetAttribute(k_icnn_fit_tc<LL, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    AWB_LAUNCH(PK_TC_FUSED, st, k_icnn_fit_tc<LL, CC><<<gd, NTHREADS, smem, st>>>(p));                             \
+  } while (0)
+  if (L == 1 && C == 2) AWB_TC_LAUNCH(1, 2);
+  else if (L == 1 && C == 3) AWB_TC_LAUNCH(1, 3);
+  else if (L == 2 && C == 2) AWB_TC_LAUNCH(2, 2);
+  else AWB_TC_LAUNCH(2, 3);
+#undef AWB_TC_LAUNCH
+  AWB_CUDA(cudaGetLastError());
+  if (n_splits_out) *n_splits_out = grid;
+  return AWB_OK;
+}
+
+}  // namespace awb
