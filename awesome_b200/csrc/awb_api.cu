@@ -51,7 +51,12 @@ static int64_t align256(int64_t b) { return round_up(b, 256); }
 Workspace carve(const awb_prior* h, int64_t N, bool training, void* base) {
   const Layout& L = h->lay;
   const int64_t O = h->desc.n_objects;
-  const int S = n_splits(N);
+  int S = n_splits(N);
+  if (h->desc.precision == AWB_PREC_F16) {   // the tensor path writes one partial per CTA = per 128-pixel tile, up to 148
+    int64_t t = (N + 127) / 128;
+    int st = (int)(t < kMaxSplits ? t : kMaxSplits);
+    if (st > S) S = st;
+  }
   char* p = (char*)base;
   int64_t off = 0;
   auto take = [&](int64_t bytes) { char* r = p ? p + off : nullptr; off += align256(bytes); return r; };
