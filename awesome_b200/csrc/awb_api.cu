@@ -201,10 +201,10 @@ static int check_common(awb_handle h, const awb_grid_spec* g, void* ws, size_t w
 int awb_prior_forward(awb_handle h, const float* params, const awb_grid_spec* g, float* logits, float* deformed,
                       int32_t training, void* ws, size_t ws_bytes, void* stream) {
   int64_t N;
-  int rc = check_common(h, g, ws, ws_bytes, training != 0, &N);
+  int rc = check_common(h, g, ws, ws_bytes, training == 1, &N);
   if (rc) return rc;
   if (!params) { set_error("null params"); return AWB_ERR_INVALID; }
-  Workspace w = carve(h, N, training != 0, ws);
+  Workspace w = carve(h, N, training == 1, ws);
   if (training == 2) {   // fast tensor-path logits (fp16 operands); the default forward stays exact fp32
     if (h->desc.precision != AWB_PREC_F16) { set_error("tensor-path forward needs an f16 handle"); return AWB_ERR_INVALID; }
     return tc_fit_forward_backward(h, params, g, nullptr, nullptr, logits, 0, w, nullptr, (cudaStream_t)stream);
