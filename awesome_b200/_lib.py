@@ -87,6 +87,7 @@ SYMBOLS = [
     ("awb_target_counts", C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
     ("awb_debug_umma_probe", C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _P]),
+    ("awb_debug_tc_trace_read", C.c_int, [C.POINTER(C.c_ulonglong), C.c_int32]),
     ("awb_profile_enable", C.c_int, [C.c_int32]),
     ("awb_profile_classes", C.c_int, []),
     ("awb_profile_class_name", C.c_char_p, [C.c_int32]),

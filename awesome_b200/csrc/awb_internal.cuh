@@ -142,6 +142,7 @@ void tc_build_map_host(const Layout& Ly, int32_t* map);   // map has tc_map_elem
 int tc_fit_forward_backward(const awb_prior* h, const float* params, const awb_grid_spec* g, const float* target,
                             const awb_loss_spec* loss, float* logits, int mode, const Workspace& ws,
                             int* n_splits_out, cudaStream_t st);
+int tc_trace_read(unsigned long long* host, int max_ctas);   // debug timeline (AWB_TC_TRACE=1): 256 stamps per CTA
 
 // ---- flows, implemented in awb_flow.cu ----
 int flow_forward(const awb_prior* h, const float* params, const awb_grid_spec* g, const Workspace& ws,

@@ -416,23 +416,20 @@ __global__ void __launch_bounds__(256) k_in_dgrad(const float* __restrict__ D0, 
 }
 
 // ------------------------------------------------------------------ optimizer (a11) + clamp (a8) + plateau (K12)
-__device__ __forceinline__ void opt_update(int kind, float& p, float g, float& m, float& v, double lr,
-                                           int step1, float beta1, float beta2, float eps, float wd) {
+// step_size = lr / (1 - beta1^t) and bc2s = sqrt(1 - beta2^t) are evaluated in double once per block
+// (torch computes them as Python floats), see k_reduce_opt.
+__device__ __forceinline__ void opt_update(int kind, float& p, float g, float& m, float& v, float step_size,
+                                           float bc2s, float beta1, float beta2, float eps, float wd) {
   // torch/optim/adam.py::_single_tensor_adam, torch/optim/adamax.py::_single_tensor_adamax
   if (wd != 0.f) g = fmaf(wd, p, g);
   m = m + (g - m) * (1.f - beta1);                       // exp_avg.lerp_(grad, 1 - beta1)
-  double bc1 = 1.0 - pow((double)beta1, (double)step1);
   if (kind == AWB_OPT_ADAM) {
     v = v * beta2 + (1.f - beta2) * g * g;               // mul_(beta2).addcmul_(g, g, 1 - beta2)
-    double bc2 = 1.0 - pow((double)beta2, (double)step1);
-    float step_size = (float)(lr / bc1);
-    float bc2s = (float)sqrt(bc2);
     float denom = sqrtf(v) / bc2s + eps;
     p = p - step_size * (m / denom);
   } else {
     v = fmaxf(v * beta2, fabsf(g) + eps);                // exp_inf
-    float clr = (float)(lr / bc1);
-    p = p - clr * (m / v);
+    p = p - step_size * (m / v);
   }
 }
 
@@ -449,68 +446,98 @@ struct OptP {
   float* loss_out;
 };
 
-__global__ void __launch_bounds__(256) k_reduce_opt(OptP a) {
+// Block = 32 consecutive parameters x 8 warps; warp w sums its fixed range of the <=148 per-CTA partials
+// (coalesced 128-byte rows, independent loads in flight), the ranges are combined in a fixed order, then
+// warp 0 applies Adam/Adamax + L2 + clamp.  The last block to finish (ticket in OptScal.pad) advances the
+// step counter and the plateau scheduler, so a fit step needs no separate scheduler launch.
+__global__ void __launch_bounds__(256) k_reduce_opt(OptP a, int n_groups, int use_loss) {
   __shared__ float s_loss;
+  __shared__ float s_part[8][32];
+  __shared__ float s_step_size[AWB_MAX_GROUPS], s_bc2s;
   const int o = blockIdx.y;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + AWB_MAX_GROUPS) {   // bias corrections, once per block
+    const int g = threadIdx.x - 32;
+    const int step1 = a.scal[o].step + 1;
+    const double bc1 = 1.0 - pow((double)a.hy.beta1, (double)step1);
+    s_step_size[g] = (float)(a.scal[o].lr[g] / bc1);
+    if (g == 0) s_bc2s = (float)sqrt(1.0 - pow((double)a.hy.beta2, (double)step1));
+  }
   if (a.lossp) {
-    if (threadIdx.x < 32) {
+    if (w == 0) {
       // fixed-order loss sum: lane-strided then butterfly
       float l = 0.f;
-      for (int s = threadIdx.x; s < a.S; s += 32) l += a.lossp[s * a.O + o];
+      for (int s = lane; s < a.S; s += 32) l += a.lossp[s * a.O + o];
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
-      if (threadIdx.x == 0) s_loss = l;
+      if (lane == 0) s_loss = l;
     }
+  }
+  __syncthreads();
+  // reference raises before backward() on a non-finite loss: leave the parameters untouched
+  const bool bad = a.lossp && !isfinite(s_loss);
+  const int64_t i = (int64_t)blockIdx.x * 32 + lane;
+  const bool mine = i < a.P && !(a.hy.active_groups && !((a.hy.active_groups >> a.group[i]) & 1));
+  if (!bad && !a.grads) {
+    float g = 0.f;
+    if (mine) {
+      const float* src;
+      int64_t stride;
+      if (i >= a.off_icnn && i < a.off_icnn + a.P_icnn) { src = a.part + (int64_t)o * a.G + a.map[i - a.off_icnn]; stride = a.sSplit; }
+      else { src = a.fpart + (int64_t)o * a.PF + (i - a.off_flow); stride = a.sFSplit; }
+      const int s0 = (a.S * w) >> 3, s1 = (a.S * (w + 1)) >> 3;
+#pragma unroll 4
+      for (int s = s0; s < s1; s++) g += src[(int64_t)s * stride];
+    }
+    s_part[w][lane] = g;
     __syncthreads();
-    if (!isfinite(s_loss)) {   // reference raises before backward(): leave the parameters untouched
-      if (blockIdx.x == 0 && threadIdx.x == 0) { a.scal[o].nonfinite = 1; a.scal[o].last_loss = s_loss; if (a.loss_out) a.loss_out[o] = s_loss; }
-      return;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { a.scal[o].last_loss = s_loss; if (a.loss_out) a.loss_out[o] = s_loss; }
   }
-  int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (i >= a.P) return;
-  if (a.hy.active_groups && !((a.hy.active_groups >> a.group[i]) & 1)) return;   // not owned by this optimizer
-  float g;
-  if (a.grads) {
-    g = a.grads[(int64_t)o * a.P + i];
-  } else if (i >= a.off_icnn && i < a.off_icnn + a.P_icnn) {
-    const float* src = a.part + (int64_t)o * a.G + a.map[i - a.off_icnn];
-    g = 0.f;
-    for (int s = 0; s < a.S; s++) g += src[(int64_t)s * a.sSplit];
-  } else {
-    const float* src = a.fpart + (int64_t)o * a.PF + (i - a.off_flow);
-    g = 0.f;
-    for (int s = 0; s < a.S; s++) g += src[(int64_t)s * a.sFSplit];
-  }
-  const OptScal sc = a.scal[o];
-  int grp = a.group[i];
-  int64_t gi = (int64_t)o * a.P + i;
-  float p = a.params[gi], m = a.m[gi], v = a.v[gi];
-  opt_update(a.hy.kind, p, g, m, v, sc.lr[grp], sc.step + 1, a.hy.beta1, a.hy.beta2, a.hy.eps,
-             a.hy.weight_decay[grp]);
-  if (a.clamp[i]) p = fmaxf(p, 0.f);                     // enforce_convexity
-  a.params[gi] = p; a.m[gi] = m; a.v[gi] = v;
-}
-
-// step counter + ReduceLROnPlateau.step(loss) (torch/optim/lr_scheduler.py), one thread per object.
-__global__ void k_step_end(OptScal* scal, awb_opt_hyper hy, int n_groups, int use_loss) {
-  int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= (int)gridDim.x * (int)blockDim.x) return;
-  OptScal& s = scal[o];
-  if (use_loss && !isfinite(s.last_loss)) return;
-  s.step += 1;
-  if (!hy.plateau_enabled || !use_loss) return;
-  double cur = (double)s.last_loss;
-  if (cur < s.best * (1.0 - (double)hy.threshold)) { s.best = cur; s.num_bad = 0; }
-  else s.num_bad += 1;
-  if (s.num_bad > hy.patience) {
-    for (int g = 0; g < n_groups; g++) {
-      double nl = s.lr[g] * (double)hy.factor;
-      if (nl < (double)hy.min_lr) nl = (double)hy.min_lr;
-      if (s.lr[g] - nl > (double)hy.plateau_eps) s.lr[g] = nl;
+  if (!bad && w == 0 && mine) {
+    float g;
+    if (a.grads) {
+      g = a.grads[(int64_t)o * a.P + i];
+    } else {
+      g = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < 8; ww++) g += s_part[ww][lane];
     }
-    s.num_bad = 0;
+    const int grp = a.group[i];
+    const int64_t gi = (int64_t)o * a.P + i;
+    float p = a.params[gi], m = a.m[gi], v = a.v[gi];
+    opt_update(a.hy.kind, p, g, m, v, s_step_size[grp], s_bc2s, a.hy.beta1, a.hy.beta2, a.hy.eps,
+               a.hy.weight_decay[grp]);
+    if (a.clamp[i]) p = fmaxf(p, 0.f);                     // enforce_convexity
+    a.params[gi] = p; a.m[gi] = m; a.v[gi] = v;
+  }
+  // ---- ticket: the last block of this object closes the step (every block has read scal by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    OptScal& s = a.scal[o];
+    const int t = atomicAdd(&s.pad, 1);
+    if (t == (int)gridDim.x - 1) {
+      s.pad = 0;
+      if (a.lossp) { s.last_loss = s_loss; if (a.loss_out) a.loss_out[o] = s_loss; }
+      if (bad) {
+        s.nonfinite = 1;
+      } else {
+        // step counter + ReduceLROnPlateau.step(loss) (torch/optim/lr_scheduler.py)
+        s.step += 1;
+        if (a.hy.plateau_enabled && use_loss) {
+          const double cur = (double)s_loss;
+          if (cur < s.best * (1.0 - (double)a.hy.threshold)) { s.best = cur; s.num_bad = 0; }
+          else s.num_bad += 1;
+          if (s.num_bad > a.hy.patience) {
+            for (int g = 0; g < n_groups; g++) {
+              double nl = s.lr[g] * (double)a.hy.factor;
+              if (nl < (double)a.hy.min_lr) nl = (double)a.hy.min_lr;
+              if (s.lr[g] - nl > (double)a.hy.plateau_eps) s.lr[g] = nl;
+            }
+            s.num_bad = 0;
+          }
+        }
+      }
+    }
   }
 }
 
@@ -702,8 +729,7 @@ int simt_reduce_opt(const awb_prior* h, float* params, void* opt_state, const aw
   a.map = h->d_map; a.clamp = h->d_clamp; a.group = h->d_group;
   a.P = L.P; a.off_icnn = L.off_icnn; a.P_icnn = L.P_icnn; a.off_flow = L.off_flow; a.G = L.G;
   a.O = O; a.hy = *hy; a.loss_out = loss_out;
-  AWB_LAUNCH(PK_OPT, st, k_reduce_opt<<<dim3((unsigned)((L.P + 255) / 256), O), 256, 0, st>>>(a));
-  AWB_LAUNCH(PK_OPT, st, k_step_end<<<1, O, 0, st>>>(a.scal, *hy, n_groups_of(h), 1));
+  AWB_LAUNCH(PK_OPT, st, k_reduce_opt<<<dim3((unsigned)((L.P + 31) / 32), O), 256, 0, st>>>(a, n_groups_of(h), 1));
   AWB_CUDA(cudaGetLastError());
   return AWB_OK;
 }
@@ -737,8 +763,7 @@ int optim_step(const awb_prior* h, float* params, const float* grads, void* opt_
   a.map = h->d_map; a.clamp = h->d_clamp; a.group = h->d_group;
   a.P = L.P; a.off_icnn = L.off_icnn; a.P_icnn = L.P_icnn; a.off_flow = L.off_flow; a.G = L.G;
   a.O = O; a.hy = *hy;
-  AWB_LAUNCH(PK_OPT, st, k_reduce_opt<<<dim3((unsigned)((L.P + 255) / 256), O), 256, 0, st>>>(a));
-  AWB_LAUNCH(PK_OPT, st, k_step_end<<<1, O, 0, st>>>(a.scal, *hy, n_groups_of(h), 0));
+  AWB_LAUNCH(PK_OPT, st, k_reduce_opt<<<dim3((unsigned)((L.P + 31) / 32), O), 256, 0, st>>>(a, n_groups_of(h), 0));
   AWB_CUDA(cudaGetLastError());
   return AWB_OK;
 }

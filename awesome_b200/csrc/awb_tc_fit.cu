@@ -8,16 +8,24 @@
 //   * activations never leaving the SM: TMEM -> registers (relu / relu-backward / loss) -> fp16
 //     shared-memory operand tiles of the next contraction;
 //   * weight gradients accumulated across all tiles of the CTA in TMEM (dW never touches HBM until
-//     the single per-CTA partial write at the end); the 130 = 128 + 2 remainder rows/columns are
-//     covered by two N=16 side contractions plus a handful of per-thread corner sums;
+//     the single per-CTA partial write at the end, staged through shared memory and written with TMA
+//     bulk stores); the 130 = 128 + 2 remainder rows/columns are covered by two N=16 side
+//     contractions plus a handful of per-thread corner sums;
 //   * loss / corner sums reduced with registers + one shared-memory pass (no atomics).
 // The cross-CTA reduction + Adam/Adamax + clamp + plateau run in k_reduce_opt (awb_simt.cu).
+//
+// Pipeline (one tile in flight; shared memory holds the weights (81 KB) + 4 operand tiles (136 KB)):
+//   epilogue warps (8) <-> issuer (1 elected lane) through two mbarriers; 2L+1 round trips per tile.
+//   Everything that is not on the round-trip critical path runs in the shadow of the next
+//   contraction: next tile's coordinates / target prefetch, corner sums, loss accumulation, the
+//   relu masks of the backward epilogues (read from the stored activations before the wait).
 //
 // Shared-memory operand tiles use the SWIZZLE_NONE interleaved layout of awb_tc.cuh with 17 stored
 // column chunks (136 columns); the 18th chunk of a K = 144 walk is redirected to a shared zero chunk
 // through the per-instruction LBO field, and as an MN-major N = 144 operand it reads whatever follows
 // (those accumulator columns, 136..143, are never read).  See DESIGN.md "tensor path".
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -30,14 +38,15 @@ namespace {
 constexpr int H_ = 130, LD_ = 136, NPAD = 144;
 constexpr int TILE_B = 17 * 2048;   // [17 chunks][128 rows][8 fp16]
 constexpr int W_B = 17 * 2304;      // [17 chunks][144 rows][8 fp16]
-constexpr int WIN_B = 2 * 2304;     // [2 chunks][144 rows][8 fp16]   input layer (K = 16)
-constexpr int TX_B = 2 * 2048;      // [2 chunks][128 rows][8 fp16]   (x, y, (t), 1, 0...)
+constexpr int WIN_B = 2304;         // [1 chunk][144 rows][8 fp16]   input layer (K = 16: 2nd chunk = zero chunk)
+constexpr int TX_B = 2048;          // [1 chunk][128 rows][8 fp16]   (x, y, (t), 1, 0...), double buffered
 constexpr int ZERO_B = 2304;
 constexpr int VEC_B = NPAD * 4;     // fp32 (w_o | s_o | b_o | 0)
 constexpr int NTHREADS = 288;       // 8 epilogue warps + 1 issuer warp
+constexpr int TRACE_N = 256;        // clock stamps per CTA (debug timeline)
 __host__ __device__ constexpr int img_bytes(int L) { return L * W_B + WIN_B + VEC_B; }
 __host__ __device__ constexpr int smem_bytes(int L) {
-  return (L + 2) * TILE_B + img_bytes(L) + TX_B + ZERO_B + 1024 + 64;
+  return (L + 2) * TILE_B + img_bytes(L) + 2 * TX_B + ZERO_B + 1024 + 64;
 }
 }  // namespace
 
@@ -67,26 +76,47 @@ struct TcP {
   float* lossp; int O;
   float* logits;
   int64_t N; int n_tiles; int mode;
+  unsigned long long* trace;
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ uint32_t relu2(uint32_t u) {   // max(x, 0) on a packed fp16 pair
+  __half2 h = *reinterpret_cast<__half2*>(&u);
+  h = __hmax2(h, __float2half2_rn(0.f));
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t gt0_mask2(uint32_t u) {   // 0xFFFF per half that is > 0
+  return __hgt2_mask(*reinterpret_cast<__half2*>(&u), __float2half2_rn(0.f));
+}
 __device__ __forceinline__ void st16(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
 }
-__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
-  const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; i++) { float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
-}
+__device__ __forceinline__ float half_lo(uint32_t u) { return __low2float(*reinterpret_cast<__half2*>(&u)); }
+__device__ __forceinline__ float half_hi(uint32_t u) { return __high2float(*reinterpret_cast<__half2*>(&u)); }
 // accumulator columns of this thread's half: half 0 -> [0,72), half 1 -> [72,136)
 __device__ __forceinline__ void load_acc(uint32_t taddr, int half, float* v) {
   const uint32_t a = taddr + (half ? 72 : 0);
   tc::tmem_ld16(a, v); tc::tmem_ld16(a + 16, v + 16); tc::tmem_ld16(a + 32, v + 32); tc::tmem_ld16(a + 48, v + 48);
   if (!half) tc::tmem_ld8(a + 64, v + 64);
   tc::tmem_ld_wait();
+}
+
+// pixel coordinates with 32-bit index arithmetic (N <= 2^30 is checked on the host)
+__device__ __forceinline__ void row_coords(const GridDev& g, uint32_t n, int C, float& x0, float& x1, float& x2) {
+  const uint32_t hw = (uint32_t)g.H * (uint32_t)g.W;
+  const uint32_t b = n / hw, r = n - b * hw;
+  const uint32_t i = r / (uint32_t)g.W, j = r - i * (uint32_t)g.W;
+  if (g.mode == AWB_GRID_EXPLICIT) {
+    const float* base = g.grid + (size_t)b * C * hw + r;
+    x0 = base[0]; x1 = base[hw]; x2 = C > 2 ? base[2 * (size_t)hw] : 0.f;
+    return;
+  }
+  x2 = C > 2 ? g.t0 + (float)b * g.t_step : 0.f;
+  if (g.mode == AWB_GRID_LINSPACE) { x0 = lin01((int)j, g.W); x1 = lin01((int)i, g.H); }
+  else { x0 = (float)j / (float)g.W; x1 = (float)i / (float)g.H; }
 }
 
 template <int L, int C>
@@ -97,11 +127,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
   constexpr int NC = 12 * L + 15;                 // per-thread corner / scalar accumulators
   uint8_t* tiles = smem;                          // ZT[0..L-1], ZL, DT
   uint8_t* simg = smem + NT * TILE_B;             // W_1..W_L | WIN | vec
-  uint8_t* stx = simg + IMG;
-  uint8_t* szero = stx + TX_B;
+  uint8_t* stx = simg + IMG;                      // TX[2]
+  uint8_t* szero = stx + 2 * TX_B;
   float* xchg = reinterpret_cast<float*>(szero + ZERO_B);          // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(szero + ZERO_B + 1024);
-  uint64_t* bar_e2m = bars;        // epilogue -> issuer (256 arrivals)
+  uint64_t* bar_e2m = bars;        // epilogue -> issuer (8 arrivals: one per epilogue warp)
   uint64_t* bar_m2e = bars + 1;    // tcgen05.commit -> epilogue
   uint64_t* bar_w = bars + 2;      // weight image landed (TMA tx bytes)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
@@ -110,9 +140,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int o = blockIdx.y;
   const bool issuer_warp = warp == 8;
+  unsigned long long* trace = p.trace ? p.trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * TRACE_N : nullptr;
+  int tr_n = 0;
+#define AWB_TR()                                                            \
+  do {                                                                      \
+    if (trace && (threadIdx.x & 255) == 0 && tr_n < TRACE_N / 2) trace[(issuer_warp ? TRACE_N / 2 : 0) + tr_n++] = clock64(); \
+  } while (0)
 
   // ---- one-time setup
-  if (threadIdx.x == 0) { tc::mbar_init(bar_e2m, 256); tc::mbar_init(bar_m2e, 1); tc::mbar_init(bar_w, 1); tc::mbar_fence_init(); }
+  if (threadIdx.x == 0) { tc::mbar_init(bar_e2m, 8); tc::mbar_init(bar_m2e, 1); tc::mbar_init(bar_w, 1); tc::mbar_fence_init(); }
   for (int i = threadIdx.x * 16; i < ZERO_B; i += NTHREADS * 16) *reinterpret_cast<uint4*>(szero + i) = make_uint4(0, 0, 0, 0);
   __syncthreads();
   if (issuer_warp) {
@@ -132,7 +168,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tbase = *tmem_slot;
-  tc::mbar_wait(bar_w, 0);
 
   constexpr uint32_t T_ACC = 0;
   auto T_DW = [](int i) { return (uint32_t)(144 * i); };                       // i = 1..L
@@ -145,14 +180,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
 
   const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const bool fit = p.mode != 0;
-  constexpr int NSTAGE_FIT = 2 * L + 2, NSTAGE_FWD = L + 1;
 
   if (issuer_warp) {
     // =========================================================== MMA issuer (one elected lane)
     if (lane == 0) {
+      tc::mbar_wait(bar_w, 0);
       uint32_t ph = 0;
       const uint32_t zero_a = tc::smem_u32(szero);
-      const uint32_t a_tx = tc::smem_u32(stx), a_win = tc::smem_u32(simg + L * W_B);
+      const uint32_t a_tx0 = tc::smem_u32(stx), a_win = tc::smem_u32(simg + L * W_B);
       auto w_addr = [&](int i) { return tc::smem_u32(simg + (i - 1) * W_B); };
       auto t_addr = [&](uint8_t* t) { return tc::smem_u32(t); };
       // K-major A (R=128) x K-major/MN-major B (R=144) over K = 144 (9 steps), N = 144
@@ -168,42 +203,60 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
           tc::umma_f16(tbase + dcol, ad, bd, idesc, k > 0);
         }
       };
-      // MN-major A window [0,128) x MN-major B, K = 128 pixels (8 steps)
-      auto mma_px = [&](uint32_t dcol, uint32_t a, uint32_t b, int N, bool acc) {
+      // MN-major A window [0,128) x MN-major B, K = 128 pixels (8 steps); b_sbo = byte distance of B's 2nd N chunk
+      auto mma_px = [&](uint32_t dcol, uint32_t a, uint32_t b, uint32_t b_sbo, int N, bool acc) {
         const uint32_t idesc = tc::make_idesc(128, N, 1, 1);
 #pragma unroll
         for (int k = 0; k < 8; k++)
-          tc::umma_f16(tbase + dcol, tc::make_desc(a + k * 256, 128, 2048), tc::make_desc(b + k * 256, 128, 2048), idesc,
+          tc::umma_f16(tbase + dcol, tc::make_desc(a + k * 256, 128, 2048), tc::make_desc(b + k * 256, 128, b_sbo), idesc,
                        (acc || k > 0) ? 1u : 0u);
       };
+      // input layer of a tile: ACC = TX[128x16] * WIN^T   (both operands: one stored K chunk + the zero chunk)
+      auto mma_input = [&](uint32_t a_tx) {
+        tc::umma_f16(tbase + T_ACC, tc::make_desc(a_tx, zero_a - a_tx, 128), tc::make_desc(a_win, zero_a - a_win, 128),
+                     tc::make_idesc(128, 144, 0, 0), 0);
+      };
+      // prologue: input layer of the first tile
+      tc::mbar_wait(bar_e2m, ph); ph ^= 1;
+      tc::fence_after_sync();
+      mma_input(a_tx0);
+      tc::umma_commit(bar_m2e);
+      AWB_TR();
       for (int it = 0; it < n_my; it++) {
         const bool acc = it > 0;
-        const int nstage = fit ? NSTAGE_FIT : NSTAGE_FWD;
-        for (int s = 0; s < nstage; s++) {
+        const bool more = it + 1 < n_my;
+        const uint32_t a_tx = a_tx0 + (it & 1) * TX_B, a_txn = a_tx0 + ((it + 1) & 1) * TX_B;
+        if (!fit) {
+          for (int s = 1; s <= L + 1; s++) {
+            tc::mbar_wait(bar_e2m, ph); ph ^= 1;
+            tc::fence_after_sync();
+            if (s <= L) mma_k144(T_ACC, t_addr(tile_ptr(s - 1)), w_addr(s), false);
+            else if (more) mma_input(a_txn);
+            tc::umma_commit(bar_m2e);
+          }
+          continue;
+        }
+        for (int s = 1; s <= 2 * L + 1; s++) {
           tc::mbar_wait(bar_e2m, ph); ph ^= 1;
           tc::fence_after_sync();
-          if (s == 0) {
-            // input layer: ACC = TX[128x16] * WIN^T
-            tc::umma_f16(tbase + T_ACC, tc::make_desc(a_tx, 2048, 128), tc::make_desc(a_win, 2304, 128),
-                         tc::make_idesc(128, 144, 0, 0), 0);
-            tc::umma_commit(bar_m2e);
-          } else if (s <= L) {
+          AWB_TR();
+          if (s <= L) {
             mma_k144(T_ACC, t_addr(tile_ptr(s - 1)), w_addr(s), false);          // forward layer s
             tc::umma_commit(bar_m2e);
-          } else {
+          } else if (s <= 2 * L) {
             const int i = L - (s - (L + 1));                                      // delta_i was just written
-            if (i >= 1) {
-              const uint32_t d = t_addr(dbuf(i)), zprev = t_addr(tile_ptr(i - 1));
-              mma_k144(T_ACC, d, w_addr(i), true);                                // dgrad_i: ACC = delta_i * W_i
-              if (i == L) mma_px(T_GO, t_addr(tile_ptr(L)), d + 16 * 2048, 16, acc);   // z_L^T * [d128 d129 dy ..]
-              tc::umma_commit(bar_m2e);
-              mma_px(T_DW(i), d, zprev, 144, acc);                                // wgrad_i main rows 0..127
-              mma_px(T_PB(i), zprev, d + 16 * 2048, 16, acc);                     // wgrad_i rows 128,129 (transposed)
-            } else {
-              mma_px(T_GIN, t_addr(dbuf(0)), a_tx, 16, acc);                      // input-layer wgrad
-              tc::umma_commit(bar_m2e);
-            }
+            const uint32_t d = t_addr(dbuf(i)), zprev = t_addr(tile_ptr(i - 1));
+            mma_k144(T_ACC, d, w_addr(i), true);                                  // dgrad_i: ACC = delta_i * W_i
+            if (i == L) mma_px(T_GO, t_addr(tile_ptr(L)), d + 16 * 2048, 2048, 16, acc);   // z_L^T * [d128 d129 dy ..]
+            tc::umma_commit(bar_m2e);
+            mma_px(T_DW(i), d, zprev, 2048, 144, acc);                            // wgrad_i main rows 0..127
+            mma_px(T_PB(i), zprev, d + 16 * 2048, 2048, 16, acc);                 // wgrad_i rows 128,129 (transposed)
+          } else {
+            mma_px(T_GIN, t_addr(dbuf(0)), a_tx, zero_a - a_tx, 16, acc);         // input-layer wgrad
+            if (more) mma_input(a_txn);                                           // next tile's input layer
+            tc::umma_commit(bar_m2e);
           }
+          AWB_TR();
         }
       }
     }
@@ -221,57 +274,73 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
     const awb_loss_spec ls = p.loss[o];
     const float S = p.scale[o];
     float v[72];
+    const float* w = wo + (half ? 72 : 0);
+
+    // arrive once per warp: every lane orders its generic-proxy stores and tcgen05.ld before the sync
+    auto stage_done = [&]() {
+      tc::fence_async_smem();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(bar_e2m);
+    };
+    auto write_tx = [&](int buf, float a0, float a1, float a2) {
+      if (half == 0) st16(stx + buf * TX_B + row * 16, pack2(a0, a1), pack2(C > 2 ? a2 : 1.f, C > 2 ? 1.f : 0.f), 0u, 0u);
+    };
+    // coordinates / target of a tile (rows past N replicate the last pixel and carry no loss)
+    float x0n = 0.f, x1n = 0.f, x2n = 0.f, tgtn = 0.f;
+    bool liven = false;
+    auto fetch_tile = [&](int tile) {
+      const int64_t n = (int64_t)tile * 128 + row;
+      liven = n < p.N;
+      const uint32_t nn = (uint32_t)(liven ? n : p.N - 1);
+      row_coords(p.g, nn, C, x0n, x1n, x2n);
+      tgtn = 0.f;
+      if (fit && liven) tgtn = p.target[(int64_t)o * p.N + n];
+    };
+
+    fetch_tile(blockIdx.x);
+    write_tx(0, x0n, x1n, x2n);
+    stage_done();
+    tc::mbar_wait(bar_w, 0);     // wo (read with plain loads below) has landed
 
     for (int it = 0; it < n_my; it++) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int64_t n = (int64_t)tile * 128 + row;
-      const bool live = n < p.N;
-      const int64_t nn = live ? n : p.N - 1;
-      const float x0 = coord(p.g, nn, 0), x1 = coord(p.g, nn, 1), x2 = C > 2 ? coord(p.g, nn, 2) : 0.f;
-      // aug values of chunk 16 columns 130..135
-      const float a2 = x0, a3 = x1, a4 = C > 2 ? x2 : 1.f, a5 = C > 2 ? 1.f : 0.f;
-      float tgt = 0.f;
-      if (fit && live) tgt = p.target[(int64_t)o * p.N + n];
-
-      // ---- stage 0: TX = (x, 1, 0..)
-      if (half == 0) {
-        st16(stx + row * 16, pack2(x0, x1), pack2(C > 2 ? x2 : 1.f, C > 2 ? 1.f : 0.f), 0u, 0u);
-        st16(stx + 2048 + row * 16, 0u, 0u, 0u, 0u);
-      }
-      tc::fence_async_smem();
-      tc::fence_before_sync();
-      tc::mbar_arrive(bar_e2m);
+      const bool live = liven;
+      const float x0 = x0n, x1 = x1n, x2 = x2n, tgt = tgtn;
+      const bool more = it + 1 < n_my;
+      // aug values of chunk 16 columns 130..135: (x, y, [t,] 1, 0..)
+      const uint32_t ax01 = pack2(x0, x1), ax2o = pack2(C > 2 ? x2 : 1.f, C > 2 ? 1.f : 0.f);
 
       // ---- stages 1..L: hidden forward epilogues (ACC -> relu -> ZT[s-1])
 #pragma unroll
       for (int s = 1; s <= L; s++) {
         tc::mbar_wait(bar_m2e, ph); ph ^= 1;
         tc::fence_after_sync();
+        AWB_TR();
         load_acc(tlane + T_ACC, half, v);
         uint8_t* dst = tile_ptr(s - 1) + ch0 * 2048 + row * 16;
 #pragma unroll
         for (int i = 0; i < 9; i++) {
           if (i < nch) {
-            float e[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) e[j] = fmaxf(v[8 * i + j], 0.f);
-            if (half && i == 7) { e[2] = a2; e[3] = a3; e[4] = a4; e[5] = a5; e[6] = 0.f; e[7] = 0.f; }
-            st16(dst + i * 2048, pack2(e[0], e[1]), pack2(e[2], e[3]), pack2(e[4], e[5]), pack2(e[6], e[7]));
+            uint32_t w0 = relu2(pack2(v[8 * i], v[8 * i + 1])), w1 = relu2(pack2(v[8 * i + 2], v[8 * i + 3]));
+            uint32_t w2 = relu2(pack2(v[8 * i + 4], v[8 * i + 5])), w3 = relu2(pack2(v[8 * i + 6], v[8 * i + 7]));
+            if (half && i == 7) { w1 = ax01; w2 = ax2o; w3 = 0u; }
+            st16(dst + i * 2048, w0, w1, w2, w3);
           }
         }
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        tc::mbar_arrive(bar_e2m);
+        stage_done();
+        AWB_TR();
       }
 
       // ---- stage L+1: last hidden activation, output layer, loss, delta_L
       tc::mbar_wait(bar_m2e, ph); ph ^= 1;
       tc::fence_after_sync();
+      AWB_TR();
       load_acc(tlane + T_ACC, half, v);
       float dot = 0.f;
       {
         const int nz = half ? 58 : 72;                    // real z columns of this half
-        const float* w = wo + (half ? 72 : 0);
 #pragma unroll
         for (int j = 0; j < 72; j++) {
           if (j < nz) { v[j] = fmaxf(v[j], 0.f); dot = fmaf(v[j], w[j], dot); }
@@ -283,14 +352,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
         }
       }
       xchg[half * 128 + row] = dot;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (fit) {   // z_L tile (operand of the output-layer wgrad) goes out while the partner warp catches up
+        uint8_t* zl = tile_ptr(L) + ch0 * 2048 + row * 16;
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+          if (i < nch) {
+            uint32_t w0 = pack2(v[8 * i], v[8 * i + 1]), w1 = pack2(v[8 * i + 2], v[8 * i + 3]);
+            uint32_t w2 = pack2(v[8 * i + 4], v[8 * i + 5]), w3 = pack2(v[8 * i + 6], v[8 * i + 7]);
+            if (half && i == 7) { w1 = 0u; w2 = 0u; w3 = 0u; }
+            st16(zl + i * 2048, w0, w1, w2, w3);
+          }
+        }
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // the two warps that share these 32 rows
       const float y = xchg[row] + xchg[128 + row];
       if (!fit) {
         if (half == 0 && live && p.logits) p.logits[(int64_t)o * p.N + n] = y;
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // xchg reuse by the next tile
+        if (more) { fetch_tile(tile + gridDim.x); write_tx((it + 1) & 1, x0n, x1n, x2n); }
+        stage_done();
         continue;
       }
-      float dys = 0.f;
+      float dys = 0.f, lossv = 0.f;
       if (live) {
         const bool fg = ls.cls_rule == AWB_CLS_UNARY_LT_HALF ? (tgt < 0.5f) : (tgt != 1.0f);
         const float coef = fg ? ls.coef_fg : ls.coef_bg;
@@ -299,101 +381,121 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
         if (ls.kind == AWB_LOSS_SE_SIGMOID) { float d = tgt - sg; l = d * d; dl = -2.f * d * sg * (1.f - sg); }
         else { l = fmaxf(y, 0.f) - y * tgt + log1pf(expf(-fabsf(y))); dl = sg - tgt; }
         dys = coef * dl * S;
-        if (half == 0) {
-          cacc[NC - 1] += coef * l;                                   // loss
-          cacc[NC - 2] += dys;                                        // d b_o
-          cacc[NC - 5] += dys * x0; cacc[NC - 4] += dys * x1;          // d s_o
-          if (C > 2) cacc[NC - 3] += dys * x2;
-        }
+        lossv = coef * l;
       }
-      if (p.logits && half == 0 && live) p.logits[(int64_t)o * p.N + n] = y;
+      float dL128 = 0.f, dL129 = 0.f, zL128 = 0.f, zL129 = 0.f;
       {
-        uint8_t* zl = tile_ptr(L) + ch0 * 2048 + row * 16;
         uint8_t* dl = dbuf(L) + ch0 * 2048 + row * 16;
-        const float* w = wo + (half ? 72 : 0);
-        float d128 = 0.f, d129 = 0.f;
 #pragma unroll
         for (int i = 0; i < 9; i++) {
           if (i < nch) {
-            float e[8], d[8];
+            float d[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) { e[j] = v[8 * i + j]; d[j] = e[j] > 0.f ? dys * w[8 * i + j] : 0.f; }
+            for (int j = 0; j < 8; j++) d[j] = v[8 * i + j] > 0.f ? dys * w[8 * i + j] : 0.f;
             if (half && i == 7) {
+              dL128 = d[0]; dL129 = d[1]; zL128 = v[56]; zL129 = v[57];
 #pragma unroll
-              for (int j = 2; j < 8; j++) { e[j] = 0.f; d[j] = 0.f; }
-              d[2] = dys; d128 = d[0]; d129 = d[1];
-              cacc[12 * L + 8] += e[0] * dys; cacc[12 * L + 9] += e[1] * dys;     // d w_o[128], [129]
+              for (int j = 3; j < 8; j++) d[j] = 0.f;
+              d[2] = dys;
             }
-            st16(zl + i * 2048, pack2(e[0], e[1]), pack2(e[2], e[3]), pack2(e[4], e[5]), pack2(e[6], e[7]));
             st16(dl + i * 2048, pack2(d[0], d[1]), pack2(d[2], d[3]), pack2(d[4], d[5]), pack2(d[6], d[7]));
           }
         }
-        if (half) {   // corner of dW_L: delta_L[128..129] x ZT[L-1][128..133]
-          float cz[8];
-          unpack8(*reinterpret_cast<const uint4*>(tile_ptr(L - 1) + 16 * 2048 + row * 16), cz);
-#pragma unroll
-          for (int b = 0; b < 6; b++) { cacc[12 * (L - 1) + b] += d128 * cz[b]; cacc[12 * (L - 1) + 6 + b] += d129 * cz[b]; }
-        }
       }
-      tc::fence_async_smem();
-      tc::fence_before_sync();
-      tc::mbar_arrive(bar_e2m);
+      stage_done();
+      AWB_TR();
+      // ---- shadow of dgrad_L: everything that is not an operand of the next contraction
+      if (p.logits && half == 0 && live) p.logits[(int64_t)o * p.N + n] = y;
+      if (half == 0) {
+        cacc[NC - 1] += lossv;                                      // loss
+        cacc[NC - 2] += dys;                                        // d b_o
+        cacc[NC - 5] += dys * x0; cacc[NC - 4] += dys * x1;          // d s_o
+        if (C > 2) cacc[NC - 3] += dys * x2;
+      } else {
+        cacc[12 * L + 8] += zL128 * dys; cacc[12 * L + 9] += zL129 * dys;     // d w_o[128], [129]
+        // corner of dW_L: delta_L[128..129] x ZT[L-1][128..133]
+        const uint4 cz = *reinterpret_cast<const uint4*>(tile_ptr(L - 1) + 16 * 2048 + row * 16);
+        const float c6[6] = {half_lo(cz.x), half_hi(cz.x), half_lo(cz.y), half_hi(cz.y), half_lo(cz.z), half_hi(cz.z)};
+#pragma unroll
+        for (int b = 0; b < 6; b++) { cacc[12 * (L - 1) + b] += dL128 * c6[b]; cacc[12 * (L - 1) + 6 + b] += dL129 * c6[b]; }
+      }
+      if (more) fetch_tile(tile + gridDim.x);     // next tile's coordinates and target (load latency hidden)
 
       // ---- stages L+2 .. 2L+1: backward hidden epilogues: ACC = dZA_{i-1} -> delta_{i-1}
 #pragma unroll
       for (int i = L; i >= 1; i--) {
+        // relu mask of z_{i-1} from the stored activations, before the wait
+        uint32_t mk[36];
+        {
+          const uint8_t* zsrc = tile_ptr(i - 1) + ch0 * 2048 + row * 16;
+#pragma unroll
+          for (int c = 0; c < 9; c++) {
+            if (c < nch) {
+              const uint4 u = *reinterpret_cast<const uint4*>(zsrc + c * 2048);
+              mk[4 * c] = gt0_mask2(u.x); mk[4 * c + 1] = gt0_mask2(u.y); mk[4 * c + 2] = gt0_mask2(u.z); mk[4 * c + 3] = gt0_mask2(u.w);
+            }
+          }
+        }
         tc::mbar_wait(bar_m2e, ph); ph ^= 1;
         tc::fence_after_sync();
+        AWB_TR();
         load_acc(tlane + T_ACC, half, v);
-        const uint8_t* zsrc = tile_ptr(i - 1) + ch0 * 2048 + row * 16;
         uint8_t* dst = dbuf(i - 1) + ch0 * 2048 + row * 16;
         float d128 = 0.f, d129 = 0.f;
 #pragma unroll
         for (int c = 0; c < 9; c++) {
           if (c < nch) {
-            float zz[8], d[8];
-            unpack8(*reinterpret_cast<const uint4*>(zsrc + c * 2048), zz);
-#pragma unroll
-            for (int j = 0; j < 8; j++) d[j] = zz[j] > 0.f ? v[8 * c + j] : 0.f;
+            uint32_t w0 = pack2(v[8 * c], v[8 * c + 1]) & mk[4 * c], w1 = pack2(v[8 * c + 2], v[8 * c + 3]) & mk[4 * c + 1];
+            uint32_t w2 = pack2(v[8 * c + 4], v[8 * c + 5]) & mk[4 * c + 2], w3 = pack2(v[8 * c + 6], v[8 * c + 7]) & mk[4 * c + 3];
             if (half && c == 7) {
-#pragma unroll
-              for (int j = 2; j < 8; j++) d[j] = 0.f;
-              d128 = d[0]; d129 = d[1];
+              w1 = 0u; w2 = 0u; w3 = 0u;
+              d128 = (mk[28] & 0xFFFFu) ? v[56] : 0.f;
+              d129 = (mk[28] >> 16) ? v[57] : 0.f;
             }
-            st16(dst + c * 2048, pack2(d[0], d[1]), pack2(d[2], d[3]), pack2(d[4], d[5]), pack2(d[6], d[7]));
+            st16(dst + c * 2048, w0, w1, w2, w3);
           }
         }
+        if (i == 1 && more) write_tx((it + 1) & 1, x0n, x1n, x2n);   // next tile's input operand rides this round trip
+        stage_done();
+        AWB_TR();
         if (half) {
           if (i - 1 >= 1) {   // corner of dW_{i-1}
-            float cz[8];
-            unpack8(*reinterpret_cast<const uint4*>(tile_ptr(i - 2) + 16 * 2048 + row * 16), cz);
+            const uint4 cz = *reinterpret_cast<const uint4*>(tile_ptr(i - 2) + 16 * 2048 + row * 16);
+            const float c6[6] = {half_lo(cz.x), half_hi(cz.x), half_lo(cz.y), half_hi(cz.y), half_lo(cz.z), half_hi(cz.z)};
 #pragma unroll
-            for (int b = 0; b < 6; b++) { cacc[12 * (i - 2) + b] += d128 * cz[b]; cacc[12 * (i - 2) + 6 + b] += d129 * cz[b]; }
+            for (int b = 0; b < 6; b++) { cacc[12 * (i - 2) + b] += d128 * c6[b]; cacc[12 * (i - 2) + 6 + b] += d129 * c6[b]; }
           } else {            // corner of the input layer: delta_0[128..129] x (x, y, t, 1)
             cacc[12 * L + 0] += d128 * x0; cacc[12 * L + 1] += d128 * x1; cacc[12 * L + 2] += d128 * x2; cacc[12 * L + 3] += d128;
             cacc[12 * L + 4] += d129 * x0; cacc[12 * L + 5] += d129 * x1; cacc[12 * L + 6] += d129 * x2; cacc[12 * L + 7] += d129;
           }
         }
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        tc::mbar_arrive(bar_e2m);
       }
-      // ---- input-layer wgrad issued; its commit frees TX / tiles for the next tile
-      tc::mbar_wait(bar_m2e, ph); ph ^= 1;
-      tc::fence_after_sync();
     }
+
+    // the last commit (input-layer wgrad of the last tile / last forward stage) closes the pipeline
+    tc::mbar_wait(bar_m2e, ph); ph ^= 1;
+    tc::fence_after_sync();
+    AWB_TR();
 
     // =========================================================== per-CTA partial write-out
     if (fit) {
       const float inv = 1.f / S;
       float* out = p.part + (int64_t)blockIdx.x * p.sSplit + (int64_t)o * p.G;
+      const int et = threadIdx.x;                         // 0..255
+      // corner sums: fixed-order reduction over the 256 epilogue threads (scratch: the dead weight image)
+      float* red = reinterpret_cast<float*>(simg);        // [NC][256]
+#pragma unroll
+      for (int i = 0; i < NC; i++) red[i * 256 + et] = cacc[i];
+      // dW_i main rows: TMEM -> registers -> staging tile [128][136] fp32 (the dead operand tiles)
+      float* stage = reinterpret_cast<float*>(tiles);     // [L][128][136]
 #pragma unroll
       for (int i = 1; i <= L; i++) {
         load_acc(tlane + T_DW(i), half, v);
-        float* dst = out + p.aug_layer + (int64_t)(i - 1) * H_ * LD_ + (int64_t)row * LD_ + (half ? 72 : 0);
-        const int nv = half ? 64 : 72;
+        float* dst = stage + (i - 1) * 128 * LD_ + row * LD_ + (half ? 72 : 0);
+        const int nv = half ? 16 : 18;
 #pragma unroll
-        for (int j = 0; j < 72; j++) if (j < nv) dst[j] = v[j] * inv;
+        for (int j = 0; j < 18; j++)
+          if (j < nv) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j] * inv, v[4 * j + 1] * inv, v[4 * j + 2] * inv, v[4 * j + 3] * inv);
         if (half == 0) {
           float pb[8];
           tc::tmem_ld8(tlane + T_PB(i), pb);
@@ -408,44 +510,59 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
         tc::tmem_ld8(tlane + T_GIN, g8);
         tc::tmem_ld_wait();
         float* gi = out + p.aug_in + row * 4;
-        gi[0] = g8[0] * inv; gi[1] = g8[1] * inv;
-        if (C > 2) { gi[2] = g8[2] * inv; gi[3] = g8[3] * inv; } else { gi[2] = 0.f; gi[3] = g8[2] * inv; }
+        float4 gv;
+        gv.x = g8[0] * inv; gv.y = g8[1] * inv;
+        if (C > 2) { gv.z = g8[2] * inv; gv.w = g8[3] * inv; } else { gv.z = 0.f; gv.w = g8[2] * inv; }
+        *reinterpret_cast<float4*>(gi) = gv;
         tc::tmem_ld8(tlane + T_GO, g8);
         tc::tmem_ld_wait();
         out[p.aug_out + row] = g8[2] * inv;
       }
-      // corner sums: fixed-order reduction over the 256 epilogue threads through shared memory
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      float* red = reinterpret_cast<float*>(tiles);       // [NC][256], tiles are dead now
-      const int et = threadIdx.x;                         // 0..255
+      tc::fence_async_smem();
+      asm volatile("bar.sync 5, 256;" ::: "memory");
+      if (et == 0) {   // TMA bulk stores of the staged main rows (contiguous [128][136] fp32 per layer)
 #pragma unroll
-      for (int i = 0; i < NC; i++) red[i * 256 + et] = cacc[i];
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (et < NC) {
+        for (int i = 1; i <= L; i++) {
+          float* gdst = out + p.aug_layer + (int64_t)(i - 1) * H_ * LD_;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                       "r"(tc::smem_u32(stage + (i - 1) * 128 * LD_)), "r"((uint32_t)(128 * LD_ * 4)) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      // corner sums, one warp per accumulator, lanes stride the 256 partials (conflict-free), fixed order
+      for (int i = warp; i < NC; i += 8) {
         float a = 0.f;
-        for (int t = 0; t < 256; t++) a += red[et * 256 + t];
-        if (et == NC - 1) {
-          p.lossp[blockIdx.x * p.O + o] = a;
-        } else if (et < 12 * L) {
-          const int li = et / 12, r = (et % 12) / 6, b = et % 6;
-          if (b < 3 + C) out[p.aug_layer + (int64_t)li * H_ * LD_ + (int64_t)(128 + r) * LD_ + 128 + b] = a * inv;
-        } else if (et < 12 * L + 8) {
-          const int r = (et - 12 * L) / 4, c = (et - 12 * L) % 4;
-          out[p.aug_in + (128 + r) * 4 + c] = a * inv;
-        } else if (et < 12 * L + 10) {
-          out[p.aug_out + 128 + (et - 12 * L - 8)] = a * inv;
-        } else if (et < NC - 2) {
-          const int c = et - (NC - 5);
-          if (c < C) out[p.aug_out + H_ + c] = a * inv;
-        } else {   // NC - 2
-          out[p.aug_out + H_ + C] = a * inv;
+#pragma unroll
+        for (int k = 0; k < 8; k++) a += red[i * 256 + lane + 32 * k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        if (lane == 0) {
+          if (i == NC - 1) {
+            p.lossp[blockIdx.x * p.O + o] = a;
+          } else if (i < 12 * L) {
+            const int li = i / 12, r = (i % 12) / 6, b = i % 6;
+            if (b < 3 + C) out[p.aug_layer + (int64_t)li * H_ * LD_ + (int64_t)(128 + r) * LD_ + 128 + b] = a * inv;
+          } else if (i < 12 * L + 8) {
+            const int r = (i - 12 * L) / 4, c = (i - 12 * L) % 4;
+            // (x, y, t, 1) order of the accumulators -> (w_x, w_y, w_t, bias) slots; C == 2 keeps slot 2 zero
+            out[p.aug_in + (128 + r) * 4 + c] = (C == 2 && c == 2) ? 0.f : a * inv;
+          } else if (i < 12 * L + 10) {
+            out[p.aug_out + 128 + (i - 12 * L - 8)] = a * inv;
+          } else if (i < NC - 2) {
+            const int c = i - (NC - 5);
+            if (c < C) out[p.aug_out + H_ + c] = a * inv;
+          } else {   // NC - 2
+            out[p.aug_out + H_ + C] = a * inv;
+          }
         }
       }
+      if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   }
   tc::fence_before_sync();
   __syncthreads();
   if (issuer_warp) tc::tmem_dealloc<512>(tbase);
+#undef AWB_TR
 }
 
 // ======================================================================= host launcher
@@ -464,7 +581,7 @@ void tc_build_map_host(const Layout& Ly, int32_t* map) {
   // out.ln.weight [h], out.ln.bias, out.skp.weight [C]
   int64_t a = Ly.off_icnn;
   auto w_elem = [&](int l, int j, int k) { return l * (W_B / 2) + (k / 8) * (NPAD * 8) + j * 8 + (k % 8); };
-  auto win_elem = [&](int j, int k) { return L * (W_B / 2) + (k / 8) * (NPAD * 8) + j * 8 + (k % 8); };
+  auto win_elem = [&](int j, int k) { return L * (W_B / 2) + j * 8 + k; };   // one stored K chunk (k < 8)
   for (int j = 0; j < H_; j++) for (int c = 0; c < C; c++) map[win_elem(j, c)] = (int32_t)a++;
   for (int j = 0; j < H_; j++) map[win_elem(j, C)] = (int32_t)a++;
   for (int l = 0; l < L; l++) {
@@ -475,6 +592,17 @@ void tc_build_map_host(const Layout& Ly, int32_t* map) {
   for (int k = 0; k < H_; k++) map[n_half + k] = (int32_t)a++;
   map[n_half + H_ + C] = (int32_t)a++;
   for (int c = 0; c < C; c++) map[n_half + H_ + c] = (int32_t)a++;
+}
+
+static unsigned long long* g_trace_dev = nullptr;   // debug timeline buffer (AWB_TC_TRACE=1), [grid][TRACE_N]
+static int g_trace_ctas = 0;
+
+int tc_trace_read(unsigned long long* host, int max_ctas) {
+  if (!g_trace_dev) return 0;
+  int n = g_trace_ctas < max_ctas ? g_trace_ctas : max_ctas;
+  cudaDeviceSynchronize();
+  cudaMemcpy(host, g_trace_dev, sizeof(unsigned long long) * TRACE_N * n, cudaMemcpyDeviceToHost);
+  return n;
 }
 
 int tc_fit_forward_backward(const awb_prior* h, const float* params, const awb_grid_spec* g, const float* target,
@@ -508,6 +636,11 @@ int tc_fit_forward_backward(const awb_prior* h, const float* params, const awb_g
   }
   p.part = ws.part; p.sSplit = (int64_t)O * Ly.G; p.G = Ly.G; p.aug_in = Ly.aug_in; p.aug_layer = Ly.aug_layer; p.aug_out = Ly.aug_out;
   p.lossp = ws.lossp; p.O = O; p.logits = logits; p.N = N; p.n_tiles = n_tiles; p.mode = mode;
+  p.trace = nullptr;
+  if (getenv("AWB_TC_TRACE")) {
+    if (!g_trace_dev) cudaMalloc(&g_trace_dev, sizeof(unsigned long long) * TRACE_N * kMaxSplits * 16);
+    if (g_trace_dev) { cudaMemsetAsync(g_trace_dev, 0, sizeof(unsigned long long) * TRACE_N * grid * O, st); p.trace = g_trace_dev; g_trace_ctas = grid * O; }
+  }
   const size_t smem = smem_bytes(L);
   dim3 gd(grid, O);
 #define AWB_TC_LAUNCH(LL, CC)                                                                                      \

@@ -80,3 +80,8 @@ extern "C" int awb_debug_umma_probe(const void* a_bytes, int32_t a_size, const v
   AWB_CUDA(cudaGetLastError());
   return AWB_OK;
 }
+
+extern "C" int awb_debug_tc_trace_read(unsigned long long* host, int32_t max_ctas) {
+  if (!host || max_ctas < 1) { set_error("bad argument"); return AWB_ERR_INVALID; }
+  return tc_trace_read(host, max_ctas);
+}

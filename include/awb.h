@@ -197,6 +197,11 @@ int awb_debug_umma_probe(const void* a_bytes, int32_t a_size, const void* b_byte
                          int32_t N, int32_t K, int32_t a_mn_major, int32_t b_mn_major, const uint32_t* a_desc4,
                          const uint32_t* b_desc4, void* stream);
 
+/* Debug hook: with AWB_TC_TRACE=1 in the environment the fused tensor-path kernel records clock64() stamps of its
+ * pipeline stages (256 per CTA: [0,128) first epilogue thread, [128,256) MMA issuer); copies up to max_ctas CTAs of the
+ * last launch to host and returns the number of CTAs copied. */
+int awb_debug_tc_trace_read(unsigned long long* host, int32_t max_ctas);
+
 /* Measurement hooks (bench.py): CUDA-event timing per kernel class on the launch stream, and the number
  * of kernels this library has launched.  awb_profile_read synchronises the device and returns, for each
  * of awb_profile_classes() classes, the summed duration [ms] and the number of timed launches. */

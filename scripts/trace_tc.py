@@ -1,0 +1,43 @@
+"""Debug helper (GPU box): timeline of the fused tensor-path kernel from its in-kernel clock64 stamps.
+AWB_TC_TRACE=1 python scripts/trace_tc.py  ->  per-stage cycle deltas of CTA 0 (epilogue thread 0, issuer)."""
+import ctypes as C
+import os
+import sys
+
+os.environ["AWB_TC_TRACE"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import awesome_b200 as A
+from awesome_b200 import _lib
+
+L = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+H, W = 480, 640
+torch.manual_seed(0)
+m = A.ConvexNextNet(n_hidden_layers=L, precision="f16").cuda()
+yy, xx = torch.meshgrid(torch.linspace(0, 1, H), torch.linspace(0, 1, W), indexing="ij")
+un = torch.sigmoid((torch.sqrt(((xx - 0.52) / 0.27) ** 2 + ((yy - 0.47) / 0.31) ** 2) - 1) / 0.08).cuda()
+grid = A.GridSpecHost("linspace", 1, H, W)
+f = m.make_fitter(grid, un, A.LossConfig("mse"), A.OptimConfig("adam", lr=1e-3), use_graph=False)
+f.run(5)
+torch.cuda.synchronize()
+lib = _lib.load()
+n_cta = 4
+buf = (C.c_ulonglong * (256 * n_cta))()
+got = lib.awb_debug_tc_trace_read(buf, n_cta)
+print("ctas read:", got)
+for c in range(got):
+    ep = [buf[c * 256 + i] for i in range(128)]
+    ms = [buf[c * 256 + 128 + i] for i in range(128)]
+    ep = [x for x in ep if x]
+    ms = [x for x in ms if x]
+    t0 = min(ep[0], ms[0])
+    print(f"--- CTA {c}: epilogue stamps (wait-done, arrive-done alternating), relative cycles")
+    print(" ".join(str(x - t0) for x in ep[:40]))
+    print("    deltas:", " ".join(str(b - a) for a, b in zip(ep[:40], ep[1:41])))
+    print(f"--- CTA {c}: issuer stamps (first after prologue commit; then per stage: wake, issued)")
+    print(" ".join(str(x - t0) for x in ms[:40]))
+    print("    deltas:", " ".join(str(b - a) for a, b in zip(ms[:40], ms[1:41])))
+    nst = 2 * L + 1
+    if len(ep) > 2 * nst * 3:
+        per_tile = (ep[2 * nst * 3] - ep[2 * nst * 1]) / 2.0
+        print(f"    cycles per tile (tiles 1..2): {per_tile:.0f}")
