@@ -42,11 +42,15 @@ constexpr int WIN_B = 2304;         // [1 chunk][144 rows][8 fp16]   input layer
 constexpr int TX_B = 2048;          // [1 chunk][128 rows][8 fp16]   (x, y, (t), 1, 0...), double buffered
 constexpr int ZERO_B = 2304;
 constexpr int VEC_B = NPAD * 4;     // fp32 (w_o | s_o | b_o | 0)
-constexpr int NTHREADS = 288;       // 8 epilogue warps + 1 issuer warp
+constexpr int VEC16_B = NPAD * 2;   // the same vector as fp16 (operand of the packed delta_L product)
+constexpr int NCG = 3;              // epilogue column groups per TMEM lane quadrant
+constexpr int NEW = 4 * NCG;        // epilogue warps (3 per warp scheduler)
+constexpr int NTHREADS = (NEW + 1) * 32;   // + 1 issuer warp
+constexpr int XCHG_B = NCG * 128 * 4;
 constexpr int TRACE_N = 256;        // clock stamps per CTA (debug timeline)
-__host__ __device__ constexpr int img_bytes(int L) { return L * W_B + WIN_B + VEC_B; }
+__host__ __device__ constexpr int img_bytes(int L) { return L * W_B + WIN_B + VEC_B + VEC16_B; }
 __host__ __device__ constexpr int smem_bytes(int L) {
-  return (L + 2) * TILE_B + img_bytes(L) + 2 * TX_B + ZERO_B + 1024 + 64;
+  return (L + 2) * TILE_B + img_bytes(L) + 2 * TX_B + ZERO_B + XCHG_B + 64;
 }
 }  // namespace
 
@@ -63,7 +67,8 @@ __global__ void k_pack_tc(const float* __restrict__ params, uint8_t* __restrict_
   const int n_half = (L * W_B + WIN_B) / 2;
   uint8_t* base = img + (int64_t)o * img_stride;
   if (i < n_half) reinterpret_cast<__half*>(base)[i] = __float2half_rn(v);
-  else reinterpret_cast<float*>(base + 2 * n_half)[i - n_half] = v;
+  else if (i < n_half + NPAD) reinterpret_cast<float*>(base + 2 * n_half)[i - n_half] = v;
+  else reinterpret_cast<__half*>(base + 2 * n_half + VEC_B)[i - n_half - NPAD] = __float2half_rn(v);
 }
 
 struct TcP {
@@ -96,14 +101,6 @@ __device__ __forceinline__ void st16(uint8_t* p, uint32_t a, uint32_t b, uint32_
 }
 __device__ __forceinline__ float half_lo(uint32_t u) { return __low2float(*reinterpret_cast<__half2*>(&u)); }
 __device__ __forceinline__ float half_hi(uint32_t u) { return __high2float(*reinterpret_cast<__half2*>(&u)); }
-// accumulator columns of this thread's half: half 0 -> [0,72), half 1 -> [72,136)
-__device__ __forceinline__ void load_acc(uint32_t taddr, int half, float* v) {
-  const uint32_t a = taddr + (half ? 72 : 0);
-  tc::tmem_ld16(a, v); tc::tmem_ld16(a + 16, v + 16); tc::tmem_ld16(a + 32, v + 32); tc::tmem_ld16(a + 48, v + 48);
-  if (!half) tc::tmem_ld8(a + 64, v + 64);
-  tc::tmem_ld_wait();
-}
-
 // pixel coordinates with 32-bit index arithmetic (N <= 2^30 is checked on the host)
 __device__ __forceinline__ void row_coords(const GridDev& g, uint32_t n, int C, float& x0, float& x1, float& x2) {
   const uint32_t hw = (uint32_t)g.H * (uint32_t)g.W;
@@ -119,36 +116,57 @@ __device__ __forceinline__ void row_coords(const GridDev& g, uint32_t n, int C, 
   else { x0 = (float)j / (float)g.W; x1 = (float)i / (float)g.H; }
 }
 
+// Sum of v[i] over the 32 lanes of a warp for 16 values at once: one butterfly round, then four
+// reduce-scatter rounds; afterwards lane l holds the total of value (l & 15).  31 shuffles instead of 80.
+__device__ __forceinline__ float warp_reduce_scatter16(float* v, int lane) {
+#pragma unroll
+  for (int k = 0; k < 16; k++) v[k] += __shfl_xor_sync(0xffffffffu, v[k], 16);
+#pragma unroll
+  for (int off = 8, n = 16; off >= 1; off >>= 1, n >>= 1) {
+    const bool up = lane & off;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (k < n / 2) {
+        const float send = up ? v[k] : v[k + n / 2];
+        const float keep = up ? v[k + n / 2] : v[k];
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+  }
+  return v[0];
+}
+
 template <int L, int C>
 __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int NT = L + 2;
   constexpr int IMG = img_bytes(L);
-  constexpr int NC = 12 * L + 15;                 // per-thread corner / scalar accumulators
   uint8_t* tiles = smem;                          // ZT[0..L-1], ZL, DT
-  uint8_t* simg = smem + NT * TILE_B;             // W_1..W_L | WIN | vec
+  uint8_t* simg = smem + NT * TILE_B;             // W_1..W_L | WIN | vec | vec16
   uint8_t* stx = simg + IMG;                      // TX[2]
   uint8_t* szero = stx + 2 * TX_B;
-  float* xchg = reinterpret_cast<float*>(szero + ZERO_B);          // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(szero + ZERO_B + 1024);
-  uint64_t* bar_e2m = bars;        // epilogue -> issuer (8 arrivals: one per epilogue warp)
+  float* xchg = reinterpret_cast<float*>(szero + ZERO_B);          // [NCG][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(szero + ZERO_B + XCHG_B);
+  uint64_t* bar_e2m = bars;        // epilogue -> issuer (one arrival per epilogue warp)
   uint64_t* bar_m2e = bars + 1;    // tcgen05.commit -> epilogue
   uint64_t* bar_w = bars + 2;      // weight image landed (TMA tx bytes)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
   const float* wo = reinterpret_cast<const float*>(simg + L * W_B + WIN_B);
+  const uint8_t* wo16 = simg + L * W_B + WIN_B + VEC_B;            // fp16 copy, 16 bytes per column chunk
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int o = blockIdx.y;
-  const bool issuer_warp = warp == 8;
+  const bool issuer_warp = warp == NEW;
   unsigned long long* trace = p.trace ? p.trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * TRACE_N : nullptr;
   int tr_n = 0;
 #define AWB_TR()                                                            \
   do {                                                                      \
-    if (trace && (threadIdx.x & 255) == 0 && tr_n < TRACE_N / 2) trace[(issuer_warp ? TRACE_N / 2 : 0) + tr_n++] = clock64(); \
+    if (trace && (threadIdx.x == 0 || threadIdx.x == NEW * 32) && tr_n < TRACE_N / 2) \
+      trace[(issuer_warp ? TRACE_N / 2 : 0) + tr_n++] = clock64();          \
   } while (0)
 
   // ---- one-time setup
-  if (threadIdx.x == 0) { tc::mbar_init(bar_e2m, 8); tc::mbar_init(bar_m2e, 1); tc::mbar_init(bar_w, 1); tc::mbar_fence_init(); }
+  if (threadIdx.x == 0) { tc::mbar_init(bar_e2m, NEW); tc::mbar_init(bar_m2e, 1); tc::mbar_init(bar_w, 1); tc::mbar_fence_init(); }
   for (int i = threadIdx.x * 16; i < ZERO_B; i += NTHREADS * 16) *reinterpret_cast<uint4*>(szero + i) = make_uint4(0, 0, 0, 0);
   __syncthreads();
   if (issuer_warp) {
@@ -252,30 +270,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
             mma_px(T_DW(i), d, zprev, 2048, 144, acc);                            // wgrad_i main rows 0..127
             mma_px(T_PB(i), zprev, d + 16 * 2048, 2048, 16, acc);                 // wgrad_i rows 128,129 (transposed)
           } else {
-            mma_px(T_GIN, t_addr(dbuf(0)), a_tx, zero_a - a_tx, 16, acc);         // input-layer wgrad
-            if (more) mma_input(a_txn);                                           // next tile's input layer
-            tc::umma_commit(bar_m2e);
+            if (more) {                                                           // next tile's input layer first:
+              mma_input(a_txn);                                                   // its epilogue does not wait for
+              tc::umma_commit(bar_m2e);                                           // this tile's input-layer wgrad
+              mma_px(T_GIN, t_addr(dbuf(0)), a_tx, zero_a - a_tx, 16, acc);
+            } else {
+              mma_px(T_GIN, t_addr(dbuf(0)), a_tx, zero_a - a_tx, 16, acc);
+              tc::umma_commit(bar_m2e);
+            }
           }
           AWB_TR();
         }
       }
     }
   } else {
-    // =========================================================== epilogue warps (256 threads)
-    const int q = warp & 3, half = warp >> 2;
+    // =========================================================== epilogue warps (12: 3 column groups x 4 lane quadrants)
+    const int q = warp & 3, cg = warp >> 2;       // TMEM lanes [32q, 32q+32), stored chunks [6cg, 6cg + nch)
     const int row = q * 32 + lane;
     const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
-    const int nch = half ? 8 : 9;                 // stored chunks handled by this thread
-    const int ch0 = half ? 9 : 0;
+    const int nch = cg == NCG - 1 ? 5 : 6;        // 6 + 6 + 5 = 17 stored chunks
+    const int ch0 = 6 * cg;
+    const bool last = cg == NCG - 1;              // owns chunk 16: columns 128..135 = (z128, z129, x, y, [t,] 1, 0..)
     uint32_t ph = 0;
-    float cacc[NC];
+    float s_loss = 0.f, s_bo = 0.f, s_so0 = 0.f, s_so1 = 0.f, s_so2 = 0.f;   // cg 0: per-thread scalar sums
+    float accC[L + 1];                            // cg 2: corner sums, lane-distributed (value = lane & 15)
 #pragma unroll
-    for (int i = 0; i < NC; i++) cacc[i] = 0.f;
+    for (int i = 0; i <= L; i++) accC[i] = 0.f;
     const awb_loss_spec ls = p.loss[o];
     const float S = p.scale[o];
-    float v[72];
-    const float* w = wo + (half ? 72 : 0);
+    float v[48];
+    const float* w = wo + 48 * cg;
 
+    // accumulator columns [48cg, 48cg + 8nch) of this thread's row
+    auto load_acc = [&](uint32_t taddr) {
+      const uint32_t a = taddr + 48 * cg;
+      tc::tmem_ld16(a, v); tc::tmem_ld16(a + 16, v + 16);
+      if (last) tc::tmem_ld8(a + 32, v + 32); else tc::tmem_ld16(a + 32, v + 32);
+      tc::tmem_ld_wait();
+    };
     // arrive once per warp: every lane orders its generic-proxy stores and tcgen05.ld before the sync
     auto stage_done = [&]() {
       tc::fence_async_smem();
@@ -284,7 +316,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
       if (lane == 0) tc::mbar_arrive(bar_e2m);
     };
     auto write_tx = [&](int buf, float a0, float a1, float a2) {
-      if (half == 0) st16(stx + buf * TX_B + row * 16, pack2(a0, a1), pack2(C > 2 ? a2 : 1.f, C > 2 ? 1.f : 0.f), 0u, 0u);
+      if (cg == 0) st16(stx + buf * TX_B + row * 16, pack2(a0, a1), pack2(C > 2 ? a2 : 1.f, C > 2 ? 1.f : 0.f), 0u, 0u);
     };
     // coordinates / target of a tile (rows past N replicate the last pixel and carry no loss)
     float x0n = 0.f, x1n = 0.f, x2n = 0.f, tgtn = 0.f;
@@ -296,6 +328,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
       row_coords(p.g, nn, C, x0n, x1n, x2n);
       tgtn = 0.f;
       if (fit && liven) tgtn = p.target[(int64_t)o * p.N + n];
+    };
+    auto chunk16_f32 = [&](const uint8_t* tile, float* c6) {   // columns 128..133 of a stored tile row
+      const uint4 cz = *reinterpret_cast<const uint4*>(tile + 16 * 2048 + row * 16);
+      c6[0] = half_lo(cz.x); c6[1] = half_hi(cz.x); c6[2] = half_lo(cz.y); c6[3] = half_hi(cz.y); c6[4] = half_lo(cz.z); c6[5] = half_hi(cz.z);
     };
 
     fetch_tile(blockIdx.x);
@@ -318,17 +354,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
         tc::mbar_wait(bar_m2e, ph); ph ^= 1;
         tc::fence_after_sync();
         AWB_TR();
-        load_acc(tlane + T_ACC, half, v);
+        load_acc(tlane + T_ACC);
+        AWB_TR();
         uint8_t* dst = tile_ptr(s - 1) + ch0 * 2048 + row * 16;
 #pragma unroll
-        for (int i = 0; i < 9; i++) {
+        for (int i = 0; i < 6; i++) {
           if (i < nch) {
             uint32_t w0 = relu2(pack2(v[8 * i], v[8 * i + 1])), w1 = relu2(pack2(v[8 * i + 2], v[8 * i + 3]));
             uint32_t w2 = relu2(pack2(v[8 * i + 4], v[8 * i + 5])), w3 = relu2(pack2(v[8 * i + 6], v[8 * i + 7]));
-            if (half && i == 7) { w1 = ax01; w2 = ax2o; w3 = 0u; }
+            if (last && i == 4) { w1 = ax01; w2 = ax2o; w3 = 0u; }
             st16(dst + i * 2048, w0, w1, w2, w3);
           }
         }
+        AWB_TR();
         stage_done();
         AWB_TR();
       }
@@ -337,37 +375,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
       tc::mbar_wait(bar_m2e, ph); ph ^= 1;
       tc::fence_after_sync();
       AWB_TR();
-      load_acc(tlane + T_ACC, half, v);
-      float dot = 0.f;
+      load_acc(tlane + T_ACC);
+      AWB_TR();
       {
-        const int nz = half ? 58 : 72;                    // real z columns of this half
+        const int nz = last ? 34 : 48;                    // real z columns of this group
+        float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 72; j++) {
-          if (j < nz) { v[j] = fmaxf(v[j], 0.f); dot = fmaf(v[j], w[j], dot); }
+        for (int j = 0; j < 48; j++) {
+          if (j < nz) d4[j & 3] = fmaf(fmaxf(v[j], 0.f), w[j], d4[j & 3]);
         }
-        if (half) {
+        float dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+        if (last) {
           dot = fmaf(x0, wo[H_], dot); dot = fmaf(x1, wo[H_ + 1], dot);
           if (C > 2) dot = fmaf(x2, wo[H_ + 2], dot);
           dot += wo[H_ + C];
         }
+        xchg[cg * 128 + row] = dot;
       }
-      xchg[half * 128 + row] = dot;
-      if (fit) {   // z_L tile (operand of the output-layer wgrad) goes out while the partner warp catches up
+      // z_L as packed fp16 pairs: operand tile of the output-layer wgrad, then turned into the relu mask
+      uint32_t zp[24];
+#pragma unroll
+      for (int k = 0; k < 24; k++) zp[k] = relu2(pack2(v[2 * k], v[2 * k + 1]));
+      const float zL128 = last ? half_lo(zp[16]) : 0.f, zL129 = last ? half_hi(zp[16]) : 0.f;
+      if (fit) {
         uint8_t* zl = tile_ptr(L) + ch0 * 2048 + row * 16;
 #pragma unroll
-        for (int i = 0; i < 9; i++) {
+        for (int i = 0; i < 6; i++) {
           if (i < nch) {
-            uint32_t w0 = pack2(v[8 * i], v[8 * i + 1]), w1 = pack2(v[8 * i + 2], v[8 * i + 3]);
-            uint32_t w2 = pack2(v[8 * i + 4], v[8 * i + 5]), w3 = pack2(v[8 * i + 6], v[8 * i + 7]);
-            if (half && i == 7) { w1 = 0u; w2 = 0u; w3 = 0u; }
-            st16(zl + i * 2048, w0, w1, w2, w3);
+            if (last && i == 4) st16(zl + i * 2048, zp[16], 0u, 0u, 0u);
+            else st16(zl + i * 2048, zp[4 * i], zp[4 * i + 1], zp[4 * i + 2], zp[4 * i + 3]);
           }
         }
+#pragma unroll
+        for (int k = 0; k < 24; k++) zp[k] = gt0_mask2(zp[k]);
       }
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // the two warps that share these 32 rows
-      const float y = xchg[row] + xchg[128 + row];
+      AWB_TR();
+      asm volatile("bar.sync %0, 96;" ::"r"(1 + q) : "memory");   // the three warps that share these 32 rows
+      const float y = (xchg[row] + xchg[128 + row]) + xchg[256 + row];
+      AWB_TR();
       if (!fit) {
-        if (half == 0 && live && p.logits) p.logits[(int64_t)o * p.N + n] = y;
+        if (cg == 0 && live && p.logits) p.logits[(int64_t)o * p.N + n] = y;
         if (more) { fetch_tile(tile + gridDim.x); write_tx((it + 1) & 1, x0n, x1n, x2n); }
         stage_done();
         continue;
@@ -383,41 +430,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
         dys = coef * dl * S;
         lossv = coef * l;
       }
-      float dL128 = 0.f, dL129 = 0.f, zL128 = 0.f, zL129 = 0.f;
+      // delta_L = dy * w_o .* (z_L > 0) on packed fp16 pairs
+      float dL128 = 0.f, dL129 = 0.f;
       {
         uint8_t* dl = dbuf(L) + ch0 * 2048 + row * 16;
+        const uint32_t dys2 = pack2(dys, dys);
+        const __half2 dh = *reinterpret_cast<const __half2*>(&dys2);
+        auto dmul = [&](uint32_t wq, uint32_t m) {
+          __half2 r = __hmul2(dh, *reinterpret_cast<const __half2*>(&wq));
+          return *reinterpret_cast<uint32_t*>(&r) & m;
+        };
 #pragma unroll
-        for (int i = 0; i < 9; i++) {
+        for (int i = 0; i < 6; i++) {
           if (i < nch) {
-            float d[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) d[j] = v[8 * i + j] > 0.f ? dys * w[8 * i + j] : 0.f;
-            if (half && i == 7) {
-              dL128 = d[0]; dL129 = d[1]; zL128 = v[56]; zL129 = v[57];
-#pragma unroll
-              for (int j = 3; j < 8; j++) d[j] = 0.f;
-              d[2] = dys;
+            const uint4 wq = *reinterpret_cast<const uint4*>(wo16 + (ch0 + i) * 16);
+            uint32_t w0 = dmul(wq.x, zp[4 * i]), w1 = dmul(wq.y, zp[4 * i + 1]), w2 = dmul(wq.z, zp[4 * i + 2]), w3 = dmul(wq.w, zp[4 * i + 3]);
+            if (last && i == 4) {
+              dL128 = half_lo(w0); dL129 = half_hi(w0);
+              w1 = pack2(dys, 0.f); w2 = 0u; w3 = 0u;
             }
-            st16(dl + i * 2048, pack2(d[0], d[1]), pack2(d[2], d[3]), pack2(d[4], d[5]), pack2(d[6], d[7]));
+            st16(dl + i * 2048, w0, w1, w2, w3);
           }
         }
       }
+      AWB_TR();
       stage_done();
       AWB_TR();
       // ---- shadow of dgrad_L: everything that is not an operand of the next contraction
-      if (p.logits && half == 0 && live) p.logits[(int64_t)o * p.N + n] = y;
-      if (half == 0) {
-        cacc[NC - 1] += lossv;                                      // loss
-        cacc[NC - 2] += dys;                                        // d b_o
-        cacc[NC - 5] += dys * x0; cacc[NC - 4] += dys * x1;          // d s_o
-        if (C > 2) cacc[NC - 3] += dys * x2;
-      } else {
-        cacc[12 * L + 8] += zL128 * dys; cacc[12 * L + 9] += zL129 * dys;     // d w_o[128], [129]
-        // corner of dW_L: delta_L[128..129] x ZT[L-1][128..133]
-        const uint4 cz = *reinterpret_cast<const uint4*>(tile_ptr(L - 1) + 16 * 2048 + row * 16);
-        const float c6[6] = {half_lo(cz.x), half_hi(cz.x), half_lo(cz.y), half_hi(cz.y), half_lo(cz.z), half_hi(cz.z)};
+      if (cg == 0) {
+        if (p.logits && live) p.logits[(int64_t)o * p.N + n] = y;
+        s_loss += lossv; s_bo += dys;
+        s_so0 += dys * x0; s_so1 += dys * x1;
+        if (C > 2) s_so2 += dys * x2;
+      } else if (last) {
+        // corner of dW_L: delta_L[128..129] x ZT[L-1][128..133], and d w_o[128], [129]
+        float c6[6], cv[16];
+        chunk16_f32(tile_ptr(L - 1), c6);
 #pragma unroll
-        for (int b = 0; b < 6; b++) { cacc[12 * (L - 1) + b] += dL128 * c6[b]; cacc[12 * (L - 1) + 6 + b] += dL129 * c6[b]; }
+        for (int b = 0; b < 6; b++) { cv[b] = dL128 * c6[b]; cv[6 + b] = dL129 * c6[b]; }
+        cv[12] = zL128 * dys; cv[13] = zL129 * dys; cv[14] = 0.f; cv[15] = 0.f;
+        accC[L] += warp_reduce_scatter16(cv, lane);
       }
       if (more) fetch_tile(tile + gridDim.x);     // next tile's coordinates and target (load latency hidden)
 
@@ -425,11 +477,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
 #pragma unroll
       for (int i = L; i >= 1; i--) {
         // relu mask of z_{i-1} from the stored activations, before the wait
-        uint32_t mk[36];
+        uint32_t mk[24];
         {
           const uint8_t* zsrc = tile_ptr(i - 1) + ch0 * 2048 + row * 16;
 #pragma unroll
-          for (int c = 0; c < 9; c++) {
+          for (int c = 0; c < 6; c++) {
             if (c < nch) {
               const uint4 u = *reinterpret_cast<const uint4*>(zsrc + c * 2048);
               mk[4 * c] = gt0_mask2(u.x); mk[4 * c + 1] = gt0_mask2(u.y); mk[4 * c + 2] = gt0_mask2(u.z); mk[4 * c + 3] = gt0_mask2(u.w);
@@ -439,18 +491,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
         tc::mbar_wait(bar_m2e, ph); ph ^= 1;
         tc::fence_after_sync();
         AWB_TR();
-        load_acc(tlane + T_ACC, half, v);
+        load_acc(tlane + T_ACC);
         uint8_t* dst = dbuf(i - 1) + ch0 * 2048 + row * 16;
         float d128 = 0.f, d129 = 0.f;
 #pragma unroll
-        for (int c = 0; c < 9; c++) {
+        for (int c = 0; c < 6; c++) {
           if (c < nch) {
             uint32_t w0 = pack2(v[8 * c], v[8 * c + 1]) & mk[4 * c], w1 = pack2(v[8 * c + 2], v[8 * c + 3]) & mk[4 * c + 1];
             uint32_t w2 = pack2(v[8 * c + 4], v[8 * c + 5]) & mk[4 * c + 2], w3 = pack2(v[8 * c + 6], v[8 * c + 7]) & mk[4 * c + 3];
-            if (half && c == 7) {
+            if (last && c == 4) {
               w1 = 0u; w2 = 0u; w3 = 0u;
-              d128 = (mk[28] & 0xFFFFu) ? v[56] : 0.f;
-              d129 = (mk[28] >> 16) ? v[57] : 0.f;
+              d128 = (mk[16] & 0xFFFFu) ? v[32] : 0.f;
+              d129 = (mk[16] >> 16) ? v[33] : 0.f;
             }
             st16(dst + c * 2048, w0, w1, w2, w3);
           }
@@ -458,16 +510,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
         if (i == 1 && more) write_tx((it + 1) & 1, x0n, x1n, x2n);   // next tile's input operand rides this round trip
         stage_done();
         AWB_TR();
-        if (half) {
+        if (last) {
+          float cv[16];
           if (i - 1 >= 1) {   // corner of dW_{i-1}
-            const uint4 cz = *reinterpret_cast<const uint4*>(tile_ptr(i - 2) + 16 * 2048 + row * 16);
-            const float c6[6] = {half_lo(cz.x), half_hi(cz.x), half_lo(cz.y), half_hi(cz.y), half_lo(cz.z), half_hi(cz.z)};
+            float c6[6];
+            chunk16_f32(tile_ptr(i - 2), c6);
 #pragma unroll
-            for (int b = 0; b < 6; b++) { cacc[12 * (i - 2) + b] += d128 * c6[b]; cacc[12 * (i - 2) + 6 + b] += d129 * c6[b]; }
+            for (int b = 0; b < 6; b++) { cv[b] = d128 * c6[b]; cv[6 + b] = d129 * c6[b]; }
+            cv[12] = 0.f; cv[13] = 0.f; cv[14] = 0.f; cv[15] = 0.f;
           } else {            // corner of the input layer: delta_0[128..129] x (x, y, t, 1)
-            cacc[12 * L + 0] += d128 * x0; cacc[12 * L + 1] += d128 * x1; cacc[12 * L + 2] += d128 * x2; cacc[12 * L + 3] += d128;
-            cacc[12 * L + 4] += d129 * x0; cacc[12 * L + 5] += d129 * x1; cacc[12 * L + 6] += d129 * x2; cacc[12 * L + 7] += d129;
+            cv[0] = d128 * x0; cv[1] = d128 * x1; cv[2] = d128 * x2; cv[3] = d128;
+            cv[4] = d129 * x0; cv[5] = d129 * x1; cv[6] = d129 * x2; cv[7] = d129;
+#pragma unroll
+            for (int b = 8; b < 16; b++) cv[b] = 0.f;
           }
+          accC[i - 1] += warp_reduce_scatter16(cv, lane);
         }
       }
     }
@@ -481,22 +538,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
     if (fit) {
       const float inv = 1.f / S;
       float* out = p.part + (int64_t)blockIdx.x * p.sSplit + (int64_t)o * p.G;
-      const int et = threadIdx.x;                         // 0..255
-      // corner sums: fixed-order reduction over the 256 epilogue threads (scratch: the dead weight image)
-      float* red = reinterpret_cast<float*>(simg);        // [NC][256]
+      const int et = threadIdx.x;                         // 0..383
+      // scalar / corner sums: fixed-order reduction through shared memory (scratch: the dead weight image)
+      float* redS = reinterpret_cast<float*>(simg);       // [5][128]   per-row scalars of column group 0
+      float* redC = redS + 5 * 128;                       // [L+1][4][16] lane-distributed corner sums of group 2
+      if (cg == 0) {
+        redS[row] = s_loss; redS[128 + row] = s_bo; redS[256 + row] = s_so0; redS[384 + row] = s_so1; redS[512 + row] = s_so2;
+      } else if (last && lane < 16) {
 #pragma unroll
-      for (int i = 0; i < NC; i++) red[i * 256 + et] = cacc[i];
+        for (int i = 0; i <= L; i++) redC[(i * 4 + q) * 16 + lane] = accC[i];
+      }
       // dW_i main rows: TMEM -> registers -> staging tile [128][136] fp32 (the dead operand tiles)
       float* stage = reinterpret_cast<float*>(tiles);     // [L][128][136]
 #pragma unroll
       for (int i = 1; i <= L; i++) {
-        load_acc(tlane + T_DW(i), half, v);
-        float* dst = stage + (i - 1) * 128 * LD_ + row * LD_ + (half ? 72 : 0);
-        const int nv = half ? 16 : 18;
+        load_acc(tlane + T_DW(i));
+        float* dst = stage + (i - 1) * 128 * LD_ + row * LD_ + 48 * cg;
+        const int nv = 2 * nch;
 #pragma unroll
-        for (int j = 0; j < 18; j++)
+        for (int j = 0; j < 12; j++)
           if (j < nv) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j] * inv, v[4 * j + 1] * inv, v[4 * j + 2] * inv, v[4 * j + 3] * inv);
-        if (half == 0) {
+        if (cg == 0) {
           float pb[8];
           tc::tmem_ld8(tlane + T_PB(i), pb);
           tc::tmem_ld_wait();
@@ -505,7 +567,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
           l[(int64_t)129 * LD_ + row] = pb[1] * inv;
         }
       }
-      if (half == 0) {
+      if (cg == 0) {
         float g8[8];
         tc::tmem_ld8(tlane + T_GIN, g8);
         tc::tmem_ld_wait();
@@ -519,7 +581,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
         out[p.aug_out + row] = g8[2] * inv;
       }
       tc::fence_async_smem();
-      asm volatile("bar.sync 5, 256;" ::: "memory");
+      asm volatile("bar.sync 5, %0;" ::"n"(NEW * 32) : "memory");
       if (et == 0) {   // TMA bulk stores of the staged main rows (contiguous [128][136] fp32 per layer)
 #pragma unroll
         for (int i = 1; i <= L; i++) {
@@ -529,30 +591,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-      // corner sums, one warp per accumulator, lanes stride the 256 partials (conflict-free), fixed order
-      for (int i = warp; i < NC; i += 8) {
+      if (warp >= 1 && warp <= 5) {   // scalars: lanes stride the 128 rows, fixed order
+        const int i = warp - 1;
         float a = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; k++) a += red[i * 256 + lane + 32 * k];
+        for (int k = 0; k < 4; k++) a += redS[i * 128 + lane + 32 * k];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
         if (lane == 0) {
-          if (i == NC - 1) {
-            p.lossp[blockIdx.x * p.O + o] = a;
-          } else if (i < 12 * L) {
-            const int li = i / 12, r = (i % 12) / 6, b = i % 6;
-            if (b < 3 + C) out[p.aug_layer + (int64_t)li * H_ * LD_ + (int64_t)(128 + r) * LD_ + 128 + b] = a * inv;
-          } else if (i < 12 * L + 8) {
-            const int r = (i - 12 * L) / 4, c = (i - 12 * L) % 4;
-            // (x, y, t, 1) order of the accumulators -> (w_x, w_y, w_t, bias) slots; C == 2 keeps slot 2 zero
-            out[p.aug_in + (128 + r) * 4 + c] = (C == 2 && c == 2) ? 0.f : a * inv;
-          } else if (i < 12 * L + 10) {
-            out[p.aug_out + 128 + (i - 12 * L - 8)] = a * inv;
-          } else if (i < NC - 2) {
-            const int c = i - (NC - 5);
-            if (c < C) out[p.aug_out + H_ + c] = a * inv;
-          } else {   // NC - 2
-            out[p.aug_out + H_ + C] = a * inv;
+          if (i == 0) p.lossp[blockIdx.x * p.O + o] = a;
+          else if (i == 1) out[p.aug_out + H_ + C] = a * inv;             // d b_o
+          else if (i - 2 < C) out[p.aug_out + H_ + (i - 2)] = a * inv;    // d s_o
+        }
+      } else if (warp >= 6 && et - 192 < (L + 1) * 16) {   // corners: four quadrant partials each
+        const int li = (et - 192) >> 4, sl = (et - 192) & 15;
+        float a = 0.f;
+#pragma unroll
+        for (int qq = 0; qq < 4; qq++) a += redC[(li * 4 + qq) * 16 + sl];
+        a *= inv;
+        if (li == 0) {
+          // (x, y, t, 1) order of the accumulators -> (w_x, w_y, w_t, bias) slots; C == 2 keeps slot 2 zero
+          if (sl < 8) out[p.aug_in + (128 + (sl >> 2)) * 4 + (sl & 3)] = (C == 2 && (sl & 3) == 2) ? 0.f : a;
+        } else {
+          if (sl < 12) {
+            const int r = sl / 6, b = sl % 6;
+            if (b < 3 + C) out[p.aug_layer + (int64_t)(li - 1) * H_ * LD_ + (int64_t)(128 + r) * LD_ + 128 + b] = a;
+          } else if (li == L && sl < 14) {
+            out[p.aug_out + 128 + (sl - 12)] = a;
           }
         }
       }
@@ -570,13 +635,13 @@ int tc_supported(const awb_prior* h) {
   return h->desc.kind == AWB_KIND_ICNN && h->lay.h == H_ && (h->lay.L == 1 || h->lay.L == 2) && h->lay.ld == LD_;
 }
 
-int tc_map_elems(int L) { return (L * W_B + WIN_B) / 2 + NPAD; }
+int tc_map_elems(int L) { return (L * W_B + WIN_B) / 2 + 2 * NPAD; }
 
 // image element index -> arena index (or -1)
 void tc_build_map_host(const Layout& Ly, int32_t* map) {
   const int L = Ly.L, C = Ly.C;
   const int n_half = (L * W_B + WIN_B) / 2;
-  for (int i = 0; i < n_half + NPAD; i++) map[i] = -1;
+  for (int i = 0; i < n_half + 2 * NPAD; i++) map[i] = -1;
   // arena order (state_dict): input.weight [h][C], input.bias [h], {ln.weight [h][h], ln.bias [h], skp.weight [h][C]} x L,
   // out.ln.weight [h], out.ln.bias, out.skp.weight [C]
   int64_t a = Ly.off_icnn;
@@ -592,6 +657,7 @@ void tc_build_map_host(const Layout& Ly, int32_t* map) {
   for (int k = 0; k < H_; k++) map[n_half + k] = (int32_t)a++;
   map[n_half + H_ + C] = (int32_t)a++;
   for (int c = 0; c < C; c++) map[n_half + H_ + c] = (int32_t)a++;
+  for (int k = 0; k < NPAD; k++) map[n_half + NPAD + k] = map[n_half + k];   // fp16 copy of the output vector
 }
 
 static unsigned long long* g_trace_dev = nullptr;   // debug timeline buffer (AWB_TC_TRACE=1), [grid][TRACE_N]
@@ -618,7 +684,7 @@ int tc_fit_forward_backward(const awb_prior* h, const float* params, const awb_g
   const int grid = n_tiles < sms ? n_tiles : sms;
   if (grid > kMaxSplits) { set_error("internal: grid exceeds split capacity"); return AWB_ERR_INVALID; }
   const int64_t img_stride = tc_image_bytes(L);
-  const int n_elems = (L * W_B + WIN_B) / 2 + NPAD;
+  const int n_elems = tc_map_elems(L);
   AWB_LAUNCH(PK_PACK, st, k_pack_tc<<<dim3((n_elems + 255) / 256, O), 256, 0, st>>>(params, (uint8_t*)ws.tc, h->d_tcmap, n_elems,
                                                                                     L, Ly.P, img_stride));
   TcP p = {};
