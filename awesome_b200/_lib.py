@@ -19,6 +19,7 @@ AWB_LOSS_SE_SIGMOID, AWB_LOSS_BCE_LOGITS = 0, 1
 AWB_CLS_UNARY_LT_HALF, AWB_CLS_NOT_ONE = 0, 1
 AWB_OPT_ADAM, AWB_OPT_ADAMAX = 0, 1
 AWB_MAX_GROUPS = 4
+AWB_FIT_REUSE_PACKED = 1
 
 
 class AwbLibraryError(RuntimeError):
@@ -75,7 +76,7 @@ SYMBOLS = [
     ("awb_prior_forward", C.c_int, [_P, _P, C.POINTER(GridSpec), _P, _P, C.c_int32, _P, C.c_size_t, _P]),
     ("awb_prior_backward", C.c_int, [_P, _P, C.POINTER(GridSpec), _P, _P, _P, _P, C.c_size_t, _P]),
     ("awb_prior_fit_step", C.c_int, [_P, _P, _P, C.POINTER(GridSpec), _P, C.POINTER(LossSpec),
-                                     C.POINTER(OptHyper), _P, _P, C.c_size_t, _P]),
+                                     C.POINTER(OptHyper), _P, _P, C.c_size_t, C.c_int32, _P]),
     ("awb_flow_identity_step", C.c_int, [_P, _P, _P, C.POINTER(GridSpec), C.POINTER(OptHyper), _P, _P,
                                          C.c_size_t, _P]),
     ("awb_optim_step", C.c_int, [_P, _P, _P, _P, C.POINTER(OptHyper), _P]),

@@ -103,7 +103,7 @@ int awb_prior_create(const awb_desc* d, awb_handle* out) {
   if (d->kind == AWB_KIND_ICNN) { h->desc.F = 0; h->desc.m = 0; }
   h->lay = make_layout(h->desc);
   h->fc_set = false;
-  h->d_map = nullptr; h->d_clamp = nullptr; h->d_group = nullptr; h->d_tcmap = nullptr;
+  h->d_map = nullptr; h->d_clamp = nullptr; h->d_group = nullptr; h->d_tcmap = nullptr; h->d_imap = nullptr; h->d_aug2img = nullptr;
   const Layout& L = h->lay;
   // arena (state_dict order) -> augmented index; clamp mask; optimizer groups
   std::vector<int32_t> map(L.P_icnn);
@@ -124,7 +124,15 @@ int awb_prior_create(const awb_desc* d, awb_handle* out) {
   if (i != L.P_icnn) { set_error("internal: layout mismatch"); delete h; return AWB_ERR_INVALID; }
   for (int64_t k = L.off_flow; k < L.off_flow + L.P_flow; k++) group[k] = 0;
   for (int64_t k = L.off_lin; k < L.P; k++) group[k] = 2;
+  std::vector<int32_t> imap(L.G, -1);
+  for (int64_t k = 0; k < L.P_icnn; k++) imap[map[k]] = (int32_t)k;
   cudaError_t e;
+  if ((e = cudaMalloc(&h->d_imap, sizeof(int32_t) * L.G)) != cudaSuccess ||
+      (e = cudaMemcpy(h->d_imap, imap.data(), sizeof(int32_t) * L.G, cudaMemcpyHostToDevice)) != cudaSuccess) {
+    cudaFree(h->d_imap);
+    delete h;
+    return cuda_fail(e, "awb_prior_create (inverse map)");
+  }
   if ((e = cudaGetDevice(&h->device)) != cudaSuccess ||
       (e = cudaMalloc(&h->d_map, sizeof(int32_t) * L.P_icnn)) != cudaSuccess ||
       (e = cudaMalloc(&h->d_clamp, L.P)) != cudaSuccess || (e = cudaMalloc(&h->d_group, L.P)) != cudaSuccess ||
@@ -136,16 +144,19 @@ int awb_prior_create(const awb_desc* d, awb_handle* out) {
     return cuda_fail(e, "awb_prior_create");
   }
   if (tc_supported(h)) {
-    std::vector<int32_t> tmap(tc_map_elems(L.L));
+    std::vector<int32_t> tmap(tc_map_elems(L.L)), a2i(L.G);
     tc_build_map_host(L, tmap.data());
+    tc_build_aug2img_host(L, a2i.data());
     if ((e = cudaMalloc(&h->d_tcmap, sizeof(int32_t) * tmap.size())) != cudaSuccess ||
-        (e = cudaMemcpy(h->d_tcmap, tmap.data(), sizeof(int32_t) * tmap.size(), cudaMemcpyHostToDevice)) != cudaSuccess) {
-      cudaFree(h->d_map); cudaFree(h->d_clamp); cudaFree(h->d_group); cudaFree(h->d_tcmap);
+        (e = cudaMemcpy(h->d_tcmap, tmap.data(), sizeof(int32_t) * tmap.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMalloc(&h->d_aug2img, sizeof(int32_t) * L.G)) != cudaSuccess ||
+        (e = cudaMemcpy(h->d_aug2img, a2i.data(), sizeof(int32_t) * L.G, cudaMemcpyHostToDevice)) != cudaSuccess) {
+      cudaFree(h->d_map); cudaFree(h->d_clamp); cudaFree(h->d_group); cudaFree(h->d_tcmap); cudaFree(h->d_imap); cudaFree(h->d_aug2img);
       delete h;
       return cuda_fail(e, "awb_prior_create (tensor path)");
     }
   } else if (d->precision == AWB_PREC_F16) {
-    cudaFree(h->d_map); cudaFree(h->d_clamp); cudaFree(h->d_group);
+    cudaFree(h->d_map); cudaFree(h->d_clamp); cudaFree(h->d_group); cudaFree(h->d_imap);
     delete h;
     set_error("precision f16 (tcgen05 path) supports ICNN priors with h=130 and L in {1,2}; use fp32 for this shape");
     return AWB_ERR_UNSUPPORTED;
@@ -156,7 +167,7 @@ int awb_prior_create(const awb_desc* d, awb_handle* out) {
 
 int awb_prior_destroy(awb_handle h) {
   if (!h) return AWB_OK;
-  cudaFree(h->d_map); cudaFree(h->d_clamp); cudaFree(h->d_group); cudaFree(h->d_tcmap);
+  cudaFree(h->d_map); cudaFree(h->d_clamp); cudaFree(h->d_group); cudaFree(h->d_tcmap); cudaFree(h->d_imap); cudaFree(h->d_aug2img);
   delete h;
   return AWB_OK;
 }
@@ -234,7 +245,7 @@ int awb_prior_backward(awb_handle h, const float* params, const awb_grid_spec* g
 
 int awb_prior_fit_step(awb_handle h, float* params, void* opt_state, const awb_grid_spec* g, const float* target,
                        const awb_loss_spec* loss, const awb_opt_hyper* hy, float* loss_out, void* ws, size_t ws_bytes,
-                       void* stream) {
+                       int32_t flags, void* stream) {
   int64_t N;
   int rc = check_common(h, g, ws, ws_bytes, true, &N);
   if (rc) return rc;
@@ -243,7 +254,7 @@ int awb_prior_fit_step(awb_handle h, float* params, void* opt_state, const awb_g
   cudaStream_t st = (cudaStream_t)stream;
   if (h->desc.precision == AWB_PREC_F16) {
     int n_part = 0;
-    rc = tc_fit_forward_backward(h, params, g, target, loss, nullptr, 1, w, &n_part, st);
+    rc = tc_fit_forward_backward(h, params, g, target, loss, nullptr, 1, w, &n_part, st, (flags & AWB_FIT_REUSE_PACKED) != 0);
     if (rc) return rc;
     return simt_reduce_opt(h, params, opt_state, hy, loss_out, w, N, st, n_part);
   }

@@ -61,6 +61,8 @@ struct awb_prior {
   uint8_t* d_clamp;   // [P] 1 where enforce_convexity clamps
   uint8_t* d_group;   // [P] optimizer group: 0 flow_net, 1 convex_net, 2 linear
   int32_t* d_tcmap;   // tensor path: weight-image element -> arena index (or -1), null when unsupported
+  int32_t* d_imap;    // [G] augmented index -> arena-local ICNN index (or -1 for padding)
+  int32_t* d_aug2img; // tensor path: [G] augmented index -> fp16 element of the weight image (or -1)
   awb::FlowConsts fc;
   bool fc_set;
   int device;
@@ -138,10 +140,12 @@ int tc_supported(const awb_prior* h);
 int tc_image_bytes(int L);
 int tc_map_elems(int L);
 void tc_build_map_host(const Layout& Ly, int32_t* map);   // map has tc_map_elems(L) entries
+void tc_build_aug2img_host(const Layout& Ly, int32_t* a2i);   // a2i has Ly.G entries
+int64_t tc_vec_offset_bytes(int L);                       // byte offset of the fp32 output vector inside the image
 // mode 0: forward only (logits), mode 1: forward + loss + backward partials (part / lossp, *n_splits_out CTAs)
 int tc_fit_forward_backward(const awb_prior* h, const float* params, const awb_grid_spec* g, const float* target,
                             const awb_loss_spec* loss, float* logits, int mode, const Workspace& ws,
-                            int* n_splits_out, cudaStream_t st);
+                            int* n_splits_out, cudaStream_t st, bool reuse_packed = false);
 int tc_trace_read(unsigned long long* host, int max_ctas);   // debug timeline (AWB_TC_TRACE=1): 256 stamps per CTA
 
 // ---- flows, implemented in awb_flow.cu ----

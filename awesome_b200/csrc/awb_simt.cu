@@ -5,6 +5,7 @@
 // loss, clamp) is fused into a producing kernel's epilogue.  Cross-pixel reductions
 // (weight gradients, loss) are per-pixel-range partial sums reduced in a fixed order by
 // the optimizer kernel: deterministic, no atomics.
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "awb_internal.cuh"
@@ -541,6 +542,122 @@ __global__ void __launch_bounds__(256) k_reduce_opt(OptP a, int n_groups, int us
   }
 }
 
+// ICNN priors: the same step in augmented-index space.  A block owns 128 consecutive augmented entries; warp w
+// sums its fixed slice of the partials with coalesced float4 loads (all in flight at once), the slices are
+// combined in a fixed order, and one thread per entry applies the optimizer through the inverse map.  With a
+// tensor-path workspace the updated parameter is also written into the fp16 weight image of the next step.
+struct OptA {
+  float* params; float* m; float* v; OptScal* scal;
+  const float* part; int64_t sSplit; int S;
+  const float* lossp;
+  const int32_t* imap; const uint8_t* clamp; const uint8_t* group;
+  int64_t P, off_icnn, G, aug_out;
+  int O, ld;
+  awb_opt_hyper hy;
+  float* loss_out;
+  uint8_t* img; int64_t img_stride, vec_off; const int32_t* aug2img;
+};
+
+__global__ void __launch_bounds__(256) k_reduce_opt_aug(OptA a, int n_groups) {
+  __shared__ float s_loss;
+  __shared__ float4 s_part[8][32];
+  __shared__ float s_step_size[AWB_MAX_GROUPS], s_bc2s;
+  const int o = blockIdx.y;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + AWB_MAX_GROUPS) {   // bias corrections, once per block
+    const int g = threadIdx.x - 32;
+    const int step1 = a.scal[o].step + 1;
+    const double bc1 = 1.0 - pow((double)a.hy.beta1, (double)step1);
+    s_step_size[g] = (float)(a.scal[o].lr[g] / bc1);
+    if (g == 0) s_bc2s = (float)sqrt(1.0 - pow((double)a.hy.beta2, (double)step1));
+  }
+  if (w == 0) {
+    float l = 0.f;
+    for (int s = lane; s < a.S; s += 32) l += a.lossp[s * a.O + o];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
+    if (lane == 0) s_loss = l;
+  }
+  __syncthreads();
+  const bool bad = !isfinite(s_loss);
+  const int64_t g0 = (int64_t)blockIdx.x * 128;
+  if (!bad) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g0 + 4 * lane < a.G) {
+      const float4* src = reinterpret_cast<const float4*>(a.part + (int64_t)o * a.G + g0) + lane;
+      const int64_t stride4 = a.sSplit / 4;
+      const int s0 = (a.S * w) >> 3, s1 = (a.S * (w + 1)) >> 3;
+#pragma unroll 5
+      for (int s = s0; s < s1; s++) {
+        const float4 t = src[(int64_t)s * stride4];
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
+    }
+    s_part[w][lane] = acc;
+    __syncthreads();
+    const int t = threadIdx.x;
+    const int64_t aug = g0 + t;
+    if (t < 128 && aug < a.G) {
+      const int32_t li = a.imap[aug];
+      if (li >= 0) {
+        const int64_t i = a.off_icnn + li;
+        const int grp = a.group[i];
+        if (!(a.hy.active_groups && !((a.hy.active_groups >> grp) & 1))) {
+          float g = 0.f;
+#pragma unroll
+          for (int ww = 0; ww < 8; ww++) g += reinterpret_cast<const float*>(&s_part[ww][0])[t];
+          const int64_t gi = (int64_t)o * a.P + i;
+          float p = a.params[gi], m = a.m[gi], v = a.v[gi];
+          opt_update(a.hy.kind, p, g, m, v, s_step_size[grp], s_bc2s, a.hy.beta1, a.hy.beta2, a.hy.eps,
+                     a.hy.weight_decay[grp]);
+          if (a.clamp[i]) p = fmaxf(p, 0.f);                     // enforce_convexity
+          a.params[gi] = p; a.m[gi] = m; a.v[gi] = v;
+          if (a.img) {   // keep the tensor path's fp16 weight image in step
+            uint8_t* base = a.img + (int64_t)o * a.img_stride;
+            const int32_t e = a.aug2img[aug];
+            if (e >= 0) reinterpret_cast<__half*>(base)[e] = __float2half_rn(p);
+            if (aug >= a.aug_out) {
+              const int k = (int)(aug - a.aug_out);
+              reinterpret_cast<float*>(base + a.vec_off)[k] = p;
+              reinterpret_cast<__half*>(base + a.vec_off + 4 * 144)[k] = __float2half_rn(p);
+            }
+          }
+        }
+      }
+    }
+  }
+  // ---- ticket: the last block of this object closes the step (every block has read scal by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    OptScal& s = a.scal[o];
+    const int t = atomicAdd(&s.pad, 1);
+    if (t == (int)gridDim.x - 1) {
+      s.pad = 0;
+      s.last_loss = s_loss;
+      if (a.loss_out) a.loss_out[o] = s_loss;
+      if (bad) {
+        s.nonfinite = 1;
+      } else {
+        s.step += 1;
+        if (a.hy.plateau_enabled) {
+          const double cur = (double)s_loss;
+          if (cur < s.best * (1.0 - (double)a.hy.threshold)) { s.best = cur; s.num_bad = 0; }
+          else s.num_bad += 1;
+          if (s.num_bad > a.hy.patience) {
+            for (int g = 0; g < n_groups; g++) {
+              double nl = s.lr[g] * (double)a.hy.factor;
+              if (nl < (double)a.hy.min_lr) nl = (double)a.hy.min_lr;
+              if (s.lr[g] - nl > (double)a.hy.plateau_eps) s.lr[g] = nl;
+            }
+            s.num_bad = 0;
+          }
+        }
+      }
+    }
+  }
+}
+
 __global__ void k_reduce_grads(float* grads, const float* part, int64_t sSplit, int S, const float* fpart,
                                int64_t sFSplit, const int32_t* map, int64_t P, int64_t off_icnn,
                                int64_t P_icnn, int64_t off_flow, int64_t PF, int64_t G) {
@@ -729,7 +846,20 @@ int simt_reduce_opt(const awb_prior* h, float* params, void* opt_state, const aw
   a.map = h->d_map; a.clamp = h->d_clamp; a.group = h->d_group;
   a.P = L.P; a.off_icnn = L.off_icnn; a.P_icnn = L.P_icnn; a.off_flow = L.off_flow; a.G = L.G;
   a.O = O; a.hy = *hy; a.loss_out = loss_out;
-  AWB_LAUNCH(PK_OPT, st, k_reduce_opt<<<dim3((unsigned)((L.P + 31) / 32), O), 256, 0, st>>>(a, n_groups_of(h), 1));
+  if (h->desc.kind == AWB_KIND_ICNN) {
+    OptA b = {};
+    b.params = params; b.m = a.m; b.v = a.v; b.scal = a.scal;
+    b.part = a.part; b.sSplit = a.sSplit; b.S = a.S; b.lossp = a.lossp;
+    b.imap = h->d_imap; b.clamp = h->d_clamp; b.group = h->d_group;
+    b.P = L.P; b.off_icnn = L.off_icnn; b.G = L.G; b.aug_out = L.aug_out; b.O = O; b.ld = L.ld;
+    b.hy = *hy; b.loss_out = loss_out;
+    if (ws.tc && h->d_aug2img) {
+      b.img = (uint8_t*)ws.tc; b.img_stride = tc_image_bytes(L.L); b.vec_off = tc_vec_offset_bytes(L.L); b.aug2img = h->d_aug2img;
+    }
+    AWB_LAUNCH(PK_OPT, st, k_reduce_opt_aug<<<dim3((unsigned)((L.G + 127) / 128), O), 256, 0, st>>>(b, n_groups_of(h)));
+  } else {
+    AWB_LAUNCH(PK_OPT, st, k_reduce_opt<<<dim3((unsigned)((L.P + 31) / 32), O), 256, 0, st>>>(a, n_groups_of(h), 1));
+  }
   AWB_CUDA(cudaGetLastError());
   return AWB_OK;
 }

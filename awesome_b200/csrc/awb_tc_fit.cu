@@ -660,6 +660,23 @@ void tc_build_map_host(const Layout& Ly, int32_t* map) {
   for (int k = 0; k < NPAD; k++) map[n_half + NPAD + k] = map[n_half + k];   // fp16 copy of the output vector
 }
 
+// augmented index -> fp16 element index of the weight image (hidden layers and input layer; the output vector
+// is handled by its own fp32 + fp16 slots, see k_reduce_opt_aug)
+void tc_build_aug2img_host(const Layout& Ly, int32_t* a2i) {
+  const int L = Ly.L, C = Ly.C;
+  for (int64_t i = 0; i < Ly.G; i++) a2i[i] = -1;
+  for (int j = 0; j < H_; j++) {
+    for (int c = 0; c < C; c++) a2i[Ly.aug_in + j * 4 + c] = L * (W_B / 2) + j * 8 + c;
+    a2i[Ly.aug_in + j * 4 + 3] = L * (W_B / 2) + j * 8 + C;
+  }
+  for (int l = 0; l < L; l++)
+    for (int j = 0; j < H_; j++)
+      for (int k = 0; k < H_ + C + 1; k++)
+        a2i[Ly.aug_layer + (int64_t)l * H_ * LD_ + (int64_t)j * LD_ + k] = l * (W_B / 2) + (k / 8) * (NPAD * 8) + j * 8 + (k % 8);
+}
+
+int64_t tc_vec_offset_bytes(int L) { return (int64_t)L * W_B + WIN_B; }
+
 static unsigned long long* g_trace_dev = nullptr;   // debug timeline buffer (AWB_TC_TRACE=1), [grid][TRACE_N]
 static int g_trace_ctas = 0;
 
@@ -673,7 +690,7 @@ int tc_trace_read(unsigned long long* host, int max_ctas) {
 
 int tc_fit_forward_backward(const awb_prior* h, const float* params, const awb_grid_spec* g, const float* target,
                             const awb_loss_spec* loss, float* logits, int mode, const Workspace& ws, int* n_splits_out,
-                            cudaStream_t st) {
+                            cudaStream_t st, bool reuse_packed) {
   const Layout& Ly = h->lay;
   const int O = h->desc.n_objects, L = Ly.L, C = Ly.C;
   const int64_t N = (int64_t)g->B * g->H * g->W;
@@ -685,8 +702,9 @@ int tc_fit_forward_backward(const awb_prior* h, const float* params, const awb_g
   if (grid > kMaxSplits) { set_error("internal: grid exceeds split capacity"); return AWB_ERR_INVALID; }
   const int64_t img_stride = tc_image_bytes(L);
   const int n_elems = tc_map_elems(L);
-  AWB_LAUNCH(PK_PACK, st, k_pack_tc<<<dim3((n_elems + 255) / 256, O), 256, 0, st>>>(params, (uint8_t*)ws.tc, h->d_tcmap, n_elems,
-                                                                                    L, Ly.P, img_stride));
+  if (!reuse_packed)   // otherwise the optimizer kernel of the previous fit step left the image up to date
+    AWB_LAUNCH(PK_PACK, st, k_pack_tc<<<dim3((n_elems + 255) / 256, O), 256, 0, st>>>(params, (uint8_t*)ws.tc, h->d_tcmap, n_elems,
+                                                                                      L, Ly.P, img_stride));
   TcP p = {};
   p.g.mode = g->mode; p.g.B = g->B; p.g.H = g->H; p.g.W = g->W; p.g.C = C; p.g.t0 = g->t0; p.g.t_step = g->t_step; p.g.grid = g->grid;
   p.img = (const uint8_t*)ws.tc; p.img_stride = img_stride;

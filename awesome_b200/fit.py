@@ -126,6 +126,8 @@ class PriorFitter:
         self.use_graph = use_graph
         self._ring = torch.zeros((self.K, O), dtype=torch.float32, device=self.device)
         self._graph = None
+        self._pool = None
+        self._run_pos = 0
         self.steps_done = 0
         self.reset_optimizer()
 
@@ -149,12 +151,31 @@ class PriorFitter:
                 self._specs = (L.LossSpec * len(specs))(*specs)
                 self._graph = None      # coefficients are baked into the captured launches
 
-    def _step(self, k: int) -> None:
+    def _step(self, k: int, reuse: bool = False) -> None:
+        """One fused step.  ``reuse``: this call directly follows another ``_step`` of this fitter inside the
+        same loop (nobody else can have written the parameters), so the packed weights may be reused."""
         loss_ptr = self._ring.data_ptr() + 4 * k * self.prior.n_objects
         L.check(self.lib.awb_prior_fit_step(self.prior.handle, self.params.data_ptr(), self.opt_state.data_ptr(),
-                                            C.byref(self._gs), self.target.data_ptr(), self._specs,
+                                            C.byref(self._gs), self._target_ptr(k), self._specs,
                                             C.byref(self._hyper), loss_ptr, self.ws.data_ptr(), self.ws.numel(),
-                                            L.stream_ptr()))
+                                            L.AWB_FIT_REUSE_PACKED if reuse else 0, L.stream_ptr()))
+
+    def set_target_pool(self, pool: Optional[torch.Tensor]) -> None:
+        """Fit against a rotating pool of targets ``[F,O,N]``: step ``s`` uses frame ``s % F`` (multi-frame fitting of
+        one prior; also what ``bench.py`` uses to keep the per-step input out of the L2 cache)."""
+        if pool is not None:
+            if pool.dim() != 3 or pool.shape[1:] != self.target.shape or pool.dtype != torch.float32 \
+                    or not pool.is_contiguous() or pool.device != self.device:
+                raise ValueError("target pool must be a contiguous fp32 [F,O,N] tensor on the fitter's device")
+        self._pool = pool
+        self._graph = None
+
+    def _target_ptr(self, k: int) -> int:
+        pool = getattr(self, "_pool", None)
+        if pool is None:
+            return self.target.data_ptr()
+        f = (self.steps_done + self._run_pos + k) % pool.shape[0]
+        return pool.data_ptr() + 4 * f * pool.shape[1] * pool.shape[2]
 
     def _capture(self) -> None:
         g = torch.cuda.CUDAGraph()
@@ -167,29 +188,35 @@ class PriorFitter:
         # the warm-up step must not count: restore by re-running from a snapshot
         with torch.cuda.graph(g, stream=s):
             for k in range(self.K):
-                self._step(k)
+                self._step(k, reuse=k > 0)
         self._graph = g
 
     def run(self, steps: int, record: bool = True) -> Optional[torch.Tensor]:
         """Run ``steps`` fused fit steps.  Returns the device loss history ``[steps,O]`` (no sync)."""
         hist = torch.empty((steps, self.prior.n_objects), dtype=torch.float32, device=self.device) if record else None
         done = 0
+        self._run_pos = 0
+        use_graph = self.use_graph and self._pool is None     # a captured graph bakes the target pointer
         with torch.cuda.device(self.device):
-            if self.use_graph and steps >= self.K and self._graph is None:
+            if use_graph and steps >= self.K and self._graph is None:
                 snap_p, snap_o = self.params.clone(), self.opt_state.clone()
                 self._capture()
                 self.params.copy_(snap_p)
                 self.opt_state.copy_(snap_o)
-            while self.use_graph and self._graph is not None and steps - done >= self.K:
+            while use_graph and self._graph is not None and steps - done >= self.K:
                 self._graph.replay()
                 if record:
                     hist[done:done + self.K].copy_(self._ring)
                 done += self.K
+            first = True
             while done < steps:
-                self._step(0)
+                self._run_pos = done
+                self._step(0, reuse=not first)
+                first = False
                 if record:
                     hist[done].copy_(self._ring[0])
                 done += 1
+        self._run_pos = 0
         self.steps_done += steps
         return hist
 
@@ -228,10 +255,12 @@ class FlowIdentityFitter(PriorFitter):
         self.use_graph = use_graph
         self._ring = torch.zeros((self.K, prior.n_objects), dtype=torch.float32, device=self.device)
         self._graph = None
+        self._pool = None
+        self._run_pos = 0
         self.steps_done = 0
         self.reset_optimizer()
 
-    def _step(self, k: int) -> None:
+    def _step(self, k: int, reuse: bool = False) -> None:
         loss_ptr = self._ring.data_ptr() + 4 * k * self.prior.n_objects
         L.check(self.lib.awb_flow_identity_step(self.prior.handle, self.params.data_ptr(), self.opt_state.data_ptr(),
                                                 C.byref(self._gs), C.byref(self._hyper), loss_ptr,

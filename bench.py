@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 
 H, W = 480, 640
 N_PIX = H * W
+POOL_FRAMES = 112          # 112 x 1.2288 MB = 137.6 MB of unaries > 126 MB L2
 HID, LAYERS, CH = 130, 2, 2
 MAC_FWD = CH * HID + LAYERS * (HID * HID + CH * HID) + HID + CH        # 34 712
 FLOP_PER_PX_STEP = 6 * MAC_FWD                                          # 208 272
@@ -72,7 +73,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -168,10 +169,10 @@ def run_reference(args, rank: int, world: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("AWB_BENCH_PRECISION", "fp32"), choices=["fp32", "f16"])
+    ap.add_argument("--precision", default=os.environ.get("AWB_BENCH_PRECISION", "f16"), choices=["fp32", "f16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -206,6 +207,14 @@ def main():
     unaries = unaries_host.to(dev, non_blocking=True)
     grid = A.GridSpecHost("linspace", 1, H, W)
     fitter = model.make_fitter(grid, unaries, A.LossConfig("mse"), A.OptimConfig("adam", lr=1e-3), use_graph=False)
+    # The per-step input (the frame's unaries, 1.2 MB) would sit in the 126 MB L2: rotate through a pool of
+    # POOL_FRAMES distinct frames (> L2) so that every timed step reads its unaries from HBM.
+    base = unaries.reshape(1, 1, -1)
+    shifts = torch.arange(POOL_FRAMES, device=dev).view(-1, 1, 1)
+    idx = (torch.arange(N_PIX, device=dev).view(1, 1, -1) + 37 * shifts) % N_PIX     # cheap distinct frames: rolled copies
+    pool = torch.gather(base.expand(POOL_FRAMES, 1, N_PIX), 2, idx).contiguous()
+    pool[0].copy_(base[0])
+    fitter.set_target_pool(pool)
 
     def barrier():
         if world > 1:
@@ -228,6 +237,7 @@ def main():
     ms_total = ev0.elapsed_time(ev1)
 
     # ---- end to end through the public API: the step's unaries arrive from pinned host memory, loss read back
+    fitter.set_target_pool(None)
     e2e_warm = 3
     t_e2e = 0.0
     for i in range(e2e_warm + args.steps):
@@ -299,8 +309,8 @@ def main():
             "config": {"workload": WORKLOAD, "prior": f"ConvexNextNet(h={HID},L={LAYERS},C={CH})",
                        "loss": "MSE(sigmoid(y), unaries)", "optimizer": "Adam lr=1e-3 + enforce_convexity",
                        "pixels_per_step_per_gpu": N_PIX, "precision": args.precision,
-                       "l2": "per-step working set (activations, deltas, partials) ~0.85 GB > 126 MB L2: no flush needed"
-                       if args.precision == "fp32" else "see DESIGN.md",
+                       "l2": f"each step reads its unaries from a rotating pool of {POOL_FRAMES} distinct frames "
+                             f"({POOL_FRAMES * N_PIX * 4 / 1e6:.0f} MB > 126 MB L2); no explicit flush",
                        "frames_per_s_at_400_steps_per_frame": value / N_PIX / 400.0,
                        "frames_per_s_at_4000_steps_per_frame": value / N_PIX / 4000.0},
             "e2e": {"value": e2e_val, "unit": "pixel-samples/s", "h2d_bytes_per_step": 4 * N_PIX,

@@ -151,10 +151,14 @@ int awb_prior_backward(awb_handle h, const float* params, const awb_grid_spec* g
  * (path_connected_net.py:939-953, :364-379; notebooks/how_to/convexity.ipynb cell 9):
  * forward, sigmoid/loss, backward, cross-pixel gradient reduction, Adam/Adamax (+L2),
  * enforce_convexity clamp (convex_net.py:151-154,216-220), ReduceLROnPlateau.step(loss).
- * target [O][N]; loss/lr per object; loss_out (optional) device [O]. */
+ * target [O][N]; loss/lr per object; loss_out (optional) device [O].
+ * flags: AWB_FIT_REUSE_PACKED -- the previous call on this workspace was a fit step of the same handle on the same
+ * params and nothing has written params since (the caller is inside its own step loop): the tensor path then
+ * reuses the fp16 weight image its optimizer kernel left in the workspace instead of re-packing it. */
+#define AWB_FIT_REUSE_PACKED 1
 int awb_prior_fit_step(awb_handle h, float* params, void* opt_state, const awb_grid_spec* grid,
                        const float* target, const awb_loss_spec* loss, const awb_opt_hyper* hyper,
-                       float* loss_out, void* workspace, size_t workspace_bytes, void* stream);
+                       float* loss_out, void* workspace, size_t workspace_bytes, int32_t flags, void* stream);
 
 /* One step of PathConnectedNet.learn_flow_identity (path_connected_net.py:155-250): the NormNet-wrapped
  * flow alone (no 1x1 conv) is regressed onto its own input grid with SE("mean"); only the flow_net
