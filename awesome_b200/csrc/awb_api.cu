@@ -158,7 +158,7 @@ int awb_prior_create(const awb_desc* d, awb_handle* out) {
   } else if (d->precision == AWB_PREC_F16) {
     cudaFree(h->d_map); cudaFree(h->d_clamp); cudaFree(h->d_group); cudaFree(h->d_imap);
     delete h;
-    set_error("precision f16 (tcgen05 path) supports ICNN priors with h=130 and L in {1,2}; use fp32 for this shape");
+    set_error("precision f16 (tcgen05 path) supports priors with ICNN width h=130 and L in {1,2}; use fp32 for this shape");
     return AWB_ERR_UNSUPPORTED;
   }
   *out = h;
@@ -254,6 +254,17 @@ int awb_prior_fit_step(awb_handle h, float* params, void* opt_state, const awb_g
   cudaStream_t st = (cudaStream_t)stream;
   if (h->desc.precision == AWB_PREC_F16) {
     int n_part = 0;
+    if (h->desc.kind == AWB_KIND_FLOW_ICNN) {
+      // RealNVP on CUDA cores (K = C is too thin for tensor cores) around the tensor-path ICNN: the flow writes the
+      // deformed coordinates X, the fused kernel returns d loss / d X, the flow backward consumes it.
+      rc = flow_forward(h, params, g, w, nullptr, st);
+      if (rc) return rc;
+      rc = tc_fit_forward_backward(h, params, g, target, loss, nullptr, 1, w, &n_part, st, false, w.X, w.dX);
+      if (rc) return rc;
+      rc = flow_backward(h, params, g, w, st);
+      if (rc) return rc;
+      return simt_reduce_opt(h, params, opt_state, hy, loss_out, w, N, st, n_part);
+    }
     rc = tc_fit_forward_backward(h, params, g, target, loss, nullptr, 1, w, &n_part, st, (flags & AWB_FIT_REUSE_PACKED) != 0);
     if (rc) return rc;
     return simt_reduce_opt(h, params, opt_state, hy, loss_out, w, N, st, n_part);

@@ -126,6 +126,8 @@ int simt_forward(const awb_prior* h, const float* params, const awb_grid_spec* g
 int simt_backward(const awb_prior* h, const float* params, const awb_grid_spec* g, const float* target,
                   const awb_loss_spec* loss, const float* dlogits, bool need_dx, const Workspace& ws,
                   cudaStream_t st);
+// n_partials: number of ICNN gradient partials ([S][O][G]) the producer wrote (-1: n_splits(N)); the flow
+// partials always come from flow_backward's n_splits(N) pixel ranges.
 int simt_reduce_opt(const awb_prior* h, float* params, void* opt_state, const awb_opt_hyper* hy,
                     float* loss_out, const Workspace& ws, int64_t N, cudaStream_t st, int n_partials = -1);
 int simt_reduce_grads(const awb_prior* h, float* grads, const Workspace& ws, int64_t N, cudaStream_t st);
@@ -145,7 +147,8 @@ int64_t tc_vec_offset_bytes(int L);                       // byte offset of the 
 // mode 0: forward only (logits), mode 1: forward + loss + backward partials (part / lossp, *n_splits_out CTAs)
 int tc_fit_forward_backward(const awb_prior* h, const float* params, const awb_grid_spec* g, const float* target,
                             const awb_loss_spec* loss, float* logits, int mode, const Workspace& ws,
-                            int* n_splits_out, cudaStream_t st, bool reuse_packed = false);
+                            int* n_splits_out, cudaStream_t st, bool reuse_packed = false,
+                            const float* Xrows = nullptr, float* dXrows = nullptr);
 int tc_trace_read(unsigned long long* host, int max_ctas);   // debug timeline (AWB_TC_TRACE=1): 256 stamps per CTA
 
 // ---- flows, implemented in awb_flow.cu ----

@@ -437,7 +437,7 @@ __device__ __forceinline__ void opt_update(int kind, float& p, float g, float& m
 struct OptP {
   float* params; float* m; float* v; OptScal* scal;
   const float* part; int64_t sSplit; int S;      // ICNN partials [S][O][G]
-  const float* fpart; int64_t sFSplit;           // flow+linear partials [S][O][PF]
+  const float* fpart; int64_t sFSplit; int SF;   // flow+linear partials [SF][O][PF]
   const float* lossp;                            // [S][O]
   const float* grads;                            // direct gradients (awb_optim_step) or null
   const int32_t* map; const uint8_t* clamp; const uint8_t* group;
@@ -484,9 +484,10 @@ __global__ void __launch_bounds__(256) k_reduce_opt(OptP a, int n_groups, int us
     if (mine) {
       const float* src;
       int64_t stride;
-      if (i >= a.off_icnn && i < a.off_icnn + a.P_icnn) { src = a.part + (int64_t)o * a.G + a.map[i - a.off_icnn]; stride = a.sSplit; }
-      else { src = a.fpart + (int64_t)o * a.PF + (i - a.off_flow); stride = a.sFSplit; }
-      const int s0 = (a.S * w) >> 3, s1 = (a.S * (w + 1)) >> 3;
+      int S;
+      if (i >= a.off_icnn && i < a.off_icnn + a.P_icnn) { src = a.part + (int64_t)o * a.G + a.map[i - a.off_icnn]; stride = a.sSplit; S = a.S; }
+      else { src = a.fpart + (int64_t)o * a.PF + (i - a.off_flow); stride = a.sFSplit; S = a.SF; }
+      const int s0 = (S * w) >> 3, s1 = (S * (w + 1)) >> 3;
 #pragma unroll 4
       for (int s = s0; s < s1; s++) g += src[(int64_t)s * stride];
     }
@@ -840,6 +841,7 @@ int simt_reduce_opt(const awb_prior* h, float* params, void* opt_state, const aw
   a.params = params;
   opt_ptrs(h, opt_state, &a.m, &a.v, &a.scal);
   a.part = ws.part; a.sSplit = (int64_t)O * L.G; a.S = n_partials > 0 ? n_partials : n_splits(N);
+  a.SF = n_splits(N);
   a.PF = L.P_flow + 2 * L.C;
   a.fpart = ws.fpart; a.sFSplit = (int64_t)O * a.PF;
   a.lossp = ws.lossp; a.grads = nullptr;

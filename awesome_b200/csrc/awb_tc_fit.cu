@@ -47,10 +47,11 @@ constexpr int NCG = 3;              // epilogue column groups per TMEM lane quad
 constexpr int NEW = 4 * NCG;        // epilogue warps (3 per warp scheduler)
 constexpr int NTHREADS = (NEW + 1) * 32;   // + 1 issuer warp
 constexpr int XCHG_B = NCG * 128 * 4;
+constexpr int XCHG2_B = (NCG - 1) * 128 * 3 * 4;   // input-layer coordinate-gradient partials (flow priors)
 constexpr int TRACE_N = 256;        // clock stamps per CTA (debug timeline)
 __host__ __device__ constexpr int img_bytes(int L) { return L * W_B + WIN_B + VEC_B + VEC16_B; }
 __host__ __device__ constexpr int smem_bytes(int L) {
-  return (L + 2) * TILE_B + img_bytes(L) + 2 * TX_B + ZERO_B + XCHG_B + 64;
+  return (L + 2) * TILE_B + img_bytes(L) + 2 * TX_B + ZERO_B + XCHG_B + XCHG2_B + 64;
 }
 }  // namespace
 
@@ -82,6 +83,8 @@ struct TcP {
   float* logits;
   int64_t N; int n_tiles; int mode;
   unsigned long long* trace;
+  const float* X;   // optional [O][N][4]: coordinates produced by the flow (x, y, t, 1) instead of the generated grid
+  float* dX;        // optional [O][N][4]: gradient w.r.t. those coordinates (consumed by the flow backward)
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -146,7 +149,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
   uint8_t* stx = simg + IMG;                      // TX[2]
   uint8_t* szero = stx + 2 * TX_B;
   float* xchg = reinterpret_cast<float*>(szero + ZERO_B);          // [NCG][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(szero + ZERO_B + XCHG_B);
+  float* xchg2 = xchg + NCG * 128;                                  // [NCG-1][128][3]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(szero + ZERO_B + XCHG_B + XCHG2_B);
   uint64_t* bar_e2m = bars;        // epilogue -> issuer (one arrival per epilogue warp)
   uint64_t* bar_m2e = bars + 1;    // tcgen05.commit -> epilogue
   uint64_t* bar_w = bars + 2;      // weight image landed (TMA tx bytes)
@@ -298,6 +302,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
     for (int i = 0; i <= L; i++) accC[i] = 0.f;
     const awb_loss_spec ls = p.loss[o];
     const float S = p.scale[o];
+    const bool has_dx = p.dX != nullptr;
+    float adx0 = 0.f, adx1 = 0.f, adx2 = 0.f;     // last group: d loss / d (x, y, t) of this row (scaled by S)
     float v[48];
     const float* w = wo + 48 * cg;
 
@@ -325,7 +331,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
       const int64_t n = (int64_t)tile * 128 + row;
       liven = n < p.N;
       const uint32_t nn = (uint32_t)(liven ? n : p.N - 1);
-      row_coords(p.g, nn, C, x0n, x1n, x2n);
+      if (p.X) {
+        const float4 xv = *reinterpret_cast<const float4*>(p.X + ((int64_t)o * p.N + nn) * 4);
+        x0n = xv.x; x1n = xv.y; x2n = C > 2 ? xv.z : 0.f;
+      } else {
+        row_coords(p.g, nn, C, x0n, x1n, x2n);
+      }
       tgtn = 0.f;
       if (fit && liven) tgtn = p.target[(int64_t)o * p.N + n];
     };
@@ -470,6 +481,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
         for (int b = 0; b < 6; b++) { cv[b] = dL128 * c6[b]; cv[6 + b] = dL129 * c6[b]; }
         cv[12] = zL128 * dys; cv[13] = zL129 * dys; cv[14] = 0.f; cv[15] = 0.f;
         accC[L] += warp_reduce_scatter16(cv, lane);
+        if (has_dx) { adx0 = dys * wo[H_]; adx1 = dys * wo[H_ + 1]; adx2 = C > 2 ? dys * wo[H_ + 2] : 0.f; }   // out.skp
       }
       if (more) fetch_tile(tile + gridDim.x);     // next tile's coordinates and target (load latency hidden)
 
@@ -492,8 +504,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
         tc::fence_after_sync();
         AWB_TR();
         load_acc(tlane + T_ACC);
+        if (last && has_dx) { adx0 += v[34]; adx1 += v[35]; if (C > 2) adx2 += v[36]; }   // skip-connection columns of dZA
         uint8_t* dst = dbuf(i - 1) + ch0 * 2048 + row * 16;
         float d128 = 0.f, d129 = 0.f;
+        uint32_t d0w[24];            // delta_0 words, kept for the input-layer coordinate gradient
 #pragma unroll
         for (int c = 0; c < 6; c++) {
           if (c < nch) {
@@ -505,6 +519,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
               d129 = (mk[16] >> 16) ? v[33] : 0.f;
             }
             st16(dst + c * 2048, w0, w1, w2, w3);
+            if (i == 1) { d0w[4 * c] = w0; d0w[4 * c + 1] = w1; d0w[4 * c + 2] = w2; d0w[4 * c + 3] = w3; }
           }
         }
         if (i == 1 && more) write_tx((it + 1) & 1, x0n, x1n, x2n);   // next tile's input operand rides this round trip
@@ -525,6 +540,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
             for (int b = 8; b < 16; b++) cv[b] = 0.f;
           }
           accC[i - 1] += warp_reduce_scatter16(cv, lane);
+        }
+        if (i == 1 && has_dx) {
+          // d x += delta_0 * W_in (K = 130 split over the three column groups of the row; W_in rows from the fp16 image)
+          const uint8_t* win = simg + L * W_B;     // [144 rows j][8 halfs]: (w_x, w_y, [w_t,] bias, 0..)
+          float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+#pragma unroll
+          for (int c = 0; c < 6; c++) {
+            if (c < nch) {
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                const int j = (ch0 + c) * 8 + 2 * k;
+                const uint2 wa = *reinterpret_cast<const uint2*>(win + j * 16);
+                const uint2 wb = *reinterpret_cast<const uint2*>(win + (j + 1) * 16);
+                const float da = half_lo(d0w[4 * c + k]), db = half_hi(d0w[4 * c + k]);
+                g0 = fmaf(da, half_lo(wa.x), g0); g1 = fmaf(da, half_hi(wa.x), g1);
+                g0 = fmaf(db, half_lo(wb.x), g0); g1 = fmaf(db, half_hi(wb.x), g1);
+                if (C > 2) { g2 = fmaf(da, half_lo(wa.y), g2); g2 = fmaf(db, half_lo(wb.y), g2); }
+              }
+            }
+          }
+          if (!last) { float* xs = xchg2 + (cg * 128 + row) * 3; xs[0] = g0; xs[1] = g1; xs[2] = g2; }
+          asm volatile("bar.sync %0, 96;" ::"r"(1 + q) : "memory");
+          if (last && live) {
+            const float inv = 1.f / S;
+            const float* xa = xchg2 + row * 3;
+            const float* xb = xchg2 + (128 + row) * 3;
+            *reinterpret_cast<float4*>(p.dX + ((int64_t)o * p.N + n) * 4) =
+                make_float4((adx0 + g0 + xa[0] + xb[0]) * inv, (adx1 + g1 + xa[1] + xb[1]) * inv,
+                            C > 2 ? (adx2 + g2 + xa[2] + xb[2]) * inv : 0.f, 0.f);
+          }
         }
       }
     }
@@ -632,7 +677,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
 
 // ======================================================================= host launcher
 int tc_supported(const awb_prior* h) {
-  return h->desc.kind == AWB_KIND_ICNN && h->lay.h == H_ && (h->lay.L == 1 || h->lay.L == 2) && h->lay.ld == LD_;
+  return (h->desc.kind == AWB_KIND_ICNN || h->desc.kind == AWB_KIND_FLOW_ICNN) && h->lay.h == H_ &&
+         (h->lay.L == 1 || h->lay.L == 2) && h->lay.ld == LD_;
 }
 
 int tc_map_elems(int L) { return (L * W_B + WIN_B) / 2 + 2 * NPAD; }
@@ -690,11 +736,11 @@ int tc_trace_read(unsigned long long* host, int max_ctas) {
 
 int tc_fit_forward_backward(const awb_prior* h, const float* params, const awb_grid_spec* g, const float* target,
                             const awb_loss_spec* loss, float* logits, int mode, const Workspace& ws, int* n_splits_out,
-                            cudaStream_t st, bool reuse_packed) {
+                            cudaStream_t st, bool reuse_packed, const float* Xrows, float* dXrows) {
   const Layout& Ly = h->lay;
   const int O = h->desc.n_objects, L = Ly.L, C = Ly.C;
   const int64_t N = (int64_t)g->B * g->H * g->W;
-  if (!tc_supported(h)) { set_error("precision f16 supports ICNN priors with h=130, L in {1,2}"); return AWB_ERR_UNSUPPORTED; }
+  if (!tc_supported(h)) { set_error("precision f16 supports ICNN / flow+ICNN priors with h=130, L in {1,2}"); return AWB_ERR_UNSUPPORTED; }
   const int n_tiles = (int)((N + 127) / 128);
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
@@ -720,6 +766,7 @@ int tc_fit_forward_backward(const awb_prior* h, const float* params, const awb_g
   }
   p.part = ws.part; p.sSplit = (int64_t)O * Ly.G; p.G = Ly.G; p.aug_in = Ly.aug_in; p.aug_layer = Ly.aug_layer; p.aug_out = Ly.aug_out;
   p.lossp = ws.lossp; p.O = O; p.logits = logits; p.N = N; p.n_tiles = n_tiles; p.mode = mode;
+  p.X = Xrows; p.dX = dXrows;
   p.trace = nullptr;
   if (getenv("AWB_TC_TRACE")) {
     if (!g_trace_dev) cudaMalloc(&g_trace_dev, sizeof(unsigned long long) * TRACE_N * kMaxSplits * 16);
