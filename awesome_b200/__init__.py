@@ -7,7 +7,10 @@ All arithmetic runs in ``csrc/libawb.so`` (hand-written sm_100a CUDA); there is 
 """
 from .core import GridSpecHost, Prior, iou_counts, target_counts  # noqa: F401
 from .fit import FlowIdentityFitter, LossConfig, OptimConfig, PriorFitter  # noqa: F401
-from .model import (ConvexNet, ConvexNextNet, MinMax, NormNet, PathConnectedNet, PixelizeNet, get_norm,  # noqa: F401
-                    init_realnvp, real_nvp_path_connected_net)
+from .optim import FusedAdam, FusedAdamax  # noqa: F401
+from .pretrain import FitSchedule, FrameResult, fit_frames, fit_sequence, mask_iou  # noqa: F401
+from .prior_cache import DevicePriorCache, PriorManager  # noqa: F401
+from .model import (ConvexNet, ConvexNextNet, MinMax, NormNet, NumberBasedMultiPriorModule, PathConnectedNet,  # noqa: F401
+                    PixelizeNet, get_norm, init_realnvp, real_nvp_path_connected_net)
 
 __version__ = "0.1.0"

@@ -82,6 +82,7 @@ SYMBOLS = [
     ("awb_optim_step", C.c_int, [_P, _P, _P, _P, C.POINTER(OptHyper), _P]),
     ("awb_prior_enforce_convexity", C.c_int, [_P, _P, _P]),
     ("awb_opt_state_init", C.c_int, [_P, _P, C.POINTER(C.c_double), _P]),
+    ("awb_opt_set_lr", C.c_int, [_P, _P, C.POINTER(C.c_double), _P]),
     ("awb_opt_read_scalars", C.c_int, [_P, _P, C.c_int32, C.POINTER(OptScalars), _P]),
     ("awb_prior_actnorm_init", C.c_int, [_P, _P, C.POINTER(GridSpec), _P, C.c_size_t, _P]),
     ("awb_mask_iou_counts", C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),

@@ -91,13 +91,14 @@ class Prior:
     def handle(self):
         return self._h
 
-    def workspace_bytes(self, n_pixels: int, training: bool) -> int:
+    def workspace_bytes(self, n_pixels: int, training) -> int:
+        """``training``: False / True, or 2 for a fit-step-only workspace (see ``awb_prior_workspace_bytes``)."""
         b = int(self.lib.awb_prior_workspace_bytes(self._h, n_pixels, int(training)))
         if b < 0:
             raise L.AwbError(b, "workspace size query failed")
         return b
 
-    def new_workspace(self, n_pixels: int, training: bool, device) -> torch.Tensor:
+    def new_workspace(self, n_pixels: int, training, device) -> torch.Tensor:
         return torch.empty(self.workspace_bytes(n_pixels, training), dtype=torch.uint8, device=device)
 
     def cached_workspace(self, n_pixels: int, training: bool, device) -> torch.Tensor:

@@ -48,7 +48,9 @@ static Layout make_layout(const awb_desc& d) {
 
 static int64_t align256(int64_t b) { return round_up(b, 256); }
 
-Workspace carve(const awb_prior* h, int64_t N, bool training, void* base) {
+// fit_only: layout for awb_prior_fit_step on a tensor-path handle -- the fused kernel keeps activations on the SM, so
+// the [N][ld] activation / delta planes of the CUDA-core path are not carved (0.85 GB per 640x480 frame).
+Workspace carve(const awb_prior* h, int64_t N, bool training, void* base, bool fit_only) {
   const Layout& L = h->lay;
   const int64_t O = h->desc.n_objects;
   int S = n_splits(N);
@@ -67,8 +69,9 @@ Workspace carve(const awb_prior* h, int64_t N, bool training, void* base) {
   w.fpart = (float*)take(training ? 4 * (int64_t)S * O * (L.P_flow + 2 * L.C) : 0);
   w.X = (float*)take(4 * O * N * 4);
   w.dX = (float*)take(training ? 4 * O * N * 4 : 0);
-  w.ZA = (float*)take(4 * O * (L.L + 1) * N * L.ld);
-  w.D = (float*)take(training ? 4 * O * 2 * N * L.ld : 0);
+  const bool planes = !(fit_only && h->desc.precision == AWB_PREC_F16 && tc_supported(h));
+  w.ZA = (float*)take(planes ? 4 * O * (L.L + 1) * N * L.ld : 0);
+  w.D = (float*)take(training && planes ? 4 * O * 2 * N * L.ld : 0);
   w.logits = (float*)take(4 * O * N);
   w.flowz = (float*)take(training ? 4 * O * N * (int64_t)L.F * L.C : 0);
   if (!training || L.F == 0) w.flowz = nullptr;
@@ -176,7 +179,7 @@ int64_t awb_prior_param_count(awb_handle h) { return h ? h->lay.P : -1; }
 
 int64_t awb_prior_workspace_bytes(awb_handle h, int64_t n_pixels, int32_t training) {
   if (!h || n_pixels < 1) return -1;
-  return carve(h, n_pixels, training != 0, nullptr).bytes;
+  return carve(h, n_pixels, training != 0, nullptr, training == 2).bytes;
 }
 
 int64_t awb_opt_state_bytes(awb_handle h) {
@@ -196,14 +199,15 @@ int awb_prior_set_flow_consts(awb_handle h, const float* nmin, const float* nmax
   return AWB_OK;
 }
 
-static int check_common(awb_handle h, const awb_grid_spec* g, void* ws, size_t ws_bytes, bool training, int64_t* N) {
+static int check_common(awb_handle h, const awb_grid_spec* g, void* ws, size_t ws_bytes, bool training, int64_t* N,
+                        bool fit_only = false) {
   if (!h || !g || !ws) { set_error("null argument"); return AWB_ERR_INVALID; }
   if (g->B < 1 || g->H < 1 || g->W < 1) { set_error("empty grid %dx%dx%d", g->B, g->H, g->W); return AWB_ERR_INVALID; }
   if (g->mode == AWB_GRID_EXPLICIT && !g->grid) { set_error("explicit grid needs a pointer"); return AWB_ERR_INVALID; }
   if (g->mode < 0 || g->mode > 2) { set_error("unknown grid mode %d", g->mode); return AWB_ERR_INVALID; }
   *N = (int64_t)g->B * g->H * g->W;
   if (*N > (int64_t)1 << 30) { set_error("too many pixel rows"); return AWB_ERR_UNSUPPORTED; }
-  int64_t need = carve(h, *N, training, nullptr).bytes;
+  int64_t need = carve(h, *N, training, nullptr, fit_only).bytes;
   if ((int64_t)ws_bytes < need) { set_error("workspace too small: %lld < %lld", (long long)ws_bytes, (long long)need); return AWB_ERR_WORKSPACE; }
   if (h->desc.kind == AWB_KIND_FLOW_ICNN && !h->fc_set) { set_error("awb_prior_set_flow_consts not called"); return AWB_ERR_INVALID; }
   return AWB_OK;
@@ -247,10 +251,10 @@ int awb_prior_fit_step(awb_handle h, float* params, void* opt_state, const awb_g
                        const awb_loss_spec* loss, const awb_opt_hyper* hy, float* loss_out, void* ws, size_t ws_bytes,
                        int32_t flags, void* stream) {
   int64_t N;
-  int rc = check_common(h, g, ws, ws_bytes, true, &N);
+  int rc = check_common(h, g, ws, ws_bytes, true, &N, /*fit_only=*/true);
   if (rc) return rc;
   if (!params || !opt_state || !target || !loss || !hy) { set_error("null argument"); return AWB_ERR_INVALID; }
-  Workspace w = carve(h, N, true, ws);
+  Workspace w = carve(h, N, true, ws, true);
   cudaStream_t st = (cudaStream_t)stream;
   if (h->desc.precision == AWB_PREC_F16) {
     int n_part = 0;
@@ -310,6 +314,11 @@ int awb_prior_enforce_convexity(awb_handle h, float* params, void* stream) {
 int awb_opt_state_init(awb_handle h, void* opt_state, const double* lr, void* stream) {
   if (!h || !opt_state || !lr) { set_error("null argument"); return AWB_ERR_INVALID; }
   return opt_state_init(h, opt_state, lr, (cudaStream_t)stream);
+}
+
+int awb_opt_set_lr(awb_handle h, void* opt_state, const double* lr, void* stream) {
+  if (!h || !opt_state || !lr) { set_error("null argument"); return AWB_ERR_INVALID; }
+  return opt_set_lr(h, opt_state, lr, (cudaStream_t)stream);
 }
 
 int awb_opt_read_scalars(awb_handle h, const void* opt_state, int32_t obj, awb_opt_scalars* out, void* stream) {

@@ -100,7 +100,7 @@ struct Workspace {
   void* tc;       // tensor-core path scratch
   int64_t bytes;
 };
-Workspace carve(const awb_prior* h, int64_t N, bool training, void* base);
+Workspace carve(const awb_prior* h, int64_t N, bool training, void* base, bool fit_only = false);
 
 // ---- per-kernel-class timing (CUDA events on the launch stream) and launch counting ----
 enum { PK_PACK = 0, PK_INPUT, PK_GEMM_FWD, PK_OUT_LOSS, PK_GEMM_WGRAD, PK_GEMM_DGRAD, PK_IN_BWD, PK_OPT,
@@ -136,6 +136,7 @@ int optim_step(const awb_prior* h, float* params, const float* grads, void* opt_
                const awb_opt_hyper* hy, cudaStream_t st);
 int clamp_only(const awb_prior* h, float* params, cudaStream_t st);
 int opt_state_init(const awb_prior* h, void* opt_state, const double* lr, cudaStream_t st);
+int opt_set_lr(const awb_prior* h, void* opt_state, const double* lr, cudaStream_t st);
 
 // ---- tensor path (tcgen05), implemented in awb_tc_fit.cu ----
 int tc_supported(const awb_prior* h);

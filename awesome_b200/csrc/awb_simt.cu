@@ -691,6 +691,12 @@ __global__ void k_opt_init(OptScal* scal, double l0, double l1, double l2, doubl
   scal[o] = s;
 }
 
+__global__ void k_opt_set_lr(OptScal* scal, double l0, double l1, double l2, double l3, int O) {
+  int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= O) return;
+  scal[o].lr[0] = l0; scal[o].lr[1] = l1; scal[o].lr[2] = l2; scal[o].lr[3] = l3;
+}
+
 // dgrid[b][c][i][j] = dX[n][c]   (planar reference layout)
 __global__ void k_dgrid(const float* dX, float* dgrid, int64_t N, int64_t HW, int C) {
   int64_t n = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -902,6 +908,14 @@ int optim_step(const awb_prior* h, float* params, const float* grads, void* opt_
 
 int clamp_only(const awb_prior* h, float* params, cudaStream_t st) {
   AWB_LAUNCH(PK_OPT, st, k_clamp<<<dim3((unsigned)((h->lay.P + 255) / 256), h->desc.n_objects), 256, 0, st>>>(params, h->d_clamp, h->lay.P));
+  AWB_CUDA(cudaGetLastError());
+  return AWB_OK;
+}
+
+int opt_set_lr(const awb_prior* h, void* opt_state, const double* lr, cudaStream_t st) {
+  float* m; float* v; OptScal* sc;
+  opt_ptrs(h, opt_state, &m, &v, &sc);
+  AWB_LAUNCH(PK_MISC, st, k_opt_set_lr<<<1, 64, 0, st>>>(sc, lr[0], lr[1], lr[2], lr[3], h->desc.n_objects));
   AWB_CUDA(cudaGetLastError());
   return AWB_OK;
 }

@@ -30,6 +30,18 @@ class LossConfig:
     ratio: float = 1.0
     fg_weight: float = 0.4    # fgbg_* kinds
 
+    @classmethod
+    def from_reference(cls, criterion) -> "LossConfig":
+        """Map a reference loss object onto the fused per-pixel loss (duck-typed by class name / attributes):
+        ``UnariesWeightedLoss(SE, mode=...)`` (``awesome/measures/unaries_weighted_loss.py:35-69``),
+        ``SE`` (``se.py``), ``torch.nn.MSELoss`` -> "mse"; ``BCEWithLogitsLoss`` -> fg/bg BCE with equal weights."""
+        name = type(criterion).__name__
+        if name == "UnariesWeightedLoss":
+            return cls("mse", mode=getattr(criterion, "mode", "none") or "none", ratio=float(getattr(criterion, "ratio", 1.0) or 1.0))
+        if name in ("SE", "MSELoss"):
+            return cls("mse")
+        raise ValueError(f"criterion {name} has no fused equivalent; pass an awesome_b200.LossConfig")
+
     def to_specs(self, target: torch.Tensor) -> List[L.LossSpec]:
         """target ``[O,N]``.  Folds 1/N, class weights and fg/bg means into two coefficients per object."""
         O, N = target.shape
@@ -115,7 +127,7 @@ class PriorFitter:
             raise ValueError("params must be a contiguous fp32 [O,P] arena")
         self.lib = prior.lib
         with torch.cuda.device(self.device):
-            self.ws = prior.new_workspace(grid.n_pixels, True, self.device)
+            self.ws = prior.new_workspace(grid.n_pixels, 2, self.device)     # fit-step-only layout
             self.opt_state = torch.empty(prior.opt_state_bytes(), dtype=torch.uint8, device=self.device)
             self._specs_list = loss.to_specs(self.target)
         self._specs = (L.LossSpec * O)(*self._specs_list)

@@ -81,6 +81,12 @@ class ArenaPriorModule(nn.Module):
         self._arena: Optional[torch.Tensor] = None
         self._prior: Optional[Prior] = None
         self._prior_device = None
+        from ..optim import _ARENA_MODULES
+        _ARENA_MODULES.add(self)
+
+    def _optimizer_group_ids(self) -> List[int]:
+        """Native optimizer group of every arena parameter (0 flow_net, 1 convex_net, 2 linear), in arena order."""
+        return [1] * len(self._arena_params())
 
     # ---- arena
     def _arena_params(self) -> List[nn.Parameter]:

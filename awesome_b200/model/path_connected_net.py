@@ -161,6 +161,12 @@ class PathConnectedNet(ArenaPriorModule):
         self.linear = _Conv1x1(in_channels)
         self._flatten_()
 
+    def _optimizer_group_ids(self):
+        """Arena order is convex_net, flow_net, linear (registration order) -> native groups 1, 0, 2
+        (the reference's per-frame optimizer groups: ``path_connected_net.py:923-929``)."""
+        return ([1] * len(list(self.convex_net.parameters())) + [0] * len(list(self.flow_net.parameters()))
+                + [2] * len(list(self.linear.parameters())))
+
     # ---- native handle
     @property
     def _rnvp(self) -> RealNVP:
@@ -304,6 +310,15 @@ class PathConnectedNet(ArenaPriorModule):
         hist = fitter.run(max_iter)
         fitter.raise_if_nonfinite()
         return hist.reshape(-1)
+
+    def pretrain(self, *args, **kwargs):
+        """``PretrainableModule.pretrain`` (``path_connected_net.py:472-509``), see ``awesome_b200/pretrain.py``."""
+        from .. import pretrain as P
+        return P.pretrain(self, *args, **kwargs)
+
+    def pretrain_load_state(self, *args, **kwargs):
+        from .. import pretrain as P
+        return P.pretrain_load_state(self, *args, **kwargs)
 
     @classmethod
     def create_coordinate_grid(cls, grid_shape: Tuple[int, ...]) -> torch.Tensor:

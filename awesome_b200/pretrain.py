@@ -1,0 +1,266 @@
+"""The reference's per-frame / per-sequence pretrain loops as fused fits:
+
+* ``fit_frames``  -- ``PathConnectedNet._prior_based_pretrain`` (``awesome/model/path_connected_net.py:730-1007``):
+  one prior state per frame, optional warm start from the previous frame (``reuse_state``), optional prefits
+  (``learn_flow_identity`` / ``learn_convex_net``), the main Adamax + ReduceLROnPlateau fit, the "proper prior fit"
+  IoU check with retry after ``reset_parameters`` (``:964-982``), the no-foreground skip (``:848-855``).
+* ``fit_sequence`` -- ``_non_prior_based_pretrain`` (``:511-728``): ONE (x, y, t) prior for all frames, batches of
+  ``batch_size`` frames per step, ``num_epochs`` passes.
+
+Every inner loop is ``PriorFitter.run`` (one native call per step, replayed from CUDA graphs); the host only sees a
+frame once per fit, not once per step.  ``pretrain`` / ``pretrain_load_state`` glue these into the reference's
+``PretrainableModule`` protocol (``awesome/model/pretrainable_module.py:16-82``) by duck-typing the agent, dataset
+and wrapper module the reference hands in."""
+from __future__ import annotations
+
+import logging
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+from .core import GridSpecHost, iou_counts, target_counts
+from .fit import LossConfig, OptimConfig, PriorFitter
+
+
+@dataclass
+class FitSchedule:
+    """The recognised ``pretrain_args`` (``path_connected_net.py:536-560,756-786``) with the reference defaults."""
+    num_epochs: int = 2000
+    lr: float = 1e-3
+    flow_weight_decay: float = 1e-5
+    reuse_state: bool = True
+    reuse_state_epochs: int = 200
+    batch_size: int = 1
+    prefit_flow_net_identity: bool = False
+    prefit_flow_net_identity_lr: float = 1e-2
+    prefit_flow_net_identity_weight_decay: float = 1e-5
+    prefit_flow_net_identity_num_epochs: int = 100
+    prefit_convex_net: bool = False
+    prefit_convex_net_lr: float = 1e-3
+    prefit_convex_net_weight_decay: float = 0.0
+    prefit_convex_net_num_epochs: int = 200
+    proper_prior_fit_threshold: float = 0.5
+    proper_prior_fit_retrys: int = 1
+    criterion: LossConfig = field(default_factory=lambda: LossConfig("mse"))
+    optimizer: str = "adamax"            # the pretrain loops use Adamax + plateau(200, 0.5) (:929-933)
+    plateau: bool = True
+    steps_per_graph: int = 50
+
+    @classmethod
+    def from_pretrain_args(cls, kwargs: Dict[str, Any]) -> "FitSchedule":
+        known = {f for f in cls.__dataclass_fields__}
+        vals = {k: v for k, v in kwargs.items() if k in known and k != "criterion"}
+        s = cls(**vals)
+        crit = kwargs.get("criterion")
+        if crit is not None:
+            s.criterion = crit if isinstance(crit, LossConfig) else LossConfig.from_reference(crit)
+        return s
+
+    def optim(self, has_flow: bool) -> OptimConfig:
+        wd = [self.flow_weight_decay if has_flow else 0.0, 0.0, 0.0, 0.0]
+        return OptimConfig(self.optimizer, lr=self.lr, weight_decay=wd, plateau=self.plateau, patience=200, factor=0.5)
+
+
+@dataclass
+class FrameResult:
+    index: int
+    skipped: bool = False
+    iou: float = -1.0
+    proper_fit: bool = False
+    retries: int = 0
+    steps: int = 0
+    final_loss: float = float("nan")
+    state: Optional[torch.Tensor] = None      # the fitted arena (device), one row
+
+
+def _as_grid(grid, device) -> GridSpecHost:
+    if isinstance(grid, GridSpecHost):
+        return grid
+    g = grid.to(device)
+    return GridSpecHost.from_tensor(g)
+
+
+def mask_iou(pred_prob: torch.Tensor, target_prob: torch.Tensor) -> float:
+    """``MIOU(average="binary", invert=True)`` on masks thresholded at 0.5 (``awesome/measures/miou.py:29-48``):
+    Jaccard of the foreground (value <= 0.5); 0 when the target has no foreground.  Exact integer counts on device."""
+    c = iou_counts(pred_prob, target_prob, pred_is_logit=False).cpu()[0]
+    inter, pf, tf = int(c[0]), int(c[1]), int(c[2])
+    if tf == 0:
+        return 0.0
+    return inter / float(pf + tf - inter)
+
+
+def fit_frames(model, grids: Sequence, unaries: Sequence[torch.Tensor], schedule: Optional[FitSchedule] = None,
+               on_frame: Optional[Callable[[FrameResult], None]] = None, frame_indices: Optional[Sequence[int]] = None
+               ) -> List[FrameResult]:
+    """Fit ``model`` (ConvexNextNet or PathConnectedNet drop-in) to every frame in turn.  ``grids[i]`` is a
+    ``[1,C,H,W]`` tensor or ``GridSpecHost``; ``unaries[i]`` the frame's soft segmentation (any shape with H*W
+    elements; convention fg = 0, bg = 1 like the reference).  The model ends holding the last proper state."""
+    s = schedule or FitSchedule()
+    arena = model._ensure_flat()
+    dev = arena.device
+    has_flow = hasattr(model, "flow_net")
+    results: List[FrameResult] = []
+    previous: Optional[torch.Tensor] = None
+    fitter: Optional[PriorFitter] = None
+    fitter_key = None
+    for k, (grid, un) in enumerate(zip(grids, unaries)):
+        idx = frame_indices[k] if frame_indices is not None else k
+        res = FrameResult(index=idx)
+        un = un.detach().to(dev).float().reshape(1, -1)
+        spec = _as_grid(grid, dev)
+        cnt = target_counts(un, L.AWB_CLS_UNARY_LT_HALF).cpu()[0]
+        if int(cnt[0]) == 0 or int(cnt[1]) == 0:       # torch.unique(unaries >= 0.5) has one value (:848-855)
+            logging.warning("Unaries of segmentation model contain no foreground. Skipping image. %s", idx)
+            res.skipped = True
+            results.append(res)
+            if on_frame:
+                on_frame(res)
+            continue
+        warm = s.reuse_state and previous is not None
+        if warm:
+            with torch.no_grad():
+                arena.copy_(previous)
+        else:
+            if has_flow and s.prefit_flow_net_identity:
+                model.learn_flow_identity(spec.materialize(model.in_channels, dev), lr=s.prefit_flow_net_identity_lr,
+                                          weight_decay=s.prefit_flow_net_identity_weight_decay,
+                                          max_iter=s.prefit_flow_net_identity_num_epochs, use_progress_bar=False)
+            if has_flow and s.prefit_convex_net:
+                model.learn_convex_net(spec.materialize(model.in_channels, dev), un.reshape(spec.B, 1, spec.H, spec.W),
+                                       lr=s.prefit_convex_net_lr, weight_decay=s.prefit_convex_net_weight_decay,
+                                       max_iter=s.prefit_convex_net_num_epochs, use_progress_bar=False)
+        if has_flow:
+            model._maybe_actnorm_init(spec.materialize(model.in_channels, dev))
+        key = (spec.mode, spec.B, spec.H, spec.W, spec.t0, spec.t_step, id(spec.grid))
+        if fitter is None or fitter_key != key:
+            fitter = model.make_fitter(spec, un, s.criterion, s.optim(has_flow), steps_per_graph=s.steps_per_graph)
+            fitter_key = key
+        else:
+            fitter.set_target(un, s.criterion)
+        proper = False
+        while not proper and res.retries <= s.proper_prior_fit_retrys:
+            epochs = s.reuse_state_epochs if (warm and res.retries == 0) else s.num_epochs
+            fitter.reset_optimizer()                   # fresh optimizer + scheduler per attempt (:923-933)
+            hist = fitter.run(epochs)
+            fitter.raise_if_nonfinite()
+            res.steps += epochs
+            res.final_loss = float(hist[-1, 0]) if epochs > 0 else float("nan")
+            with torch.no_grad():
+                prob = torch.sigmoid(model(spec.materialize(getattr(model, "in_channels", getattr(model, "in_features", 2)), dev)))
+            res.iou = mask_iou(prob.reshape(1, -1), un)
+            proper = res.iou >= s.proper_prior_fit_threshold
+            if not proper and res.retries < s.proper_prior_fit_retrys:
+                logging.info("Prior fit not proper on image index: %s. Retrying. Metric: %s", idx, res.iou)
+                model.reset_parameters()
+                model._ensure_flat()
+                if has_flow:
+                    model._maybe_actnorm_init(spec.materialize(model.in_channels, dev))
+            res.retries += 1
+        res.retries -= 1
+        res.proper_fit = proper
+        res.state = model._ensure_flat().detach().clone()
+        if s.reuse_state and proper:
+            previous = res.state
+        results.append(res)
+        if on_frame:
+            on_frame(res)
+    return results
+
+
+def fit_sequence(model, n_frames: int, H: int, W: int, unaries: torch.Tensor, schedule: Optional[FitSchedule] = None,
+                 grid_mode: str = "linspace") -> torch.Tensor:
+    """Spatio-temporal fit (``_non_prior_based_pretrain``, ``path_connected_net.py:652-719``): one (x, y, t) prior,
+    ``num_epochs`` passes over the ``ceil(T / batch_size)`` frame batches in order.  ``unaries`` ``[T,H,W]``;
+    frame ``i`` has ``t = i / (T - 1)`` (``awesome/dataset/transformator.py:54-60``).  Returns the loss history
+    ``[num_epochs * n_batches]`` (device)."""
+    s = schedule or FitSchedule()
+    arena = model._ensure_flat()
+    dev = arena.device
+    T, bs = int(n_frames), max(1, int(s.batch_size))
+    t_step = 1.0 / (T - 1) if T > 1 else 0.0
+    un = unaries.detach().to(dev).float().reshape(T, H * W)
+    has_flow = hasattr(model, "flow_net")
+    if has_flow:
+        model._maybe_actnorm_init(GridSpecHost(grid_mode, T, H, W, t0=0.0, t_step=t_step).materialize(model.in_channels, dev))
+    fitters = []
+    for b0 in range(0, T, bs):
+        nb = min(bs, T - b0)
+        spec = GridSpecHost(grid_mode, nb, H, W, t0=b0 * t_step, t_step=t_step)
+        f = model.make_fitter(spec, un[b0:b0 + nb].reshape(1, -1), s.criterion, s.optim(has_flow), use_graph=False)
+        fitters.append(f)
+    # all batches share ONE optimizer state (the reference builds the optimizer once, outside the loops: :642-645)
+    for f in fitters[1:]:
+        f.opt_state = fitters[0].opt_state
+        if f.ws.numel() == fitters[0].ws.numel():
+            f.ws = fitters[0].ws                     # batches run one after the other: one scratch area
+    hist = []
+    for _ in range(s.num_epochs):
+        for f in fitters:
+            hist.append(f.run(1)[0, 0])
+    fitters[0].raise_if_nonfinite()
+    return torch.stack(hist) if hist else torch.empty(0, device=dev)
+
+
+# ------------------------------------------------------------------ PretrainableModule protocol (duck-typed)
+def pretrain(self, train_set, test_set=None, device=None, agent=None, use_progress_bar: bool = True,
+             do_pretrain_checkpoints: bool = False, use_pretrain_checkpoints: bool = False,
+             pretrain_checkpoint_dir: Optional[str] = None, wrapper_module=None, **kwargs) -> Any:
+    """``PathConnectedNet.pretrain`` (``path_connected_net.py:472-509``) with the reference's arguments.  The agent,
+    dataset and wrapper module are the reference's objects (this module is plugged into ``scripts/run.py``):
+    ``agent._decompose_training_item`` splits a dataset item, ``wrapper_module(...)`` with ``evaluate_prior=False``
+    yields the UNet unaries, ``wrapper_module.get_prior_args`` the coordinate grid."""
+    if wrapper_module is None:
+        raise ValueError("Wrapper model must be provided for pretraining.")
+    sched = FitSchedule.from_pretrain_args(kwargs)
+    device = torch.device(device) if device is not None else self._ensure_flat().device
+    ds = getattr(agent, "training_dataset", None)
+    cache = getattr(ds, "__prior_cache__", None)
+    per_frame = cache is not None and bool(getattr(ds, "has_prior", getattr(ds, "__has_prior__", False)))
+    from torch.utils.data import DataLoader
+    loader = DataLoader(train_set, batch_size=1, shuffle=False)
+    was_training = wrapper_module.training
+    wrapper_module.eval()
+    grids, uns, keys = [], [], []
+    try:
+        for i, item in enumerate(loader):
+            inputs, labels, indices, prior_state = agent._decompose_training_item(item)
+            dev_in = [x.to(device) if torch.is_tensor(x) else x for x in (inputs if isinstance(inputs, (list, tuple)) else [inputs])]
+            old = getattr(wrapper_module, "evaluate_prior", True)
+            wrapper_module.evaluate_prior = False
+            try:
+                with torch.no_grad():
+                    u = wrapper_module(*dev_in)
+            finally:
+                wrapper_module.evaluate_prior = old
+            pa, _ = wrapper_module.get_prior_args(dev_in[0], *dev_in[1:], segm=u[0, ...])
+            grids.append(pa[0].detach())
+            uns.append(u.detach())
+            keys.append(int(prior_state[0]) if prior_state is not None else i)
+        if per_frame:
+            def keep(res: FrameResult):
+                if not res.skipped and hasattr(cache, "store_from"):
+                    cache.store_from(self, res.index)
+                elif not res.skipped:
+                    cache[res.index] = {k: v.detach().clone() for k, v in self.state_dict().items()}
+            fit_frames(self, [g if g.dim() == 4 else g.unsqueeze(0) for g in grids], uns, sched, on_frame=keep,
+                       frame_indices=keys)
+            return cache.get_state()
+        T = len(grids)
+        H, W = grids[0].shape[-2:]
+        fit_sequence(self, T, H, W, torch.stack([u.reshape(H, W) for u in uns]), sched)
+        return {k: v.detach().cpu().clone() for k, v in self.state_dict().items()}
+    finally:
+        wrapper_module.train(was_training)
+
+
+def pretrain_load_state(self, train_set, test_set, device, agent, state, use_progress_bar: bool = True,
+                        wrapper_module=None, **kwargs):
+    """``path_connected_net.py:1010-1019``: the per-frame states go back into the dataset's prior cache."""
+    cache = getattr(getattr(agent, "training_dataset", None), "__prior_cache__", None)
+    if cache is not None and isinstance(state, dict) and "cache" in state:
+        cache.set_state(state)
+    elif isinstance(state, dict):
+        self.load_state_dict(state)

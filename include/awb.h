@@ -123,7 +123,9 @@ int awb_prior_destroy(awb_handle h);
 
 /* Number of trainable fp32 parameters per object, in state_dict order. */
 int64_t awb_prior_param_count(awb_handle h);
-/* Bytes of scratch the caller must provide for n_pixels rows (all objects). */
+/* Bytes of scratch the caller must provide for n_pixels rows (all objects).  training: 0 forward only,
+ * 1 forward + backward / any call, 2 awb_prior_fit_step only (much smaller on tensor-path handles, whose fused
+ * kernel keeps the activations on the SM). */
 int64_t awb_prior_workspace_bytes(awb_handle h, int64_t n_pixels, int32_t training);
 int64_t awb_opt_state_bytes(awb_handle h);
 
@@ -176,6 +178,9 @@ int awb_prior_enforce_convexity(awb_handle h, float* params, void* stream);
 
 /* Optimizer / plateau state (fresh optimizer per frame: path_connected_net.py:923-933). */
 int awb_opt_state_init(awb_handle h, void* opt_state, const double* lr_per_group, void* stream);
+/* Overwrite the learning rates only (torch lr schedulers mutate param_group["lr"] between steps:
+ * awesome/agent/torch_agent.py:308-325); moments, step counter and plateau state are kept. */
+int awb_opt_set_lr(awb_handle h, void* opt_state, const double* lr_per_group, void* stream);
 /* synchronises the stream and copies the scalars of object obj to the host. */
 int awb_opt_read_scalars(awb_handle h, const void* opt_state, int32_t obj, awb_opt_scalars* out,
                          void* stream);

@@ -1,0 +1,175 @@
+"""GPU tests of the host-side mirror of the reference's callers: drop-in optimizers (agent loop), the per-frame /
+per-sequence pretrain loops, the multi-object container with grouped launches, the device-resident prior cache."""
+import pytest
+import torch
+
+import __graft_entry__ as entry
+from oracle import prior_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    entry.build()
+
+
+@pytest.fixture(scope="module")
+def A():
+    import awesome_b200
+    return awesome_b200
+
+
+def blob(H, W, cx=0.5, cy=0.5, rx=0.27, ry=0.31, tau=0.08):
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, H), torch.linspace(0, 1, W), indexing="ij")
+    return torch.sigmoid((torch.sqrt(((xx - cx) / rx) ** 2 + ((yy - cy) / ry) ** 2) - 1) / tau)
+
+
+@pytest.mark.parametrize("kind", ["adam", "adamax"])
+def test_fused_optimizer_matches_torch_in_agent_loop(A, kind):
+    """optimizer_type drop-in: 3 steps of loss.backward(); optimizer.step(); enforce_convexity() on a wrapper that
+    also holds a non-prior (UNet stand-in) parameter, against torch.optim on an identical copy."""
+    torch.manual_seed(0)
+    H, W = 40, 56
+    prior = A.ConvexNextNet(n_hidden_layers=2).to(DEV)
+    ref = A.ConvexNextNet(n_hidden_layers=2).to(DEV)
+    ref.load_state_dict(prior.state_dict())
+    extra = torch.nn.Linear(4, 4).to(DEV)
+    extra_ref = torch.nn.Linear(4, 4).to(DEV)
+    extra_ref.load_state_dict(extra.state_dict())
+    cls = A.FusedAdam if kind == "adam" else A.FusedAdamax
+    tcls = torch.optim.Adam if kind == "adam" else torch.optim.Adamax
+    opt = cls([dict(params=list(prior.parameters()), weight_decay=1e-4), dict(params=list(extra.parameters()))], lr=2e-3)
+    topt = tcls([dict(params=list(ref.parameters()), weight_decay=1e-4), dict(params=list(extra_ref.parameters()))], lr=2e-3)
+    grid = O.grid_linspace(H, W)[None].to(DEV)
+    un = blob(H, W).to(DEV)
+    xin = torch.randn(8, 4, device=DEV)
+    for _ in range(3):
+        for m, e, o in ((prior, extra, opt), (ref, extra_ref, topt)):
+            o.zero_grad()
+            loss = ((torch.sigmoid(m(grid))[0, 0] - un) ** 2).mean() + e(xin).pow(2).mean()
+            loss.backward()
+            o.step()
+            if m is ref:
+                m.enforce_convexity()
+    for (k, a), b in zip(prior.state_dict().items(), ref.state_dict().values()):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7, msg=lambda s: f"{k}: {s}")
+    for a, b in zip(extra.parameters(), extra_ref.parameters()):
+        torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-8)
+    for k in O.icnn_clamp_keys(dict(prior.state_dict())):
+        assert float(prior.state_dict()[k].min()) >= 0.0
+
+
+def test_fit_frames_warm_start_chain_and_skip(A):
+    """_prior_based_pretrain semantics on a 4-frame synthetic sequence: cold first frame (num_epochs), warm
+    successors (reuse_state_epochs), a frame without foreground is skipped and keeps the chain, IoU check passes."""
+    H, W = 60, 80
+    torch.manual_seed(1)
+    m = A.ConvexNextNet(n_hidden_layers=2, precision="f16").to(DEV)
+    frames = [blob(H, W, cx=0.45 + 0.03 * i, cy=0.5) for i in range(4)]
+    frames[2] = torch.ones(H, W)                      # background only -> skipped
+    grid = A.GridSpecHost("linspace", 1, H, W)
+    sched = A.FitSchedule(num_epochs=600, reuse_state_epochs=150, optimizer="adam", plateau=False, lr=2e-3,
+                          proper_prior_fit_threshold=0.5)
+    seen = []
+    res = A.fit_frames(m, [grid] * 4, frames, sched, on_frame=lambda r: seen.append(r.index))
+    assert seen == [0, 1, 2, 3]
+    assert [r.skipped for r in res] == [False, False, True, False]
+    assert [r.steps for r in res] == [600, 150, 0, 150]
+    for r in (res[0], res[1], res[3]):
+        assert r.proper_fit and r.iou > 0.9, (r.index, r.iou)
+        assert r.state is not None and r.state.numel() == m._arena.numel()
+    # the warm fits continue from the previous frame: their first losses are far below a cold start's
+    assert res[1].final_loss < 0.02 and res[3].final_loss < 0.02
+    # the stored per-frame state reproduces the frame's mask
+    m._arena.copy_(res[1].state)
+    prob = torch.sigmoid(m(grid.materialize(2, DEV)))
+    assert A.mask_iou(prob.reshape(1, -1), frames[1].to(DEV).reshape(1, -1)) == pytest.approx(res[1].iou)
+
+
+def test_fit_frames_retry_after_bad_fit(A):
+    """proper_prior_fit_retrys: an impossible threshold forces the reset_parameters() retry path exactly once."""
+    H, W = 32, 48
+    torch.manual_seed(2)
+    m = A.ConvexNextNet(n_hidden_layers=1).to(DEV)
+    sched = A.FitSchedule(num_epochs=20, optimizer="adam", plateau=False, proper_prior_fit_threshold=1.1,
+                          proper_prior_fit_retrys=1, reuse_state=False)
+    res = A.fit_frames(m, [A.GridSpecHost("linspace", 1, H, W)], [blob(H, W)], sched)
+    assert res[0].retries == 1 and res[0].steps == 40 and not res[0].proper_fit
+
+
+def test_fit_sequence_spatio_temporal(A):
+    """_non_prior_based_pretrain: one (x,y,t) flow prior over T frames, 2 frames per step, shared optimizer state."""
+    T, H, W = 6, 40, 48
+    torch.manual_seed(3)
+    m = A.real_nvp_path_connected_net(channels=3, hidden_units=32, flow_n_flows=6, flow_output_fn="tanh",
+                                      convex_net_hidden_layers=2, precision="f16").to(DEV)
+    un = torch.stack([blob(H, W, cx=0.4 + 0.04 * i) for i in range(T)])
+    sched = A.FitSchedule(num_epochs=60, batch_size=2, lr=2e-3)
+    hist = A.fit_sequence(m, T, H, W, un, sched)
+    assert hist.numel() == 60 * 3 and bool(torch.isfinite(hist).all())
+    assert float(hist[-3:].mean()) < 0.5 * float(hist[:3].mean())
+    # t really enters: the fitted masks follow the moving blob
+    grid = A.GridSpecHost("linspace", T, H, W, t0=0.0, t_step=1.0 / (T - 1)).materialize(3, DEV)
+    prob = torch.sigmoid(m(grid))[:, 0]
+    cx = [float((1 - p).mul(torch.linspace(0, 1, W, device=DEV)).sum() / (1 - p).sum()) for p in prob]
+    assert cx[-1] > cx[0] + 0.05, cx
+
+
+@pytest.mark.parametrize("precision", ["fp32", "f16"])
+def test_multi_object_grouped_fit_equals_independent_fits(A, precision):
+    """Config 4 semantics: O priors fitted jointly in one grouped launch == O independent single-object fits
+    (bit for bit: the object index is a grid dimension, the arithmetic per object is unchanged)."""
+    O_, H, W = 3, 48, 64
+    torch.manual_seed(4)
+    multi = A.NumberBasedMultiPriorModule(prior_type=A.ConvexNextNet,
+                                          prior_args=dict(n_hidden_layers=2, precision=precision), min_priors=O_).to(DEV)
+    singles = []
+    for k in range(O_):
+        s = A.ConvexNextNet(n_hidden_layers=2, precision=precision).to(DEV)
+        s.load_state_dict(multi.priors[k].state_dict())
+        singles.append(s)
+    un = torch.stack([blob(H, W, cx=0.3 + 0.2 * k, rx=0.15, ry=0.2) for k in range(O_)]).to(DEV)
+    grid = A.GridSpecHost("linspace", 1, H, W)
+    f = multi.make_fitter(grid, un, A.LossConfig("mse"), A.OptimConfig("adam", lr=1e-3), use_graph=False)
+    hist = f.run(5)
+    for k in range(O_):
+        fk = singles[k].make_fitter(grid, un[k], A.LossConfig("mse"), A.OptimConfig("adam", lr=1e-3), use_graph=False)
+        hk = fk.run(5)
+        assert torch.equal(hist[:, k], hk[:, 0]), (k, hist[:, k], hk[:, 0])
+        for (name, a), b in zip(multi.priors[k].state_dict().items(), singles[k].state_dict().values()):
+            assert torch.equal(a, b), f"object {k} {name}"
+    out = multi(grid.materialize(2, DEV), num_priors=O_)
+    assert out.shape == (1, O_, 1, H, W)
+    torch.testing.assert_close(out[:, 1], singles[1](grid.materialize(2, DEV)))
+    assert list(multi.state_dict().keys())[0] == "priors.0.input.weight"
+
+
+def test_device_prior_cache_and_manager(A):
+    """Per-frame weight swap as row copies; on-disk format of the reference's PriorCache."""
+    import io
+    torch.manual_seed(5)
+    m = A.ConvexNextNet(n_hidden_layers=2).to(DEV)
+    cache = A.DevicePriorCache(A.ConvexNextNet, dict(n_hidden_layers=2), capacity=2)
+    H, W = 24, 32
+    grid = A.GridSpecHost("linspace", 1, H, W)
+    states = {}
+    for key in (7, 3, 11):                # more frames than the initial capacity
+        with A.PriorManager(m, prior_state=(key, None), prior_cache=cache, training=True):
+            f = m.make_fitter(grid, blob(H, W, cx=0.3 + 0.02 * key).to(DEV), A.LossConfig("mse"), A.OptimConfig("adam"),
+                              use_graph=False)
+            f.run(3)
+            states[key] = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    for key in (3, 7, 11):
+        with A.PriorManager(m, prior_state=(key, None), prior_cache=cache):
+            for k, v in m.state_dict().items():
+                assert torch.equal(v, states[key][k]), (key, k)
+    buf = io.BytesIO()
+    cache.save(buf)
+    buf.seek(0)
+    st = torch.load(buf, map_location="cpu", weights_only=False)
+    assert set(st) == {"model_type", "model_args", "store_device", "cache"} and set(st["cache"]) == {"7", "3", "11"}
+    assert st["model_type"].endswith("ConvexNextNet")
+    for k, v in states[11].items():
+        assert torch.equal(st["cache"]["11"][k], v.cpu())

@@ -76,3 +76,55 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dp, fn)).read()
                 for pat in ("import oracle", "from oracle", "oracle.", "oracle/"):
                     assert pat not in src, f"{fn} reaches into the oracle ({pat!r})"
+
+
+def test_device_prior_cache_format_cpu():
+    """DevicePriorCache keeps the reference PriorCache on-disk format (model_type, model_args, store_device, cache)."""
+    import io
+    import torch
+    import awesome_b200 as A
+    torch.manual_seed(0)
+    c = A.DevicePriorCache(A.ConvexNextNet, dict(n_hidden_layers=2), capacity=1)
+    m = A.ConvexNextNet(n_hidden_layers=2)
+    c[3] = m.state_dict()
+    c[5] = c.generate_prior(5)
+    assert 3 in c and 5 in c and 4 not in c and len(c) == 2
+    for k, v in m.state_dict().items():
+        assert torch.equal(c[3][k], v)
+    buf = io.BytesIO()
+    c.save(buf)
+    buf.seek(0)
+    c2 = A.DevicePriorCache.load(buf)
+    assert c2.model_type is A.ConvexNextNet and c2.model_args == dict(n_hidden_layers=2)
+    m2 = A.ConvexNextNet(n_hidden_layers=2)
+    c2.load_into(m2, 3)
+    for a, b in zip(m2.state_dict().values(), m.state_dict().values()):
+        assert torch.equal(a, b)
+
+
+def test_fused_optimizer_delegates_non_arena_params_cpu():
+    """Parameters outside a prior arena follow torch.optim exactly (the UNet side of a joint WrapperModule)."""
+    import torch
+    import awesome_b200 as A
+    torch.manual_seed(0)
+    a, b = torch.nn.Linear(5, 3), torch.nn.Linear(5, 3)
+    b.load_state_dict(a.state_dict())
+    oa, ob = A.FusedAdamax(a.parameters(), lr=1e-2, weight_decay=1e-3), torch.optim.Adamax(b.parameters(), lr=1e-2, weight_decay=1e-3)
+    x = torch.randn(7, 5)
+    for _ in range(3):
+        for m, o in ((a, oa), (b, ob)):
+            o.zero_grad()
+            m(x).pow(2).sum().backward()
+            o.step()
+    for p, q in zip(a.parameters(), b.parameters()):
+        assert torch.equal(p, q)
+
+
+def test_multi_prior_container_keys_and_resize_cpu():
+    import awesome_b200 as A
+    m = A.NumberBasedMultiPriorModule(prior_type=A.ConvexNextNet, prior_args=dict(n_hidden_layers=1), min_priors=2)
+    sd = m.state_dict()
+    assert "priors.1.out.skp.weight" in sd and len({k.split(".")[1] for k in sd}) == 2
+    big = A.NumberBasedMultiPriorModule(prior_type=A.ConvexNextNet, prior_args=dict(n_hidden_layers=1), min_priors=4)
+    m.load_state_dict(big.state_dict())          # resizes like abstract_multi_prior_module.py:91-96
+    assert len(m.priors) == 4
