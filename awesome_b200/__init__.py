@@ -10,6 +10,8 @@ from .fit import FlowIdentityFitter, LossConfig, OptimConfig, PriorFitter  # noq
 from .optim import FusedAdam, FusedAdamax  # noqa: F401
 from .pretrain import FitSchedule, FrameResult, fit_frames, fit_sequence, mask_iou  # noqa: F401
 from .prior_cache import DevicePriorCache, PriorManager  # noqa: F401
+from .joint import GradBucket, JointTrainer  # noqa: F401
+from . import measures  # noqa: F401
 from .model import (ConvexNet, ConvexNextNet, MinMax, NormNet, NumberBasedMultiPriorModule, PathConnectedNet,  # noqa: F401
                     PixelizeNet, get_norm, init_realnvp, real_nvp_path_connected_net)
 

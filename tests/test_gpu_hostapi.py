@@ -173,3 +173,52 @@ def test_device_prior_cache_and_manager(A):
     assert st["model_type"].endswith("ConvexNextNet")
     for k, v in states[11].items():
         assert torch.equal(st["cache"]["11"][k], v.cpu())
+
+
+def test_joint_trainer_matches_manual_agent_step(A):
+    """Config 5 on one rank: JointTrainer(FusedAdam, grads as bucket views) == the reference's step written out by hand
+    (zero_grad; cat(sigmoid(seg), sigmoid(prior)); FBMSJointLoss; backward; Adam.step; enforce_convexity)."""
+    from awesome_b200 import measures as M
+    torch.manual_seed(6)
+    B, H, W = 2, 32, 40
+
+    def nets():
+        torch.manual_seed(6)
+        seg = torch.nn.Sequential(torch.nn.Conv2d(4, 8, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(8, 1, 3, padding=1)).to(DEV)
+        pri = A.real_nvp_path_connected_net(channels=3, hidden_units=32, flow_n_flows=6, flow_output_fn="tanh",
+                                            convex_net_hidden_layers=2).to(DEV)
+        return seg, pri
+
+    g = torch.Generator().manual_seed(0)
+    img = torch.randn(B, 4, H, W, generator=g).to(DEV)
+    grid = A.GridSpecHost("linspace", B, H, W, t0=0.2, t_step=0.1).materialize(3, DEV)
+    lab = torch.full((B, 1, H, W), 2.0)
+    lab[torch.rand(B, 1, H, W, generator=g) < 0.15] = 0.0
+    lab[torch.rand(B, 1, H, W, generator=g) < 0.3] = 1.0
+    lab = lab.to(DEV)
+
+    seg, pri = nets()
+    pri(grid)                                            # ActNorm data-dependent init happens on the first forward
+    tr = A.JointTrainer(seg, pri, M.FBMSJointLoss(), optimizer_args=dict(lr=1e-3))
+    l_ours = [float(tr.step(img, grid, lab)) for _ in range(3)]
+
+    seg2, pri2 = nets()
+    pri2(grid)
+    opt = torch.optim.Adam(list(seg2.parameters()) + list(pri2.parameters()), lr=1e-3)
+    crit = M.FBMSJointLoss()
+    l_ref = []
+    for _ in range(3):
+        opt.zero_grad()
+        out = torch.cat([torch.sigmoid(seg2(img)), torch.sigmoid(pri2(grid))], 1)
+        loss = crit(out, lab)
+        loss.backward()
+        opt.step()
+        pri2.enforce_convexity()
+        l_ref.append(float(loss))
+    torch.testing.assert_close(torch.tensor(l_ours), torch.tensor(l_ref), rtol=1e-5, atol=1e-7)
+    for (k, a), b in zip(pri.state_dict().items(), pri2.state_dict().values()):
+        if a.dtype.is_floating_point:
+            torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-6, msg=lambda s: f"{k}: {s}")
+    for a, b in zip(seg.parameters(), seg2.parameters()):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7)
+    assert tr.bucket.nbytes == 4 * sum(p.numel() for p in list(seg.parameters()) + list(pri.parameters()))
