@@ -13,6 +13,6 @@ from .prior_cache import DevicePriorCache, PriorManager  # noqa: F401
 from .joint import GradBucket, JointTrainer  # noqa: F401
 from . import measures  # noqa: F401
 from .model import (ConvexNet, ConvexNextNet, MinMax, NormNet, NumberBasedMultiPriorModule, PathConnectedNet,  # noqa: F401
-                    PixelizeNet, get_norm, init_realnvp, real_nvp_path_connected_net)
+                    PixelizeNet, StarFitter, StarShapedNet, get_norm, init_realnvp, real_nvp_path_connected_net)
 
 __version__ = "0.1.0"

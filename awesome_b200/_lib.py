@@ -12,7 +12,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libawb.so")
 
-AWB_KIND_ICNN, AWB_KIND_FLOW_ICNN = 0, 1
+AWB_KIND_ICNN, AWB_KIND_FLOW_ICNN, AWB_KIND_STAR = 0, 1, 2
 AWB_PREC_FP32, AWB_PREC_F16 = 0, 1
 AWB_GRID_EXPLICIT, AWB_GRID_LINSPACE, AWB_GRID_INDEX = 0, 1, 2
 AWB_LOSS_SE_SIGMOID, AWB_LOSS_BCE_LOGITS = 0, 1
@@ -82,6 +82,10 @@ SYMBOLS = [
     ("awb_optim_step", C.c_int, [_P, _P, _P, _P, C.POINTER(OptHyper), _P]),
     ("awb_prior_enforce_convexity", C.c_int, [_P, _P, _P]),
     ("awb_opt_state_init", C.c_int, [_P, _P, C.POINTER(C.c_double), _P]),
+    ("awb_star_forward", C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
+    ("awb_star_workspace_bytes", C.c_int64, [_P, C.c_int64]),
+    ("awb_star_fit_step", C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.POINTER(LossSpec), C.POINTER(OptHyper), _P, _P,
+                                    C.c_size_t, _P]),
     ("awb_opt_set_lr", C.c_int, [_P, _P, C.POINTER(C.c_double), _P]),
     ("awb_opt_read_scalars", C.c_int, [_P, _P, C.c_int32, C.POINTER(OptScalars), _P]),
     ("awb_prior_actnorm_init", C.c_int, [_P, _P, C.POINTER(GridSpec), _P, C.c_size_t, _P]),

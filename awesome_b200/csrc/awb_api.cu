@@ -91,7 +91,11 @@ const char* awb_last_error(void) { return g_err; }
 
 int awb_prior_create(const awb_desc* d, awb_handle* out) {
   if (!d || !out) { set_error("null argument"); return AWB_ERR_INVALID; }
-  if (d->kind != AWB_KIND_ICNN && d->kind != AWB_KIND_FLOW_ICNN) { set_error("unknown prior kind %d", d->kind); return AWB_ERR_INVALID; }
+  if (d->kind != AWB_KIND_ICNN && d->kind != AWB_KIND_FLOW_ICNN && d->kind != AWB_KIND_STAR) { set_error("unknown prior kind %d", d->kind); return AWB_ERR_INVALID; }
+  if (d->kind == AWB_KIND_STAR && (d->C != 2 || d->h > 160 || d->n_objects != 1 || d->precision != AWB_PREC_FP32)) {
+    set_error("star prior: C = 2, n_hidden <= 160, one object, fp32");
+    return AWB_ERR_UNSUPPORTED;
+  }
   if (d->C < 2 || d->C > 3) { set_error("C must be 2 or 3, got %d", d->C); return AWB_ERR_UNSUPPORTED; }
   if (d->h < 8 || d->h > 256) { set_error("h must be in [8,256], got %d", d->h); return AWB_ERR_UNSUPPORTED; }
   if (d->L < 0 || d->L > 8) { set_error("L must be in [0,8], got %d", d->L); return AWB_ERR_UNSUPPORTED; }
@@ -103,8 +107,14 @@ int awb_prior_create(const awb_desc* d, awb_handle* out) {
   if (d->precision != AWB_PREC_FP32 && d->precision != AWB_PREC_F16) { set_error("unknown precision %d", d->precision); return AWB_ERR_INVALID; }
   awb_prior* h = new awb_prior();
   h->desc = *d;
-  if (d->kind == AWB_KIND_ICNN) { h->desc.F = 0; h->desc.m = 0; }
+  if (d->kind == AWB_KIND_ICNN || d->kind == AWB_KIND_STAR) { h->desc.F = 0; h->desc.m = 0; }
+  if (d->kind == AWB_KIND_STAR) h->desc.L = 0;
   h->lay = make_layout(h->desc);
+  if (d->kind == AWB_KIND_STAR) {   // plain state_dict-order arena, no augmented space
+    const int64_t hh = d->h;
+    h->lay.P = hh * hh + 8 * hh + 4;
+    h->lay.P_icnn = 0; h->lay.off_flow = 0; h->lay.P_flow = 0; h->lay.off_lin = h->lay.P;
+  }
   h->fc_set = false;
   h->d_map = nullptr; h->d_clamp = nullptr; h->d_group = nullptr; h->d_tcmap = nullptr; h->d_imap = nullptr; h->d_aug2img = nullptr;
   const Layout& L = h->lay;
@@ -113,6 +123,7 @@ int awb_prior_create(const awb_desc* d, awb_handle* out) {
   std::vector<uint8_t> clamp(L.P, 0), group(L.P, 1);
   int64_t i = 0;
   const int hh = L.h, C = L.C, ld = L.ld;
+  if (d->kind != AWB_KIND_STAR) {
   for (int j = 0; j < hh; j++) for (int c = 0; c < C; c++) map[i++] = (int32_t)(L.aug_in + j * 4 + c);  // input.weight
   for (int j = 0; j < hh; j++) map[i++] = (int32_t)(L.aug_in + j * 4 + 3);                               // input.bias
   for (int l = 0; l < L.L; l++) {
@@ -124,6 +135,13 @@ int awb_prior_create(const awb_desc* d, awb_handle* out) {
   for (int k = 0; k < hh; k++) { clamp[L.off_icnn + i] = 1; map[i++] = (int32_t)(L.aug_out + k); }       // out.ln.weight
   map[i++] = (int32_t)(L.aug_out + hh + C);                                                             // out.ln.bias
   for (int c = 0; c < C; c++) map[i++] = (int32_t)(L.aug_out + hh + c);                                  // out.skp.weight
+  }
+  if (d->kind == AWB_KIND_STAR) {
+    i = 0;
+    group[0] = 2; group[1] = 2;                                         // offset: its own optimizer group
+    const int64_t o_W2r = 2 + 3 * (int64_t)hh + (int64_t)hh * hh + hh + hh + 1 + hh + hh;
+    for (int k = 0; k < hh; k++) clamp[o_W2r + k] = 1;                  // W2_r.weight >= 0 (cell 3)
+  }
   if (i != L.P_icnn) { set_error("internal: layout mismatch"); delete h; return AWB_ERR_INVALID; }
   for (int64_t k = L.off_flow; k < L.off_flow + L.P_flow; k++) group[k] = 0;
   for (int64_t k = L.off_lin; k < L.P; k++) group[k] = 2;
@@ -146,7 +164,7 @@ int awb_prior_create(const awb_desc* d, awb_handle* out) {
     delete h;
     return cuda_fail(e, "awb_prior_create");
   }
-  if (tc_supported(h)) {
+  if (d->kind != AWB_KIND_STAR && tc_supported(h)) {
     std::vector<int32_t> tmap(tc_map_elems(L.L)), a2i(L.G);
     tc_build_map_host(L, tmap.data());
     tc_build_aug2img_host(L, a2i.data());
@@ -314,6 +332,35 @@ int awb_prior_enforce_convexity(awb_handle h, float* params, void* stream) {
 int awb_opt_state_init(awb_handle h, void* opt_state, const double* lr, void* stream) {
   if (!h || !opt_state || !lr) { set_error("null argument"); return AWB_ERR_INVALID; }
   return opt_state_init(h, opt_state, lr, (cudaStream_t)stream);
+}
+
+int awb_star_forward(awb_handle h, const float* params, const float* x, int64_t n, float* logits, void* stream) {
+  if (!h || !params || !x || !logits || n < 1) { set_error("bad argument"); return AWB_ERR_INVALID; }
+  if (h->desc.kind != AWB_KIND_STAR) { set_error("not a star prior"); return AWB_ERR_INVALID; }
+  return star_run(h, params, x, nullptr, n, nullptr, logits, nullptr, nullptr, false, nullptr, (cudaStream_t)stream);
+}
+
+int64_t awb_star_workspace_bytes(awb_handle h, int64_t n) {
+  if (!h || n < 1 || h->desc.kind != AWB_KIND_STAR) return -1;
+  const int S = star_n_ctas(n);
+  return round_up(4 * (int64_t)S * h->lay.P, 256) + round_up(4 * (int64_t)S, 256);
+}
+
+int awb_star_fit_step(awb_handle h, float* params, void* opt_state, const float* x, const float* target, int64_t n,
+                      const awb_loss_spec* loss, const awb_opt_hyper* hy, float* loss_out, void* ws, size_t ws_bytes,
+                      void* stream) {
+  if (!h || !params || !opt_state || !x || !target || !loss || !hy || !ws || n < 1) { set_error("bad argument"); return AWB_ERR_INVALID; }
+  if (h->desc.kind != AWB_KIND_STAR) { set_error("not a star prior"); return AWB_ERR_INVALID; }
+  const int64_t need = awb_star_workspace_bytes(h, n);
+  if ((int64_t)ws_bytes < need) { set_error("workspace too small: %lld < %lld", (long long)ws_bytes, (long long)need); return AWB_ERR_WORKSPACE; }
+  const int S = star_n_ctas(n);
+  float* part = (float*)ws;
+  float* lossp = (float*)((char*)ws + round_up(4 * (int64_t)S * h->lay.P, 256));
+  int nc = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = star_run(h, params, x, target, n, loss, nullptr, part, lossp, true, &nc, st);
+  if (rc) return rc;
+  return reduce_opt_plain(h, params, opt_state, hy, loss_out, part, nc, lossp, st);
 }
 
 int awb_opt_set_lr(awb_handle h, void* opt_state, const double* lr, void* stream) {

@@ -44,6 +44,8 @@ struct OptScal {  // per object, device resident
   int32_t pad;
   float last_loss;
   float pad2;
+  int32_t group_start[AWB_MAX_GROUPS];   // optimizer step at which a group last was inactive (torch keeps a step
+                                         // counter per parameter: a group that joins late starts its bias correction at 1)
 };
 
 struct FlowConsts {
@@ -135,6 +137,13 @@ int simt_dgrid(const awb_prior* h, const awb_grid_spec* g, float* dgrid, const W
 int optim_step(const awb_prior* h, float* params, const float* grads, void* opt_state,
                const awb_opt_hyper* hy, cudaStream_t st);
 int clamp_only(const awb_prior* h, float* params, cudaStream_t st);
+// reduce [S][P] plain (state_dict order) gradient partials + [S] loss partials, then the optimizer step
+int reduce_opt_plain(const awb_prior* h, float* params, void* opt_state, const awb_opt_hyper* hy, float* loss_out,
+                     const float* partials, int S, const float* lossp, cudaStream_t st);
+// ---- star-shape prior, implemented in awb_star.cu
+int star_n_ctas(int64_t n);
+int star_run(const awb_prior* h, const float* params, const float* x, const float* target, int64_t n,
+             const awb_loss_spec* loss, float* logits, float* part, float* lossp, bool fit, int* n_ctas, cudaStream_t st);
 int opt_state_init(const awb_prior* h, void* opt_state, const double* lr, cudaStream_t st);
 int opt_set_lr(const awb_prior* h, void* opt_state, const double* lr, cudaStream_t st);
 

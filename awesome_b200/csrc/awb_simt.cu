@@ -454,21 +454,23 @@ struct OptP {
 __global__ void __launch_bounds__(256) k_reduce_opt(OptP a, int n_groups, int use_loss) {
   __shared__ float s_loss;
   __shared__ float s_part[8][32];
-  __shared__ float s_step_size[AWB_MAX_GROUPS], s_bc2s;
+  __shared__ float s_step_size[AWB_MAX_GROUPS], s_bc2s[AWB_MAX_GROUPS];
   const int o = blockIdx.y;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x >= 32 && threadIdx.x < 32 + AWB_MAX_GROUPS) {   // bias corrections, once per block
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + AWB_MAX_GROUPS) {   // bias corrections, once per block and group
     const int g = threadIdx.x - 32;
-    const int step1 = a.scal[o].step + 1;
+    int step1 = a.scal[o].step + 1 - a.scal[o].group_start[g];
+    if (step1 < 1) step1 = 1;
     const double bc1 = 1.0 - pow((double)a.hy.beta1, (double)step1);
     s_step_size[g] = (float)(a.scal[o].lr[g] / bc1);
-    if (g == 0) s_bc2s = (float)sqrt(1.0 - pow((double)a.hy.beta2, (double)step1));
+    s_bc2s[g] = (float)sqrt(1.0 - pow((double)a.hy.beta2, (double)step1));
   }
   if (a.lossp) {
     if (w == 0) {
       // fixed-order loss sum: lane-strided then butterfly
       float l = 0.f;
-      for (int s = lane; s < a.S; s += 32) l += a.lossp[s * a.O + o];
+      const int SL = a.S > 0 ? a.S : a.SF;
+      for (int s = lane; s < SL; s += 32) l += a.lossp[s * a.O + o];
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
       if (lane == 0) s_loss = l;
@@ -506,7 +508,7 @@ __global__ void __launch_bounds__(256) k_reduce_opt(OptP a, int n_groups, int us
     const int grp = a.group[i];
     const int64_t gi = (int64_t)o * a.P + i;
     float p = a.params[gi], m = a.m[gi], v = a.v[gi];
-    opt_update(a.hy.kind, p, g, m, v, s_step_size[grp], s_bc2s, a.hy.beta1, a.hy.beta2, a.hy.eps,
+    opt_update(a.hy.kind, p, g, m, v, s_step_size[grp], s_bc2s[grp], a.hy.beta1, a.hy.beta2, a.hy.eps,
                a.hy.weight_decay[grp]);
     if (a.clamp[i]) p = fmaxf(p, 0.f);                     // enforce_convexity
     a.params[gi] = p; a.m[gi] = m; a.v[gi] = v;
@@ -525,6 +527,9 @@ __global__ void __launch_bounds__(256) k_reduce_opt(OptP a, int n_groups, int us
       } else {
         // step counter + ReduceLROnPlateau.step(loss) (torch/optim/lr_scheduler.py)
         s.step += 1;
+        if (a.hy.active_groups)
+          for (int g = 0; g < AWB_MAX_GROUPS; g++)
+            if (!((a.hy.active_groups >> g) & 1)) s.group_start[g] = s.step;
         if (a.hy.plateau_enabled && use_loss) {
           const double cur = (double)s_loss;
           if (cur < s.best * (1.0 - (double)a.hy.threshold)) { s.best = cur; s.num_bad = 0; }
@@ -688,6 +693,7 @@ __global__ void k_opt_init(OptScal* scal, double l0, double l1, double l2, doubl
   OptScal s;
   s.lr[0] = l0; s.lr[1] = l1; s.lr[2] = l2; s.lr[3] = l3;
   s.best = INFINITY; s.step = 0; s.num_bad = 0; s.nonfinite = 0; s.pad = 0; s.last_loss = 0.f; s.pad2 = 0.f;
+  for (int g = 0; g < AWB_MAX_GROUPS; g++) s.group_start[g] = 0;
   scal[o] = s;
 }
 
@@ -868,6 +874,23 @@ int simt_reduce_opt(const awb_prior* h, float* params, void* opt_state, const aw
   } else {
     AWB_LAUNCH(PK_OPT, st, k_reduce_opt<<<dim3((unsigned)((L.P + 31) / 32), O), 256, 0, st>>>(a, n_groups_of(h), 1));
   }
+  AWB_CUDA(cudaGetLastError());
+  return AWB_OK;
+}
+
+int reduce_opt_plain(const awb_prior* h, float* params, void* opt_state, const awb_opt_hyper* hy, float* loss_out,
+                     const float* partials, int S, const float* lossp, cudaStream_t st) {
+  const Layout& L = h->lay;
+  OptP a = {};
+  a.params = params;
+  opt_ptrs(h, opt_state, &a.m, &a.v, &a.scal);
+  a.part = nullptr; a.sSplit = 0; a.S = 0;
+  a.fpart = partials; a.PF = L.P; a.sFSplit = L.P; a.SF = S;
+  a.lossp = lossp; a.grads = nullptr;
+  a.map = nullptr; a.clamp = h->d_clamp; a.group = h->d_group;
+  a.P = L.P; a.off_icnn = 0; a.P_icnn = 0; a.off_flow = 0; a.G = 0;
+  a.O = 1; a.hy = *hy; a.loss_out = loss_out;
+  AWB_LAUNCH(PK_OPT, st, k_reduce_opt<<<dim3((unsigned)((L.P + 31) / 32), 1), 256, 0, st>>>(a, AWB_MAX_GROUPS, 1));
   AWB_CUDA(cudaGetLastError());
   return AWB_OK;
 }

@@ -39,6 +39,7 @@ extern "C" {
 /* prior kinds */
 #define AWB_KIND_ICNN 0      /* ConvexNextNet / ConvexNet: awesome/model/convex_net.py:177-220 */
 #define AWB_KIND_FLOW_ICNN 1 /* PathConnectedNet(RealNVP o ConvexNextNet): awesome/model/path_connected_net.py:53-85 */
+#define AWB_KIND_STAR 2      /* star-shape prior myNet(h): notebooks/icml_teaser_code/star_shaped/star.ipynb cell 2 */
 
 /* arithmetic of the hidden-layer contractions */
 #define AWB_PREC_FP32 0 /* CUDA-core fp32, bit-level comparable with the reference */
@@ -189,6 +190,18 @@ int awb_opt_read_scalars(awb_handle h, const void* opt_state, int32_t obj, awb_o
  * ActNorm from the pixel statistics of this grid, flow by flow. */
 int awb_prior_actnorm_init(awb_handle h, float* params, const awb_grid_spec* grid, void* workspace,
                            size_t workspace_bytes, void* stream);
+
+/* Star-shape prior (AWB_KIND_STAR; desc.h = n_hidden <= 160, desc.C = 2).  Parameters in state_dict order of the
+ * notebook class: offset[1,2], W0.{weight[h,2],bias}, W1.{weight[h,h],bias}, W2.{weight[1,h],bias},
+ * W1_r.{weight[h,1],bias}, W2_r.{weight[1,h],bias}.  x: device [n][2] sample points, logits: device [n]. */
+int awb_star_forward(awb_handle h, const float* params, const float* x, int64_t n, float* logits, void* stream);
+int64_t awb_star_workspace_bytes(awb_handle h, int64_t n);
+/* One step of the notebook's training loop (cell 3): y = net(x); loss = sum_n coef(t_n) * l(y_n, t_n) (MSE on the
+ * sigmoid with coef = 1/n in the notebook); backward; Adam/Adamax; W2_r.weight <- relu(W2_r.weight).  Optimizer
+ * groups: 1 = network weights, 2 = offset (frozen until hyper->active_groups includes bit 2, cell 3 "epoch == 1000"). */
+int awb_star_fit_step(awb_handle h, float* params, void* opt_state, const float* x, const float* target, int64_t n,
+                      const awb_loss_spec* loss, const awb_opt_hyper* hyper, float* loss_out, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 /* counts[O][4] (int64 device): {fg&fg, pred_fg, target_fg, n} for masks thresholded at 0.5 with
  * fg = value < 0.5 (MIOU(average="binary", invert=True): awesome/measures/miou.py:29-48;
