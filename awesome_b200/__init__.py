@@ -12,7 +12,7 @@ from .pretrain import FitSchedule, FrameResult, fit_frames, fit_sequence, mask_i
 from .prior_cache import DevicePriorCache, PriorManager  # noqa: F401
 from .joint import GradBucket, JointTrainer  # noqa: F401
 from . import measures  # noqa: F401
-from .model import (ConvexNet, ConvexNextNet, MinMax, NormNet, NumberBasedMultiPriorModule, PathConnectedNet,  # noqa: F401
+from .model import (ConvexDiffeomorphismNet, ConvexNet, ConvexNextNet, MinMax, NormNet, NumberBasedMultiPriorModule, PathConnectedNet,  # noqa: F401
                     PixelizeNet, StarFitter, StarShapedNet, get_norm, init_realnvp, real_nvp_path_connected_net)
 
 __version__ = "0.1.0"

@@ -12,7 +12,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libawb.so")
 
-AWB_KIND_ICNN, AWB_KIND_FLOW_ICNN, AWB_KIND_STAR = 0, 1, 2
+AWB_KIND_ICNN, AWB_KIND_FLOW_ICNN, AWB_KIND_STAR, AWB_KIND_DIFFEO_ICNN = 0, 1, 2, 3
 AWB_PREC_FP32, AWB_PREC_F16 = 0, 1
 AWB_GRID_EXPLICIT, AWB_GRID_LINSPACE, AWB_GRID_INDEX = 0, 1, 2
 AWB_LOSS_SE_SIGMOID, AWB_LOSS_BCE_LOGITS = 0, 1

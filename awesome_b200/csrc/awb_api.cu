@@ -30,12 +30,22 @@ static Layout make_layout(const awb_desc& d) {
   L.P_icnn = (int64_t)d.h * d.C + d.h + (int64_t)d.L * ((int64_t)d.h * d.h + d.h + (int64_t)d.h * d.C) + d.h + 1 + d.C;
   L.off_icnn = 0;
   L.per_flow = 2 * ((int64_t)d.m * d.C + d.m + (int64_t)d.C * d.m + d.C) + 2 * d.C;
+  L.n_lin = 0;
   if (d.kind == AWB_KIND_FLOW_ICNN) {
     // module registration order of PathConnectedNet: convex_net, flow_net, linear
     L.off_flow = L.P_icnn;
     L.P_flow = L.per_flow * d.F;
     L.off_lin = L.off_flow + L.P_flow;
-    L.P = L.off_lin + 2 * d.C;
+    L.n_lin = 2 * d.C;
+    L.P = L.off_lin + L.n_lin;
+  } else if (d.kind == AWB_KIND_DIFFEO_ICNN) {
+    // ConvexDiffeomorphismNet: convex_net, diffeo_net (s.0..F-1, t.0..F-1, scale.0..F-1), linear (full C x C)
+    L.per_flow = 2 * (3 * (int64_t)d.m + 3) + 4;
+    L.off_flow = L.P_icnn;
+    L.P_flow = L.per_flow * d.F;
+    L.off_lin = L.off_flow + L.P_flow;
+    L.n_lin = (int64_t)d.C * d.C + d.C;
+    L.P = L.off_lin + L.n_lin;
   } else {
     L.off_flow = L.P_icnn; L.P_flow = 0; L.off_lin = L.P_icnn; L.P = L.P_icnn;
   }
@@ -66,7 +76,7 @@ Workspace carve(const awb_prior* h, int64_t N, bool training, void* base, bool f
   w.waug = (float*)take(4 * O * L.G);
   w.part = (float*)take(training ? 4 * (int64_t)S * O * L.G : 0);
   w.lossp = (float*)take(4 * (int64_t)S * O);
-  w.fpart = (float*)take(training ? 4 * (int64_t)S * O * (L.P_flow + 2 * L.C) : 0);
+  w.fpart = (float*)take(training ? 4 * (int64_t)S * O * (L.P_flow + L.n_lin) : 0);
   w.X = (float*)take(4 * O * N * 4);
   w.dX = (float*)take(training ? 4 * O * N * 4 : 0);
   const bool planes = !(fit_only && h->desc.precision == AWB_PREC_F16 && tc_supported(h));
@@ -91,7 +101,7 @@ const char* awb_last_error(void) { return g_err; }
 
 int awb_prior_create(const awb_desc* d, awb_handle* out) {
   if (!d || !out) { set_error("null argument"); return AWB_ERR_INVALID; }
-  if (d->kind != AWB_KIND_ICNN && d->kind != AWB_KIND_FLOW_ICNN && d->kind != AWB_KIND_STAR) { set_error("unknown prior kind %d", d->kind); return AWB_ERR_INVALID; }
+  if (d->kind != AWB_KIND_ICNN && d->kind != AWB_KIND_FLOW_ICNN && d->kind != AWB_KIND_STAR && d->kind != AWB_KIND_DIFFEO_ICNN) { set_error("unknown prior kind %d", d->kind); return AWB_ERR_INVALID; }
   if (d->kind == AWB_KIND_STAR && (d->C != 2 || d->h > 160 || d->n_objects != 1 || d->precision != AWB_PREC_FP32)) {
     set_error("star prior: C = 2, n_hidden <= 160, one object, fp32");
     return AWB_ERR_UNSUPPORTED;
@@ -100,6 +110,10 @@ int awb_prior_create(const awb_desc* d, awb_handle* out) {
   if (d->h < 8 || d->h > 256) { set_error("h must be in [8,256], got %d", d->h); return AWB_ERR_UNSUPPORTED; }
   if (d->L < 0 || d->L > 8) { set_error("L must be in [0,8], got %d", d->L); return AWB_ERR_UNSUPPORTED; }
   if (d->n_objects < 1 || d->n_objects > 16) { set_error("n_objects must be in [1,16], got %d", d->n_objects); return AWB_ERR_UNSUPPORTED; }
+  if (d->kind == AWB_KIND_DIFFEO_ICNN && (d->C != 2 || d->m < 1 || d->m > 96 || (d->F != 2 && d->F != 4 && d->F != 6 && d->F != 8))) {
+    set_error("NormalizingFlow1D needs C=2, num_coupling in {2,4,6,8} and width <= 96, got C=%d F=%d m=%d", d->C, d->F, d->m);
+    return AWB_ERR_UNSUPPORTED;
+  }
   if (d->kind == AWB_KIND_FLOW_ICNN && (d->F < 1 || d->F > 64 || d->m < 1 || d->m > 32)) {
     set_error("flow needs 1<=F<=64 and 1<=m<=32, got F=%d m=%d", d->F, d->m);
     return AWB_ERR_UNSUPPORTED;
@@ -276,14 +290,14 @@ int awb_prior_fit_step(awb_handle h, float* params, void* opt_state, const awb_g
   cudaStream_t st = (cudaStream_t)stream;
   if (h->desc.precision == AWB_PREC_F16) {
     int n_part = 0;
-    if (h->desc.kind == AWB_KIND_FLOW_ICNN) {
+    if (has_flow(h)) {
       // RealNVP on CUDA cores (K = C is too thin for tensor cores) around the tensor-path ICNN: the flow writes the
       // deformed coordinates X, the fused kernel returns d loss / d X, the flow backward consumes it.
-      rc = flow_forward(h, params, g, w, nullptr, st);
+      rc = any_flow_forward(h, params, g, w, nullptr, st);
       if (rc) return rc;
       rc = tc_fit_forward_backward(h, params, g, target, loss, nullptr, 1, w, &n_part, st, false, w.X, w.dX);
       if (rc) return rc;
-      rc = flow_backward(h, params, g, w, st);
+      rc = any_flow_backward(h, params, g, w, st);
       if (rc) return rc;
       return simt_reduce_opt(h, params, opt_state, hy, loss_out, w, N, st, n_part);
     }

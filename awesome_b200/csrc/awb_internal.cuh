@@ -27,7 +27,8 @@ struct Layout {
   int64_t off_flow;  // arena offset of flows.0.s.net.0.weight
   int64_t P_flow;    // F * per_flow
   int64_t per_flow;  // 2*(m*C + m + C*m + C) + 2*C
-  int64_t off_lin;   // arena offset of linear.weight [C], linear.bias [C]
+  int64_t off_lin;   // arena offset of linear.weight, linear.bias
+  int64_t n_lin;     // their size: 2C (grouped 1x1 conv of PathConnectedNet) or C*C + C (nn.Linear of ConvexDiffeomorphismNet)
   // augmented space
   int64_t G;         // 4*h + L*h*ld + ld
   int64_t aug_in;    // [h][4]: (w_x, w_y, w_t, bias)
@@ -169,6 +170,22 @@ int flow_backward(const awb_prior* h, const float* params, const awb_grid_spec* 
                   cudaStream_t st, bool use_linear = true);
 int flow_actnorm_init(const awb_prior* h, float* params, const awb_grid_spec* g, const Workspace& ws,
                       cudaStream_t st);
+
+// ---- NormalizingFlow1D coupling flow (ConvexDiffeomorphismNet), implemented in awb_diffeo.cu
+int diffeo_forward(const awb_prior* h, const float* params, const awb_grid_spec* g, const Workspace& ws, float* deformed,
+                   cudaStream_t st);
+int diffeo_backward(const awb_prior* h, const float* params, const awb_grid_spec* g, const Workspace& ws, cudaStream_t st);
+inline bool has_flow(const awb_prior* h) { return h->desc.kind == AWB_KIND_FLOW_ICNN || h->desc.kind == AWB_KIND_DIFFEO_ICNN; }
+// the coordinate transform in front of the ICNN, whichever flow the prior has
+inline int any_flow_forward(const awb_prior* h, const float* params, const awb_grid_spec* g, const Workspace& ws,
+                            float* deformed, cudaStream_t st) {
+  return h->desc.kind == AWB_KIND_DIFFEO_ICNN ? diffeo_forward(h, params, g, ws, deformed, st)
+                                              : flow_forward(h, params, g, ws, deformed, st);
+}
+inline int any_flow_backward(const awb_prior* h, const float* params, const awb_grid_spec* g, const Workspace& ws,
+                             cudaStream_t st) {
+  return h->desc.kind == AWB_KIND_DIFFEO_ICNN ? diffeo_backward(h, params, g, ws, st) : flow_backward(h, params, g, ws, st);
+}
 
 // Pixel coordinate of row n, channel c.  torch.linspace semantics for
 // AWB_GRID_LINSPACE: step = 1/(n-1); first half start+i*step, second half end-(n-1-i)*step.

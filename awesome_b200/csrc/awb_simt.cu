@@ -735,8 +735,8 @@ int simt_forward(const awb_prior* h, const float* params, const awb_grid_spec* g
   AWB_LAUNCH(PK_PACK, st, k_pack<<<dim3((unsigned)((L.P_icnn + 255) / 256), O), 256, 0, st>>>(params, ws.waug, h->d_map, (int)L.P_icnn,
                                                                        L.P, L.off_icnn, L.G));
   int x_ready = 0;
-  if (h->desc.kind == AWB_KIND_FLOW_ICNN) {
-    int rc = flow_forward(h, params, g, ws, deformed, st);
+  if (has_flow(h)) {
+    int rc = any_flow_forward(h, params, g, ws, deformed, st);
     if (rc) return rc;
     x_ready = 1;
   }
@@ -788,7 +788,7 @@ int simt_backward(const awb_prior* h, const float* params, const awb_grid_spec* 
   const int64_t chunk = split_chunk(N);
   const int64_t sLayer = N * L.ld, sZAobj = (L.L + 1) * sLayer, sDobj = 2 * sLayer;
   const int64_t sSplit = (int64_t)O * L.G;
-  if (h->desc.kind == AWB_KIND_FLOW_ICNN) need_dx = true;
+  if (has_flow(h)) need_dx = true;
 
   OutP q = {};
   q.ZA = ws.ZA + L.L * sLayer; q.sZA = sZAobj;
@@ -836,8 +836,8 @@ int simt_backward(const awb_prior* h, const float* params, const awb_grid_spec* 
     AWB_LAUNCH(PK_IN_BWD, st, k_in_dgrad<<<dim3((unsigned)((N + 7) / 8), O), 256, 0, st>>>(ws.D, sDobj, ws.waug, L.G, L.aug_in, ws.dX, N,
                                                                  L.h, L.ld));
   AWB_CUDA(cudaGetLastError());
-  if (h->desc.kind == AWB_KIND_FLOW_ICNN) {
-    int rc = flow_backward(h, params, g, ws, st);
+  if (has_flow(h)) {
+    int rc = any_flow_backward(h, params, g, ws, st);
     if (rc) return rc;
   }
   return AWB_OK;
@@ -854,7 +854,7 @@ int simt_reduce_opt(const awb_prior* h, float* params, void* opt_state, const aw
   opt_ptrs(h, opt_state, &a.m, &a.v, &a.scal);
   a.part = ws.part; a.sSplit = (int64_t)O * L.G; a.S = n_partials > 0 ? n_partials : n_splits(N);
   a.SF = n_splits(N);
-  a.PF = L.P_flow + 2 * L.C;
+  a.PF = L.P_flow + L.n_lin;
   a.fpart = ws.fpart; a.sFSplit = (int64_t)O * a.PF;
   a.lossp = ws.lossp; a.grads = nullptr;
   a.map = h->d_map; a.clamp = h->d_clamp; a.group = h->d_group;
@@ -898,7 +898,7 @@ int reduce_opt_plain(const awb_prior* h, float* params, void* opt_state, const a
 int simt_reduce_grads(const awb_prior* h, float* grads, const Workspace& ws, int64_t N, cudaStream_t st) {
   const Layout& L = h->lay;
   const int O = h->desc.n_objects;
-  int64_t PF = L.P_flow + 2 * L.C;
+  int64_t PF = L.P_flow + L.n_lin;
   AWB_LAUNCH(PK_OPT, st, k_reduce_grads<<<dim3((unsigned)((L.P + 255) / 256), O), 256, 0, st>>>(
       grads, ws.part, (int64_t)O * L.G, n_splits(N), ws.fpart, (int64_t)O * PF, h->d_map, L.P, L.off_icnn,
       L.P_icnn, L.off_flow, PF, L.G));

@@ -677,7 +677,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
 
 // ======================================================================= host launcher
 int tc_supported(const awb_prior* h) {
-  return (h->desc.kind == AWB_KIND_ICNN || h->desc.kind == AWB_KIND_FLOW_ICNN) && h->lay.h == H_ &&
+  return (h->desc.kind == AWB_KIND_ICNN || h->desc.kind == AWB_KIND_FLOW_ICNN || h->desc.kind == AWB_KIND_DIFFEO_ICNN) && h->lay.h == H_ &&
          (h->lay.L == 1 || h->lay.L == 2) && h->lay.ld == LD_;
 }
 

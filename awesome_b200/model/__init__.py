@@ -3,3 +3,4 @@ from .path_connected_net import (MinMax, NormNet, PathConnectedNet, PixelizeNet,
                                  init_realnvp, real_nvp_path_connected_net, realnvp_masks)
 from .multi_prior import NumberBasedMultiPriorModule  # noqa: F401
 from .star_net import StarFitter, StarShapedNet  # noqa: F401
+from .convex_diffeomorphism_net import ConvexDiffeomorphismNet, NormalizingFlow1D  # noqa: F401

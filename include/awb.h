@@ -39,6 +39,7 @@ extern "C" {
 /* prior kinds */
 #define AWB_KIND_ICNN 0      /* ConvexNextNet / ConvexNet: awesome/model/convex_net.py:177-220 */
 #define AWB_KIND_FLOW_ICNN 1 /* PathConnectedNet(RealNVP o ConvexNextNet): awesome/model/path_connected_net.py:53-85 */
+#define AWB_KIND_DIFFEO_ICNN 3 /* ConvexDiffeomorphismNet(Linear -> NormalizingFlow1D -> ConvexNextNet): awesome/model/convex_diffeomorphism_net.py:130-178; desc.F = num_coupling (2/4/6/8), desc.m = backbone width (<= 96), C = 2 */
 #define AWB_KIND_STAR 2      /* star-shape prior myNet(h): notebooks/icml_teaser_code/star_shaped/star.ipynb cell 2 */
 
 /* arithmetic of the hidden-layer contractions */

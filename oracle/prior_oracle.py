@@ -260,10 +260,13 @@ def _simple_backbone(p: Params, pre: str, x: torch.Tensor) -> torch.Tensor:
 
 
 def _wn_scale(p: Params, pre: str, x: torch.Tensor) -> torch.Tensor:
-    """``WNScale`` (``awesome/model/diffeomorphism_net.py:208-232``)."""
+    """``WNScale`` (``awesome/model/diffeomorphism_net.py:208-232``): ``forward()`` ignores its input and returns
+    the scalar ``scale(weight)`` with ``scale = weight_norm(nn.Linear(1, 1))`` (default ``dim=0``); the coupling
+    multiplies the backbone output by it (``:291,294``)."""
     v = p[pre + "scale.weight_v"]
-    w = p[pre + "scale.weight_g"] * v / v.norm()
-    return p[pre + "weight"] * (x @ w.T + p[pre + "scale.bias"])
+    w = p[pre + "scale.weight_g"] * v / v.norm(dim=1, keepdim=True)
+    c = p[pre + "weight"] @ w.T + p[pre + "scale.bias"]
+    return c * x
 
 
 def flow1d_num(p: Params, prefix: str) -> int:

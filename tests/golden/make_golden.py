@@ -220,7 +220,24 @@ def gen_diffeo():
         lin = rows @ model.linear.weight.T + model.linear.bias
         xd = model.diffeo_net(lin)
         y = model(x)
-    return {"H": H, "W": W, "init": sd(model), "grid": x, "lin": lin, "deformed": xd, "logits": y}
+    out = {"H": H, "W": W, "init": sd(model), "grid": x, "lin": lin, "deformed": xd, "logits": y}
+    # a trained-like state (every parameter perturbed, in particular the WNScale bias, which is 0 at init):
+    # forward, MSE(sigmoid(y), unaries) and all parameter gradients incl. the weight-norm (g, v) pairs
+    g = torch.Generator().manual_seed(17)
+    with torch.no_grad():
+        for p_ in model.parameters():
+            p_.add_(0.15 * torch.randn(p_.shape, generator=g))
+        model.enforce_convexity()
+    un = torch.rand(1, 1, H, W, generator=g)
+    y2 = model(x)
+    loss = ((torch.sigmoid(y2) - un) ** 2).mean()
+    loss.backward()
+    with torch.no_grad():
+        rows2 = x.permute(0, 2, 3, 1).reshape(-1, 2)
+        xd2 = model.diffeo_net(rows2 @ model.linear.weight.T + model.linear.bias)
+    out.update({"pert": sd(model), "pert_unaries": un, "pert_deformed": xd2, "pert_logits": y2.detach().clone(),
+                "pert_loss": loss.detach().clone(), "pert_grads": grads(model)})
+    return out
 
 
 def gen_star():
@@ -286,7 +303,10 @@ def main():
         "star.pt": gen_star,
         "losses.pt": gen_losses,
     }
+    only = set(sys.argv[1:])
     for name, fn in jobs.items():
+        if only and name not in only:
+            continue
         data = fn()
         path = os.path.join(HERE, name)
         torch.save(data, path)

@@ -188,6 +188,20 @@ def test_diffeo_flow1d(golden):
     close(xd, g["deformed"], atol=1e-5)
     y = O.icnn_forward(p, xd, "convex_net.")
     close(O.unpixelize(y, 1, g["H"], g["W"]), g["logits"], atol=1e-5)
+    # perturbed ("trained-like") state: non-zero WNScale bias, weight-norm gradients
+    p = O.clone_params(g["pert"], requires_grad=True)
+    lin = rows_ @ p["linear.weight"].T + p["linear.bias"]
+    xd = O.flow1d_forward(p, lin)
+    close(xd.detach(), g["pert_deformed"], atol=1e-5)
+    y = O.unpixelize(O.icnn_forward(p, xd, "convex_net."), 1, g["H"], g["W"])
+    close(y.detach(), g["pert_logits"], atol=2e-5)
+    loss = ((torch.sigmoid(y) - g["pert_unaries"]) ** 2).mean()
+    close(loss.detach(), g["pert_loss"])
+    keys = list(g["pert_grads"])
+    grads = torch.autograd.grad(loss, [p[k] for k in keys], allow_unused=True)
+    for k, gr in zip(keys, grads):
+        gr = torch.zeros_like(p[k]) if gr is None else gr
+        close(gr, g["pert_grads"][k], rtol=2e-3, atol=1e-7)
 
 
 def test_star(golden):
