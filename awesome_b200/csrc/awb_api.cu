@@ -159,6 +159,16 @@ int awb_prior_create(const awb_desc* d, awb_handle* out) {
   if (i != L.P_icnn) { set_error("internal: layout mismatch"); delete h; return AWB_ERR_INVALID; }
   for (int64_t k = L.off_flow; k < L.off_flow + L.P_flow; k++) group[k] = 0;
   for (int64_t k = L.off_lin; k < L.P; k++) group[k] = 2;
+  if (d->kind == AWB_KIND_DIFFEO_ICNN) {
+    // weight-norm gains form their own optimizer group (3): the reference decays only `*weight_g`
+    // (awesome/util/torch.py:19-35, convex_diffeomorphism_net.py "weight_decay_on_weight_g")
+    const int64_t bsz = 3 * (int64_t)d->m + 3;
+    for (int b = 0; b < 2 * d->F; b++) {
+      group[L.off_flow + b * bsz + d->m] = 3;
+      group[L.off_flow + b * bsz + 2 * d->m + 2] = 3;
+    }
+    for (int i = 0; i < d->F; i++) group[L.off_flow + 2 * d->F * bsz + 4 * i + 2] = 3;
+  }
   std::vector<int32_t> imap(L.G, -1);
   for (int64_t k = 0; k < L.P_icnn; k++) imap[map[k]] = (int32_t)k;
   cudaError_t e;

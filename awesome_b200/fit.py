@@ -36,6 +36,10 @@ class LossConfig:
         ``UnariesWeightedLoss(SE, mode=...)`` (``awesome/measures/unaries_weighted_loss.py:35-69``),
         ``SE`` (``se.py``), ``torch.nn.MSELoss`` -> "mse"; ``BCEWithLogitsLoss`` -> fg/bg BCE with equal weights."""
         name = type(criterion).__name__
+        if name == "UnariesWeightedLoss" and type(getattr(criterion, "criterion", None)).__name__ == "BCELoss":
+            if (getattr(criterion, "mode", "none") or "none") != "none":
+                raise ValueError("weighted BCE fits are not fused; use mode='none'")
+            return cls("bce")
         if name == "UnariesWeightedLoss":
             return cls("mse", mode=getattr(criterion, "mode", "none") or "none", ratio=float(getattr(criterion, "ratio", 1.0) or 1.0))
         if name in ("SE", "MSELoss"):
@@ -63,6 +67,8 @@ class LossConfig:
                     raise ValueError(f"Mode {self.mode} is not supported")
                 specs.append(L.LossSpec(L.AWB_LOSS_SE_SIGMOID, L.AWB_CLS_UNARY_LT_HALF, float(w) / N, 1.0 / N))
             return specs
+        if self.kind == "bce":     # UnariesWeightedLoss(nn.BCELoss(), mode="none") on sigmoid(y), soft targets allowed
+            return [L.LossSpec(L.AWB_LOSS_BCE_LOGITS, L.AWB_CLS_UNARY_LT_HALF, 1.0 / N, 1.0 / N) for _ in range(O)]
         if self.kind in ("fgbg_se", "fgbg_bce_logits"):
             cnt = target_counts(target, L.AWB_CLS_NOT_ONE, O).cpu()
             k = L.AWB_LOSS_SE_SIGMOID if self.kind == "fgbg_se" else L.AWB_LOSS_BCE_LOGITS

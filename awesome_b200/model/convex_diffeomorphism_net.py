@@ -99,8 +99,69 @@ class ConvexDiffeomorphismNet(ArenaPriorModule):
         self._flatten_()
 
     def _optimizer_group_ids(self):
-        return ([1] * len(list(self.convex_net.parameters())) + [0] * len(list(self.diffeo_net.parameters()))
-                + [2] * len(list(self.linear.parameters())))
+        """convex_net -> 1, flow -> 0 with the weight-norm gains in their own group 3, linear -> 2."""
+        flow = [3 if k.endswith("weight_g") else 0 for k, _ in self.diffeo_net.named_parameters()]
+        return [1] * len(list(self.convex_net.parameters())) + flow + [2] * len(list(self.linear.parameters()))
+
+    # ---- affine re-positioning of the prior (convex_diffeomorphism_net.py:43-128)
+    def translate(self, from_points: torch.Tensor, to_points: torch.Tensor) -> None:
+        """Refit ``linear`` so that ``to_points`` map where ``from_points`` used to (least squares on the affine map)."""
+        if from_points.shape != to_points.shape:
+            raise ValueError("From and to points must have the same shape.")
+        w, b = self.linear.weight, self.linear.bias
+        if from_points.shape[0] < w.shape[0]:
+            raise ValueError(f"Not enough points to sample from. Need at least {w.shape[0]} points, got {from_points.shape[0]}.")
+        to_points = to_points.to(dtype=w.dtype, device=w.device)
+        from_points = from_points.to(dtype=w.dtype, device=w.device)
+        with torch.no_grad():
+            from_transf = from_points @ w.T + b
+            X = torch.cat((to_points, torch.ones((to_points.shape[0], 1), device=w.device, dtype=w.dtype)), dim=1)
+            theta = torch.linalg.inv(X.T @ X) @ (X.T @ from_transf)
+            w.copy_(theta[:-1, :].T)          # in place: the parameters are views into the arena
+            b.copy_(theta[-1, :])
+
+    def translate_only_point(self, from_point: torch.Tensor, to_point: torch.Tensor, grid: torch.Tensor) -> None:
+        """Shift (no rotation / scale): ``to_point`` (pixel x, y) takes the place of ``from_point`` (``:43-79``)."""
+        n = self.in_features
+        rf = torch.zeros((n + 1, n), device=from_point.device, dtype=from_point.dtype)
+        rt = torch.zeros((n + 1, n), device=to_point.device, dtype=to_point.dtype)
+        rf[0], rt[0] = from_point, to_point
+        for i in range(n):
+            v = torch.zeros(n, device=from_point.device, dtype=from_point.dtype)
+            v[i] += 3
+            rf[i + 1], rt[i + 1] = rf[0] + v, rt[0] + v
+        grid = grid.squeeze()
+        rf = grid[..., rf[:, 1].long(), rf[:, 0].long()].T
+        rt = grid[..., rt[:, 1].long(), rt[:, 0].long()].T
+        self.translate(rf, rt)
+
+    def pretrain(self, *args, **kwargs):
+        """``ConvexDiffeomorphismNet.pretrain`` (``:190-475``): per-frame fits with Adam (lr 3e-3), BCE on the
+        sigmoid, L2 only on the weight-norm gains, warm start + centre-of-mass re-translation (``:341-348``)."""
+        from .. import pretrain as P
+        from ..fit import LossConfig
+        kwargs.setdefault("lr", 0.003)
+        kwargs.setdefault("criterion", LossConfig("bce"))
+        kwargs.setdefault("optimizer", "adam")
+        kwargs.setdefault("weight_decay_on_weight_g", 5e-5)
+        kwargs.setdefault("flow_weight_decay", 0.0)
+        state = {"com": None}
+
+        def hook(model, un, spec):
+            fg = (un.reshape(spec.H, spec.W) <= 0.5)
+            if not bool(fg.any()):
+                return
+            com = (torch.argwhere(fg).sum(dim=0) / fg.sum()).long()           # (row, col), like the reference's helper
+            if state["com"] is not None:
+                model.translate_only_point(state["com"].flip(dims=(-1,)), com.flip(dims=(-1,)),
+                                           grid=spec.materialize(2, un.device).squeeze())
+            state["com"] = com
+        kwargs["_warm_start_hook"] = hook
+        return P.pretrain(self, *args, **kwargs)
+
+    def pretrain_load_state(self, *args, **kwargs):
+        from .. import pretrain as P
+        return P.pretrain_load_state(self, *args, **kwargs)
 
     def _make_prior(self, device) -> Prior:
         d = self.diffeo_net

@@ -44,6 +44,7 @@ class FitSchedule:
     proper_prior_fit_threshold: float = 0.5
     proper_prior_fit_retrys: int = 1
     criterion: LossConfig = field(default_factory=lambda: LossConfig("mse"))
+    weight_decay_on_weight_g: float = 0.0    # ConvexDiffeomorphismNet.pretrain decays only the weight-norm gains
     optimizer: str = "adamax"            # the pretrain loops use Adamax + plateau(200, 0.5) (:929-933)
     plateau: bool = True
     steps_per_graph: int = 50
@@ -59,7 +60,7 @@ class FitSchedule:
         return s
 
     def optim(self, has_flow: bool) -> OptimConfig:
-        wd = [self.flow_weight_decay if has_flow else 0.0, 0.0, 0.0, 0.0]
+        wd = [self.flow_weight_decay if has_flow else 0.0, 0.0, 0.0, self.weight_decay_on_weight_g]
         return OptimConfig(self.optimizer, lr=self.lr, weight_decay=wd, plateau=self.plateau, patience=200, factor=0.5)
 
 
@@ -93,8 +94,8 @@ def mask_iou(pred_prob: torch.Tensor, target_prob: torch.Tensor) -> float:
 
 
 def fit_frames(model, grids: Sequence, unaries: Sequence[torch.Tensor], schedule: Optional[FitSchedule] = None,
-               on_frame: Optional[Callable[[FrameResult], None]] = None, frame_indices: Optional[Sequence[int]] = None
-               ) -> List[FrameResult]:
+               on_frame: Optional[Callable[[FrameResult], None]] = None, frame_indices: Optional[Sequence[int]] = None,
+               warm_start_hook: Optional[Callable[[Any, torch.Tensor, Any], None]] = None) -> List[FrameResult]:
     """Fit ``model`` (ConvexNextNet or PathConnectedNet drop-in) to every frame in turn.  ``grids[i]`` is a
     ``[1,C,H,W]`` tensor or ``GridSpecHost``; ``unaries[i]`` the frame's soft segmentation (any shape with H*W
     elements; convention fg = 0, bg = 1 like the reference).  The model ends holding the last proper state."""
@@ -102,6 +103,7 @@ def fit_frames(model, grids: Sequence, unaries: Sequence[torch.Tensor], schedule
     arena = model._ensure_flat()
     dev = arena.device
     has_flow = hasattr(model, "flow_net")
+    flow_group = has_flow or hasattr(model, "diffeo_net")
     results: List[FrameResult] = []
     previous: Optional[torch.Tensor] = None
     fitter: Optional[PriorFitter] = None
@@ -123,6 +125,8 @@ def fit_frames(model, grids: Sequence, unaries: Sequence[torch.Tensor], schedule
         if warm:
             with torch.no_grad():
                 arena.copy_(previous)
+            if warm_start_hook is not None:
+                warm_start_hook(model, un, spec)         # e.g. centre-of-mass re-translation of the diffeomorphism prior
         else:
             if has_flow and s.prefit_flow_net_identity:
                 model.learn_flow_identity(spec.materialize(model.in_channels, dev), lr=s.prefit_flow_net_identity_lr,
@@ -136,7 +140,7 @@ def fit_frames(model, grids: Sequence, unaries: Sequence[torch.Tensor], schedule
             model._maybe_actnorm_init(spec.materialize(model.in_channels, dev))
         key = (spec.mode, spec.B, spec.H, spec.W, spec.t0, spec.t_step, id(spec.grid))
         if fitter is None or fitter_key != key:
-            fitter = model.make_fitter(spec, un, s.criterion, s.optim(has_flow), steps_per_graph=s.steps_per_graph)
+            fitter = model.make_fitter(spec, un, s.criterion, s.optim(flow_group), steps_per_graph=s.steps_per_graph)
             fitter_key = key
         else:
             fitter.set_target(un, s.criterion)
@@ -246,7 +250,7 @@ def pretrain(self, train_set, test_set=None, device=None, agent=None, use_progre
                 elif not res.skipped:
                     cache[res.index] = {k: v.detach().clone() for k, v in self.state_dict().items()}
             fit_frames(self, [g if g.dim() == 4 else g.unsqueeze(0) for g in grids], uns, sched, on_frame=keep,
-                       frame_indices=keys)
+                       frame_indices=keys, warm_start_hook=kwargs.get("_warm_start_hook"))
             return cache.get_state()
         T = len(grids)
         H, W = grids[0].shape[-2:]

@@ -222,3 +222,76 @@ def test_joint_trainer_matches_manual_agent_step(A):
     for a, b in zip(seg.parameters(), seg2.parameters()):
         torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7)
     assert tr.bucket.nbytes == 4 * sum(p.numel() for p in list(seg.parameters()) + list(pri.parameters()))
+
+
+class _FakeWrapper(torch.nn.Module):
+    """Stands in for the reference WrapperModule on the pretrain path: with evaluate_prior=False the call returns the
+    segmentation unaries [B,1,H,W] (wrapper_module.py:157-228); get_prior_args hands out the coordinate grid."""
+
+    def __init__(self):
+        super().__init__()
+        self.evaluate_prior = True
+        self.dummy = torch.nn.Parameter(torch.zeros(1))
+
+    def forward(self, image, grid):
+        assert self.evaluate_prior is False
+        return image[:, :1]                       # the "UNet" output is stored in the image's first channel
+
+    def get_prior_args(self, image, grid, segm=None):
+        return (grid,), {}
+
+
+class _FakeDataset(torch.utils.data.Dataset):
+    def __init__(self, frames, grid, cache):
+        self.frames, self.grid = frames, grid
+        self.__prior_cache__ = cache
+        self.has_prior = cache is not None
+
+    def __len__(self):
+        return len(self.frames)
+
+    def __getitem__(self, i):
+        return (i, 0), ((self.frames[i][None], self.grid[0]), torch.zeros(1))
+
+
+class _FakeAgent:
+    def __init__(self, ds):
+        self.training_dataset = ds
+
+    def _decompose_training_item(self, item):
+        (key, _state), (inputs, labels) = item
+        return list(inputs), labels, None, (int(key), None)
+
+
+@pytest.mark.parametrize("kind", ["pcn", "diffeo"])
+def test_pretrain_protocol_with_duck_typed_agent(A, kind):
+    """PretrainableModule.pretrain(train_set, test_set, device, agent, use_progress_bar, wrapper_module=..., **args):
+    per-frame states land in the dataset's prior cache and come back in the reference's PriorCache state format."""
+    H, W = 40, 56
+    torch.manual_seed(7)
+    if kind == "pcn":
+        m = A.real_nvp_path_connected_net(channels=2, hidden_units=32, flow_n_flows=6, flow_output_fn="tanh",
+                                          convex_net_hidden_layers=2, precision="f16").to(DEV)
+        typ, args = A.real_nvp_path_connected_net, dict(channels=2, hidden_units=32, flow_n_flows=6, flow_output_fn="tanh")
+    else:
+        m = A.ConvexDiffeomorphismNet(n_hidden_layers=1, precision="f16").to(DEV)
+        typ, args = A.ConvexDiffeomorphismNet, dict(n_hidden_layers=1)
+    frames = [blob(H, W, cx=0.45 + 0.05 * i) for i in range(3)]
+    grid = A.GridSpecHost("linspace", 1, H, W).materialize(2, "cpu")
+    cache = A.DevicePriorCache(typ, args)
+    ds = _FakeDataset(frames, grid, cache)
+    state = m.pretrain(ds, None, torch.device(DEV), _FakeAgent(ds), use_progress_bar=False, wrapper_module=_FakeWrapper().to(DEV),
+                       num_epochs=300, reuse_state_epochs=80, lr=3e-3, proper_prior_fit_threshold=0.5,
+                       prefit_flow_net_identity=(kind == "pcn"), prefit_flow_net_identity_num_epochs=20,
+                       prefit_convex_net=(kind == "pcn"), prefit_convex_net_num_epochs=30)
+    assert set(state) == {"model_type", "model_args", "store_device", "cache"} and set(state["cache"]) == {"0", "1", "2"}
+    # every stored frame state reproduces that frame's mask
+    for i in range(3):
+        m.load_state_dict(state["cache"][str(i)])
+        prob = torch.sigmoid(m(grid.to(DEV)))
+        assert A.mask_iou(prob.reshape(1, -1), frames[i].to(DEV).reshape(1, -1)) > 0.85, (kind, i)
+    # and pretrain_load_state puts them back into a fresh cache
+    cache2 = A.DevicePriorCache(typ, args)
+    ds2 = _FakeDataset(frames, grid, cache2)
+    m.pretrain_load_state(ds2, None, torch.device(DEV), _FakeAgent(ds2), state, wrapper_module=None)
+    assert 1 in cache2 and torch.equal(cache2[1]["convex_net.input.weight"].cpu(), state["cache"]["1"]["convex_net.input.weight"])

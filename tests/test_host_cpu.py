@@ -128,3 +128,19 @@ def test_multi_prior_container_keys_and_resize_cpu():
     big = A.NumberBasedMultiPriorModule(prior_type=A.ConvexNextNet, prior_args=dict(n_hidden_layers=1), min_priors=4)
     m.load_state_dict(big.state_dict())          # resizes like abstract_multi_prior_module.py:91-96
     assert len(m.priors) == 4
+
+
+def test_diffeo_translate_keeps_arena_views_cpu():
+    """ConvexDiffeomorphismNet.translate (reference :81-128): after the refit, `to` points land where `from` did."""
+    import torch
+    import awesome_b200 as A
+    torch.manual_seed(0)
+    m = A.ConvexDiffeomorphismNet()
+    w0, b0 = m.linear.weight.detach().clone(), m.linear.bias.detach().clone()
+    frm = torch.tensor([[0.2, 0.3], [0.7, 0.3], [0.2, 0.9]])
+    to = frm + torch.tensor([0.1, -0.05])
+    ptr = m.linear.weight.data_ptr()
+    m.translate(frm, to)
+    assert m.linear.weight.data_ptr() == ptr                      # still a view into the flat arena
+    torch.testing.assert_close(to @ m.linear.weight.T + m.linear.bias, frm @ w0.T + b0, rtol=1e-4, atol=1e-5)
+    assert [g for g in m._optimizer_group_ids()].count(3) == 4 * 2 * 2 + 4
