@@ -269,6 +269,13 @@ int awb_prior_forward(awb_handle h, const float* params, const awb_grid_spec* g,
   return simt_forward(h, params, g, logits, deformed, training != 0, w, (cudaStream_t)stream);
 }
 
+int awb_prior_flow_inverse(awb_handle h, const float* params, const awb_grid_spec* g, float* out, void* stream) {
+  if (!h || !params || !g || !out) { set_error("null argument"); return AWB_ERR_INVALID; }
+  if (h->desc.kind != AWB_KIND_FLOW_ICNN || !h->fc_set) { set_error("needs a flow prior with its constants set"); return AWB_ERR_INVALID; }
+  if (g->mode != AWB_GRID_EXPLICIT || !g->grid || g->B < 1 || g->H < 1 || g->W < 1) { set_error("inverse takes an explicit [B,C,H,W] tensor"); return AWB_ERR_INVALID; }
+  return flow_inverse(h, params, g, out, (cudaStream_t)stream);
+}
+
 int awb_prior_backward(awb_handle h, const float* params, const awb_grid_spec* g, const float* dlogits, float* grads,
                        float* dgrid, void* ws, size_t ws_bytes, void* stream) {
   int64_t N;

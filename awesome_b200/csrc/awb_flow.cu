@@ -102,6 +102,65 @@ __global__ void __launch_bounds__(256) k_flow_fwd(FlowP p) {
   }
 }
 
+// ---------------------------------------------------------------- inverse (PathConnectedNet.inverse, path_connected_net.py:107-122)
+// x (a get_deformation output) -> MinMax -> flows in reverse order, each inverted (ActNorm: (z - t) exp(-s);
+// coupling: zm + (1 - b)(z - t(zm)) exp(-s(zm)), normflows MaskedAffineFlow.inverse) -> inverse MinMax -> inverse 1x1 conv.
+template <int C>
+__global__ void __launch_bounds__(256) k_flow_inv(FlowP p, float* out) {
+  extern __shared__ float sp[];   // [P_flow + 2C]
+  const int o = blockIdx.y;
+  const float* par = p.params + (int64_t)o * p.P + p.off_flow;
+  const int PF = (int)p.P_flow + 2 * C;
+  for (int i = threadIdx.x; i < PF; i += blockDim.x) sp[i] = par[i];
+  __syncthreads();
+  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= p.N) return;
+  const float* lin = sp + p.P_flow;
+  float z[C];
+#pragma unroll
+  for (int c = 0; c < C; c++) z[c] = mm_fwd(coord(p.g, n, c), p.fc.nmin[c], p.fc.nmax[c], p.fc.new_min, p.fc.new_max);
+  const int m = p.m;
+  const int half = 2 * m * C + m + C;
+  for (int f = p.F - 1; f >= 0; f--) {
+    const float* w = sp + (int64_t)f * p.per_flow;
+    const float* an = w + 2 * half;
+    float zm[C];
+    bool b[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      z[c] = (z[c] - an[C + c]) * expf(-an[c]);          // ActNorm inverse
+      b[c] = p.fc.masks[f * C + c] != 0; zm[c] = b[c] ? z[c] : 0.f;
+    }
+    float so[C], to[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) { so[c] = w[m * C + m + C * m + c]; to[c] = w[half + m * C + m + C * m + c]; }
+    for (int k = 0; k < m; k++) {
+      float ps = w[m * C + k], pt = w[half + m * C + k];
+#pragma unroll
+      for (int c = 0; c < C; c++) { ps = fmaf(w[k * C + c], zm[c], ps); pt = fmaf(w[half + k * C + c], zm[c], pt); }
+      float hs = fmaxf(ps, 0.f), ht = fmaxf(pt, 0.f);
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        so[c] = fmaf(w[m * C + m + c * m + k], hs, so[c]);
+        to[c] = fmaf(w[half + m * C + m + c * m + k], ht, to[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      float s_ = p.tanh_out ? tanhf(so[c]) : so[c];
+      float t_ = p.tanh_out ? tanhf(to[c]) : to[c];
+      if (!isfinite(s_)) s_ = NAN;
+      if (!isfinite(t_)) t_ = NAN;
+      if (!b[c]) z[c] = (z[c] - t_) * expf(-s_);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; c++) {
+    float x = mm_fwd(z[c], p.fc.new_min, p.fc.new_max, p.fc.nmin[c], p.fc.nmax[c]);
+    out[((int64_t)o * p.N + n) * C + c] = (1.0f / lin[c]) * (x - lin[C + c]);
+  }
+}
+
 // ---------------------------------------------------------------- backward
 template <int C>
 __global__ void k_flow_bwd(FlowP p, int gs, int nbuf) {
@@ -387,6 +446,23 @@ int flow_forward(const awb_prior* h, const float* params, const awb_grid_spec* g
   } else {
     AWB_CUDA(cudaFuncSetAttribute(k_flow_fwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AWB_LAUNCH(PK_FLOW_FWD, st, k_flow_fwd<3><<<grid, 256, smem, st>>>(p));
+  }
+  AWB_CUDA(cudaGetLastError());
+  return AWB_OK;
+}
+
+int flow_inverse(const awb_prior* h, const float* params, const awb_grid_spec* g, float* out, cudaStream_t st) {
+  Workspace none = {};
+  FlowP p = make_p(h, params, g, none);
+  const int PF = (int)(h->lay.P_flow + 2 * h->lay.C);
+  size_t smem = sizeof(float) * PF;
+  dim3 grid((unsigned)((p.N + 255) / 256), h->desc.n_objects);
+  if (h->lay.C == 2) {
+    AWB_CUDA(cudaFuncSetAttribute(k_flow_inv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AWB_LAUNCH(PK_FLOW_FWD, st, k_flow_inv<2><<<grid, 256, smem, st>>>(p, out));
+  } else {
+    AWB_CUDA(cudaFuncSetAttribute(k_flow_inv<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AWB_LAUNCH(PK_FLOW_FWD, st, k_flow_inv<3><<<grid, 256, smem, st>>>(p, out));
   }
   AWB_CUDA(cudaGetLastError());
   return AWB_OK;

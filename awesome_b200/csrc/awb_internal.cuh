@@ -165,6 +165,7 @@ int tc_trace_read(unsigned long long* host, int max_ctas);   // debug timeline (
 // ---- flows, implemented in awb_flow.cu ----
 int flow_forward(const awb_prior* h, const float* params, const awb_grid_spec* g, const Workspace& ws,
                  float* deformed, cudaStream_t st, bool use_linear = true);
+int flow_inverse(const awb_prior* h, const float* params, const awb_grid_spec* g, float* out, cudaStream_t st);
 int flow_identity_loss(const awb_prior* h, const awb_grid_spec* g, const Workspace& ws, cudaStream_t st);
 int flow_backward(const awb_prior* h, const float* params, const awb_grid_spec* g, const Workspace& ws,
                   cudaStream_t st, bool use_linear = true);

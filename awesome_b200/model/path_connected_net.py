@@ -239,6 +239,23 @@ class PathConnectedNet(ArenaPriorModule):
         out = deformed.reshape(B, H, W, C_).permute(0, 3, 1, 2).contiguous()
         return out[0] if squeeze else out
 
+    def inverse(self, x: torch.Tensor, *args, **kwargs) -> torch.Tensor:
+        """``path_connected_net.py:107-122``: inverse of ``get_deformation``.  ``[B,C,H,W] -> [B,C,H,W]``."""
+        squeeze = x.dim() == 3
+        if squeeze:
+            x = x.unsqueeze(0)
+        arena = self._ensure_flat()
+        prior = self._prior_for(arena.device)
+        spec = GridSpecHost.from_tensor(x.to(arena.device))
+        gs = spec.to_c()
+        B, C_, H, W = x.shape
+        out = torch.empty((spec.n_pixels, C_), dtype=torch.float32, device=arena.device)
+        with torch.no_grad(), torch.cuda.device(arena.device):
+            L.check(prior.lib.awb_prior_flow_inverse(prior.handle, arena.data_ptr(), C.byref(gs), out.data_ptr(),
+                                                     L.stream_ptr()))
+        out = out.reshape(B, H, W, C_).permute(0, 3, 1, 2).contiguous()
+        return out[0] if squeeze else out
+
     def _maybe_actnorm_init(self, x: torch.Tensor) -> None:
         """normflows ``ActNorm.forward`` initialises ``s,t`` from the first batch it sees; the same
         happens here the first time the full prior runs with un-initialised ActNorms."""

@@ -144,6 +144,11 @@ int awb_prior_forward(awb_handle h, const float* params, const awb_grid_spec* gr
                       float* deformed, int32_t training, void* workspace, size_t workspace_bytes,
                       void* stream);
 
+/* PathConnectedNet.inverse (path_connected_net.py:86-122): maps get_deformation() outputs back to grid coordinates
+ * (inverse flow, inverse MinMax, inverse 1x1 conv).  grid: the deformed coordinates as [B,C,H,W]
+ * (AWB_GRID_EXPLICIT); out: device [O][N][C] pixel rows. */
+int awb_prior_flow_inverse(awb_handle h, const float* params, const awb_grid_spec* grid, float* out, void* stream);
+
 /* autograd backward of forward(): dlogits [O][N] -> grads [O][P] (overwritten), optional
  * dgrid [B,C,H,W] (ICNN, single object; model_input_requires_grad configs).  Must follow
  * awb_prior_forward(training=1) on the same workspace. */
