@@ -85,6 +85,7 @@ Workspace carve(const awb_prior* h, int64_t N, bool training, void* base, bool f
   w.logits = (float*)take(4 * O * N);
   w.flowz = (float*)take(training ? 4 * O * N * (int64_t)L.F * L.C : 0);
   if (!training || L.F == 0) w.flowz = nullptr;
+  w.flowg = (training && h->desc.kind == AWB_KIND_FLOW_ICNN) ? (float*)take(4 * O * N * (int64_t)L.F * 4 * L.C) : nullptr;
   w.tc = (h->desc.precision == AWB_PREC_F16 && tc_supported(h)) ? (void*)take(O * (int64_t)tc_image_bytes(L.L)) : nullptr;
   w.bytes = off;
   return w;

@@ -8,9 +8,9 @@
 // forward : one thread per pixel (no cross-pixel reduction).  Writes the deformed coordinates
 //           X[n] = (x, y, t, 1) consumed by the ICNN and, when training, the input of every
 //           coupling (F*C floats per pixel) so that the backward pass needs no forward sweep.
-// backward: one lane per hidden unit (m <= 32), 32/gs pixels per warp: hidden-unit gradients
-//           accumulate lane-locally into a private shared-memory buffer per lane group (no
-//           atomics), outputs use log2(gs) warp shuffles.  Buffers are reduced in a fixed order.
+// backward: (A) one thread per pixel propagates the coordinate gradient through the flows and records the per-pixel
+//           factors of every weight gradient; (B) one lane per hidden unit and flow sums them over pixels in
+//           registers.  No atomics, no per-pixel shuffles; partials are reduced in a fixed order.
 #include <math.h>
 
 #include "awb_internal.cuh"
@@ -162,131 +162,208 @@ __global__ void __launch_bounds__(256) k_flow_inv(FlowP p, float* out) {
 }
 
 // ---------------------------------------------------------------- backward
+// Two kernels, neither with a per-pixel cross-lane exchange:
+//  (A) k_flow_bwd_px: one thread per pixel walks the flows in reverse (recomputing each coupling from its stored
+//      input), propagates d loss / d z, and records per flow the 4C per-pixel factors every parameter gradient of
+//      that flow is linear in:  dsr, dtr (gradients at the pre-tanh outputs of the s / t nets) and the ActNorm terms.
+//      It also owns the 1x1-conv gradients (block reduction at the end).
+//  (B) k_flow_wgrad: grid = (pixel range, flow, object); lane k of every warp owns hidden unit k of that flow's two
+//      MLPs and accumulates its weight gradients in registers over the pixels of the range (broadcast loads of the
+//      per-pixel record, no shuffles, no atomics); the 8 warps are combined in a fixed order through shared memory.
 template <int C>
-__global__ void k_flow_bwd(FlowP p, int gs, int nbuf) {
-  extern __shared__ float sm[];                     // [PF] weights + [nbuf][PF] gradient buffers
-  const int PF = (int)p.P_flow + 2 * C;
+__global__ void __launch_bounds__(1024) k_flow_bwd_px(FlowP p, float* __restrict__ rec) {
+  extern __shared__ float sp[];   // [P_flow + 2C]
   const int o = blockIdx.y, s = blockIdx.x;
-  float* sp = sm;
-  float* gbuf = sm + PF;
   const float* par = p.params + (int64_t)o * p.P + p.off_flow;
+  const int PF = (int)p.P_flow + 2 * C;
   for (int i = threadIdx.x; i < PF; i += blockDim.x) sp[i] = par[i];
-  for (int i = threadIdx.x; i < nbuf * PF; i += blockDim.x) gbuf[i] = 0.f;
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ppw = 32 / gs;                 // pixels per warp iteration
-  const int grp = lane / gs, k = lane % gs;
-  const bool act = k < p.m;
-  const int nw = blockDim.x >> 5;
-  float* g = gbuf + (int64_t)(warp * ppw + grp) * PF;
   const int m = p.m, half = 2 * m * C + m + C;
   const int64_t r0 = (int64_t)s * p.chunk, r1 = r0 + p.chunk < p.N ? r0 + p.chunk : p.N;
-  const int64_t span = (r1 > r0 ? r1 - r0 : 0);
-  const int64_t iters = (span + (int64_t)nw * ppw - 1) / ((int64_t)nw * ppw);
-  for (int64_t it = 0; it < iters; it++) {
-    int64_t n = r0 + (it * nw + warp) * ppw + grp;
-    bool live = n < r1;                      // whole warp keeps iterating (shuffles stay converged)
-    int64_t nn = live ? n : r0;
-    float dz[C];
-    const float* dx = p.dX + ((int64_t)o * p.N + nn) * 4;
+  float glw[C], glb[C];
 #pragma unroll
-    for (int c = 0; c < C; c++)
-      dz[c] = live ? dx[c] * ((p.fc.nmax[c] - p.fc.nmin[c]) / (p.fc.new_max - p.fc.new_min)) : 0.f;
-    const float* zin = p.zin + ((int64_t)o * p.N + nn) * (p.F * C);
+  for (int c = 0; c < C; c++) { glw[c] = 0.f; glb[c] = 0.f; }
+  for (int64_t n = r0 + threadIdx.x; n < r1; n += blockDim.x) {
+    float dz[C];
+    const float* dx = p.dX + ((int64_t)o * p.N + n) * 4;
+#pragma unroll
+    for (int c = 0; c < C; c++) dz[c] = dx[c] * ((p.fc.nmax[c] - p.fc.nmin[c]) / (p.fc.new_max - p.fc.new_min));
+    const float* zin = p.zin + ((int64_t)o * p.N + n) * (p.F * C);
+    float* rn = rec + ((int64_t)o * p.N + n) * (p.F * 4 * C);
     for (int f = p.F - 1; f >= 0; f--) {
       const float* w = sp + (int64_t)f * p.per_flow;
-      float* gw = g + (int64_t)f * p.per_flow;
       float z[C], zm[C];
       bool b[C];
 #pragma unroll
       for (int c = 0; c < C; c++) { z[c] = zin[f * C + c]; b[c] = p.fc.masks[f * C + c] != 0; zm[c] = b[c] ? z[c] : 0.f; }
-      float ps = 0.f, pt = 0.f, hs = 0.f, ht = 0.f;
-      if (act) {
-        ps = w[m * C + k]; pt = w[half + m * C + k];
-#pragma unroll
-        for (int c = 0; c < C; c++) { ps = fmaf(w[k * C + c], zm[c], ps); pt = fmaf(w[half + k * C + c], zm[c], pt); }
-        hs = fmaxf(ps, 0.f); ht = fmaxf(pt, 0.f);
-      }
       float so[C], to[C];
 #pragma unroll
-      for (int c = 0; c < C; c++) {
-        so[c] = (act && !b[c]) ? w[m * C + m + c * m + k] * hs : 0.f;
-        to[c] = (act && !b[c]) ? w[half + m * C + m + c * m + k] * ht : 0.f;
-      }
-      for (int off = gs >> 1; off > 0; off >>= 1) {
+      for (int c = 0; c < C; c++) { so[c] = w[m * C + m + C * m + c]; to[c] = w[half + m * C + m + C * m + c]; }
+      for (int k = 0; k < m; k++) {
+        float ps = w[m * C + k], pt = w[half + m * C + k];
+#pragma unroll
+        for (int c = 0; c < C; c++) { ps = fmaf(w[k * C + c], zm[c], ps); pt = fmaf(w[half + k * C + c], zm[c], pt); }
+        const float hs = fmaxf(ps, 0.f), ht = fmaxf(pt, 0.f);
 #pragma unroll
         for (int c = 0; c < C; c++) {
-          so[c] += __shfl_xor_sync(0xffffffffu, so[c], off);
-          to[c] += __shfl_xor_sync(0xffffffffu, to[c], off);
+          so[c] = fmaf(w[m * C + m + c * m + k], hs, so[c]);
+          to[c] = fmaf(w[half + m * C + m + c * m + k], ht, to[c]);
         }
       }
       const float* an = w + 2 * half;
       float dsr[C], dtr[C], dzin[C];
 #pragma unroll
       for (int c = 0; c < C; c++) {
-        float ea = expf(an[c]);
-        float dzp = dz[c] * ea;
+        const float ea = expf(an[c]);
+        const float dzp = dz[c] * ea;
+        float das;
         if (b[c]) {
-          // masked component passes through the coupling
-          if (k == 0 && live) { gw[2 * half + c] += dz[c] * z[c] * ea; gw[2 * half + C + c] += dz[c]; }
+          das = dz[c] * z[c] * ea;            // masked component passes through the coupling
           dsr[c] = 0.f; dtr[c] = 0.f; dzin[c] = dzp;
         } else {
-          float sr = so[c] + w[m * C + m + C * m + c], tr = to[c] + w[half + m * C + m + C * m + c];
-          float sv = p.tanh_out ? tanhf(sr) : sr, tv = p.tanh_out ? tanhf(tr) : tr;
-          float e = expf(sv);
-          float zp = fmaf(z[c], e, tv);
-          if (k == 0 && live) { gw[2 * half + c] += dz[c] * zp * ea; gw[2 * half + C + c] += dz[c]; }
-          float ds = dzp * z[c] * e, dt = dzp;
+          const float sv = p.tanh_out ? tanhf(so[c]) : so[c], tv = p.tanh_out ? tanhf(to[c]) : to[c];
+          const float e = expf(sv);
+          das = dz[c] * fmaf(z[c], e, tv) * ea;
+          const float ds = dzp * z[c] * e;
           dsr[c] = p.tanh_out ? ds * (1.f - sv * sv) : ds;
-          dtr[c] = p.tanh_out ? dt * (1.f - tv * tv) : dt;
+          dtr[c] = p.tanh_out ? dzp * (1.f - tv * tv) : dzp;
           dzin[c] = dzp * e;
-          if (k == 0 && live) { gw[m * C + m + C * m + c] += dsr[c]; gw[half + m * C + m + C * m + c] += dtr[c]; }
         }
+        rn[f * 4 * C + c] = dsr[c];
+        rn[f * 4 * C + C + c] = dtr[c];
+        rn[f * 4 * C + 2 * C + c] = das;      // d ActNorm.s
+        rn[f * 4 * C + 3 * C + c] = dz[c];    // d ActNorm.t
       }
-      float dps = 0.f, dpt = 0.f;
-      if (act) {
-        float dhs = 0.f, dht = 0.f;
-#pragma unroll
-        for (int c = 0; c < C; c++) {
-          if (!b[c]) {
-            dhs = fmaf(dsr[c], w[m * C + m + c * m + k], dhs);
-            dht = fmaf(dtr[c], w[half + m * C + m + c * m + k], dht);
-            if (live) { gw[m * C + m + c * m + k] += dsr[c] * hs; gw[half + m * C + m + c * m + k] += dtr[c] * ht; }
-          }
-        }
-        dps = ps > 0.f ? dhs : 0.f;
-        dpt = pt > 0.f ? dht : 0.f;
-        if (live) {
-          gw[m * C + k] += dps; gw[half + m * C + k] += dpt;
-#pragma unroll
-          for (int c = 0; c < C; c++) if (b[c]) { gw[k * C + c] += dps * zm[c]; gw[half + k * C + c] += dpt * zm[c]; }
-        }
-      }
+      // gradient reaching the masked inputs through the two MLPs
       float dzm[C];
 #pragma unroll
-      for (int c = 0; c < C; c++) dzm[c] = (act && b[c]) ? fmaf(dps, w[k * C + c], dpt * w[half + k * C + c]) : 0.f;
-      for (int off = gs >> 1; off > 0; off >>= 1) {
+      for (int c = 0; c < C; c++) dzm[c] = 0.f;
+      for (int k = 0; k < m; k++) {
+        float ps = w[m * C + k], pt = w[half + m * C + k];
 #pragma unroll
-        for (int c = 0; c < C; c++) dzm[c] += __shfl_xor_sync(0xffffffffu, dzm[c], off);
+        for (int c = 0; c < C; c++) { ps = fmaf(w[k * C + c], zm[c], ps); pt = fmaf(w[half + k * C + c], zm[c], pt); }
+        float dps = 0.f, dpt = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          dps = fmaf(dsr[c], w[m * C + m + c * m + k], dps);
+          dpt = fmaf(dtr[c], w[half + m * C + m + c * m + k], dpt);
+        }
+        dps = ps > 0.f ? dps : 0.f;
+        dpt = pt > 0.f ? dpt : 0.f;
+#pragma unroll
+        for (int c = 0; c < C; c++) dzm[c] = fmaf(dps, w[k * C + c], fmaf(dpt, w[half + k * C + c], dzm[c]));
       }
 #pragma unroll
       for (int c = 0; c < C; c++) dz[c] = dzin[c] + (b[c] ? dzm[c] : 0.f);
     }
-    if (k == 0 && live && p.use_linear) {
+    if (p.use_linear) {
 #pragma unroll
       for (int c = 0; c < C; c++) {
-        float dxc = dz[c] * ((p.fc.new_max - p.fc.new_min) / (p.fc.nmax[c] - p.fc.nmin[c]));
-        g[p.P_flow + c] += dxc * coord(p.g, n, c);     // linear.weight
-        g[p.P_flow + C + c] += dxc;                    // linear.bias
+        const float dxc = dz[c] * ((p.fc.new_max - p.fc.new_min) / (p.fc.nmax[c] - p.fc.nmin[c]));
+        glw[c] = fmaf(dxc, coord(p.g, n, c), glw[c]);     // linear.weight
+        glb[c] += dxc;                                     // linear.bias
       }
     }
   }
+  // 1x1-conv gradients: fixed-order block reduction
+  __shared__ float red[32][2 * C];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < C; c++) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      glw[c] += __shfl_xor_sync(0xffffffffu, glw[c], off);
+      glb[c] += __shfl_xor_sync(0xffffffffu, glb[c], off);
+    }
+    if (lane == 0) { red[warp][c] = glw[c]; red[warp][C + c] = glb[c]; }
+  }
   __syncthreads();
-  float* out = p.fpart + ((int64_t)s * p.O + o) * PF;
-  for (int i = threadIdx.x; i < PF; i += blockDim.x) {
+  if (threadIdx.x < 2 * C) {
     float a = 0.f;
-    for (int bb = 0; bb < nbuf; bb++) a += gbuf[(int64_t)bb * PF + i];
-    out[i] = a;
+    for (int i = 0; i < (int)(blockDim.x >> 5); i++) a += red[i][threadIdx.x];
+    p.fpart[((int64_t)s * p.O + o) * PF + p.P_flow + threadIdx.x] = p.use_linear ? a : 0.f;
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) k_flow_wgrad(FlowP p, const float* __restrict__ rec) {
+  constexpr int NA = 2 * (2 * C + 1);      // per-lane accumulators: (W1[k][C], b1[k], W2[C][k]) x {s, t}
+  __shared__ float red[8][NA + 1][32];
+  __shared__ float red4[8][4 * C];
+  const int s = blockIdx.x, f = blockIdx.y, o = blockIdx.z;
+  const int m = p.m, half = 2 * m * C + m + C;
+  const float* w = p.params + (int64_t)o * p.P + p.off_flow + (int64_t)f * p.per_flow;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool act = lane < m;
+  const int k = act ? lane : 0;
+  float w1s[C], w1t[C], w2s[C], w2t[C];
+  bool b[C];
+#pragma unroll
+  for (int c = 0; c < C; c++) {
+    w1s[c] = w[k * C + c]; w1t[c] = w[half + k * C + c];
+    w2s[c] = w[m * C + m + c * m + k]; w2t[c] = w[half + m * C + m + c * m + k];
+    b[c] = p.fc.masks[f * C + c] != 0;
+  }
+  const float b1s = w[m * C + k], b1t = w[half + m * C + k];
+  float acc[NA];
+#pragma unroll
+  for (int i = 0; i < NA; i++) acc[i] = 0.f;
+  float a4 = 0.f;                          // lanes < 4C: output biases of s / t and the ActNorm pair
+  const int64_t r0 = (int64_t)s * p.chunk, r1 = r0 + p.chunk < p.N ? r0 + p.chunk : p.N;
+  const int FC = p.F * C;
+#pragma unroll 4
+  for (int64_t n = r0 + warp; n < r1; n += 8) {
+    const float* zin = p.zin + ((int64_t)o * p.N + n) * FC + f * C;
+    const float* rn = rec + ((int64_t)o * p.N + n) * (4 * FC) + f * 4 * C;
+    float zm[C], dsr[C], dtr[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) { zm[c] = b[c] ? zin[c] : 0.f; dsr[c] = rn[c]; dtr[c] = rn[C + c]; }
+    if (lane < 4 * C) a4 += rn[lane];
+    float ps = b1s, pt = b1t, dps = 0.f, dpt = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      ps = fmaf(w1s[c], zm[c], ps); pt = fmaf(w1t[c], zm[c], pt);
+      dps = fmaf(dsr[c], w2s[c], dps); dpt = fmaf(dtr[c], w2t[c], dpt);
+    }
+    const float hs = fmaxf(ps, 0.f), ht = fmaxf(pt, 0.f);
+    dps = ps > 0.f ? dps : 0.f;
+    dpt = pt > 0.f ? dpt : 0.f;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      acc[c] = fmaf(dps, zm[c], acc[c]);                               // d s.W1[k][c]
+      acc[C + 1 + c] = fmaf(dsr[c], hs, acc[C + 1 + c]);               // d s.W2[c][k]
+      acc[2 * C + 1 + c] = fmaf(dpt, zm[c], acc[2 * C + 1 + c]);       // d t.W1[k][c]
+      acc[3 * C + 2 + c] = fmaf(dtr[c], ht, acc[3 * C + 2 + c]);       // d t.W2[c][k]
+    }
+    acc[C] += dps;                                                     // d s.b1[k]
+    acc[3 * C + 1] += dpt;                                             // d t.b1[k]
+  }
+#pragma unroll
+  for (int i = 0; i < NA; i++) red[warp][i][lane] = acc[i];
+  if (lane < 4 * C) red4[warp][lane] = a4;
+  __syncthreads();
+  const int PF = (int)p.P_flow + 2 * C;
+  float* out = p.fpart + ((int64_t)s * p.O + o) * PF + (int64_t)f * p.per_flow;
+  for (int t = threadIdx.x; t < NA * 32; t += blockDim.x) {
+    const int i = t >> 5, kk = t & 31;
+    if (kk >= m) continue;
+    float a = 0.f;
+    for (int ww = 0; ww < 8; ww++) a += red[ww][i][kk];
+    const int net = i / (2 * C + 1), j = i % (2 * C + 1);
+    int idx;
+    if (j < C) idx = kk * C + j;                                   // W1[k][c]
+    else if (j == C) idx = m * C + kk;                             // b1[k]
+    else idx = m * C + m + (j - C - 1) * m + kk;                   // W2[c][k]
+    out[net * half + idx] = a;
+  }
+  if (threadIdx.x < 4 * C) {
+    float a = 0.f;
+    for (int ww = 0; ww < 8; ww++) a += red4[ww][threadIdx.x];
+    const int q = threadIdx.x / C, c = threadIdx.x % C;
+    if (q == 0) out[m * C + m + C * m + c] = a;                    // s.b2[c]
+    else if (q == 1) out[half + m * C + m + C * m + c] = a;        // t.b2[c]
+    else if (q == 2) out[2 * half + c] = a;                        // ActNorm.s[c]
+    else out[2 * half + C + c] = a;                                // ActNorm.t[c]
   }
 }
 
@@ -473,23 +550,20 @@ int flow_backward(const awb_prior* h, const float* params, const awb_grid_spec* 
   FlowP p = make_p(h, params, g, ws);
   p.use_linear = use_linear ? 1 : 0;
   p.zin = ws.flowz;
-  if (!p.zin) { set_error("flow backward needs a training workspace"); return AWB_ERR_WORKSPACE; }
+  if (!p.zin || !ws.flowg) { set_error("flow backward needs a training workspace"); return AWB_ERR_WORKSPACE; }
+  if (h->lay.m > 32) { set_error("flow MLP width must be <= 32"); return AWB_ERR_UNSUPPORTED; }
   const int PF = (int)(h->lay.P_flow + 2 * h->lay.C);
-  int gs = 8;
-  while (gs < h->lay.m) gs <<= 1;
-  const int ppw = 32 / gs;
-  // as many warps as the gradient buffers allow within ~200 KB of shared memory
-  int nw = 8;
-  while (nw > 1 && sizeof(float) * PF * (1 + (size_t)nw * ppw) > 200 * 1024) nw--;
-  size_t smem = sizeof(float) * PF * (1 + (size_t)nw * ppw);
-  if (smem > 220 * 1024) { set_error("flow too large for the shared-memory gradient buffers (%zu bytes)", smem); return AWB_ERR_UNSUPPORTED; }
-  dim3 grid(n_splits(p.N), h->desc.n_objects);
+  const size_t smem = sizeof(float) * PF;
+  const int S = n_splits(p.N);
+  dim3 gridA(S, h->desc.n_objects), gridB(S, h->lay.F, h->desc.n_objects);
   if (h->lay.C == 2) {
-    AWB_CUDA(cudaFuncSetAttribute(k_flow_bwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AWB_LAUNCH(PK_FLOW_BWD, st, k_flow_bwd<2><<<grid, 32 * nw, smem, st>>>(p, gs, nw * ppw));
+    AWB_CUDA(cudaFuncSetAttribute(k_flow_bwd_px<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AWB_LAUNCH(PK_FLOW_BWD, st, k_flow_bwd_px<2><<<gridA, 1024, smem, st>>>(p, ws.flowg));
+    AWB_LAUNCH(PK_FLOW_BWD, st, k_flow_wgrad<2><<<gridB, 256, 0, st>>>(p, ws.flowg));
   } else {
-    AWB_CUDA(cudaFuncSetAttribute(k_flow_bwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AWB_LAUNCH(PK_FLOW_BWD, st, k_flow_bwd<3><<<grid, 32 * nw, smem, st>>>(p, gs, nw * ppw));
+    AWB_CUDA(cudaFuncSetAttribute(k_flow_bwd_px<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AWB_LAUNCH(PK_FLOW_BWD, st, k_flow_bwd_px<3><<<gridA, 1024, smem, st>>>(p, ws.flowg));
+    AWB_LAUNCH(PK_FLOW_BWD, st, k_flow_wgrad<3><<<gridB, 256, 0, st>>>(p, ws.flowg));
   }
   AWB_CUDA(cudaGetLastError());
   return AWB_OK;

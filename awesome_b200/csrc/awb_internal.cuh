@@ -100,6 +100,7 @@ struct Workspace {
   float* D;       // [O][2][N][ld]
   float* logits;  // [O][N]
   float* flowz;   // [O][N][F*C] inputs of every coupling (training, flow priors)
+  float* flowg;   // [O][N][F*4C] per-pixel gradient factors of every coupling (RealNVP backward, phase A -> B)
   void* tc;       // tensor-core path scratch
   int64_t bytes;
 };
