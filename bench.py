@@ -202,6 +202,8 @@ def secondary_workloads(A, dev, unaries640):
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)      # torchrun pins OMP_NUM_THREADS=1: the CPU arm uses every host core
     thr, ms, cores, sample = cpu_oracle_throughput(args.steps, args.warmup, budget_s=120.0)
     line = {
         "impl": "reference", "metric": "prior-fit pixel-samples/sec (fwd+bwd+step)", "value": thr,
@@ -247,6 +249,7 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("AWB_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     warmup = max(3, args.warmup)
