@@ -348,9 +348,14 @@ def main():
             peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
             note = ("fp32 CUDA-core contraction (exact-parity path); reported against the sustained cuBLAS bf16 "
                     "tensor peak the north star names")
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r1_tc_v4_traffic.json")
+        if dom == "tc_fused" and os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")      # from the committed ncu --set full capture
         ach = dom_flop / (per_class[dom]["ms_per_launch"] * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": ach / peak_tf, "traffic": None, "peak_source": pk_src,
+                    "frac": ach / peak_tf, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
+                    "algorithmic_flop_per_launch": dom_flop, "peak_source": pk_src,
                     "ms_per_launch": per_class[dom]["ms_per_launch"],
                     "share_of_step": per_class[dom]["ms_per_step"] / step_ms_prof,
                     "whole_step_tflops": FLOP_PER_PX_STEP * N_PIX / (ms_total / args.steps * 1e-3) / 1e12,
