@@ -357,6 +357,15 @@ class PathConnectedNet(ArenaPriorModule):
         return (grid - mn) / (mx - mn) * (1.0 - 0.0) + 0.0
 
 
+class NoisyPathConnectedNet(PathConnectedNet):
+    """``awesome/model/noisy_path_connected_net.py``: the spatio-temporal fit with a fraction of the frames' unaries
+    replaced by noise (``pretrain_args["noisy_percentage"]``, default 1/3) -- robustness experiment of the paper."""
+
+    def pretrain(self, *args, **kwargs):
+        kwargs.setdefault("noisy_percentage", 0.333)
+        return super().pretrain(*args, **kwargs)
+
+
 def real_nvp_path_connected_net(channels: int = 2, hidden_units: int = 130, flow_n_flows: int = 6,
                                 flow_output_fn: Optional[str] = None, flow_output_scale: Optional[float] = None,
                                 norm: Literal["minmax"] = "minmax", spatial_shape: tuple = (1000, 1000),

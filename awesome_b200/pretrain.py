@@ -33,6 +33,7 @@ class FitSchedule:
     reuse_state: bool = True
     reuse_state_epochs: int = 200
     batch_size: int = 1
+    noisy_percentage: float = 0.0        # NoisyPathConnectedNet (noisy_path_connected_net.py:87): frames with noise unaries
     prefit_flow_net_identity: bool = False
     prefit_flow_net_identity_lr: float = 1e-2
     prefit_flow_net_identity_weight_decay: float = 1e-5
@@ -174,6 +175,25 @@ def fit_frames(model, grids: Sequence, unaries: Sequence[torch.Tensor], schedule
     return results
 
 
+def noisy_unaries(unaries: torch.Tensor, noisy_percentage: float, seed: Optional[int] = None):
+    """``NoisyPathConnectedNet._non_prior_based_pretrain`` (``awesome/model/noisy_path_connected_net.py:179-228``):
+    a fraction of the frames (never the first or the last) gets its unaries replaced ONCE by
+    ``clamp(randn + 0.5, 0, 1)``; the replacement is kept for every later epoch.  Returns (unaries, noisy indices)."""
+    import numpy as np
+    T = unaries.shape[0]
+    rng = np.random.RandomState(seed) if seed is not None else np.random
+    candidates = np.arange(1, T - 1)
+    k = min(int(round(T * noisy_percentage)), len(candidates))
+    idx = sorted(rng.choice(candidates, size=k, replace=False).tolist()) if k > 0 else []
+    out = unaries.clone()
+    g = torch.Generator(device=unaries.device)
+    if seed is not None:
+        g.manual_seed(seed)
+    for i in idx:
+        out[i] = torch.clamp(torch.randn(out[i].shape, device=out.device, generator=g) + 0.5, 0.0, 1.0)
+    return out, idx
+
+
 def fit_sequence(model, n_frames: int, H: int, W: int, unaries: torch.Tensor, schedule: Optional[FitSchedule] = None,
                  grid_mode: str = "linspace") -> torch.Tensor:
     """Spatio-temporal fit (``_non_prior_based_pretrain``, ``path_connected_net.py:652-719``): one (x, y, t) prior,
@@ -186,6 +206,8 @@ def fit_sequence(model, n_frames: int, H: int, W: int, unaries: torch.Tensor, sc
     T, bs = int(n_frames), max(1, int(s.batch_size))
     t_step = 1.0 / (T - 1) if T > 1 else 0.0
     un = unaries.detach().to(dev).float().reshape(T, H * W)
+    if s.noisy_percentage > 0:
+        un, _ = noisy_unaries(un, s.noisy_percentage)
     has_flow = hasattr(model, "flow_net")
     if has_flow:
         model._maybe_actnorm_init(GridSpecHost(grid_mode, T, H, W, t0=0.0, t_step=t_step).materialize(model.in_channels, dev))

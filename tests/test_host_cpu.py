@@ -144,3 +144,16 @@ def test_diffeo_translate_keeps_arena_views_cpu():
     assert m.linear.weight.data_ptr() == ptr                      # still a view into the flat arena
     torch.testing.assert_close(to @ m.linear.weight.T + m.linear.bias, frm @ w0.T + b0, rtol=1e-4, atol=1e-5)
     assert [g for g in m._optimizer_group_ids()].count(3) == 4 * 2 * 2 + 4
+
+
+def test_noisy_unaries_selection_cpu():
+    """NoisyPathConnectedNet: round(T * p) frames, never the first / last, replaced once by clamp(randn + 0.5, 0, 1)."""
+    import torch
+    import awesome_b200 as A
+    un = torch.rand(10, 6, 8)
+    out, idx = A.noisy_unaries(un, 0.333, seed=0)
+    assert len(idx) == 3 and 0 not in idx and 9 not in idx
+    for i in range(10):
+        assert torch.equal(out[i], un[i]) == (i not in idx)
+    assert float(out.min()) >= 0.0 and float(out.max()) <= 1.0
+    assert issubclass(A.NoisyPathConnectedNet, A.PathConnectedNet)
