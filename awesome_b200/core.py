@@ -121,8 +121,9 @@ class Prior:
         L.check(self.lib.awb_prior_set_flow_consts(self._h, a, b, new_min, new_max, m))
 
     # ---- kernels
-    def forward(self, params: torch.Tensor, grid: GridSpecHost, training: bool, ws: torch.Tensor,
+    def forward(self, params: torch.Tensor, grid: GridSpecHost, training, ws: torch.Tensor,
                 want_deformed: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """``training``: 0 / False inference, 1 / True exact training forward, 3 tensor-path training forward."""
         N = grid.n_pixels
         logits = torch.empty((self.n_objects, N), dtype=torch.float32, device=params.device)
         deformed = torch.empty((self.n_objects, N, self.C), dtype=torch.float32, device=params.device) \

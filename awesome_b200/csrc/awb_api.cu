@@ -75,7 +75,7 @@ Workspace carve(const awb_prior* h, int64_t N, bool training, void* base, bool f
   Workspace w = {};
   w.waug = (float*)take(4 * O * L.G);
   w.part = (float*)take(training ? 4 * (int64_t)S * O * L.G : 0);
-  w.lossp = (float*)take(4 * (int64_t)S * O);
+  w.lossp = (float*)take(4 * ((int64_t)kMaxSplits * O + O));   // [S][O] loss partials + [O] spare scalars (max |dlogits|)
   w.fpart = (float*)take(training ? 4 * (int64_t)S * O * (L.P_flow + L.n_lin) : 0);
   w.X = (float*)take(4 * O * N * 4);
   w.dX = (float*)take(training ? 4 * O * N * 4 : 0);
@@ -259,13 +259,21 @@ static int check_common(awb_handle h, const awb_grid_spec* g, void* ws, size_t w
 int awb_prior_forward(awb_handle h, const float* params, const awb_grid_spec* g, float* logits, float* deformed,
                       int32_t training, void* ws, size_t ws_bytes, void* stream) {
   int64_t N;
-  int rc = check_common(h, g, ws, ws_bytes, training == 1, &N);
+  int rc = check_common(h, g, ws, ws_bytes, training == 1 || training == 3, &N);
   if (rc) return rc;
   if (!params) { set_error("null params"); return AWB_ERR_INVALID; }
   Workspace w = carve(h, N, training == 1, ws);
-  if (training == 2) {   // fast tensor-path logits (fp16 operands); the default forward stays exact fp32
+  if (training == 2 || training == 3) {   // tensor-path logits (fp16 operands); the default forward stays exact fp32
     if (h->desc.precision != AWB_PREC_F16) { set_error("tensor-path forward needs an f16 handle"); return AWB_ERR_INVALID; }
-    return tc_fit_forward_backward(h, params, g, nullptr, nullptr, logits, 0, w, nullptr, (cudaStream_t)stream);
+    if (!logits) { set_error("null logits"); return AWB_ERR_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (training == 3) w = carve(h, N, true, ws);
+    if (has_flow(h)) {
+      rc = any_flow_forward(h, params, g, w, deformed, st);   // keeps X (and the coupling inputs when training)
+      if (rc) return rc;
+    }
+    return tc_fit_forward_backward(h, params, g, nullptr, nullptr, logits, 0, w, nullptr, st, false,
+                                   has_flow(h) ? w.X : nullptr, nullptr);
   }
   return simt_forward(h, params, g, logits, deformed, training != 0, w, (cudaStream_t)stream);
 }
@@ -289,6 +297,26 @@ int awb_prior_backward(awb_handle h, const float* params, const awb_grid_spec* g
   }
   Workspace w = carve(h, N, true, ws);
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->desc.precision == AWB_PREC_F16) {
+    // tensor path: one fused kernel recomputes the forward and runs the backward on the upstream gradient
+    // (must follow awb_prior_forward(training = 3) on the same workspace: the flow's X / coupling inputs live there)
+    const int O = h->desc.n_objects;
+    awb_loss_spec up[16];
+    for (int o = 0; o < O && o < 16; o++) { up[o].kind = AWB_LOSS_UPSTREAM; up[o].cls_rule = AWB_CLS_UNARY_LT_HALF; up[o].coef_fg = 1.f; up[o].coef_bg = 1.f; }
+    float* amax = w.lossp + (int64_t)kMaxSplits * O;       // spare floats behind the loss partials (lossp is [S][O], S <= 148 ... see carve)
+    rc = absmax_per_object(dlogits, N, O, amax, st);
+    if (rc) return rc;
+    int n_part = 0;
+    const bool flow = has_flow(h);
+    rc = tc_fit_forward_backward(h, params, g, dlogits, up, nullptr, 1, w, &n_part, st, false, flow ? w.X : nullptr,
+                                 (flow || dgrid) ? w.dX : nullptr, amax);
+    if (rc) return rc;
+    if (flow) { rc = any_flow_backward(h, params, g, w, st); if (rc) return rc; }
+    rc = simt_reduce_grads(h, grads, w, N, st, n_part);
+    if (rc) return rc;
+    if (dgrid) rc = simt_dgrid(h, g, dgrid, w, st);
+    return rc;
+  }
   rc = simt_backward(h, params, g, nullptr, nullptr, dlogits, dgrid != nullptr, w, st);
   if (rc) return rc;
   rc = simt_reduce_grads(h, grads, w, N, st);

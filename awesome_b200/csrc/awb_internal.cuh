@@ -134,7 +134,8 @@ int simt_backward(const awb_prior* h, const float* params, const awb_grid_spec* 
 // partials always come from flow_backward's n_splits(N) pixel ranges.
 int simt_reduce_opt(const awb_prior* h, float* params, void* opt_state, const awb_opt_hyper* hy,
                     float* loss_out, const Workspace& ws, int64_t N, cudaStream_t st, int n_partials = -1);
-int simt_reduce_grads(const awb_prior* h, float* grads, const Workspace& ws, int64_t N, cudaStream_t st);
+int simt_reduce_grads(const awb_prior* h, float* grads, const Workspace& ws, int64_t N, cudaStream_t st, int n_partials = -1);
+int absmax_per_object(const float* x, int64_t n, int O, float* out, cudaStream_t st);   // out[o] = max |x[o][:]|
 int simt_dgrid(const awb_prior* h, const awb_grid_spec* g, float* dgrid, const Workspace& ws, cudaStream_t st);
 int optim_step(const awb_prior* h, float* params, const float* grads, void* opt_state,
                const awb_opt_hyper* hy, cudaStream_t st);
@@ -160,7 +161,7 @@ int64_t tc_vec_offset_bytes(int L);                       // byte offset of the 
 int tc_fit_forward_backward(const awb_prior* h, const float* params, const awb_grid_spec* g, const float* target,
                             const awb_loss_spec* loss, float* logits, int mode, const Workspace& ws,
                             int* n_splits_out, cudaStream_t st, bool reuse_packed = false,
-                            const float* Xrows = nullptr, float* dXrows = nullptr);
+                            const float* Xrows = nullptr, float* dXrows = nullptr, const float* amax = nullptr);
 int tc_trace_read(unsigned long long* host, int max_ctas);   // debug timeline (AWB_TC_TRACE=1): 256 stamps per CTA
 
 // ---- flows, implemented in awb_flow.cu ----

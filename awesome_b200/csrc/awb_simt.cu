@@ -664,7 +664,28 @@ __global__ void __launch_bounds__(256) k_reduce_opt_aug(OptA a, int n_groups) {
   }
 }
 
-__global__ void k_reduce_grads(float* grads, const float* part, int64_t sSplit, int S, const float* fpart,
+__global__ void k_absmax(const float* __restrict__ x, int64_t n, float* out) {
+  const int o = blockIdx.x;
+  const float* p = x + (int64_t)o * n;
+  float m = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(p[i]));
+  __shared__ float red[32];
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < (int)(blockDim.x >> 5); i++) m = fmaxf(m, red[i]);
+    out[o] = m;
+  }
+}
+
+int absmax_per_object(const float* x, int64_t n, int O, float* out, cudaStream_t st) {
+  AWB_LAUNCH(PK_MISC, st, k_absmax<<<O, 1024, 0, st>>>(x, n, out));
+  AWB_CUDA(cudaGetLastError());
+  return AWB_OK;
+}
+
+__global__ void k_reduce_grads(float* grads, const float* part, int64_t sSplit, int S, int SF, const float* fpart,
                                int64_t sFSplit, const int32_t* map, int64_t P, int64_t off_icnn,
                                int64_t P_icnn, int64_t off_flow, int64_t PF, int64_t G) {
   int o = blockIdx.y;
@@ -676,7 +697,7 @@ __global__ void k_reduce_grads(float* grads, const float* part, int64_t sSplit, 
     for (int s = 0; s < S; s++) g += src[(int64_t)s * sSplit];
   } else {
     const float* src = fpart + (int64_t)o * PF + (i - off_flow);
-    for (int s = 0; s < S; s++) g += src[(int64_t)s * sFSplit];
+    for (int s = 0; s < SF; s++) g += src[(int64_t)s * sFSplit];
   }
   grads[(int64_t)o * P + i] = g;
 }
@@ -895,12 +916,12 @@ int reduce_opt_plain(const awb_prior* h, float* params, void* opt_state, const a
   return AWB_OK;
 }
 
-int simt_reduce_grads(const awb_prior* h, float* grads, const Workspace& ws, int64_t N, cudaStream_t st) {
+int simt_reduce_grads(const awb_prior* h, float* grads, const Workspace& ws, int64_t N, cudaStream_t st, int n_partials) {
   const Layout& L = h->lay;
   const int O = h->desc.n_objects;
   int64_t PF = L.P_flow + L.n_lin;
   AWB_LAUNCH(PK_OPT, st, k_reduce_grads<<<dim3((unsigned)((L.P + 255) / 256), O), 256, 0, st>>>(
-      grads, ws.part, (int64_t)O * L.G, n_splits(N), ws.fpart, (int64_t)O * PF, h->d_map, L.P, L.off_icnn,
+      grads, ws.part, (int64_t)O * L.G, n_partials > 0 ? n_partials : n_splits(N), n_splits(N), ws.fpart, (int64_t)O * PF, h->d_map, L.P, L.off_icnn,
       L.P_icnn, L.off_flow, PF, L.G));
   AWB_CUDA(cudaGetLastError());
   return AWB_OK;

@@ -83,6 +83,7 @@ struct TcP {
   float* logits;
   int64_t N; int n_tiles; int mode;
   unsigned long long* trace;
+  const float* amax;   // optional device [O]: max |dlogits| per object; sets the fp16 loss scale of the upstream-gradient mode
   const float* X;   // optional [O][N][4]: coordinates produced by the flow (x, y, t, 1) instead of the generated grid
   float* dX;        // optional [O][N][4]: gradient w.r.t. those coordinates (consumed by the flow backward)
 };
@@ -301,7 +302,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
 #pragma unroll
     for (int i = 0; i <= L; i++) accC[i] = 0.f;
     const awb_loss_spec ls = p.loss[o];
-    const float S = p.scale[o];
+    // loss scale: host-chosen power of two, or (upstream-gradient mode) derived from the device-side max |dlogits|
+    float S = p.scale[o];
+    if (p.amax) { const float am = p.amax[o]; S = (am > 0.f && isfinite(am)) ? exp2f(rintf(log2f(64.f / am))) : 1.f; }
     const bool has_dx = p.dX != nullptr;
     float adx0 = 0.f, adx1 = 0.f, adx2 = 0.f;     // last group: d loss / d (x, y, t) of this row (scaled by S)
     float v[48];
@@ -437,6 +440,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
         const float sg = 1.f / (1.f + expf(-y));
         float l, dl;
         if (ls.kind == AWB_LOSS_SE_SIGMOID) { float d = tgt - sg; l = d * d; dl = -2.f * d * sg * (1.f - sg); }
+        else if (ls.kind == AWB_LOSS_UPSTREAM) { l = 0.f; dl = tgt; }       // `target` holds d loss / d logits (autograd)
         else { l = fmaxf(y, 0.f) - y * tgt + log1pf(expf(-fabsf(y))); dl = sg - tgt; }
         dys = coef * dl * S;
         lossv = coef * l;
@@ -736,7 +740,7 @@ int tc_trace_read(unsigned long long* host, int max_ctas) {
 
 int tc_fit_forward_backward(const awb_prior* h, const float* params, const awb_grid_spec* g, const float* target,
                             const awb_loss_spec* loss, float* logits, int mode, const Workspace& ws, int* n_splits_out,
-                            cudaStream_t st, bool reuse_packed, const float* Xrows, float* dXrows) {
+                            cudaStream_t st, bool reuse_packed, const float* Xrows, float* dXrows, const float* amax) {
   const Layout& Ly = h->lay;
   const int O = h->desc.n_objects, L = Ly.L, C = Ly.C;
   const int64_t N = (int64_t)g->B * g->H * g->W;
@@ -766,7 +770,7 @@ int tc_fit_forward_backward(const awb_prior* h, const float* params, const awb_g
   }
   p.part = ws.part; p.sSplit = (int64_t)O * Ly.G; p.G = Ly.G; p.aug_in = Ly.aug_in; p.aug_layer = Ly.aug_layer; p.aug_out = Ly.aug_out;
   p.lossp = ws.lossp; p.O = O; p.logits = logits; p.N = N; p.n_tiles = n_tiles; p.mode = mode;
-  p.X = Xrows; p.dX = dXrows;
+  p.X = Xrows; p.dX = dXrows; p.amax = amax;
   p.trace = nullptr;
   if (getenv("AWB_TC_TRACE")) {
     if (!g_trace_dev) cudaMalloc(&g_trace_dev, sizeof(unsigned long long) * TRACE_N * kMaxSplits * 16);

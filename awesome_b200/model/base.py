@@ -47,7 +47,10 @@ class _PriorFunction(torch.autograd.Function):
             ws = prior.new_workspace(spec.n_pixels, True, arena.device)   # private: several forwards may precede backward
         else:
             ws = prior.cached_workspace(spec.n_pixels, False, arena.device)
-        logits, _ = prior.forward(arena, spec, needs_grad, ws)
+        # training forward of a tensor-path module: logits from the fused tcgen05 kernel (mode 3); backward re-runs it
+        # with the upstream gradient.  Inference (no grad) always takes the exact fp32 path.
+        mode = (3 if module.precision == "f16" else 1) if needs_grad else 0
+        logits, _ = prior.forward(arena, spec, mode, ws)
         ctx.module, ctx.spec, ctx.ws, ctx.prior = module, spec, ws, prior
         ctx.shapes = [p.shape for p in params]
         return logits

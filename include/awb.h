@@ -54,6 +54,7 @@ extern "C" {
 /* per-pixel loss kinds */
 #define AWB_LOSS_SE_SIGMOID 0 /* (t - sigmoid(y))^2: awesome/measures/se.py:21-23 on WrapperModule.process_prior_output */
 #define AWB_LOSS_BCE_LOGITS 1 /* BCEWithLogitsLoss: notebooks/how_to/path-connectedness.ipynb cell 9 */
+#define AWB_LOSS_UPSTREAM 2   /* internal: `target` carries d loss / d logits from autograd (awb_prior_backward on the tensor path) */
 #define AWB_CLS_UNARY_LT_HALF 0 /* fg = target < 0.5: awesome/measures/unaries_weighted_loss.py:35-69 */
 #define AWB_CLS_NOT_ONE 1       /* fg = target != 1: how-to notebooks, cell 9 */
 
@@ -139,7 +140,11 @@ int awb_prior_set_flow_consts(awb_handle h, const float* norm_min, const float* 
 /* forward(grid) -> raw logits [O][N]  (ConvexNextNet.forward convex_net.py:205-214;
  * PathConnectedNet.forward path_connected_net.py:79-85).  Leaves activations in the
  * workspace for awb_prior_backward when training != 0.  deformed (optional, [O][N][C])
- * receives get_deformation() (path_connected_net.py:125-129). */
+ * receives get_deformation() (path_connected_net.py:125-129).
+ * training: 0 inference (exact fp32), 1 exact fp32 forward that keeps its activations for awb_prior_backward,
+ * 2 tensor-path logits only (f16 handles), 3 tensor-path training forward (f16 handles): logits from the tcgen05
+ * kernel, nothing kept but the flow's deformed coordinates -- awb_prior_backward then re-runs the fused
+ * forward+backward kernel with the upstream gradient (joint UNet + prior step, torch_agent.py:470-492). */
 int awb_prior_forward(awb_handle h, const float* params, const awb_grid_spec* grid, float* logits,
                       float* deformed, int32_t training, void* workspace, size_t workspace_bytes,
                       void* stream);

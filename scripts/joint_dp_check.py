@@ -46,7 +46,7 @@ class MiniUNet(torch.nn.Module):
 
 seg = MiniUNet().to(dev)
 pri = A.real_nvp_path_connected_net(channels=3, hidden_units=32, flow_n_flows=18, flow_output_fn="tanh",
-                                    convex_net_hidden_layers=2).to(dev)
+                                    convex_net_hidden_layers=2, precision=os.environ.get("AWB_PRECISION", "f16")).to(dev)
 g = torch.Generator().manual_seed(1000 + rank)
 img = torch.randn(B, 4, H, W, generator=g).to(dev)
 f0 = rank * B

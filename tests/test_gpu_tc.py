@@ -153,3 +153,43 @@ def test_frame_size_steps_vs_fp32_and_determinism(A):
         runs.append((f16.run(10).cpu().reshape(-1), m16._arena.clone()))
     assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1]), "tensor path must be deterministic"
     torch.testing.assert_close(runs[0][0], h32, rtol=5e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("kind", ["icnn", "flow3"])
+def test_autograd_bridge_on_tensor_path(A, kind):
+    """Joint / agent mode on the tensor path: loss.backward() through an f16 module re-runs the fused kernel with the
+    upstream gradient (loss scale from the device-side max |dlogits|) -- gradients vs the exact fp32 module, for a
+    mean-reduced and for a sum-reduced loss (six orders of magnitude apart in dlogits)."""
+    torch.manual_seed(3)
+    H, W = 72, 96
+    if kind == "icnn":
+        m32 = A.ConvexNextNet(n_hidden_layers=2).to(DEV)
+        m16 = A.ConvexNextNet(n_hidden_layers=2, precision="f16")
+        grid = A.GridSpecHost("linspace", 1, H, W).materialize(2, DEV)
+    else:
+        kw = dict(channels=3, hidden_units=32, flow_n_flows=6, flow_output_fn="tanh", convex_net_hidden_layers=2)
+        m32 = A.real_nvp_path_connected_net(**kw).to(DEV)
+        m16 = A.real_nvp_path_connected_net(precision="f16", **kw)
+        grid = A.GridSpecHost("linspace", 2, H, W, t0=0.1, t_step=0.5).materialize(3, DEV)
+        m32(grid)                                   # ActNorm data-dependent init, then copy
+    m16.load_state_dict(m32.state_dict())
+    m16 = m16.to(DEV)
+    un = blob(H, W).to(DEV)
+    for reduce in ("mean", "sum"):
+        gs = {}
+        for key, m in (("fp32", m32), ("f16", m16)):
+            m.zero_grad()
+            gin = grid.clone().requires_grad_(kind == "icnn")
+            y = m(gin)
+            l = (torch.sigmoid(y)[:, 0] - un) ** 2
+            loss = l.mean() if reduce == "mean" else l.sum()
+            loss.backward()
+            gs[key] = (float(loss), torch.cat([p.grad.reshape(-1) for p in m.parameters()]),
+                       gin.grad.clone() if kind == "icnn" else None)
+        l32, g32, d32 = gs["fp32"]
+        l16, g16, d16 = gs["f16"]
+        assert abs(l16 - l32) <= 2e-3 * abs(l32), (reduce, l16, l32)
+        rel = float((g16 - g32).norm() / g32.norm())
+        assert rel < 2e-2, (kind, reduce, rel)
+        if d32 is not None:
+            assert float((d16 - d32).norm() / d32.norm()) < 2e-2
