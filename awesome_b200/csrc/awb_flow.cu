@@ -36,17 +36,53 @@ __device__ __forceinline__ float mm_fwd(float v, float vmin, float vmax, float n
   return (v - vmin) / (vmax - vmin) * (nmax - nmin) + nmin;
 }
 
+// ---- k-packed weight staging for the per-pixel kernels.  The MLP loops read, per hidden unit k, the 4C+2 scalars
+// (w1s[C], b1s, w2s[C], w1t[C], b1t, w2t[C]); in state_dict order they sit in 6 different arrays (6 broadcast LDS per
+// unit).  Staged as one padded record per (flow, unit) they are 3 (C=2) / 4 (C=3) LDS.128 -- the loops are
+// shared-memory-issue bound, not FMA bound.  Per flow: [m records | b2s[C] | b2t[C] | an_s[C] | an_t[C]].
+template <int C> struct FlowPack {
+  static constexpr int RK = (4 * C + 2 + 3) / 4 * 4;       // 12 (C=2), 16 (C=3)
+  __host__ __device__ static int flow_stride(int m) { return m * RK + 4 * C; }
+};
+template <int C>
+__device__ void stage_flow_packed(const float* __restrict__ par, int F, int m, int64_t per_flow, float* sp) {
+  constexpr int RK = FlowPack<C>::RK;
+  const int half = 2 * m * C + m + C, FS = FlowPack<C>::flow_stride(m);
+  for (int t = threadIdx.x; t < F * m; t += blockDim.x) {
+    const int f = t / m, k = t - f * m;
+    const float* w = par + (int64_t)f * per_flow;
+    float* r = sp + f * FS + k * RK;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      r[c] = w[k * C + c];                               // s.W1[k][c]
+      r[C + 1 + c] = w[m * C + m + c * m + k];           // s.W2[c][k]
+      r[2 * C + 1 + c] = w[half + k * C + c];            // t.W1[k][c]
+      r[3 * C + 2 + c] = w[half + m * C + m + c * m + k];   // t.W2[c][k]
+    }
+    r[C] = w[m * C + k];                                 // s.b1[k]
+    r[3 * C + 1] = w[half + m * C + k];                  // t.b1[k]
+  }
+  for (int t = threadIdx.x; t < F * 4 * C; t += blockDim.x) {
+    const int f = t / (4 * C), j = t - f * 4 * C, q = j / C, c = j - q * C;
+    const float* w = par + (int64_t)f * per_flow;
+    const float v = q == 0 ? w[m * C + m + C * m + c] : q == 1 ? w[half + m * C + m + C * m + c] : w[2 * half + (q - 2) * C + c];
+    sp[f * FS + m * RK + j] = v;
+  }
+}
+
 template <int C>
 __global__ void __launch_bounds__(256) k_flow_fwd(FlowP p) {
-  extern __shared__ float sp[];   // [P_flow + 2C]
+  extern __shared__ __align__(16) float sp[];   // k-packed flow weights + [2C] linear
+  constexpr int RK = FlowPack<C>::RK;
   const int o = blockIdx.y;
   const float* par = p.params + (int64_t)o * p.P + p.off_flow;
-  const int PF = (int)p.P_flow + 2 * C;
-  for (int i = threadIdx.x; i < PF; i += blockDim.x) sp[i] = par[i];
+  const int m = p.m, FS = FlowPack<C>::flow_stride(m);
+  stage_flow_packed<C>(par, p.F, m, p.per_flow, sp);
+  float* lin = sp + p.F * FS;
+  if (threadIdx.x < 2 * C) lin[threadIdx.x] = par[p.P_flow + threadIdx.x];
   __syncthreads();
   int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= p.N) return;
-  const float* lin = sp + p.P_flow;
   float z[C];
 #pragma unroll
   for (int c = 0; c < C; c++) {
@@ -54,11 +90,10 @@ __global__ void __launch_bounds__(256) k_flow_fwd(FlowP p) {
     if (p.use_linear) x = x * lin[c] + lin[C + c];
     z[c] = mm_fwd(x, p.fc.nmin[c], p.fc.nmax[c], p.fc.new_min, p.fc.new_max);
   }
-  const int m = p.m;
-  const int half = 2 * m * C + m + C;
   float* zin = p.zin ? p.zin + ((int64_t)o * p.N + n) * (p.F * C) : nullptr;
   for (int f = 0; f < p.F; f++) {
-    const float* w = sp + (int64_t)f * p.per_flow;
+    const float* wf = sp + f * FS;
+    const float* tail = wf + m * RK;          // b2s[C] | b2t[C] | an_s[C] | an_t[C]
     if (zin) {
 #pragma unroll
       for (int c = 0; c < C; c++) zin[f * C + c] = z[c];
@@ -69,27 +104,30 @@ __global__ void __launch_bounds__(256) k_flow_fwd(FlowP p) {
     for (int c = 0; c < C; c++) { b[c] = p.fc.masks[f * C + c] != 0; zm[c] = b[c] ? z[c] : 0.f; }
     float so[C], to[C];
 #pragma unroll
-    for (int c = 0; c < C; c++) { so[c] = w[m * C + m + C * m + c]; to[c] = w[half + m * C + m + C * m + c]; }
+    for (int c = 0; c < C; c++) { so[c] = tail[c]; to[c] = tail[C + c]; }
+#pragma unroll 4
     for (int k = 0; k < m; k++) {
-      float ps = w[m * C + k], pt = w[half + m * C + k];
+      float rk[RK];
 #pragma unroll
-      for (int c = 0; c < C; c++) { ps = fmaf(w[k * C + c], zm[c], ps); pt = fmaf(w[half + k * C + c], zm[c], pt); }
+      for (int q4 = 0; q4 < RK / 4; q4++) *reinterpret_cast<float4*>(&rk[4 * q4]) = reinterpret_cast<const float4*>(wf + k * RK)[q4];
+      float ps = rk[C], pt = rk[3 * C + 1];
+#pragma unroll
+      for (int c = 0; c < C; c++) { ps = fmaf(rk[c], zm[c], ps); pt = fmaf(rk[2 * C + 1 + c], zm[c], pt); }
       float hs = fmaxf(ps, 0.f), ht = fmaxf(pt, 0.f);
 #pragma unroll
       for (int c = 0; c < C; c++) {
-        so[c] = fmaf(w[m * C + m + c * m + k], hs, so[c]);
-        to[c] = fmaf(w[half + m * C + m + c * m + k], ht, to[c]);
+        so[c] = fmaf(rk[C + 1 + c], hs, so[c]);
+        to[c] = fmaf(rk[3 * C + 2 + c], ht, to[c]);
       }
     }
-    const float* an = w + 2 * half;
 #pragma unroll
     for (int c = 0; c < C; c++) {
-      float s = p.tanh_out ? tanhf(so[c]) : so[c];
-      float t = p.tanh_out ? tanhf(to[c]) : to[c];
-      if (!isfinite(s)) s = NAN;
-      if (!isfinite(t)) t = NAN;
-      float zc = b[c] ? z[c] : fmaf(z[c], expf(s), t);
-      z[c] = fmaf(zc, expf(an[c]), an[C + c]);      // ActNorm
+      float s_ = p.tanh_out ? tanhf(so[c]) : so[c];
+      float t_ = p.tanh_out ? tanhf(to[c]) : to[c];
+      if (!isfinite(s_)) s_ = NAN;
+      if (!isfinite(t_)) t_ = NAN;
+      float zc = b[c] ? z[c] : fmaf(z[c], expf(s_), t_);
+      z[c] = fmaf(zc, expf(tail[2 * C + c]), tail[3 * C + c]);      // ActNorm
     }
   }
   float xd[3] = {0.f, 0.f, 0.f};
@@ -172,13 +210,14 @@ __global__ void __launch_bounds__(256) k_flow_inv(FlowP p, float* out) {
 //      per-pixel record, no shuffles, no atomics); the 8 warps are combined in a fixed order through shared memory.
 template <int C>
 __global__ void __launch_bounds__(1024) k_flow_bwd_px(FlowP p, float* __restrict__ rec) {
-  extern __shared__ float sp[];   // [P_flow + 2C]
+  extern __shared__ __align__(16) float sp[];   // k-packed flow weights
+  constexpr int RK = FlowPack<C>::RK;
   const int o = blockIdx.y, s = blockIdx.x;
   const float* par = p.params + (int64_t)o * p.P + p.off_flow;
   const int PF = (int)p.P_flow + 2 * C;
-  for (int i = threadIdx.x; i < PF; i += blockDim.x) sp[i] = par[i];
+  const int m = p.m, FS = FlowPack<C>::flow_stride(m);
+  stage_flow_packed<C>(par, p.F, m, p.per_flow, sp);
   __syncthreads();
-  const int m = p.m, half = 2 * m * C + m + C;
   const int64_t r0 = (int64_t)s * p.chunk, r1 = r0 + p.chunk < p.N ? r0 + p.chunk : p.N;
   float glw[C], glb[C];
 #pragma unroll
@@ -191,30 +230,34 @@ __global__ void __launch_bounds__(1024) k_flow_bwd_px(FlowP p, float* __restrict
     const float* zin = p.zin + ((int64_t)o * p.N + n) * (p.F * C);
     float* rn = rec + ((int64_t)o * p.N + n) * (p.F * 4 * C);
     for (int f = p.F - 1; f >= 0; f--) {
-      const float* w = sp + (int64_t)f * p.per_flow;
+      const float* wf = sp + f * FS;
+      const float* tail = wf + m * RK;
       float z[C], zm[C];
       bool b[C];
 #pragma unroll
       for (int c = 0; c < C; c++) { z[c] = zin[f * C + c]; b[c] = p.fc.masks[f * C + c] != 0; zm[c] = b[c] ? z[c] : 0.f; }
       float so[C], to[C];
 #pragma unroll
-      for (int c = 0; c < C; c++) { so[c] = w[m * C + m + C * m + c]; to[c] = w[half + m * C + m + C * m + c]; }
+      for (int c = 0; c < C; c++) { so[c] = tail[c]; to[c] = tail[C + c]; }
+#pragma unroll 4
       for (int k = 0; k < m; k++) {
-        float ps = w[m * C + k], pt = w[half + m * C + k];
+        float rk[RK];
 #pragma unroll
-        for (int c = 0; c < C; c++) { ps = fmaf(w[k * C + c], zm[c], ps); pt = fmaf(w[half + k * C + c], zm[c], pt); }
+        for (int q4 = 0; q4 < RK / 4; q4++) *reinterpret_cast<float4*>(&rk[4 * q4]) = reinterpret_cast<const float4*>(wf + k * RK)[q4];
+        float ps = rk[C], pt = rk[3 * C + 1];
+#pragma unroll
+        for (int c = 0; c < C; c++) { ps = fmaf(rk[c], zm[c], ps); pt = fmaf(rk[2 * C + 1 + c], zm[c], pt); }
         const float hs = fmaxf(ps, 0.f), ht = fmaxf(pt, 0.f);
 #pragma unroll
         for (int c = 0; c < C; c++) {
-          so[c] = fmaf(w[m * C + m + c * m + k], hs, so[c]);
-          to[c] = fmaf(w[half + m * C + m + c * m + k], ht, to[c]);
+          so[c] = fmaf(rk[C + 1 + c], hs, so[c]);
+          to[c] = fmaf(rk[3 * C + 2 + c], ht, to[c]);
         }
       }
-      const float* an = w + 2 * half;
       float dsr[C], dtr[C], dzin[C];
 #pragma unroll
       for (int c = 0; c < C; c++) {
-        const float ea = expf(an[c]);
+        const float ea = expf(tail[2 * C + c]);
         const float dzp = dz[c] * ea;
         float das;
         if (b[c]) {
@@ -238,20 +281,24 @@ __global__ void __launch_bounds__(1024) k_flow_bwd_px(FlowP p, float* __restrict
       float dzm[C];
 #pragma unroll
       for (int c = 0; c < C; c++) dzm[c] = 0.f;
+#pragma unroll 4
       for (int k = 0; k < m; k++) {
-        float ps = w[m * C + k], pt = w[half + m * C + k];
+        float rk[RK];
 #pragma unroll
-        for (int c = 0; c < C; c++) { ps = fmaf(w[k * C + c], zm[c], ps); pt = fmaf(w[half + k * C + c], zm[c], pt); }
+        for (int q4 = 0; q4 < RK / 4; q4++) *reinterpret_cast<float4*>(&rk[4 * q4]) = reinterpret_cast<const float4*>(wf + k * RK)[q4];
+        float ps = rk[C], pt = rk[3 * C + 1];
+#pragma unroll
+        for (int c = 0; c < C; c++) { ps = fmaf(rk[c], zm[c], ps); pt = fmaf(rk[2 * C + 1 + c], zm[c], pt); }
         float dps = 0.f, dpt = 0.f;
 #pragma unroll
         for (int c = 0; c < C; c++) {
-          dps = fmaf(dsr[c], w[m * C + m + c * m + k], dps);
-          dpt = fmaf(dtr[c], w[half + m * C + m + c * m + k], dpt);
+          dps = fmaf(dsr[c], rk[C + 1 + c], dps);
+          dpt = fmaf(dtr[c], rk[3 * C + 2 + c], dpt);
         }
         dps = ps > 0.f ? dps : 0.f;
         dpt = pt > 0.f ? dpt : 0.f;
 #pragma unroll
-        for (int c = 0; c < C; c++) dzm[c] = fmaf(dps, w[k * C + c], fmaf(dpt, w[half + k * C + c], dzm[c]));
+        for (int c = 0; c < C; c++) dzm[c] = fmaf(dps, rk[c], fmaf(dpt, rk[2 * C + 1 + c], dzm[c]));
       }
 #pragma unroll
       for (int c = 0; c < C; c++) dz[c] = dzin[c] + (b[c] ? dzm[c] : 0.f);
@@ -514,8 +561,7 @@ int flow_forward(const awb_prior* h, const float* params, const awb_grid_spec* g
   p.use_linear = use_linear ? 1 : 0;
   p.zin = ws.flowz;
   p.deformed = deformed;
-  const int PF = (int)(h->lay.P_flow + 2 * h->lay.C);
-  size_t smem = sizeof(float) * PF;
+  size_t smem = sizeof(float) * ((size_t)h->lay.F * (h->lay.C == 2 ? FlowPack<2>::flow_stride(h->lay.m) : FlowPack<3>::flow_stride(h->lay.m)) + 2 * h->lay.C);
   dim3 grid((unsigned)((p.N + 255) / 256), h->desc.n_objects);
   if (h->lay.C == 2) {
     AWB_CUDA(cudaFuncSetAttribute(k_flow_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -552,8 +598,7 @@ int flow_backward(const awb_prior* h, const float* params, const awb_grid_spec* 
   p.zin = ws.flowz;
   if (!p.zin || !ws.flowg) { set_error("flow backward needs a training workspace"); return AWB_ERR_WORKSPACE; }
   if (h->lay.m > 32) { set_error("flow MLP width must be <= 32"); return AWB_ERR_UNSUPPORTED; }
-  const int PF = (int)(h->lay.P_flow + 2 * h->lay.C);
-  const size_t smem = sizeof(float) * PF;
+  const size_t smem = sizeof(float) * ((size_t)h->lay.F * (h->lay.C == 2 ? FlowPack<2>::flow_stride(h->lay.m) : FlowPack<3>::flow_stride(h->lay.m)));
   const int S = n_splits(p.N);
   dim3 gridA(S, h->desc.n_objects), gridB(S, h->lay.F, h->desc.n_objects);
   if (h->lay.C == 2) {
