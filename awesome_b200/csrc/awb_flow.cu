@@ -358,14 +358,25 @@ __global__ void __launch_bounds__(256) k_flow_wgrad(FlowP p, const float* __rest
   float a4 = 0.f;                          // lanes < 4C: output biases of s / t and the ActNorm pair
   const int64_t r0 = (int64_t)s * p.chunk, r1 = r0 + p.chunk < p.N ? r0 + p.chunk : p.N;
   const int FC = p.F * C;
+  // running pointers (8 pixels per step of the warp); the per-pixel record of this flow is 4C contiguous floats,
+  // 16-byte aligned: float4 loads; the coupling input pair is 8-byte aligned for C = 2
+  const float* zp = p.zin + ((int64_t)o * p.N + r0 + warp) * FC + f * C;
+  const float* rp = rec + ((int64_t)o * p.N + r0 + warp) * (4 * FC) + f * 4 * C;
+  const int64_t zstep = (int64_t)8 * FC, rstep = (int64_t)8 * 4 * FC;
+  const int n_it = (int)((r1 - r0 - warp + 7) / 8);
 #pragma unroll 4
-  for (int64_t n = r0 + warp; n < r1; n += 8) {
-    const float* zin = p.zin + ((int64_t)o * p.N + n) * FC + f * C;
-    const float* rn = rec + ((int64_t)o * p.N + n) * (4 * FC) + f * 4 * C;
+  for (int it = 0; it < (n_it > 0 ? n_it : 0); it++, zp += zstep, rp += rstep) {
     float zm[C], dsr[C], dtr[C];
+    if (C == 2) {
+      const float2 zz = *reinterpret_cast<const float2*>(zp);
+      const float4 r4 = *reinterpret_cast<const float4*>(rp);
+      zm[0] = b[0] ? zz.x : 0.f; zm[1] = b[1] ? zz.y : 0.f;
+      dsr[0] = r4.x; dsr[1] = r4.y; dtr[0] = r4.z; dtr[1] = r4.w;
+    } else {
 #pragma unroll
-    for (int c = 0; c < C; c++) { zm[c] = b[c] ? zin[c] : 0.f; dsr[c] = rn[c]; dtr[c] = rn[C + c]; }
-    if (lane < 4 * C) a4 += rn[lane];
+      for (int c = 0; c < C; c++) { zm[c] = b[c] ? zp[c] : 0.f; dsr[c] = rp[c]; dtr[c] = rp[C + c]; }
+    }
+    if (lane < 4 * C) a4 += rp[lane];
     float ps = b1s, pt = b1t, dps = 0.f, dpt = 0.f;
 #pragma unroll
     for (int c = 0; c < C; c++) {
