@@ -199,6 +199,35 @@ def secondary_workloads(A, dev, unaries640):
     return out
 
 
+def eager_gpu_throughput(dev, steps: int = 10):
+    """The same oracle port (the reference's eager ATen op sequence: per-op kernels, autograd, per-tensor Adam, one
+    clamp per tensor, a host sync on the loss every step) on the SAME B200 -- the GPU-vs-GPU comparison SURVEY 8d
+    asks for beside the CPU arm.  Reported as a baseline only."""
+    import torch
+    from oracle import prior_oracle as O
+    torch.manual_seed(42)
+    lin = torch.nn.Linear
+    p = {}
+    l = lin(CH, HID); p["input.weight"], p["input.bias"] = l.weight.detach(), l.bias.detach()
+    for i in range(LAYERS):
+        l = lin(HID, HID); p[f"skip.{i}.ln.weight"], p[f"skip.{i}.ln.bias"] = l.weight.detach(), l.bias.detach()
+        p[f"skip.{i}.skp.weight"] = lin(CH, HID, bias=False).weight.detach()
+    l = lin(HID, 1); p["out.ln.weight"], p["out.ln.bias"] = l.weight.detach(), l.bias.detach()
+    p["out.skp.weight"] = lin(CH, 1, bias=False).weight.detach()
+    p = {k: v.to(dev) for k, v in O.clone_params(p).items()}
+    rows = O.pixelize(O.grid_linspace(H, W)[None]).to(dev)
+    un = synth_unaries(42).reshape(-1).to(dev)
+    O.fit_icnn(p, rows, un, steps=3, optimizer="adam", lr=1e-3)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    O.fit_icnn(p, rows, un, steps=steps, optimizer="adam", lr=1e-3)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    return {"value": N_PIX * steps / dt, "unit": "pixel-samples/s", "kind": "port", "device": torch.cuda.get_device_name(dev),
+            "ms_per_step": dt / steps * 1e3,
+            "sample": f"{steps} fit steps on the full 640x480 frame, eager PyTorch fp32 ops of the reference's loop on cuda"}
+
+
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
@@ -360,8 +389,12 @@ def main():
                     "share_of_step": per_class[dom]["ms_per_step"] / step_ms_prof,
                     "whole_step_tflops": FLOP_PER_PX_STEP * N_PIX / (ms_total / args.steps * 1e-3) / 1e12,
                     "note": note, "per_class_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in per_class.items()}}
-        cpu = None
+        cpu, eager = None, None
         if not args.no_cpu_baseline:
+            try:
+                eager = eager_gpu_throughput(dev)
+            except Exception as e:       # a baseline leg must never take the bench line down
+                eager = {"unavailable": repr(e)[:200]}
             thr, ms_cpu, cores, sample = cpu_oracle_throughput(steps=8, warmup=1, budget_s=20.0)
             cpu = {"value": thr, "unit": "pixel-samples/s", "cores": cores, "kind": "port", "sample": sample,
                    "ms_per_step_sample": ms_cpu}
@@ -384,6 +417,7 @@ def main():
                        "samples": clocks["samples"]},
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "eager_gpu_baseline": eager,
             "secondary": secondary,
             "final_loss": float(loss_host),
         }
