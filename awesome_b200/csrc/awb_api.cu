@@ -214,6 +214,10 @@ int awb_prior_create(const awb_desc* d, awb_handle* out) {
 int awb_prior_destroy(awb_handle h) {
   if (!h) return AWB_OK;
   cudaFree(h->d_map); cudaFree(h->d_clamp); cudaFree(h->d_group); cudaFree(h->d_tcmap); cudaFree(h->d_imap); cudaFree(h->d_aug2img);
+  if (h->stream_made) {
+    cudaStreamDestroy(h->copy_stream);
+    for (int b = 0; b < 2; b++) { cudaEventDestroy(h->ev_ready[b]); cudaEventDestroy(h->ev_free[b]); }
+  }
   delete h;
   return AWB_OK;
 }
@@ -356,6 +360,56 @@ int awb_prior_fit_step(awb_handle h, float* params, void* opt_state, const awb_g
   rc = simt_backward(h, params, g, target, loss, nullptr, false, w, st);
   if (rc) return rc;
   return simt_reduce_opt(h, params, opt_state, hy, loss_out, w, N, st);
+}
+
+int awb_prior_fit_host_frames(awb_handle h, float* params, void* opt_state, const awb_grid_spec* g,
+                              const float* const* host_targets, int32_t n_host, int32_t n_steps, const awb_loss_spec* loss,
+                              const awb_opt_hyper* hy, float* loss_host, float* staging, void* ws, size_t ws_bytes,
+                              int32_t flags, void* stream) {
+  int64_t N;
+  int rc = check_common(h, g, ws, ws_bytes, true, &N, /*fit_only=*/true);
+  if (rc) return rc;
+  if (!params || !opt_state || !host_targets || !loss || !hy || !staging) { set_error("null argument"); return AWB_ERR_INVALID; }
+  if (n_host < 1 || n_steps < 0) { set_error("n_host must be >= 1 and n_steps >= 0"); return AWB_ERR_INVALID; }
+  for (int i = 0; i < n_host; i++)
+    if (!host_targets[i]) { set_error("host_targets[%d] is null", i); return AWB_ERR_INVALID; }
+  float* loss_dev = nullptr;
+  if (loss_host) {   // the optimizer kernel stores each step's loss straight into mapped host memory
+    cudaPointerAttributes at;
+    AWB_CUDA(cudaPointerGetAttributes(&at, loss_host));
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) {
+      set_error("loss_host must be pinned (cudaHostAlloc / cudaHostRegister) host memory");
+      return AWB_ERR_INVALID;
+    }
+    loss_dev = (float*)at.devicePointer;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!h->stream_made) {
+    AWB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+      AWB_CUDA(cudaEventCreateWithFlags(&h->ev_ready[b], cudaEventDisableTiming));
+      AWB_CUDA(cudaEventCreateWithFlags(&h->ev_free[b], cudaEventDisableTiming));
+    }
+    h->stream_made = true;
+  }
+  const int O = h->desc.n_objects;
+  const size_t frame_bytes = (size_t)O * N * sizeof(float);
+  // the staging buffers may still be read by work queued on `st` before this call
+  AWB_CUDA(cudaEventRecord(h->ev_free[0], st));
+  AWB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_free[0], 0));
+  for (int s = 0; s < n_steps; s++) {
+    const int b = s & 1;
+    float* dst = staging + (size_t)b * O * N;
+    if (s >= 2) AWB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_free[b], 0));   // step s-2 has consumed this buffer
+    AWB_CUDA(cudaMemcpyAsync(dst, host_targets[s % n_host], frame_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    AWB_CUDA(cudaEventRecord(h->ev_ready[b], h->copy_stream));
+    AWB_CUDA(cudaStreamWaitEvent(st, h->ev_ready[b], 0));
+    rc = awb_prior_fit_step(h, params, opt_state, g, dst, loss, hy, loss_dev ? loss_dev + (size_t)s * O : nullptr, ws, ws_bytes,
+                            (s > 0 || (flags & AWB_FIT_REUSE_PACKED)) ? AWB_FIT_REUSE_PACKED : 0, stream);
+    if (rc) return rc;
+    AWB_CUDA(cudaEventRecord(h->ev_free[b], st));
+  }
+  return AWB_OK;
 }
 
 int awb_flow_identity_step(awb_handle h, float* params, void* opt_state, const awb_grid_spec* g,

@@ -69,6 +69,10 @@ struct awb_prior {
   awb::FlowConsts fc;
   bool fc_set;
   int device;
+  // awb_prior_fit_host_frames: copy stream + staging-buffer events, created on first use
+  cudaStream_t copy_stream;
+  cudaEvent_t ev_ready[2], ev_free[2];
+  bool stream_made;
 };
 
 namespace awb {

@@ -166,10 +166,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
   int tr_n = 0;
 #define AWB_TR()                                                            \
   do {                                                                      \
-    if (trace && (threadIdx.x == 0 || threadIdx.x == NEW * 32) && tr_n < TRACE_N / 2) \
+    if (trace && (threadIdx.x == 0 || threadIdx.x == NEW * 32) && tr_n < 120) \
       trace[(issuer_warp ? TRACE_N / 2 : 0) + tr_n++] = clock64();          \
   } while (0)
 
+  if (trace && threadIdx.x == 0) {                             // kernel entry (SM cycles and wall-clock ns)
+    trace[120] = clock64();
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    trace[125] = ns;
+  }
   // ---- one-time setup
   if (threadIdx.x == 0) { tc::mbar_init(bar_e2m, NEW); tc::mbar_init(bar_m2e, 1); tc::mbar_init(bar_w, 1); tc::mbar_fence_init(); }
   for (int i = threadIdx.x * 16; i < ZERO_B; i += NTHREADS * 16) *reinterpret_cast<uint4*>(szero + i) = make_uint4(0, 0, 0, 0);
@@ -348,10 +354,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
       c6[0] = half_lo(cz.x); c6[1] = half_hi(cz.x); c6[2] = half_lo(cz.y); c6[3] = half_hi(cz.y); c6[4] = half_lo(cz.z); c6[5] = half_hi(cz.z);
     };
 
+    if (trace && threadIdx.x == 0) trace[121] = clock64();    // setup done
     fetch_tile(blockIdx.x);
     write_tx(0, x0n, x1n, x2n);
     stage_done();
     tc::mbar_wait(bar_w, 0);     // wo (read with plain loads below) has landed
+    if (trace && threadIdx.x == 0) trace[122] = clock64();    // weights landed: tile loop starts
 
     for (int it = 0; it < n_my; it++) {
       const int tile = blockIdx.x + it * gridDim.x;
@@ -582,6 +590,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
     tc::mbar_wait(bar_m2e, ph); ph ^= 1;
     tc::fence_after_sync();
     AWB_TR();
+    if (trace && threadIdx.x == 0) trace[123] = clock64();    // tile loop done
 
     // =========================================================== per-CTA partial write-out
     if (fit) {
@@ -671,6 +680,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
         }
       }
       if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    if (trace && threadIdx.x == 0) {                           // write-out done
+      trace[124] = clock64();
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      trace[126] = ns;
     }
   }
   tc::fence_before_sync();

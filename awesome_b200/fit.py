@@ -238,6 +238,32 @@ class PriorFitter:
         self.steps_done += steps
         return hist
 
+    def run_host_frames(self, host_frames: Sequence[torch.Tensor], steps: Optional[int] = None) -> torch.Tensor:
+        """``steps`` fused fit steps whose unaries arrive from HOST memory: step ``s`` fits
+        ``host_frames[s % len(host_frames)]`` (each ``[O,N]`` fp32; pinned memory makes the copy overlap).  One native
+        call (``awb_prior_fit_host_frames``): the host->device copy of the next frame runs on a copy stream into a
+        double-buffered staging area while the current step computes, and the optimizer kernel stores every step's
+        loss straight into pinned host memory.  Returns that pinned ``[steps,O]`` tensor; it is valid after the
+        current stream is synchronised (this method does not block)."""
+        O, N = self.target.shape
+        frames = [f.detach().reshape(O, N) for f in host_frames]
+        for f in frames:
+            if f.device.type != "cpu" or f.dtype != torch.float32 or not f.is_contiguous():
+                raise ValueError("host frames must be contiguous fp32 CPU tensors of the fitter's [O,N] shape")
+        steps = len(frames) if steps is None else int(steps)
+        losses = torch.empty((max(steps, 1), O), dtype=torch.float32).pin_memory()
+        if getattr(self, "_staging", None) is None:
+            self._staging = torch.empty((2, O, N), dtype=torch.float32, device=self.device)
+        ptrs = (C.c_void_p * len(frames))(*[f.data_ptr() for f in frames])
+        with torch.cuda.device(self.device):
+            L.check(self.lib.awb_prior_fit_host_frames(
+                self.prior.handle, self.params.data_ptr(), self.opt_state.data_ptr(), C.byref(self._gs), ptrs, len(frames),
+                steps, self._specs, C.byref(self._hyper), losses.data_ptr(), self._staging.data_ptr(), self.ws.data_ptr(),
+                self.ws.numel(), 0, L.stream_ptr()))
+        self._host_keepalive = (frames, losses)     # the copies are still in flight when this returns
+        self.steps_done += steps
+        return losses[:steps]
+
     def scalars(self, obj: int = 0) -> L.OptScalars:
         """Synchronises and returns step / lr / plateau / non-finite flag of one object."""
         out = L.OptScalars()

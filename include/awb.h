@@ -174,6 +174,17 @@ int awb_prior_fit_step(awb_handle h, float* params, void* opt_state, const awb_g
                        const float* target, const awb_loss_spec* loss, const awb_opt_hyper* hyper,
                        float* loss_out, void* workspace, size_t workspace_bytes, int32_t flags, void* stream);
 
+/* The same loop with HOST inputs: n_steps fused fit steps, step s fitting the host frame host_targets[s % n_host]
+ * ([O][N] fp32 unaries; the reference moves the frame's inputs to the device and evaluates them per frame,
+ * path_connected_net.py:812-840, before the loop of :939-953; pretrain_unaries does `(1 - unaries).to(device)`, :439).  The host->device copy of frame s+1 runs on a copy stream
+ * owned by the handle into the other half of `staging` (device, 2*O*N floats) while step s computes; every step's
+ * loss [O] is stored by the optimizer kernel at loss_host + s*O (optional; pinned, device-mapped host memory), so
+ * the host never blocks inside the loop.  Asynchronous: synchronise `stream` before reading loss_host. */
+int awb_prior_fit_host_frames(awb_handle h, float* params, void* opt_state, const awb_grid_spec* grid,
+                              const float* const* host_targets, int32_t n_host, int32_t n_steps,
+                              const awb_loss_spec* loss, const awb_opt_hyper* hyper, float* loss_host,
+                              float* staging, void* workspace, size_t workspace_bytes, int32_t flags, void* stream);
+
 /* One step of PathConnectedNet.learn_flow_identity (path_connected_net.py:155-250): the NormNet-wrapped
  * flow alone (no 1x1 conv) is regressed onto its own input grid with SE("mean"); only the flow_net
  * group is updated (hyper->active_groups is forced to the flow group). */

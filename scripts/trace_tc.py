@@ -28,7 +28,11 @@ print("ctas read:", got)
 for c in range(got):
     ep = [buf[c * 256 + i] for i in range(128)]
     ms = [buf[c * 256 + 128 + i] for i in range(128)]
-    ep = [x for x in ep if x]
+    k0, k1, k2, k3, k4 = ep[120:125]
+    ns = ep[126] - ep[125]
+    print(f"--- CTA {c}: {k4 - k0} cycles in {ns} ns -> SM clock {(k4 - k0) / max(ns, 1) * 1e3:.0f} MHz")
+    print(f"--- CTA {c}: setup {k1 - k0} | first stage + weights {k2 - k1} | tile loop {k3 - k2} | write-out {k4 - k3} cycles")
+    ep = [x for x in ep[:120] if x]
     ms = [x for x in ms if x]
     t0 = min(ep[0], ms[0])
     print(f"--- CTA {c}: epilogue stamps (wait-done, arrive-done alternating), relative cycles")

@@ -295,3 +295,41 @@ def test_pretrain_protocol_with_duck_typed_agent(A, kind):
     ds2 = _FakeDataset(frames, grid, cache2)
     m.pretrain_load_state(ds2, None, torch.device(DEV), _FakeAgent(ds2), state, wrapper_module=None)
     assert 1 in cache2 and torch.equal(cache2[1]["convex_net.input.weight"].cpu(), state["cache"]["1"]["convex_net.input.weight"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "f16"])
+def test_host_frame_fit_equals_device_frame_fit(A, precision):
+    """awb_prior_fit_host_frames (host unaries, copy stream + double-buffered staging, losses stored into pinned host
+    memory) == the same frames fitted one step at a time from device memory, bit for bit: parameters and losses."""
+    torch.manual_seed(3)
+    H, W = 48, 72
+    frames = [blob(H, W, cx=0.4 + 0.05 * k, ry=0.25 + 0.02 * k).reshape(1, -1).contiguous() for k in range(3)]
+    pinned = [f.pin_memory() if k != 1 else f for k, f in enumerate(frames)]      # one pageable frame: still correct
+    grid = A.GridSpecHost("linspace", 1, H, W)
+    steps = 7
+    m1 = A.ConvexNextNet(n_hidden_layers=2, precision=precision).to(DEV)
+    m2 = A.ConvexNextNet(n_hidden_layers=2, precision=precision).to(DEV)
+    m2.load_state_dict(m1.state_dict())
+    f1 = m1.make_fitter(grid, frames[0].to(DEV), A.LossConfig("mse"), A.OptimConfig("adam", lr=1e-3), use_graph=False)
+    f2 = m2.make_fitter(grid, frames[0].to(DEV), A.LossConfig("mse"), A.OptimConfig("adam", lr=1e-3), use_graph=False)
+    ref_losses = []
+    for s in range(steps):
+        f1.set_target(frames[s % 3].to(DEV))
+        ref_losses.append(f1.run(1)[0].cpu())
+    got = f2.run_host_frames(pinned, steps)
+    torch.cuda.synchronize()
+    assert got.shape == (steps, 1) and got.is_pinned()
+    torch.testing.assert_close(got, torch.stack(ref_losses), rtol=0, atol=0)
+    for (k, a), b in zip(m1.state_dict().items(), m2.state_dict().values()):
+        assert torch.equal(a, b), k
+    assert f2.steps_done == steps
+    from awesome_b200 import _lib as AL
+    import ctypes as C
+    with pytest.raises(AL.AwbError):     # the loss slots must be device-mapped host memory
+        lib = f2.lib
+        ptrs = (C.c_void_p * 1)(pinned[0].data_ptr())
+        bad = torch.empty(4)
+        AL.check(lib.awb_prior_fit_host_frames(f2.prior.handle, f2.params.data_ptr(), f2.opt_state.data_ptr(),
+                                                   C.byref(f2._gs), ptrs, 1, 1, f2._specs, C.byref(f2._hyper),
+                                                   bad.data_ptr(), f2._staging.data_ptr(), f2.ws.data_ptr(),
+                                                   f2.ws.numel(), 0, AL.stream_ptr()))
