@@ -122,6 +122,24 @@ void prof_end(int cls, cudaStream_t st);
     awb::prof_end(cls, st);       \
   } while (0)
 
+// Launch with (optionally) programmatic stream serialization: the kernel may become resident while its predecessor in
+// the stream drains.  Every kernel launched this way executes griddepcontrol.wait before it touches global memory
+// and griddepcontrol.launch_dependents only after that wait, so completion stays transitive along the stream.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                             Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- launchers implemented in awb_simt.cu ----
 struct GridDev {
   int mode, B, H, W, C;

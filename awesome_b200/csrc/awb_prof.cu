@@ -1,6 +1,8 @@
 // Per-kernel-class timing with CUDA events on the launching stream, and a launch counter.
 // Used by bench.py for the roofline (average duration of the dominant kernel, measured live) and for
 // its gpu_launches claim.  Timing is off by default; the counter is always on.
+#include <stdlib.h>
+
 #include "awb_internal.cuh"
 
 namespace awb {
@@ -16,6 +18,12 @@ static struct Prof {
   long long launches = 0;
   long long per_class[PK_COUNT] = {0};
 } g;
+
+// Programmatic dependent launch of the fit-step kernels is on unless AWB_NO_PDL is set (A/B measurements).
+bool pdl_enabled() {
+  static const bool on = getenv("AWB_NO_PDL") == nullptr;
+  return on;
+}
 
 void prof_begin(int cls, cudaStream_t st) {
   g.launches++;

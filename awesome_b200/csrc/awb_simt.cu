@@ -570,6 +570,8 @@ __global__ void __launch_bounds__(256) k_reduce_opt_aug(OptA a, int n_groups) {
   __shared__ float s_step_size[AWB_MAX_GROUPS], s_bc2s;
   const int o = blockIdx.y;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  grid_dep_wait();      // programmatic dependent launch: the producer of the partials has completed
+  grid_dep_launch();
   if (threadIdx.x >= 32 && threadIdx.x < 32 + AWB_MAX_GROUPS) {   // bias corrections, once per block
     const int g = threadIdx.x - 32;
     const int step1 = a.scal[o].step + 1;
@@ -593,10 +595,14 @@ __global__ void __launch_bounds__(256) k_reduce_opt_aug(OptA a, int n_groups) {
       const float4* src = reinterpret_cast<const float4*>(a.part + (int64_t)o * a.G + g0) + lane;
       const int64_t stride4 = a.sSplit / 4;
       const int s0 = (a.S * w) >> 3, s1 = (a.S * (w + 1)) >> 3;
-#pragma unroll 5
-      for (int s = s0; s < s1; s++) {
-        const float4 t = src[(int64_t)s * stride4];
-        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      // all of this warp's <= 19 partial rows in flight at once (one L2 round trip), summed in a fixed order
+      for (int sb = s0; sb < s1; sb += 20) {
+        float4 t[20];
+#pragma unroll
+        for (int k = 0; k < 20; k++)
+          t[k] = sb + k < s1 ? __ldcg(src + (int64_t)(sb + k) * stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 20; k++) { acc.x += t[k].x; acc.y += t[k].y; acc.z += t[k].z; acc.w += t[k].w; }
       }
     }
     s_part[w][lane] = acc;
@@ -891,7 +897,8 @@ int simt_reduce_opt(const awb_prior* h, float* params, void* opt_state, const aw
     if (ws.tc && h->d_aug2img) {
       b.img = (uint8_t*)ws.tc; b.img_stride = tc_image_bytes(L.L); b.vec_off = tc_vec_offset_bytes(L.L); b.aug2img = h->d_aug2img;
     }
-    AWB_LAUNCH(PK_OPT, st, k_reduce_opt_aug<<<dim3((unsigned)((L.G + 127) / 128), O), 256, 0, st>>>(b, n_groups_of(h)));
+    AWB_LAUNCH(PK_OPT, st, AWB_CUDA(launch_ex(k_reduce_opt_aug, dim3((unsigned)((L.G + 127) / 128), O), dim3(256), 0, st, true,
+                                              b, n_groups_of(h))));
   } else {
     AWB_LAUNCH(PK_OPT, st, k_reduce_opt<<<dim3((unsigned)((L.P + 31) / 32), O), 256, 0, st>>>(a, n_groups_of(h), 1));
   }

@@ -180,8 +180,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
   if (threadIdx.x == 0) { tc::mbar_init(bar_e2m, NEW); tc::mbar_init(bar_m2e, 1); tc::mbar_init(bar_w, 1); tc::mbar_fence_init(); }
   for (int i = threadIdx.x * 16; i < ZERO_B; i += NTHREADS * 16) *reinterpret_cast<uint4*>(szero + i) = make_uint4(0, 0, 0, 0);
   __syncthreads();
+  if (issuer_warp) tc::tmem_alloc<512>(tmem_slot);
+  // Everything above overlaps the tail of the previous kernel in the stream (programmatic dependent launch);
+  // from here on this kernel reads what that kernel wrote (weight image, unaries, flow coordinates).
+  grid_dep_wait();
+  grid_dep_launch();
   if (issuer_warp) {
-    tc::tmem_alloc<512>(tmem_slot);
     if (lane == 0) {
       const uint8_t* src = p.img + (int64_t)o * p.img_stride;
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar_w)), "r"((uint32_t)IMG) : "memory");
@@ -796,7 +800,7 @@ int tc_fit_forward_backward(const awb_prior* h, const float* params, const awb_g
 #define AWB_TC_LAUNCH(LL, CC)                                                                                      \
   do {                                                                                                             \
     AWB_CUDA(cudaFuncSetAttribute(k_icnn_fit_tc<LL, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    AWB_LAUNCH(PK_TC_FUSED, st, k_icnn_fit_tc<LL, CC><<<gd, NTHREADS, smem, st>>>(p));                             \
+    AWB_LAUNCH(PK_TC_FUSED, st, AWB_CUDA(launch_ex(k_icnn_fit_tc<LL, CC>, gd, dim3(NTHREADS), smem, st, true, p))); \
   } while (0)
   if (L == 1 && C == 2) AWB_TC_LAUNCH(1, 2);
   else if (L == 1 && C == 3) AWB_TC_LAUNCH(1, 3);
