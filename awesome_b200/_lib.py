@@ -10,7 +10,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libawb.so")
+LIB_PATH = os.environ.get("AWB_LIB_PATH") or os.path.join(_HERE, "csrc", "libawb.so")   # override: A/B builds
 
 AWB_KIND_ICNN, AWB_KIND_FLOW_ICNN, AWB_KIND_STAR, AWB_KIND_DIFFEO_ICNN = 0, 1, 2, 3
 AWB_PREC_FP32, AWB_PREC_F16 = 0, 1

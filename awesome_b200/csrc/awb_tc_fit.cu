@@ -83,6 +83,7 @@ struct TcP {
   float* logits;
   int64_t N; int n_tiles; int mode;
   unsigned long long* trace;
+  int trace_serial;
   const float* amax;   // optional device [O]: max |dlogits| per object; sets the fp16 loss scale of the upstream-gradient mode
   const float* X;   // optional [O][N][4]: coordinates produced by the flow (x, y, t, 1) instead of the generated grid
   float* dX;        // optional [O][N][4]: gradient w.r.t. those coordinates (consumed by the flow backward)
@@ -155,7 +156,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
   uint64_t* bar_e2m = bars;        // epilogue -> issuer (one arrival per epilogue warp)
   uint64_t* bar_m2e = bars + 1;    // tcgen05.commit -> epilogue
   uint64_t* bar_w = bars + 2;      // weight image landed (TMA tx bytes)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* bar_dbg = bars + 3;    // diagnostic build only: the issuer waits for every contraction group
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   const float* wo = reinterpret_cast<const float*>(simg + L * W_B + WIN_B);
   const uint8_t* wo16 = simg + L * W_B + WIN_B + VEC_B;            // fp16 copy, 16 bytes per column chunk
 
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
     trace[125] = ns;
   }
   // ---- one-time setup
-  if (threadIdx.x == 0) { tc::mbar_init(bar_e2m, NEW); tc::mbar_init(bar_m2e, 1); tc::mbar_init(bar_w, 1); tc::mbar_fence_init(); }
+  if (threadIdx.x == 0) { tc::mbar_init(bar_e2m, NEW); tc::mbar_init(bar_m2e, 1); tc::mbar_init(bar_w, 1); tc::mbar_init(bar_dbg, 1); tc::mbar_fence_init(); }
   for (int i = threadIdx.x * 16; i < ZERO_B; i += NTHREADS * 16) *reinterpret_cast<uint4*>(szero + i) = make_uint4(0, 0, 0, 0);
   __syncthreads();
   if (issuer_warp) tc::tmem_alloc<512>(tmem_slot);
@@ -249,6 +251,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
         tc::umma_f16(tbase + T_ACC, tc::make_desc(a_tx, zero_a - a_tx, 128), tc::make_desc(a_win, zero_a - a_win, 128),
                      tc::make_idesc(128, 144, 0, 0), 0);
       };
+      // Diagnostic build (-DAWB_TC_SERIAL, see scripts/trace_tc.py) with AWB_TC_TRACE=2: a commit + wait + clock stamp
+      // after every contraction group gives the true duration of each.  Compiled out otherwise: even a never-taken
+      // branch between the groups costs the issuing thread ~6 % of the kernel (measured).
+#ifdef AWB_TC_SERIAL
+      uint32_t phd = 0;
+      const bool serial = trace && p.trace_serial;
+      auto dbg = [&]() {
+        if (serial) { tc::umma_commit(bar_dbg); tc::mbar_wait(bar_dbg, phd); phd ^= 1; AWB_TR(); }
+      };
+#else
+      auto dbg = []() {};
+#endif
       // prologue: input layer of the first tile
       tc::mbar_wait(bar_e2m, ph); ph ^= 1;
       tc::fence_after_sync();
@@ -275,20 +289,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
           AWB_TR();
           if (s <= L) {
             mma_k144(T_ACC, t_addr(tile_ptr(s - 1)), w_addr(s), false);          // forward layer s
+            dbg();
             tc::umma_commit(bar_m2e);
           } else if (s <= 2 * L) {
             const int i = L - (s - (L + 1));                                      // delta_i was just written
             const uint32_t d = t_addr(dbuf(i)), zprev = t_addr(tile_ptr(i - 1));
             mma_k144(T_ACC, d, w_addr(i), true);                                  // dgrad_i: ACC = delta_i * W_i
-            if (i == L) mma_px(T_GO, t_addr(tile_ptr(L)), d + 16 * 2048, 2048, 16, acc);   // z_L^T * [d128 d129 dy ..]
+            dbg();
+            if (i == L) { mma_px(T_GO, t_addr(tile_ptr(L)), d + 16 * 2048, 2048, 16, acc); dbg(); }   // z_L^T * [d128 d129 dy ..]
             tc::umma_commit(bar_m2e);
             mma_px(T_DW(i), d, zprev, 2048, 144, acc);                            // wgrad_i main rows 0..127
+            dbg();
             mma_px(T_PB(i), zprev, d + 16 * 2048, 2048, 16, acc);                 // wgrad_i rows 128,129 (transposed)
+            dbg();
           } else {
             if (more) {                                                           // next tile's input layer first:
               mma_input(a_txn);                                                   // its epilogue does not wait for
+              dbg();
               tc::umma_commit(bar_m2e);                                           // this tile's input-layer wgrad
               mma_px(T_GIN, t_addr(dbuf(0)), a_tx, zero_a - a_tx, 16, acc);
+              dbg();
             } else {
               mma_px(T_GIN, t_addr(dbuf(0)), a_tx, zero_a - a_tx, 16, acc);
               tc::umma_commit(bar_m2e);
@@ -683,7 +703,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
           }
         }
       }
-      if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      // the CTA may exit once the bulk stores have read their shared-memory source; kernel completion covers the writes
+      if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     if (trace && threadIdx.x == 0) {                           // write-out done
       trace[124] = clock64();
@@ -791,7 +812,8 @@ int tc_fit_forward_backward(const awb_prior* h, const float* params, const awb_g
   p.lossp = ws.lossp; p.O = O; p.logits = logits; p.N = N; p.n_tiles = n_tiles; p.mode = mode;
   p.X = Xrows; p.dX = dXrows; p.amax = amax;
   p.trace = nullptr;
-  if (getenv("AWB_TC_TRACE")) {
+  if (const char* tr = getenv("AWB_TC_TRACE")) {
+    p.trace_serial = atoi(tr) == 2;
     if (!g_trace_dev) cudaMalloc(&g_trace_dev, sizeof(unsigned long long) * TRACE_N * kMaxSplits * 16);
     if (g_trace_dev) { cudaMemsetAsync(g_trace_dev, 0, sizeof(unsigned long long) * TRACE_N * grid * O, st); p.trace = g_trace_dev; g_trace_ctas = grid * O; }
   }

@@ -4,8 +4,22 @@ import ctypes as C
 import os
 import sys
 
-os.environ["AWB_TC_TRACE"] = "1"
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+SERIAL = "--serial" in sys.argv
+if SERIAL:
+    # diagnostic variant of the library: the issuer waits for (and stamps) every contraction group
+    sys.argv.remove("--serial")
+    import glob
+    import subprocess
+    import __graft_entry__ as entry
+    lib = os.path.join(entry.CSRC, "libawb_serial.so")
+    srcs = sorted(glob.glob(os.path.join(entry.CSRC, "*.cu")))
+    if not os.path.exists(lib) or any(os.path.getmtime(f) > os.path.getmtime(lib) for f in srcs):
+        subprocess.check_call(["nvcc"] + entry.NVCC_FLAGS + ["-DAWB_TC_SERIAL", "-o", lib] + srcs)
+    os.environ["AWB_LIB_PATH"] = lib
+    os.environ["AWB_TC_TRACE"] = "2"
+os.environ.setdefault("AWB_TC_TRACE", "1")
 import torch
 import awesome_b200 as A
 from awesome_b200 import _lib
@@ -41,6 +55,14 @@ for c in range(got):
     print(f"--- CTA {c}: issuer stamps (first after prologue commit; then per stage: wake, issued)")
     print(" ".join(str(x - t0) for x in ms[:40]))
     print("    deltas:", " ".join(str(b - a) for a, b in zip(ms[:40], ms[1:41])))
+    if SERIAL and L == 2:
+        # per tile: wake, fwd1, issued | wake, fwd2, issued | wake, dgrad2, GO, wgrad2, PB2, issued | wake, dgrad1, wgrad1,
+        # PB1, issued | wake, input', GIN, issued      (each duration includes one commit -> mbarrier -> wake round trip)
+        names = ["wake", "fwd1", "-", "wake", "fwd2", "-", "wake", "dgrad2", "GO", "wgrad2", "PB2", "-", "wake", "dgrad1",
+                 "wgrad1", "PB1", "-", "wake", "input'", "GIN", "-"]
+        base = 1 + len(names)       # second tile
+        d = [ms[base + i] - ms[base + i - 1] for i in range(len(names))]
+        print("    serialised issue, second tile: " + "  ".join(f"{n} {x}" for n, x in zip(names, d) if n != "-"))
     nst = 2 * L + 1
     if len(ep) > 2 * nst * 3:
         per_tile = (ep[2 * nst * 3] - ep[2 * nst * 1]) / 2.0
