@@ -570,15 +570,38 @@ __global__ void __launch_bounds__(256) k_reduce_opt_aug(OptA a, int n_groups) {
   __shared__ float s_step_size[AWB_MAX_GROUPS], s_bc2s;
   const int o = blockIdx.y;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  grid_dep_wait();      // programmatic dependent launch: the producer of the partials has completed
-  grid_dep_launch();
-  if (threadIdx.x >= 32 && threadIdx.x < 32 + AWB_MAX_GROUPS) {   // bias corrections, once per block
-    const int g = threadIdx.x - 32;
+  const int64_t g0 = (int64_t)blockIdx.x * 128;
+  // ---- before the producer of the partials has finished (programmatic dependent launch: these blocks become
+  // resident as the fit kernel's CTAs retire): everything that only depends on the previous optimizer step --
+  // bias corrections, index maps, the parameter and its moments.
+  if (threadIdx.x >= 128 && threadIdx.x < 128 + AWB_MAX_GROUPS) {   // bias corrections, once per block
+    const int g = threadIdx.x - 128;
     const int step1 = a.scal[o].step + 1;
     const double bc1 = 1.0 - pow((double)a.hy.beta1, (double)step1);
     s_step_size[g] = (float)(a.scal[o].lr[g] / bc1);
     if (g == 0) s_bc2s = (float)sqrt(1.0 - pow((double)a.hy.beta2, (double)step1));
   }
+  const int t = threadIdx.x;
+  const int64_t aug = g0 + t;
+  int64_t gi = -1;
+  int grp = 0, e = -1;
+  bool do_clamp = false;
+  float p = 0.f, m = 0.f, v = 0.f;
+  if (t < 128 && aug < a.G) {
+    const int32_t li = a.imap[aug];
+    if (li >= 0) {
+      const int64_t i = a.off_icnn + li;
+      grp = a.group[i];
+      if (!(a.hy.active_groups && !((a.hy.active_groups >> grp) & 1))) {
+        gi = (int64_t)o * a.P + i;
+        do_clamp = a.clamp[i] != 0;
+        p = a.params[gi]; m = a.m[gi]; v = a.v[gi];
+        if (a.img) e = a.aug2img[aug];
+      }
+    }
+  }
+  grid_dep_wait();      // the partials and the loss sums are complete
+  grid_dep_launch();
   if (w == 0) {
     float l = 0.f;
     for (int s = lane; s < a.S; s += 32) l += a.lossp[s * a.O + o];
@@ -588,7 +611,6 @@ __global__ void __launch_bounds__(256) k_reduce_opt_aug(OptA a, int n_groups) {
   }
   __syncthreads();
   const bool bad = !isfinite(s_loss);
-  const int64_t g0 = (int64_t)blockIdx.x * 128;
   if (!bad) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (g0 + 4 * lane < a.G) {
@@ -597,43 +619,31 @@ __global__ void __launch_bounds__(256) k_reduce_opt_aug(OptA a, int n_groups) {
       const int s0 = (a.S * w) >> 3, s1 = (a.S * (w + 1)) >> 3;
       // all of this warp's <= 19 partial rows in flight at once (one L2 round trip), summed in a fixed order
       for (int sb = s0; sb < s1; sb += 20) {
-        float4 t[20];
+        float4 tt[20];
 #pragma unroll
         for (int k = 0; k < 20; k++)
-          t[k] = sb + k < s1 ? __ldcg(src + (int64_t)(sb + k) * stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          tt[k] = sb + k < s1 ? __ldcg(src + (int64_t)(sb + k) * stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < 20; k++) { acc.x += t[k].x; acc.y += t[k].y; acc.z += t[k].z; acc.w += t[k].w; }
+        for (int k = 0; k < 20; k++) { acc.x += tt[k].x; acc.y += tt[k].y; acc.z += tt[k].z; acc.w += tt[k].w; }
       }
     }
     s_part[w][lane] = acc;
     __syncthreads();
-    const int t = threadIdx.x;
-    const int64_t aug = g0 + t;
-    if (t < 128 && aug < a.G) {
-      const int32_t li = a.imap[aug];
-      if (li >= 0) {
-        const int64_t i = a.off_icnn + li;
-        const int grp = a.group[i];
-        if (!(a.hy.active_groups && !((a.hy.active_groups >> grp) & 1))) {
-          float g = 0.f;
+    if (gi >= 0) {
+      float g = 0.f;
 #pragma unroll
-          for (int ww = 0; ww < 8; ww++) g += reinterpret_cast<const float*>(&s_part[ww][0])[t];
-          const int64_t gi = (int64_t)o * a.P + i;
-          float p = a.params[gi], m = a.m[gi], v = a.v[gi];
-          opt_update(a.hy.kind, p, g, m, v, s_step_size[grp], s_bc2s, a.hy.beta1, a.hy.beta2, a.hy.eps,
-                     a.hy.weight_decay[grp]);
-          if (a.clamp[i]) p = fmaxf(p, 0.f);                     // enforce_convexity
-          a.params[gi] = p; a.m[gi] = m; a.v[gi] = v;
-          if (a.img) {   // keep the tensor path's fp16 weight image in step
-            uint8_t* base = a.img + (int64_t)o * a.img_stride;
-            const int32_t e = a.aug2img[aug];
-            if (e >= 0) reinterpret_cast<__half*>(base)[e] = __float2half_rn(p);
-            if (aug >= a.aug_out) {
-              const int k = (int)(aug - a.aug_out);
-              reinterpret_cast<float*>(base + a.vec_off)[k] = p;
-              reinterpret_cast<__half*>(base + a.vec_off + 4 * 144)[k] = __float2half_rn(p);
-            }
-          }
+      for (int ww = 0; ww < 8; ww++) g += reinterpret_cast<const float*>(&s_part[ww][0])[t];
+      opt_update(a.hy.kind, p, g, m, v, s_step_size[grp], s_bc2s, a.hy.beta1, a.hy.beta2, a.hy.eps,
+                 a.hy.weight_decay[grp]);
+      if (do_clamp) p = fmaxf(p, 0.f);                     // enforce_convexity
+      a.params[gi] = p; a.m[gi] = m; a.v[gi] = v;
+      if (a.img) {   // keep the tensor path's fp16 weight image in step
+        uint8_t* base = a.img + (int64_t)o * a.img_stride;
+        if (e >= 0) reinterpret_cast<__half*>(base)[e] = __float2half_rn(p);
+        if (aug >= a.aug_out) {
+          const int k = (int)(aug - a.aug_out);
+          reinterpret_cast<float*>(base + a.vec_off)[k] = p;
+          reinterpret_cast<__half*>(base + a.vec_off + 4 * 144)[k] = __float2half_rn(p);
         }
       }
     }
