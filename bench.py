@@ -52,6 +52,15 @@ def synth_unaries(seed: int, t: float = 0.0):
     return torch.sigmoid((sdf + 0.05 * torch.randn(H, W, generator=g)) / 0.08).float()
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -61,7 +70,7 @@ def peaks():
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -78,7 +87,14 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self):
+    @staticmethod
+    def _epoch(ts: str) -> float:
+        import datetime
+        return datetime.datetime.strptime(ts.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+
+    def stop(self, t0: float = None, t1: float = None):
+        """Summary of the samples taken between wall-clock t0 and t1 (the timed regions); nvidia-smi needs a few
+        hundred ms to deliver its first sample on an 8-GPU box, so it is started well before them."""
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -95,6 +111,8 @@ class ClockSampler:
                 if len(f) < 9:
                     continue
                 try:
+                    if t0 is not None and not (t0 - 0.02 <= self._epoch(f[0]) <= t1 + 0.02):
+                        continue
                     sm.append(float(f[1]))
                     mx.append(float(f[2]))
                 except ValueError:
@@ -244,7 +262,7 @@ def run_reference(args, rank: int, world: int):
         "e2e": {"value": thr, "unit": "pixel-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -257,6 +275,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short runs of BASELINE configs 0, 2, 3")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON: everything any library prints to file descriptor 1 (NCCL's version
+    # banner, warnings of child processes) is sent to stderr, and the JSON line is written to the saved descriptor.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -281,6 +305,8 @@ def main():
         os.environ["NCCL_DEBUG"] = os.environ.get("AWB_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     warmup = max(3, args.warmup)
 
     # ---- the fit: one frame per rank (frames are independent units; rank r owns frames r, r+N, ...)
@@ -308,14 +334,12 @@ def main():
     fitter.run(warmup, record=False)
     barrier()
     launches0 = lib.awb_launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    t_load0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     fitter.run(args.steps, record=False)
     ev1.record()
     barrier()
-    clocks = sampler.stop()
     launches = lib.awb_launch_count() - launches0
     ms_total = ev0.elapsed_time(ev1)
 
@@ -333,6 +357,7 @@ def main():
     e1.record()
     barrier()
     t_e2e = e0.elapsed_time(e1)
+    clocks = sampler.stop(t_load0, time.time())      # samples under load: the device-timed and the end-to-end region
     if not bool(torch.isfinite(loss_host).all()):
         raise SystemExit("e2e: non-finite loss read back from the host-frame fit")
     fitter.raise_if_nonfinite()
@@ -380,7 +405,7 @@ def main():
             note = ("fp32 CUDA-core contraction (exact-parity path); reported against the sustained cuBLAS bf16 "
                     "tensor peak the north star names")
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r1_tc_v4_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r1_tc_v5_traffic.json")
         if dom == "tc_fused" and os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")      # from the committed ncu --set full capture
         ach = dom_flop / (per_class[dom]["ms_per_launch"] * 1e-3) / 1e12
@@ -423,7 +448,7 @@ def main():
             "secondary": secondary,
             "final_loss": float(loss_host[-1, 0]),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
