@@ -194,6 +194,18 @@ def secondary_workloads(A, dev, unaries640):
                       A.OptimConfig("adam", lr=2e-3), steps_per_graph=50)
     ms = _time_fitter(f, 200)
     out["c0_convexity_256x256_L1"] = {"ms_per_step": ms, "pixel_samples_per_s": 256 * 256 / ms * 1e3}
+    # configs[1] again, as a group: 4 independent frames (4 ConvexNextNet priors) per fused launch -- what a rank of the
+    # 60-frame sequence does when frames are fitted without warm-start chaining; the next frame's CTAs fill the SMs the
+    # 16-tile CTAs of the previous one leave idle (2400 tiles over 148 SMs = 16.2 per SM, 17 on the critical path)
+    grid640 = A.GridSpecHost("linspace", 1, H, W)
+    mg = A.NumberBasedMultiPriorModule(prior_type=A.ConvexNextNet,
+                                       prior_args=dict(n_hidden=HID, in_features=CH, n_hidden_layers=LAYERS, precision="f16"),
+                                       min_priors=4).to(dev)
+    tg4 = torch.stack([torch.roll(unaries640, shifts=(11 * k, 23 * k), dims=(0, 1)) for k in range(4)])
+    f = mg.make_fitter(grid640, tg4, A.LossConfig("mse"), A.OptimConfig("adam", lr=1e-3), steps_per_graph=25)
+    ms = _time_fitter(f, 100)
+    out["c1_convexity_4_frames_grouped_640x480"] = {"ms_per_step": ms, "pixel_samples_per_s": 4 * N_PIX / ms * 1e3}
+    del f, mg
     # configs[2]: path-connectedness -- RealNVP(12 flows, m=32, tanh) o ICNN(L=2), Adamax + plateau, flow wd 1e-5
     pc = A.real_nvp_path_connected_net(channels=2, hidden_units=32, flow_n_flows=12, flow_output_fn="tanh", norm="minmax",
                                        convex_net_hidden_units=130, convex_net_hidden_layers=2, precision="f16").to(dev)
