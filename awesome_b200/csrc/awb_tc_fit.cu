@@ -788,7 +788,12 @@ int tc_fit_forward_backward(const awb_prior* h, const float* params, const awb_g
   const int n_tiles = (int)((N + 127) / 128);
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-  const int grid = n_tiles < sms ? n_tiles : sms;
+  // One wave: the O objects share the SMs (sms / O persistent CTAs each).  Compared with sms CTAs per object in O
+  // waves this keeps the number of gradient partials (and their L2 footprint, and the optimizer kernel's reads) at
+  // one per SM in total, removes the tile quantisation (2400 tiles / 37 CTAs = 64.9 -> 65 instead of 16.2 -> 17 per
+  // frame at O = 4) and pays the per-CTA weight load and partial write-out once per SM instead of once per SM and object.
+  const int per_obj = sms / O > 0 ? sms / O : 1;
+  const int grid = n_tiles < per_obj ? n_tiles : per_obj;
   if (grid > kMaxSplits) { set_error("internal: grid exceeds split capacity"); return AWB_ERR_INVALID; }
   const int64_t img_stride = tc_image_bytes(L);
   const int n_elems = tc_map_elems(L);

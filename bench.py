@@ -6,9 +6,10 @@
 Workload (config.workload): BASELINE configs[1] -- the convexity prior ``ConvexNextNet(h=130, L=2, C=2)``
 fitted per frame on a synthetic FBMS-shaped 640x480 frame (unaries = soft UNet-like blob), loss
 ``UnariesWeightedLoss(SE)`` = MSE(sigmoid(y), unaries), Adam lr 1e-3, enforce_convexity every step.
-One "step" = one fused fit step (forward + loss + backward + gradient reduction + Adam + clamp) over
-one frame = 307 200 pixel-samples per GPU.  With N GPUs every rank fits its own frame (frames are
-independent: no data-path collective; weak scaling); value = N * 307200 * K / max-over-ranks time.
+One "step" = one fused fit step (forward + loss + backward + gradient reduction + Adam + clamp) over a group of
+G = --frames-per-step (default 4) independent frames of the rank's share of the sequence, one prior per frame,
+= G x 307 200 pixel-samples per GPU.  With N GPUs every rank fits its own frames (frames are independent: no
+data-path collective; weak scaling); value = N * G * 307200 * K / max-over-ranks time.
 
 Prints ONE JSON line (see the task contract): value (inputs resident in HBM, device-timed with CUDA
 events), e2e (same metric through the public fit API with the step's unaries coming from pinned host
@@ -38,7 +39,7 @@ HID, LAYERS, CH = 130, 2, 2
 MAC_FWD = CH * HID + LAYERS * (HID * HID + CH * HID) + HID + CH        # 34 712
 FLOP_PER_PX_STEP = 6 * MAC_FWD                                          # 208 272
 GEMM_FLOP_PER_PX_LAUNCH = 2 * HID * (HID + CH + 1)                      # one hidden-layer contraction launch
-WORKLOAD = "convexity ICNN prior fit per frame, synthetic FBMS-shaped 640x480 frame (BASELINE configs[1])"
+WORKLOAD = "convexity ICNN prior fit per frame, synthetic FBMS-shaped 640x480 frames (BASELINE configs[1])"
 
 
 def synth_unaries(seed: int, t: float = 0.0):
@@ -194,18 +195,13 @@ def secondary_workloads(A, dev, unaries640):
                       A.OptimConfig("adam", lr=2e-3), steps_per_graph=50)
     ms = _time_fitter(f, 200)
     out["c0_convexity_256x256_L1"] = {"ms_per_step": ms, "pixel_samples_per_s": 256 * 256 / ms * 1e3}
-    # configs[1] again, as a group: 4 independent frames (4 ConvexNextNet priors) per fused launch -- what a rank of the
-    # 60-frame sequence does when frames are fitted without warm-start chaining; the next frame's CTAs fill the SMs the
-    # 16-tile CTAs of the previous one leave idle (2400 tiles over 148 SMs = 16.2 per SM, 17 on the critical path)
+    # configs[1] one frame per launch (the headline groups --frames-per-step frames): 2400 tiles over 148 SMs
     grid640 = A.GridSpecHost("linspace", 1, H, W)
-    mg = A.NumberBasedMultiPriorModule(prior_type=A.ConvexNextNet,
-                                       prior_args=dict(n_hidden=HID, in_features=CH, n_hidden_layers=LAYERS, precision="f16"),
-                                       min_priors=4).to(dev)
-    tg4 = torch.stack([torch.roll(unaries640, shifts=(11 * k, 23 * k), dims=(0, 1)) for k in range(4)])
-    f = mg.make_fitter(grid640, tg4, A.LossConfig("mse"), A.OptimConfig("adam", lr=1e-3), steps_per_graph=25)
-    ms = _time_fitter(f, 100)
-    out["c1_convexity_4_frames_grouped_640x480"] = {"ms_per_step": ms, "pixel_samples_per_s": 4 * N_PIX / ms * 1e3}
-    del f, mg
+    m1 = A.ConvexNextNet(n_hidden=HID, in_features=CH, n_hidden_layers=LAYERS, precision="f16").to(dev)
+    f = m1.make_fitter(grid640, unaries640, A.LossConfig("mse"), A.OptimConfig("adam", lr=1e-3), use_graph=False)
+    ms = _time_fitter(f, 200)
+    out["c1_convexity_single_frame_640x480"] = {"ms_per_step": ms, "pixel_samples_per_s": N_PIX / ms * 1e3}
+    del f, m1
     # configs[2]: path-connectedness -- RealNVP(12 flows, m=32, tanh) o ICNN(L=2), Adamax + plateau, flow wd 1e-5
     pc = A.real_nvp_path_connected_net(channels=2, hidden_units=32, flow_n_flows=12, flow_output_fn="tanh", norm="minmax",
                                        convex_net_hidden_units=130, convex_net_hidden_layers=2, precision="f16").to(dev)
@@ -284,6 +280,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("AWB_BENCH_PRECISION", "f16"), choices=["fp32", "f16"])
+    ap.add_argument("--frames-per-step", type=int, default=4,
+                    help="independent frames of the rank's share of the sequence fitted together per fused launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short runs of BASELINE configs 0, 2, 3")
     args = ap.parse_args()
@@ -321,19 +319,27 @@ def main():
     sampler.start()
     warmup = max(3, args.warmup)
 
-    # ---- the fit: one frame per rank (frames are independent units; rank r owns frames r, r+N, ...)
+    # ---- the fit: frames are independent units (rank r owns its share of the 60-frame sequence); a rank fits
+    # G = --frames-per-step of its frames together, one ConvexNextNet prior per frame, one fused launch per kernel.
+    # With G frames per launch the next frame's CTAs fill the SMs that the 16-tile CTAs of the previous one leave idle
+    # (2400 tiles of one frame over 148 SMs = 16.2 per SM with 17 on the critical path) and the per-launch fixed cost
+    # is shared; G = 4 keeps the 4 x 23 MB of weight-gradient partials inside the 126 MB L2.
+    G = max(1, args.frames_per_step)
     torch.manual_seed(42 + rank)
-    model = A.ConvexNextNet(n_hidden=HID, in_features=CH, n_hidden_layers=LAYERS, precision=args.precision).to(dev)
-    unaries_host = synth_unaries(42 + rank, t=0.1 * rank).pin_memory()
-    unaries = unaries_host.to(dev, non_blocking=True)
+    model = A.NumberBasedMultiPriorModule(
+        prior_type=A.ConvexNextNet,
+        prior_args=dict(n_hidden=HID, in_features=CH, n_hidden_layers=LAYERS, precision=args.precision), min_priors=G).to(dev)
+    unaries_host = torch.stack([synth_unaries(42 + rank * G + k, t=0.1 * (rank * G + k)) for k in range(G)]).pin_memory()
+    unaries = unaries_host.to(dev, non_blocking=True)                       # [G,H,W]
     grid = A.GridSpecHost("linspace", 1, H, W)
     fitter = model.make_fitter(grid, unaries, A.LossConfig("mse"), A.OptimConfig("adam", lr=1e-3), use_graph=False)
-    # The per-step input (the frame's unaries, 1.2 MB) would sit in the 126 MB L2: rotate through a pool of
-    # POOL_FRAMES distinct frames (> L2) so that every timed step reads its unaries from HBM.
-    base = unaries.reshape(1, 1, -1)
-    shifts = torch.arange(POOL_FRAMES, device=dev).view(-1, 1, 1)
+    # The per-step input (G frames of unaries, 1.2 MB each) would sit in the 126 MB L2: rotate through a pool of
+    # >= POOL_FRAMES distinct frames (> L2) so that every timed step reads its unaries from HBM.
+    n_groups = (POOL_FRAMES + G - 1) // G
+    base = unaries.reshape(1, G, -1)
+    shifts = torch.arange(n_groups, device=dev).view(-1, 1, 1)
     idx = (torch.arange(N_PIX, device=dev).view(1, 1, -1) + 37 * shifts) % N_PIX     # cheap distinct frames: rolled copies
-    pool = torch.gather(base.expand(POOL_FRAMES, 1, N_PIX), 2, idx).contiguous()
+    pool = torch.gather(base.expand(n_groups, G, N_PIX), 2, idx.expand(n_groups, G, N_PIX)).contiguous()
     pool[0].copy_(base[0])
     fitter.set_target_pool(pool)
 
@@ -358,12 +364,12 @@ def main():
     # ---- end to end through the public API: the step's unaries arrive from pinned host memory, loss read back
     fitter.set_target_pool(None)
     e2e_warm = 3
-    host_pool = [unaries_host.reshape(1, -1)] + [torch.roll(unaries_host, 13 * k, 1).reshape(1, -1).pin_memory() for k in (1, 2, 3)]
+    host_pool = [unaries_host.reshape(G, -1)] + [torch.roll(unaries_host, 13 * k, 2).reshape(G, -1).pin_memory() for k in (1, 2, 3)]
     fitter.run_host_frames(host_pool, e2e_warm)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    # one C-ABI call with HOST buffers: every step copies its 4*N_PIX-byte frame host->device (copy stream, double
+    # one C-ABI call with HOST buffers: every step copies its G frames (4*N_PIX bytes each) host->device (copy stream, double
     # buffered) and stores its loss into pinned host memory; both inside the timed region
     loss_host = fitter.run_host_frames(host_pool, args.steps)
     e1.record()
@@ -377,7 +383,7 @@ def main():
     # ---- the other BASELINE configs, briefly (N = 1 only; device-timed, not part of `value`)
     secondary = None
     if rank == 0 and world == 1 and not args.no_secondary:
-        secondary = secondary_workloads(A, dev, unaries)
+        secondary = secondary_workloads(A, dev, unaries[0])
 
     # ---- roofline of the dominant kernel: hidden-layer contraction launches, timed live with CUDA events
     n_cls = lib.awb_profile_classes()
@@ -402,17 +408,17 @@ def main():
         launches = int(ln[0])
 
     if rank == 0:
-        units = world * N_PIX * args.steps
+        units = world * G * N_PIX * args.steps
         value = units / (ms_total * 1e-3)
         e2e_val = units / (t_e2e * 1e-3)
         if args.precision == "f16" and "tc_fused" in per_class:
-            dom, dom_flop = "tc_fused", FLOP_PER_PX_STEP * N_PIX
+            dom, dom_flop = "tc_fused", FLOP_PER_PX_STEP * N_PIX * G
             peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
             note = "fused fit kernel: all layer contractions of one step; peak = sustained cuBLAS bf16"
         else:
             gemm = [k for k in ("gemm_fwd", "gemm_wgrad", "gemm_dgrad") if k in per_class]
             dom = max(gemm, key=lambda k: per_class[k]["ms_per_step"])
-            dom_flop = GEMM_FLOP_PER_PX_LAUNCH * N_PIX
+            dom_flop = GEMM_FLOP_PER_PX_LAUNCH * N_PIX * G
             peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
             note = ("fp32 CUDA-core contraction (exact-parity path); reported against the sustained cuBLAS bf16 "
                     "tensor peak the north star names")
@@ -426,7 +432,7 @@ def main():
                     "algorithmic_flop_per_launch": dom_flop, "peak_source": pk_src,
                     "ms_per_launch": per_class[dom]["ms_per_launch"],
                     "share_of_step": per_class[dom]["ms_per_step"] / step_ms_prof,
-                    "whole_step_tflops": FLOP_PER_PX_STEP * N_PIX / (ms_total / args.steps * 1e-3) / 1e12,
+                    "whole_step_tflops": FLOP_PER_PX_STEP * N_PIX * G / (ms_total / args.steps * 1e-3) / 1e12,
                     "note": note, "per_class_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in per_class.items()}}
         cpu, eager = None, None
         if not args.no_cpu_baseline:
@@ -444,13 +450,15 @@ def main():
             "dtype": "f32" if args.precision == "fp32" else "f16 operands / f32 accumulate", "data": "synthetic",
             "config": {"workload": WORKLOAD, "prior": f"ConvexNextNet(h={HID},L={LAYERS},C={CH})",
                        "loss": "MSE(sigmoid(y), unaries)", "optimizer": "Adam lr=1e-3 + enforce_convexity",
-                       "pixels_per_step_per_gpu": N_PIX, "precision": args.precision,
-                       "l2": f"each step reads its unaries from a rotating pool of {POOL_FRAMES} distinct frames "
-                             f"({POOL_FRAMES * N_PIX * 4 / 1e6:.0f} MB > 126 MB L2); no explicit flush",
+                       "frames_per_step_per_gpu": G, "pixels_per_step_per_gpu": G * N_PIX, "precision": args.precision,
+                       "grouping": f"{G} independent frames of the rank's share of the sequence per fused launch "
+                                   "(one prior, optimizer state and loss per frame)",
+                       "l2": f"each step reads its unaries from a rotating pool of {n_groups * G} distinct frames "
+                             f"({n_groups * G * N_PIX * 4 / 1e6:.0f} MB > 126 MB L2); no explicit flush",
                        "frames_per_s_at_400_steps_per_frame": value / N_PIX / 400.0,
                        "frames_per_s_at_4000_steps_per_frame": value / N_PIX / 4000.0},
-            "e2e": {"value": e2e_val, "unit": "pixel-samples/s", "h2d_bytes_per_step": 4 * N_PIX,
-                    "d2h_bytes_per_step": 4, "ms_per_step": t_e2e / args.steps},
+            "e2e": {"value": e2e_val, "unit": "pixel-samples/s", "h2d_bytes_per_step": 4 * N_PIX * G,
+                    "d2h_bytes_per_step": 4 * G, "ms_per_step": t_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "samples": clocks["samples"]},
@@ -458,7 +466,7 @@ def main():
             "cpu_baseline": cpu,
             "eager_gpu_baseline": eager,
             "secondary": secondary,
-            "final_loss": float(loss_host[-1, 0]),
+            "final_loss": float(loss_host[-1].mean()),
         }
         emit(line)
     if world > 1:
