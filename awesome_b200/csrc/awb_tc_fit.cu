@@ -93,6 +93,13 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// (lo, hi) fp32 -> packed fp16 pair with relu, one instruction (cvt.rn.relu.f16x2.f32; NaN -> canonical NaN like fmaxf's
+// operand order would not matter here: the loss of a NaN row is flagged non-finite upstream)
+__device__ __forceinline__ uint32_t pack2_relu(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
 __device__ __forceinline__ uint32_t relu2(uint32_t u) {   // max(x, 0) on a packed fp16 pair
   __half2 h = *reinterpret_cast<__half2*>(&u);
   h = __hmax2(h, __float2half2_rn(0.f));
@@ -164,6 +171,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int o = blockIdx.y;
   const bool issuer_warp = warp == NEW;
+  // In-kernel timeline (clock64 stamps of one epilogue thread and of the issuer): compiled in only for the diagnostic
+  // builds (-DAWB_TC_TRACE_BUILD / -DAWB_TC_SERIAL, scripts/trace_tc.py) -- the stamps' predicated stores sit inside the
+  // issuer's and the epilogue's hot loops.
+#if defined(AWB_TC_TRACE_BUILD) || defined(AWB_TC_SERIAL)
   unsigned long long* trace = p.trace ? p.trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * TRACE_N : nullptr;
   int tr_n = 0;
 #define AWB_TR()                                                            \
@@ -171,6 +182,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
     if (trace && (threadIdx.x == 0 || threadIdx.x == NEW * 32) && tr_n < 120) \
       trace[(issuer_warp ? TRACE_N / 2 : 0) + tr_n++] = clock64();          \
   } while (0)
+#else
+  constexpr unsigned long long* trace = nullptr;
+#define AWB_TR() do {} while (0)
+#endif
 
   if (trace && threadIdx.x == 0) {                             // kernel entry (SM cycles and wall-clock ns)
     trace[120] = clock64();
@@ -360,16 +375,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
     // coordinates / target of a tile (rows past N replicate the last pixel and carry no loss)
     float x0n = 0.f, x1n = 0.f, x2n = 0.f, tgtn = 0.f;
     bool liven = false;
+    // Pixel position (frame, row, column) of this thread's row in the next tile to fetch, advanced tile by tile by
+    // the decomposed tile stride: no integer divisions inside the tile loop.
+    const uint32_t gW = (uint32_t)p.g.W, gH = (uint32_t)p.g.H, hw = gH * gW;
+    uint32_t pb, pi, pj, db, di, dj;
+    {
+      const uint32_t n0 = blockIdx.x * 128u + (uint32_t)row, d = gridDim.x * 128u;
+      pb = n0 / hw; uint32_t r = n0 - pb * hw; pi = r / gW; pj = r - pi * gW;
+      db = d / hw; r = d - db * hw; di = r / gW; dj = r - di * gW;
+    }
+    const float sx = gW > 1 ? 1.0f / (float)(gW - 1) : 0.f, sy = gH > 1 ? 1.0f / (float)(gH - 1) : 0.f;   // lin01's steps
+    auto lin = [](uint32_t i, uint32_t n, float step) {      // == lin01(i, n), bit for bit
+      return n <= 1 ? 0.f : (i < n / 2 ? (float)i * step : 1.0f - (float)(n - 1 - i) * step);
+    };
     auto fetch_tile = [&](int tile) {
       const int64_t n = (int64_t)tile * 128 + row;
       liven = n < p.N;
-      const uint32_t nn = (uint32_t)(liven ? n : p.N - 1);
       if (p.X) {
+        const uint32_t nn = (uint32_t)(liven ? n : p.N - 1);
         const float4 xv = *reinterpret_cast<const float4*>(p.X + ((int64_t)o * p.N + nn) * 4);
         x0n = xv.x; x1n = xv.y; x2n = C > 2 ? xv.z : 0.f;
+      } else if (!liven) {
+        row_coords(p.g, (uint32_t)(p.N - 1), C, x0n, x1n, x2n);     // padding rows of the last tile replicate the last pixel
+      } else if (p.g.mode == AWB_GRID_EXPLICIT) {
+        const float* base = p.g.grid + (size_t)pb * C * hw + pi * gW + pj;
+        x0n = base[0]; x1n = base[hw]; x2n = C > 2 ? base[2 * (size_t)hw] : 0.f;
       } else {
-        row_coords(p.g, nn, C, x0n, x1n, x2n);
+        x2n = C > 2 ? p.g.t0 + (float)pb * p.g.t_step : 0.f;
+        if (p.g.mode == AWB_GRID_LINSPACE) { x0n = lin(pj, gW, sx); x1n = lin(pi, gH, sy); }
+        else { x0n = (float)pj / (float)gW; x1n = (float)pi / (float)gH; }
       }
+      pj += dj; if (pj >= gW) { pj -= gW; pi += 1; }
+      pi += di; if (pi >= gH) { pi -= gH; pb += 1; }
+      pb += db;
       tgtn = 0.f;
       if (fit && liven) tgtn = p.target[(int64_t)o * p.N + n];
     };
@@ -406,8 +444,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
 #pragma unroll
         for (int i = 0; i < 6; i++) {
           if (i < nch) {
-            uint32_t w0 = relu2(pack2(v[8 * i], v[8 * i + 1])), w1 = relu2(pack2(v[8 * i + 2], v[8 * i + 3]));
-            uint32_t w2 = relu2(pack2(v[8 * i + 4], v[8 * i + 5])), w3 = relu2(pack2(v[8 * i + 6], v[8 * i + 7]));
+            uint32_t w0 = pack2_relu(v[8 * i], v[8 * i + 1]), w1 = pack2_relu(v[8 * i + 2], v[8 * i + 3]);
+            uint32_t w2 = pack2_relu(v[8 * i + 4], v[8 * i + 5]), w3 = pack2_relu(v[8 * i + 6], v[8 * i + 7]);
             if (last && i == 4) { w1 = ax01; w2 = ax2o; w3 = 0u; }
             st16(dst + i * 2048, w0, w1, w2, w3);
           }
@@ -441,7 +479,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
       // z_L as packed fp16 pairs: operand tile of the output-layer wgrad, then turned into the relu mask
       uint32_t zp[24];
 #pragma unroll
-      for (int k = 0; k < 24; k++) zp[k] = relu2(pack2(v[2 * k], v[2 * k + 1]));
+      for (int k = 0; k < 24; k++) zp[k] = pack2_relu(v[2 * k], v[2 * k + 1]);
       const float zL128 = last ? half_lo(zp[16]) : 0.f, zL129 = last ? half_hi(zp[16]) : 0.f;
       if (fit) {
         uint8_t* zl = tile_ptr(L) + ch0 * 2048 + row * 16;

@@ -8,16 +8,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 SERIAL = "--serial" in sys.argv
 if SERIAL:
-    # diagnostic variant of the library: the issuer waits for (and stamps) every contraction group
     sys.argv.remove("--serial")
-    import glob
-    import subprocess
-    import __graft_entry__ as entry
-    lib = os.path.join(entry.CSRC, "libawb_serial.so")
-    srcs = sorted(glob.glob(os.path.join(entry.CSRC, "*.cu")))
-    if not os.path.exists(lib) or any(os.path.getmtime(f) > os.path.getmtime(lib) for f in srcs):
-        subprocess.check_call(["nvcc"] + entry.NVCC_FLAGS + ["-DAWB_TC_SERIAL", "-o", lib] + srcs)
-    os.environ["AWB_LIB_PATH"] = lib
+# diagnostic variants of the library: the production build carries no stamps; --serial additionally makes the issuer
+# wait for (and stamp) every contraction group
+import glob
+import subprocess
+import __graft_entry__ as entry
+flag, name = ("-DAWB_TC_SERIAL", "libawb_serial.so") if SERIAL else ("-DAWB_TC_TRACE_BUILD", "libawb_trace.so")
+lib = os.path.join(entry.CSRC, name)
+srcs = sorted(glob.glob(os.path.join(entry.CSRC, "*.cu"))) + glob.glob(os.path.join(entry.CSRC, "*.cuh"))
+if not os.path.exists(lib) or any(os.path.getmtime(f) > os.path.getmtime(lib) for f in srcs):
+    subprocess.check_call(["nvcc"] + entry.NVCC_FLAGS + [flag, "-o", lib] + sorted(glob.glob(os.path.join(entry.CSRC, "*.cu"))))
+os.environ["AWB_LIB_PATH"] = lib
+if SERIAL:
     os.environ["AWB_TC_TRACE"] = "2"
 os.environ.setdefault("AWB_TC_TRACE", "1")
 import torch
