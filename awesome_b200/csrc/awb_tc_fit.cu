@@ -148,7 +148,10 @@ __device__ __forceinline__ float warp_reduce_scatter16(float* v, int lane) {
   return v[0];
 }
 
-template <int L, int C>
+// FIT: forward + loss + backward + partials (else forward only, logits out); DX: the coordinates come from a flow and
+// their gradient goes back to it.  Compile-time so that the forward-only and the plain ICNN instantiations carry
+// neither the branches nor the live ranges (delta_0 words, coordinate-gradient sums) of the others.
+template <int L, int C, bool FIT, bool DX>
 __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int NT = L + 2;
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
   auto dbuf = [&](int i) { return tile_ptr(((L - i) & 1) ? L : L + 1); };      // delta_i lives in DT / ZL alternately
 
   const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const bool fit = p.mode != 0;
+  constexpr bool fit = FIT;
 
   if (issuer_warp) {
     // =========================================================== MMA issuer (one elected lane)
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
         const bool acc = it > 0;
         const bool more = it + 1 < n_my;
         const uint32_t a_tx = a_tx0 + (it & 1) * TX_B, a_txn = a_tx0 + ((it + 1) & 1) * TX_B;
-        if (!fit) {
+        if constexpr (!FIT) {
           for (int s = 1; s <= L + 1; s++) {
             tc::mbar_wait(bar_e2m, ph); ph ^= 1;
             tc::fence_after_sync();
@@ -296,8 +299,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
             else if (more) mma_input(a_txn);
             tc::umma_commit(bar_m2e);
           }
-          continue;
-        }
+        } else
         for (int s = 1; s <= 2 * L + 1; s++) {
           tc::mbar_wait(bar_e2m, ph); ph ^= 1;
           tc::fence_after_sync();
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
     // loss scale: host-chosen power of two, or (upstream-gradient mode) derived from the device-side max |dlogits|
     float S = p.scale[o];
     if (p.amax) { const float am = p.amax[o]; S = (am > 0.f && isfinite(am)) ? exp2f(rintf(log2f(64.f / am))) : 1.f; }
-    const bool has_dx = p.dX != nullptr;
+    constexpr bool has_dx = DX;
     float adx0 = 0.f, adx1 = 0.f, adx2 = 0.f;     // last group: d loss / d (x, y, t) of this row (scaled by S)
     float v[48];
     const float* w = wo + 48 * cg;
@@ -862,16 +864,23 @@ int tc_fit_forward_backward(const awb_prior* h, const float* params, const awb_g
   }
   const size_t smem = smem_bytes(L);
   dim3 gd(grid, O);
-#define AWB_TC_LAUNCH(LL, CC)                                                                                      \
+#define AWB_TC_LAUNCH3(LL, CC, FF, DD)                                                                             \
   do {                                                                                                             \
-    AWB_CUDA(cudaFuncSetAttribute(k_icnn_fit_tc<LL, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    AWB_LAUNCH(PK_TC_FUSED, st, AWB_CUDA(launch_ex(k_icnn_fit_tc<LL, CC>, gd, dim3(NTHREADS), smem, st, true, p))); \
+    AWB_CUDA(cudaFuncSetAttribute(k_icnn_fit_tc<LL, CC, FF, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    AWB_LAUNCH(PK_TC_FUSED, st, AWB_CUDA(launch_ex(k_icnn_fit_tc<LL, CC, FF, DD>, gd, dim3(NTHREADS), smem, st, true, p))); \
+  } while (0)
+#define AWB_TC_LAUNCH(LL, CC)                                    \
+  do {                                                           \
+    if (mode == 0) AWB_TC_LAUNCH3(LL, CC, false, false);         \
+    else if (dXrows) AWB_TC_LAUNCH3(LL, CC, true, true);         \
+    else AWB_TC_LAUNCH3(LL, CC, true, false);                    \
   } while (0)
   if (L == 1 && C == 2) AWB_TC_LAUNCH(1, 2);
   else if (L == 1 && C == 3) AWB_TC_LAUNCH(1, 3);
   else if (L == 2 && C == 2) AWB_TC_LAUNCH(2, 2);
   else AWB_TC_LAUNCH(2, 3);
 #undef AWB_TC_LAUNCH
+#undef AWB_TC_LAUNCH3
   AWB_CUDA(cudaGetLastError());
   if (n_splits_out) *n_splits_out = grid;
   return AWB_OK;
