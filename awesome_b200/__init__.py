@@ -11,7 +11,7 @@ from .optim import FusedAdam, FusedAdamax  # noqa: F401
 from .pretrain import FitSchedule, FrameResult, fit_frames, fit_sequence, mask_iou, noisy_unaries  # noqa: F401
 from .prior_cache import DevicePriorCache, PriorManager  # noqa: F401
 from .joint import GradBucket, JointTrainer  # noqa: F401
-from . import measures  # noqa: F401
+from . import image, measures  # noqa: F401
 from .model import (ConvexDiffeomorphismNet, ConvexNet, ConvexNextNet, MinMax, NoisyPathConnectedNet, NormNet, NumberBasedMultiPriorModule, PathConnectedNet,  # noqa: F401
                     PixelizeNet, StarFitter, StarShapedNet, get_norm, init_realnvp, real_nvp_path_connected_net)
 

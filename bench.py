@@ -222,7 +222,59 @@ def secondary_workloads(A, dev, unaries640):
     out["c3_multi_object_8x640x480"] = {"ms_per_step": ms, "pixel_samples_per_s": 8 * N_PIX / ms * 1e3}
     del f, multi
     torch.cuda.empty_cache()
+    out["n4_image_preprocess_640x480"] = image_preprocess_throughput(A, dev)
     return out
+
+
+def image_preprocess_throughput(A, dev, reps: int = 80):
+    """the dataset layer's per-frame OpenCV preprocessing on the device (awb_image.cu), HBM bound.
+    Frames rotate through a pool larger than L2; achieved GB/s = algorithmic bytes (12 B read + 12 / 4 B written per
+    pixel) / CUDA-event time, against the measured copy bandwidth; OpenCV on the host timed beside it when importable."""
+    import torch
+    pk, pk_src = peaks()
+    pool = torch.rand((40, 3, H, W), device=dev)                 # 147 MB > 126 MB L2
+    res = {}
+    for name, fn, nbytes in (("process_image_blur5", A.image.process_image, 24 * N_PIX),
+                             ("create_edge_map", A.image.create_edge_map, 16 * N_PIX)):
+        for i in range(5):
+            fn(pool[i])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            fn(pool[i % pool.shape[0]])
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / reps * 1e3
+        res[name] = {"us_per_frame": us, "GBps": nbytes / us / 1e3, "frac_of_hbm_peak": nbytes / us / 1e3 / pk["hbm_gbs"],
+                     "peak_source": pk_src}
+    try:
+        import cv2
+        import numpy as np
+        img = pool[0].cpu().numpy()
+
+        def cpu_proc():
+            im = (img.transpose(1, 2, 0) * 255).astype(np.uint8)
+            return cv2.GaussianBlur(im, (5, 5), 0).astype(np.float32).transpose(2, 0, 1) / np.float32(255)
+
+        def cpu_edge():
+            im = (img.transpose(1, 2, 0) * 255).astype(np.uint8)
+            gray = cv2.cvtColor(cv2.GaussianBlur(im, (3, 3), 0), cv2.COLOR_RGB2GRAY)
+            gx, gy = cv2.Sobel(gray, cv2.CV_16S, 1, 0, ksize=3), cv2.Sobel(gray, cv2.CV_16S, 0, 1, ksize=3)
+            g = cv2.addWeighted(cv2.convertScaleAbs(gx), 0.5, cv2.convertScaleAbs(gy), 0.5, 0) / 255
+            return cv2.GaussianBlur(g, (5, 5), 0).astype(np.float32)
+        for name, fn in (("process_image_blur5", cpu_proc), ("create_edge_map", cpu_edge)):
+            fn()
+            t0 = time.perf_counter()
+            for _ in range(20):
+                fn()
+            res[name]["opencv_host_us_per_frame"] = (time.perf_counter() - t0) / 20 * 1e6
+        res["opencv"] = cv2.__version__
+    except Exception as e:            # a baseline leg must never take the bench line down
+        res["opencv"] = f"unavailable: {e!r}"[:120]
+    del pool
+    torch.cuda.empty_cache()
+    return res
 
 
 def eager_gpu_throughput(dev, steps: int = 10):
