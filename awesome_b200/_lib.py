@@ -95,8 +95,8 @@ SYMBOLS = [
     ("awb_prior_actnorm_init", C.c_int, [_P, _P, C.POINTER(GridSpec), _P, C.c_size_t, _P]),
     ("awb_mask_iou_counts", C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
     ("awb_target_counts", C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
-    ("awb_image_process", C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
-    ("awb_image_edge_map", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P]),
+    ("awb_image_process", C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    ("awb_image_edge_map", C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     ("awb_debug_umma_probe", C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _P]),
     ("awb_debug_tc_trace_read", C.c_int, [C.POINTER(C.c_ulonglong), C.c_int32]),

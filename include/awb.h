@@ -256,12 +256,13 @@ int awb_profile_read(double* total_ms, int32_t* counts);
 long long awb_launch_count(void);
 
 /* Per-frame image preprocessing of the dataset layer on the device, bit-identical to the OpenCV calls
- * the reference makes on the host.  image [3][H][W] fp32 RGB in [0,1] (device).
+ * the reference makes on the host.  image [n_frames][3][H][W] fp32 RGB in [0,1] (device), frames contiguous.
  * awb_image_process  = ImageSample._process_image  (awesome/dataset/image_sample.py:212-221): uint8 GaussianBlur 5x5 when
- *                      do_blur, channels reversed when bgr; out [3][H][W], must not alias image.
- * awb_image_edge_map = ImageSample.create_edge_map (image_sample.py:260-275): out [H][W]. */
-int awb_image_process(const float* image, float* out, int32_t H, int32_t W, int32_t do_blur, int32_t bgr, void* stream);
-int awb_image_edge_map(const float* image, float* out, int32_t H, int32_t W, void* stream);
+ *                      do_blur, channels reversed when bgr; out [n_frames][3][H][W], must not alias image.
+ * awb_image_edge_map = ImageSample.create_edge_map (image_sample.py:260-275): out [n_frames][H][W]. */
+int awb_image_process(const float* image, float* out, int32_t n_frames, int32_t H, int32_t W, int32_t do_blur, int32_t bgr,
+                      void* stream);
+int awb_image_edge_map(const float* image, float* out, int32_t n_frames, int32_t H, int32_t W, void* stream);
 
 #ifdef __cplusplus
 }

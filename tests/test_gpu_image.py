@@ -51,6 +51,9 @@ def test_properties_and_errors(A):
     assert not A.image.create_edge_map(t).any()                               # constant frame: exactly zero edges
     e = A.image.create_edge_map(torch.rand(3, 64, 64, device="cuda"))
     assert e.shape == (1, 64, 64) and float(e.min()) >= 0.0 and float(e.max()) <= 1.0
+    batch = torch.rand(5, 3, 33, 47, device="cuda")                           # a batch == its frames one by one
+    assert torch.equal(A.image.process_image(batch), torch.stack([A.image.process_image(f) for f in batch]))
+    assert torch.equal(A.image.create_edge_map(batch), torch.stack([A.image.create_edge_map(f) for f in batch]))
     flipped = A.image.process_image(t.flip(2))                                # reflect-101 borders are mirror symmetric
     assert torch.equal(flipped, A.image.process_image(t).flip(2))
     with pytest.raises(ValueError):
