@@ -27,6 +27,7 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "awb_internal.cuh"
@@ -340,9 +341,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
     const int q = warp & 3, cg = warp >> 2;       // TMEM lanes [32q, 32q+32), stored chunks [6cg, 6cg + nch)
     const int row = q * 32 + lane;
     const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
-    const int nch = cg == NCG - 1 ? 5 : 6;        // 6 + 6 + 5 = 17 stored chunks
     const int ch0 = 6 * cg;
-    const bool last = cg == NCG - 1;              // owns chunk 16: columns 128..135 = (z128, z129, x, y, [t,] 1, 0..)
+    // The body is instantiated twice: for the column group that owns chunk 16 (5 stored chunks; columns 128..135 =
+    // (z128, z129, x, y, [t,] 1, 0..), the corner sums) and for the other two (6 chunks) -- `last` and `nch` are
+    // compile-time inside, so eight of the twelve warps carry none of the special cases' predicates.
+    auto epilogue_body = [&](auto last_c) {
+    constexpr bool last = decltype(last_c)::value;
+    constexpr int nch = last ? 5 : 6;             // 6 + 6 + 5 = 17 stored chunks
     uint32_t ph = 0;
     float s_loss = 0.f, s_bo = 0.f, s_so0 = 0.f, s_so1 = 0.f, s_so2 = 0.f;   // cg 0: per-thread scalar sums
     float accC[L + 1];                            // cg 2: corner sums, lane-distributed (value = lane & 15)
@@ -752,6 +757,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
       trace[126] = ns;
     }
+    };   // epilogue_body
+    if (cg == NCG - 1) epilogue_body(std::true_type{});
+    else epilogue_body(std::false_type{});
   }
   tc::fence_before_sync();
   __syncthreads();
