@@ -115,7 +115,9 @@ __device__ __forceinline__ void st16(uint8_t* p, uint32_t a, uint32_t b, uint32_
 __device__ __forceinline__ float half_lo(uint32_t u) { return __low2float(*reinterpret_cast<__half2*>(&u)); }
 __device__ __forceinline__ float half_hi(uint32_t u) { return __high2float(*reinterpret_cast<__half2*>(&u)); }
 // pixel coordinates with 32-bit index arithmetic (N <= 2^30 is checked on the host)
-__device__ __forceinline__ void row_coords(const GridDev& g, uint32_t n, int C, float& x0, float& x1, float& x2) {
+// Out of line on purpose: the hot loop only carries the division-free linspace path; explicit grids, the notebooks'
+// index grid and the padding rows of a last tile come here (the fused kernel's speed depends on its code footprint).
+__device__ __noinline__ void row_coords(const GridDev& g, uint32_t n, int C, float& x0, float& x1, float& x2) {
   const uint32_t hw = (uint32_t)g.H * (uint32_t)g.W;
   const uint32_t b = n / hw, r = n - b * hw;
   const uint32_t i = r / (uint32_t)g.W, j = r - i * (uint32_t)g.W;
@@ -127,6 +129,10 @@ __device__ __forceinline__ void row_coords(const GridDev& g, uint32_t n, int C, 
   x2 = C > 2 ? g.t0 + (float)b * g.t_step : 0.f;
   if (g.mode == AWB_GRID_LINSPACE) { x0 = lin01((int)j, g.W); x1 = lin01((int)i, g.H); }
   else { x0 = (float)j / (float)g.W; x1 = (float)i / (float)g.H; }
+}
+
+__device__ __noinline__ float bce_logits(float y, float t) {   // BCEWithLogits, stable form; rare: kept out of the hot loop
+  return fmaxf(y, 0.f) - y * t + log1pf(expf(-fabsf(y)));
 }
 
 // Sum of v[i] over the 32 lanes of a warp for 16 values at once: one butterfly round, then four
@@ -402,15 +408,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
         const uint32_t nn = (uint32_t)(liven ? n : p.N - 1);
         const float4 xv = *reinterpret_cast<const float4*>(p.X + ((int64_t)o * p.N + nn) * 4);
         x0n = xv.x; x1n = xv.y; x2n = C > 2 ? xv.z : 0.f;
-      } else if (!liven) {
-        row_coords(p.g, (uint32_t)(p.N - 1), C, x0n, x1n, x2n);     // padding rows of the last tile replicate the last pixel
-      } else if (p.g.mode == AWB_GRID_EXPLICIT) {
-        const float* base = p.g.grid + (size_t)pb * C * hw + pi * gW + pj;
-        x0n = base[0]; x1n = base[hw]; x2n = C > 2 ? base[2 * (size_t)hw] : 0.f;
-      } else {
+      } else if (liven && p.g.mode == AWB_GRID_LINSPACE) {
         x2n = C > 2 ? p.g.t0 + (float)pb * p.g.t_step : 0.f;
-        if (p.g.mode == AWB_GRID_LINSPACE) { x0n = lin(pj, gW, sx); x1n = lin(pi, gH, sy); }
-        else { x0n = (float)pj / (float)gW; x1n = (float)pi / (float)gH; }
+        x0n = lin(pj, gW, sx); x1n = lin(pi, gH, sy);
+      } else {      // padding rows of the last tile replicate the last pixel; explicit / index grids
+        row_coords(p.g, (uint32_t)(liven ? n : p.N - 1), C, x0n, x1n, x2n);
       }
       pj += dj; if (pj >= gW) { pj -= gW; pi += 1; }
       pi += di; if (pi >= gH) { pi -= gH; pb += 1; }
@@ -514,11 +516,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
       if (live) {
         const bool fg = ls.cls_rule == AWB_CLS_UNARY_LT_HALF ? (tgt < 0.5f) : (tgt != 1.0f);
         const float coef = fg ? ls.coef_fg : ls.coef_bg;
-        const float sg = 1.f / (1.f + expf(-y));
+        const float sg = __fdividef(1.f, 1.f + __expf(-y));
         float l, dl;
         if (ls.kind == AWB_LOSS_SE_SIGMOID) { float d = tgt - sg; l = d * d; dl = -2.f * d * sg * (1.f - sg); }
         else if (ls.kind == AWB_LOSS_UPSTREAM) { l = 0.f; dl = tgt; }       // `target` holds d loss / d logits (autograd)
-        else { l = fmaxf(y, 0.f) - y * tgt + log1pf(expf(-fabsf(y))); dl = sg - tgt; }
+        else { l = bce_logits(y, tgt); dl = sg - tgt; }
         dys = coef * dl * S;
         lossv = coef * l;
       }
