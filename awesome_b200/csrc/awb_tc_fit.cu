@@ -117,7 +117,7 @@ __device__ __forceinline__ float half_hi(uint32_t u) { return __high2float(*rein
 // pixel coordinates with 32-bit index arithmetic (N <= 2^30 is checked on the host)
 // Out of line on purpose: the hot loop only carries the division-free linspace path; explicit grids, the notebooks'
 // index grid and the padding rows of a last tile come here (the fused kernel's speed depends on its code footprint).
-__device__ __noinline__ void row_coords(const GridDev& g, uint32_t n, int C, float& x0, float& x1, float& x2) {
+__device__ __noinline__ void row_coords(const GridDev g, uint32_t n, int C, float& x0, float& x1, float& x2) {
   const uint32_t hw = (uint32_t)g.H * (uint32_t)g.W;
   const uint32_t b = n / hw, r = n - b * hw;
   const uint32_t i = r / (uint32_t)g.W, j = r - i * (uint32_t)g.W;
