@@ -333,3 +333,35 @@ def test_host_frame_fit_equals_device_frame_fit(A, precision):
                                                    C.byref(f2._gs), ptrs, 1, 1, f2._specs, C.byref(f2._hyper),
                                                    bad.data_ptr(), f2._staging.data_ptr(), f2.ws.data_ptr(),
                                                    f2.ws.numel(), 0, AL.stream_ptr()))
+
+
+def test_grouped_frames_one_wave_at_frame_size_matches_single_frame_fits(A):
+    """Four independent 640x480 frames per fused launch run as ONE wave (37 persistent CTAs per frame instead of 148): the
+    gradient partials are summed in a different grouping than in a one-frame launch, so parity with four separate
+    fits is to fp32 summation order -- losses to 1e-5 relative, parameters to 2e-5 after 6 Adam steps (lr 1e-3 moves a
+    weight by <= 6e-3, so this is a tight bound on the gradients' sign and size), logits to 1e-3 -- and repeatable bit for bit."""
+    G, H, W = 4, 480, 640
+    torch.manual_seed(11)
+    multi = A.NumberBasedMultiPriorModule(prior_type=A.ConvexNextNet,
+                                          prior_args=dict(n_hidden_layers=2, precision="f16"), min_priors=G).to(DEV)
+    start = [{k: v.clone() for k, v in p.state_dict().items()} for p in multi.priors]
+    un = torch.stack([blob(H, W, cx=0.35 + 0.08 * k, cy=0.45 + 0.03 * k, rx=0.2, ry=0.26) for k in range(G)]).to(DEV)
+    grid = A.GridSpecHost("linspace", 1, H, W)
+    f = multi.make_fitter(grid, un, A.LossConfig("mse"), A.OptimConfig("adam", lr=1e-3), use_graph=False)
+    hist = f.run(6).clone()
+    grouped = [{k: v.clone() for k, v in p.state_dict().items()} for p in multi.priors]
+    for k in range(G):
+        s = A.ConvexNextNet(n_hidden_layers=2, precision="f16").to(DEV)
+        s.load_state_dict(start[k])
+        hk = s.make_fitter(grid, un[k], A.LossConfig("mse"), A.OptimConfig("adam", lr=1e-3), use_graph=False).run(6)
+        torch.testing.assert_close(hist[:, k], hk[:, 0], rtol=1e-5, atol=1e-8)
+        for name, b in s.state_dict().items():
+            torch.testing.assert_close(grouped[k][name], b, rtol=0, atol=2e-5, msg=lambda m: f"frame {k} {name}: {m}")
+    # determinism of the grouped launch itself
+    for p, st in zip(multi.priors, start):
+        p.load_state_dict(st)
+    f2 = multi.make_fitter(grid, un, A.LossConfig("mse"), A.OptimConfig("adam", lr=1e-3), use_graph=False)
+    assert torch.equal(f2.run(6), hist)
+    for p, st in zip(multi.priors, grouped):
+        for name, b in p.state_dict().items():
+            assert torch.equal(st[name], b), name
