@@ -47,6 +47,31 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       : "memory");
 }
 
+// The same instruction with each descriptor passed as two 32-bit halves.  Inside one contraction only the start
+// address field (low word) changes from K step to K step, so the issuing thread spends one add per operand and
+// instruction instead of rebuilding the 64-bit descriptors: the issue latency of the single elected thread is on the
+// critical path of the fused kernel (rolling the issue loops costs 25 %).
+struct DescLH { uint32_t lo, hi; };
+__device__ __forceinline__ DescLH make_desc_lh(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  DescLH d;
+  d.lo = ((saddr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+  d.hi = ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14);   // bit 46 of the descriptor: version 1
+  return d;
+}
+__device__ __forceinline__ void umma_f16_lh(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // all previously issued tcgen05.mma of this thread arrive on the mbarrier when complete
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

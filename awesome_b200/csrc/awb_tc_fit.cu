@@ -250,26 +250,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
       const uint32_t a_tx0 = tc::smem_u32(stx), a_win = tc::smem_u32(simg + L * W_B);
       auto w_addr = [&](int i) { return tc::smem_u32(simg + (i - 1) * W_B); };
       auto t_addr = [&](uint8_t* t) { return tc::smem_u32(t); };
-      // K-major A (R=128) x K-major/MN-major B (R=144) over K = 144 (9 steps), N = 144
+      // K-major A (R=128) x K-major/MN-major B (R=144) over K = 144 (9 steps), N = 144.  Descriptor bases once per
+      // contraction; per instruction only the start-address field advances (byte step >> 4).
       auto mma_k144 = [&](uint32_t dcol, uint32_t a, uint32_t b, bool b_mn) {
         const uint32_t idesc = tc::make_idesc(128, 144, 0, b_mn ? 1 : 0);
+        const tc::DescLH a0 = tc::make_desc_lh(a, 2048, 128);
+        const tc::DescLH a8 = tc::make_desc_lh(a + 8 * 4096, zero_a - (a + 8 * 4096), 128);     // 18th chunk -> zero chunk
+        const tc::DescLH b0 = b_mn ? tc::make_desc_lh(b, 128, 2304) : tc::make_desc_lh(b, 2304, 128);
+        const tc::DescLH b8 = b_mn ? tc::make_desc_lh(b + 8 * 256, 128, 2304)
+                                   : tc::make_desc_lh(b + 8 * 4608, zero_a - (b + 8 * 4608), 128);
+        const uint32_t binc = b_mn ? 256 / 16 : 4608 / 16;
 #pragma unroll
-        for (int k = 0; k < 9; k++) {
-          uint32_t as = a + k * 4096;
-          uint64_t ad = tc::make_desc(as, k == 8 ? zero_a - as : 2048, 128);
-          uint64_t bd;
-          if (b_mn) bd = tc::make_desc(b + k * 256, 128, 2304);
-          else { uint32_t bs = b + k * 4608; bd = tc::make_desc(bs, k == 8 ? zero_a - bs : 2304, 128); }
-          tc::umma_f16(tbase + dcol, ad, bd, idesc, k > 0);
-        }
+        for (int k = 0; k < 8; k++)
+          tc::umma_f16_lh(tbase + dcol, a0.lo + k * (4096 / 16), a0.hi, b0.lo + k * binc, b0.hi, idesc, k > 0);
+        tc::umma_f16_lh(tbase + dcol, a8.lo, a8.hi, b8.lo, b8.hi, idesc, 1);
       };
       // MN-major A window [0,128) x MN-major B, K = 128 pixels (8 steps); b_sbo = byte distance of B's 2nd N chunk
       auto mma_px = [&](uint32_t dcol, uint32_t a, uint32_t b, uint32_t b_sbo, int N, bool acc) {
         const uint32_t idesc = tc::make_idesc(128, N, 1, 1);
+        const tc::DescLH a0 = tc::make_desc_lh(a, 128, 2048), b0 = tc::make_desc_lh(b, 128, b_sbo);
 #pragma unroll
         for (int k = 0; k < 8; k++)
-          tc::umma_f16(tbase + dcol, tc::make_desc(a + k * 256, 128, 2048), tc::make_desc(b + k * 256, 128, b_sbo), idesc,
-                       (acc || k > 0) ? 1u : 0u);
+          tc::umma_f16_lh(tbase + dcol, a0.lo + k * (256 / 16), a0.hi, b0.lo + k * (256 / 16), b0.hi, idesc,
+                          (acc || k > 0) ? 1u : 0u);
       };
       // input layer of a tile: ACC = TX[128x16] * WIN^T   (both operands: one stored K chunk + the zero chunk)
       auto mma_input = [&](uint32_t a_tx) {
