@@ -8,7 +8,8 @@ All arithmetic runs in ``csrc/libawb.so`` (hand-written sm_100a CUDA); there is 
 from .core import GridSpecHost, Prior, iou_counts, target_counts  # noqa: F401
 from .fit import FlowIdentityFitter, LossConfig, OptimConfig, PriorFitter  # noqa: F401
 from .optim import FusedAdam, FusedAdamax  # noqa: F401
-from .pretrain import FitSchedule, FrameResult, fit_frames, fit_sequence, mask_iou, noisy_unaries  # noqa: F401
+from .pretrain import (FitSchedule, FrameResult, fit_frames, fit_frames_grouped, fit_sequence, mask_iou,  # noqa: F401
+                       noisy_unaries)
 from .prior_cache import DevicePriorCache, PriorManager  # noqa: F401
 from .joint import GradBucket, JointTrainer  # noqa: F401
 from . import image, measures  # noqa: F401

@@ -175,6 +175,99 @@ def fit_frames(model, grids: Sequence, unaries: Sequence[torch.Tensor], schedule
     return results
 
 
+def fit_frames_grouped(multi, grid, unaries: Sequence[torch.Tensor], schedule: Optional[FitSchedule] = None,
+                       on_frame: Optional[Callable[[FrameResult], None]] = None,
+                       frame_indices: Optional[Sequence[int]] = None) -> List[FrameResult]:
+    """``fit_frames`` for frames that are fitted WITHOUT chaining inside a group: ``multi`` (a
+    ``NumberBasedMultiPriorModule`` of G equal priors) takes G frames per fused launch, one prior per frame -- the
+    execution that ``bench.py`` measures (G = 4: one wave of 37 persistent CTAs per frame).
+
+    Semantics relative to the reference's loop (``path_connected_net.py:730-1007``): the reference carries the module
+    state from frame to frame (explicitly with ``reuse_state``, implicitly otherwise).  Here every frame of a group starts
+    from the state the group was entered with -- the last proper state of the previous group under ``reuse_state`` (then
+    ``reuse_state_epochs`` steps), else the state of ``multi.priors[0]`` at the call (``num_epochs`` steps) -- exactly the
+    cut that sharding frames over GPUs makes at shard boundaries.  The no-foreground skip, the "proper prior fit" IoU check
+    and its retry after ``reset_parameters`` (per frame, through the one-frame path) are the reference's.  All frames
+    share ``grid`` (a ``GridSpecHost`` or ``[1,C,H,W]`` tensor).  Priors with a flow need their prefits per frame and are
+    not grouped here."""
+    s = schedule or FitSchedule()
+    G = len(multi.priors)
+    if G < 1:
+        raise ValueError("the container holds no priors")
+    if any(hasattr(p, "flow_net") or hasattr(p, "diffeo_net") for p in multi.priors):
+        raise NotImplementedError("grouped frame fits are for priors without a flow (use fit_frames)")
+    big = multi._group_arena()
+    dev = big.device
+    spec = _as_grid(grid, dev)
+    entry = big[0].detach().clone()
+    previous: Optional[torch.Tensor] = None
+    results: List[FrameResult] = []
+    todo: List[tuple] = []
+    for k, un in enumerate(unaries):
+        idx = frame_indices[k] if frame_indices is not None else k
+        un = un.detach().to(dev).float().reshape(1, -1)
+        cnt = target_counts(un, L.AWB_CLS_UNARY_LT_HALF).cpu()[0]
+        if int(cnt[0]) == 0 or int(cnt[1]) == 0:       # torch.unique(unaries >= 0.5) has one value (:848-855)
+            logging.warning("Unaries of segmentation model contain no foreground. Skipping image. %s", idx)
+            results.append(FrameResult(index=idx, skipped=True))
+            if on_frame:
+                on_frame(results[-1])
+        else:
+            todo.append((idx, un))
+    fitter: Optional[PriorFitter] = None
+    C_in = getattr(multi.priors[0], "in_channels", getattr(multi.priors[0], "in_features", 2))
+    for g0 in range(0, len(todo), G):
+        chunk = todo[g0:g0 + G]
+        n_real = len(chunk)
+        chunk = chunk + [chunk[-1]] * (G - n_real)          # a short last group repeats its last frame (result ignored)
+        tg = torch.cat([u for _, u in chunk], dim=0)
+        warm = s.reuse_state and previous is not None
+        with torch.no_grad():
+            big.copy_((previous if warm else entry).unsqueeze(0).expand_as(big))
+        if fitter is None:
+            fitter = multi.make_fitter(spec, tg, s.criterion, s.optim(False), steps_per_graph=s.steps_per_graph)
+        else:
+            fitter.set_target(tg, s.criterion)
+        epochs = s.reuse_state_epochs if warm else s.num_epochs
+        fitter.reset_optimizer()                           # fresh optimizer + scheduler per frame (:923-933)
+        hist = fitter.run(epochs)
+        fitter.raise_if_nonfinite()
+        with torch.no_grad():
+            logits = multi(spec.materialize(C_in, dev), num_priors=G)           # [1,G,1,H,W]
+        cnts = iou_counts(logits.reshape(G, -1), tg, pred_is_logit=True, n_objects=G).cpu()
+        for k in range(n_real):
+            idx, un = chunk[k]
+            res = FrameResult(index=idx, steps=epochs, final_loss=float(hist[-1, k]) if epochs > 0 else float("nan"))
+            inter, pf, tf = int(cnts[k, 0]), int(cnts[k, 1]), int(cnts[k, 2])
+            res.iou = 0.0 if tf == 0 else inter / float(pf + tf - inter)
+            res.proper_fit = res.iou >= s.proper_prior_fit_threshold
+            if not res.proper_fit and s.proper_prior_fit_retrys > 0:
+                # the reference's retry: reset_parameters, full schedule -- per frame, through the one-frame path
+                logging.info("Prior fit not proper on image index: %s. Retrying. Metric: %s", idx, res.iou)
+                pk = multi.priors[k]
+                pk.reset_parameters()
+                pk._ensure_flat()
+                import dataclasses
+                again = fit_frames(pk, [spec], [un], dataclasses.replace(s, reuse_state=False,
+                                                                         proper_prior_fit_retrys=s.proper_prior_fit_retrys - 1),
+                                   frame_indices=[idx])[0]
+                multi._arena_all = None                       # the one-frame path may have re-pointed the prior's arena
+                big = multi._group_arena()
+                fitter = None
+                res.retries = 1 + again.retries
+                res.steps += again.steps
+                res.iou, res.proper_fit, res.final_loss = again.iou, again.proper_fit, again.final_loss
+            res.state = big[k].detach().clone()
+            if s.reuse_state and res.proper_fit:
+                previous = res.state
+            results.append(res)
+            if on_frame:
+                on_frame(res)
+    order = {(frame_indices[k] if frame_indices is not None else k): k for k in range(len(unaries))}
+    results.sort(key=lambda r: order[r.index])
+    return results
+
+
 def noisy_unaries(unaries: torch.Tensor, noisy_percentage: float, seed: Optional[int] = None):
     """``NoisyPathConnectedNet._non_prior_based_pretrain`` (``awesome/model/noisy_path_connected_net.py:179-228``):
     a fraction of the frames (never the first or the last) gets its unaries replaced ONCE by

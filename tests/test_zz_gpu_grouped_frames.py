@@ -1,0 +1,59 @@
+"""GPU test of the grouped per-frame pretrain loop (awesome_b200.fit_frames_grouped): G frames per fused launch."""
+import pytest
+import torch
+
+import __graft_entry__ as entry
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    entry.build()
+
+
+@pytest.fixture(scope="module")
+def A():
+    import awesome_b200
+    return awesome_b200
+
+
+def blob(H, W, cx=0.5, cy=0.5, rx=0.27, ry=0.31, tau=0.08):
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, H), torch.linspace(0, 1, W), indexing="ij")
+    return torch.sigmoid((torch.sqrt(((xx - cx) / rx) ** 2 + ((yy - cy) / ry) ** 2) - 1) / tau)
+
+
+def test_fit_frames_grouped_matches_independent_frame_fits(A):
+    """fit_frames_grouped: G frames per fused launch, every frame of a group starting from the group's entry state --
+    the same masks as fitting each frame on its own from that state; skip, short last group, warm second group, retry."""
+    H, W, G = 60, 80, 3
+    torch.manual_seed(2)
+    multi = A.NumberBasedMultiPriorModule(prior_type=A.ConvexNextNet,
+                                          prior_args=dict(n_hidden_layers=2, precision="f16"), min_priors=G).to(DEV)
+    entry = {k: v.clone() for k, v in multi.priors[0].state_dict().items()}
+    frames = [blob(H, W, cx=0.40 + 0.04 * i, cy=0.5, rx=0.2, ry=0.25) for i in range(5)]
+    frames[1] = torch.ones(H, W)                      # background only -> skipped, does not occupy a slot
+    grid = A.GridSpecHost("linspace", 1, H, W)
+    sched = A.FitSchedule(num_epochs=500, reuse_state_epochs=120, optimizer="adam", plateau=False, lr=2e-3,
+                          proper_prior_fit_threshold=0.5)
+    seen = []
+    res = A.fit_frames_grouped(multi, grid, frames, sched, on_frame=lambda r: seen.append(r.index))
+    assert [r.index for r in res] == [0, 1, 2, 3, 4] and sorted(seen) == [0, 1, 2, 3, 4]
+    assert [r.skipped for r in res] == [False, True, False, False, False]
+    assert [r.steps for r in res] == [500, 0, 500, 500, 120]           # second group (frame 4 alone) is warm
+    for r in res:
+        if not r.skipped:
+            assert r.proper_fit and r.iou > 0.9 and r.state is not None, (r.index, r.iou)
+    # frame 2 on its own from the same entry state: same mask to within a handful of boundary pixels
+    single = A.ConvexNextNet(n_hidden_layers=2, precision="f16").to(DEV)
+    single.load_state_dict(entry)
+    alone = A.fit_frames(single, [grid], [frames[2]], A.FitSchedule(num_epochs=500, optimizer="adam", plateau=False, lr=2e-3,
+                                                                   reuse_state=False))[0]
+    assert abs(alone.iou - res[2].iou) < 1e-3 and alone.final_loss == pytest.approx(res[2].final_loss, rel=1e-3)
+    # an impossible threshold sends every frame through the reference's reset + refit retry exactly once
+    hard = A.FitSchedule(num_epochs=60, optimizer="adam", plateau=False, lr=2e-3, reuse_state=False,
+                         proper_prior_fit_threshold=1.01, proper_prior_fit_retrys=1)
+    res2 = A.fit_frames_grouped(multi, grid, frames[2:4], hard)
+    assert [r.retries for r in res2] == [1, 1] and not any(r.proper_fit for r in res2)
+    assert [r.steps for r in res2] == [120, 120]
