@@ -35,20 +35,20 @@ def test_fit_frames_grouped_matches_independent_frame_fits(A):
     frames = [blob(H, W, cx=0.40 + 0.04 * i, cy=0.5, rx=0.2, ry=0.25) for i in range(5)]
     frames[1] = torch.ones(H, W)                      # background only -> skipped, does not occupy a slot
     grid = A.GridSpecHost("linspace", 1, H, W)
-    sched = A.FitSchedule(num_epochs=500, reuse_state_epochs=120, optimizer="adam", plateau=False, lr=2e-3,
+    sched = A.FitSchedule(num_epochs=600, reuse_state_epochs=150, optimizer="adam", plateau=False, lr=2e-3,
                           proper_prior_fit_threshold=0.5)
     seen = []
     res = A.fit_frames_grouped(multi, grid, frames, sched, on_frame=lambda r: seen.append(r.index))
     assert [r.index for r in res] == [0, 1, 2, 3, 4] and sorted(seen) == [0, 1, 2, 3, 4]
     assert [r.skipped for r in res] == [False, True, False, False, False]
-    assert [r.steps for r in res] == [500, 0, 500, 500, 120]           # second group (frame 4 alone) is warm
+    assert [r.steps for r in res] == [600, 0, 600, 600, 150]           # second group (frame 4 alone) is warm
     for r in res:
         if not r.skipped:
             assert r.proper_fit and r.iou > 0.9 and r.state is not None, (r.index, r.iou)
     # frame 2 on its own from the same entry state: same mask to within a handful of boundary pixels
     single = A.ConvexNextNet(n_hidden_layers=2, precision="f16").to(DEV)
     single.load_state_dict(entry)
-    alone = A.fit_frames(single, [grid], [frames[2]], A.FitSchedule(num_epochs=500, optimizer="adam", plateau=False, lr=2e-3,
+    alone = A.fit_frames(single, [grid], [frames[2]], A.FitSchedule(num_epochs=600, optimizer="adam", plateau=False, lr=2e-3,
                                                                    reuse_state=False))[0]
     assert abs(alone.iou - res[2].iou) < 1e-3 and alone.final_loss == pytest.approx(res[2].final_loss, rel=1e-3)
     # an impossible threshold sends every frame through the reference's reset + refit retry exactly once
