@@ -251,20 +251,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
       auto w_addr = [&](int i) { return tc::smem_u32(simg + (i - 1) * W_B); };
       auto t_addr = [&](uint8_t* t) { return tc::smem_u32(t); };
       // K-major A (R=128) x K-major/MN-major B (R=144) over K = 144 (9 steps), N = 144.  Descriptor bases once per
-      // contraction; per instruction only the start-address field advances (byte step >> 4).
-      auto mma_k144 = [&](uint32_t dcol, uint32_t a, uint32_t b, bool b_mn) {
-        const uint32_t idesc = tc::make_idesc(128, 144, 0, b_mn ? 1 : 0);
-        const tc::DescLH a0 = tc::make_desc_lh(a, 2048, 128);
-        const tc::DescLH a8 = tc::make_desc_lh(a + 8 * 4096, zero_a - (a + 8 * 4096), 128);     // 18th chunk -> zero chunk
-        const tc::DescLH b0 = b_mn ? tc::make_desc_lh(b, 128, 2304) : tc::make_desc_lh(b, 2304, 128);
-        const tc::DescLH b8 = b_mn ? tc::make_desc_lh(b + 8 * 256, 128, 2304)
-                                   : tc::make_desc_lh(b + 8 * 4608, zero_a - (b + 8 * 4608), 128);
-        const uint32_t binc = b_mn ? 256 / 16 : 4608 / 16;
+      // contraction -- prepared BEFORE the issuer waits for the epilogue warps, so that only the adds and the
+      // instructions themselves sit between its wake-up and the tensor pipe -- and per instruction only the
+      // start-address field advances (byte step >> 4).
+      struct K144 { tc::DescLH a0, a8, b0, b8; uint32_t binc, idesc; };
+      auto prep_k144 = [&](uint32_t a, uint32_t b, bool b_mn) {
+        K144 d;
+        d.idesc = tc::make_idesc(128, 144, 0, b_mn ? 1 : 0);
+        d.a0 = tc::make_desc_lh(a, 2048, 128);
+        d.a8 = tc::make_desc_lh(a + 8 * 4096, zero_a - (a + 8 * 4096), 128);     // 18th chunk -> zero chunk
+        d.b0 = b_mn ? tc::make_desc_lh(b, 128, 2304) : tc::make_desc_lh(b, 2304, 128);
+        d.b8 = b_mn ? tc::make_desc_lh(b + 8 * 256, 128, 2304) : tc::make_desc_lh(b + 8 * 4608, zero_a - (b + 8 * 4608), 128);
+        d.binc = b_mn ? 256 / 16 : 4608 / 16;
+        return d;
+      };
+      auto issue_k144 = [&](uint32_t dcol, const K144& d) {
 #pragma unroll
         for (int k = 0; k < 8; k++)
-          tc::umma_f16_lh(tbase + dcol, a0.lo + k * (4096 / 16), a0.hi, b0.lo + k * binc, b0.hi, idesc, k > 0);
-        tc::umma_f16_lh(tbase + dcol, a8.lo, a8.hi, b8.lo, b8.hi, idesc, 1);
+          tc::umma_f16_lh(tbase + dcol, d.a0.lo + k * (4096 / 16), d.a0.hi, d.b0.lo + k * d.binc, d.b0.hi, d.idesc, k > 0);
+        tc::umma_f16_lh(tbase + dcol, d.a8.lo, d.a8.hi, d.b8.lo, d.b8.hi, d.idesc, 1);
       };
+      auto mma_k144 = [&](uint32_t dcol, uint32_t a, uint32_t b, bool b_mn) { issue_k144(dcol, prep_k144(a, b, b_mn)); };
       // MN-major A window [0,128) x MN-major B, K = 128 pixels (8 steps); b_sbo = byte distance of B's 2nd N chunk
       auto mma_px = [&](uint32_t dcol, uint32_t a, uint32_t b, uint32_t b_sbo, int N, bool acc) {
         const uint32_t idesc = tc::make_idesc(128, N, 1, 1);
@@ -275,9 +282,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
                           (acc || k > 0) ? 1u : 0u);
       };
       // input layer of a tile: ACC = TX[128x16] * WIN^T   (both operands: one stored K chunk + the zero chunk)
+      const tc::DescLH in_b = tc::make_desc_lh(a_win, zero_a - a_win, 128);
       auto mma_input = [&](uint32_t a_tx) {
-        tc::umma_f16(tbase + T_ACC, tc::make_desc(a_tx, zero_a - a_tx, 128), tc::make_desc(a_win, zero_a - a_win, 128),
-                     tc::make_idesc(128, 144, 0, 0), 0);
+        const tc::DescLH in_a = tc::make_desc_lh(a_tx, zero_a - a_tx, 128);
+        tc::umma_f16_lh(tbase + T_ACC, in_a.lo, in_a.hi, in_b.lo, in_b.hi, tc::make_idesc(128, 144, 0, 0), 0);
       };
       // Diagnostic build (-DAWB_TC_SERIAL, see scripts/trace_tc.py) with AWB_TC_TRACE=2: a commit + wait + clock stamp
       // after every contraction group gives the true duration of each.  Compiled out otherwise: even a never-taken
@@ -311,17 +319,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
           }
         } else
         for (int s = 1; s <= 2 * L + 1; s++) {
+          // operands of the stage's first contraction are known before the epilogue warps arrive
+          const int i = s <= L ? s : L - (s - (L + 1));                           // forward layer s / delta_i just written
+          const uint32_t d = t_addr(s <= L ? tile_ptr(s - 1) : dbuf(i > 0 ? i : 0));
+          const K144 first = prep_k144(d, w_addr(i > 0 ? i : 1), s > L);
           tc::mbar_wait(bar_e2m, ph); ph ^= 1;
           tc::fence_after_sync();
           AWB_TR();
           if (s <= L) {
-            mma_k144(T_ACC, t_addr(tile_ptr(s - 1)), w_addr(s), false);          // forward layer s
+            issue_k144(T_ACC, first);                                             // forward layer s
             dbg();
             tc::umma_commit(bar_m2e);
           } else if (s <= 2 * L) {
-            const int i = L - (s - (L + 1));                                      // delta_i was just written
-            const uint32_t d = t_addr(dbuf(i)), zprev = t_addr(tile_ptr(i - 1));
-            mma_k144(T_ACC, d, w_addr(i), true);                                  // dgrad_i: ACC = delta_i * W_i
+            const uint32_t zprev = t_addr(tile_ptr(i - 1));
+            issue_k144(T_ACC, first);                                             // dgrad_i: ACC = delta_i * W_i
             dbg();
             if (i == L) { mma_px(T_GO, t_addr(tile_ptr(L)), d + 16 * 2048, 2048, 16, acc); dbg(); }   // z_L^T * [d128 d129 dy ..]
             tc::umma_commit(bar_m2e);
