@@ -13,6 +13,8 @@
 //           registers.  No atomics, no per-pixel shuffles; partials are reduced in a fixed order.
 #include <math.h>
 
+#include <type_traits>
+
 #include "awb_internal.cuh"
 
 namespace awb {
@@ -70,6 +72,75 @@ __device__ void stage_flow_packed(const float* __restrict__ par, int F, int m, i
   }
 }
 
+
+// ---- coupling MLPs with the mask pattern of the flow known at compile time.  MB: bit c set = component c is masked
+// (passes through the coupling and feeds s / t); MB < 0 = pattern only known at run time.  With the pattern fixed, the
+// multiplications by a masked-out zero and the outputs nobody reads disappear (half of the FMAs for the alternating
+// masks of net_factory.py:86-99); the surviving arithmetic is unchanged, so results are bit-identical.
+template <int C, int MB>
+__device__ __forceinline__ bool masked_c(int c, const bool* b) { return MB < 0 ? b[c] : ((MB >> c) & 1) != 0; }
+
+// s / t pre-outputs of one coupling: so[c], to[c] for the transformed components (the others are left untouched)
+template <int C, int MB>
+__device__ __forceinline__ void coupling_mlp_fwd(const float* __restrict__ wf, int m, const float* z, const bool* b,
+                                                 float* so, float* to) {
+  constexpr int RK = FlowPack<C>::RK;
+#pragma unroll 4
+  for (int k = 0; k < m; k++) {
+    float rk[RK];
+#pragma unroll
+    for (int q4 = 0; q4 < RK / 4; q4++) *reinterpret_cast<float4*>(&rk[4 * q4]) = reinterpret_cast<const float4*>(wf + k * RK)[q4];
+    float ps = rk[C], pt = rk[3 * C + 1];
+#pragma unroll
+    for (int c = 0; c < C; c++)
+      if (masked_c<C, MB>(c, b)) { ps = fmaf(rk[c], z[c], ps); pt = fmaf(rk[2 * C + 1 + c], z[c], pt); }
+    const float hs = fmaxf(ps, 0.f), ht = fmaxf(pt, 0.f);
+#pragma unroll
+    for (int c = 0; c < C; c++)
+      if (MB < 0 || !masked_c<C, MB>(c, b)) {
+        so[c] = fmaf(rk[C + 1 + c], hs, so[c]);
+        to[c] = fmaf(rk[3 * C + 2 + c], ht, to[c]);
+      }
+  }
+}
+
+// gradient reaching the masked inputs through the two MLPs: dzm[c] for masked c, from dsr / dtr of the transformed ones
+template <int C, int MB>
+__device__ __forceinline__ void coupling_mlp_bwd(const float* __restrict__ wf, int m, const float* z, const bool* b,
+                                                 const float* dsr, const float* dtr, float* dzm) {
+  constexpr int RK = FlowPack<C>::RK;
+#pragma unroll 4
+  for (int k = 0; k < m; k++) {
+    float rk[RK];
+#pragma unroll
+    for (int q4 = 0; q4 < RK / 4; q4++) *reinterpret_cast<float4*>(&rk[4 * q4]) = reinterpret_cast<const float4*>(wf + k * RK)[q4];
+    float ps = rk[C], pt = rk[3 * C + 1];
+#pragma unroll
+    for (int c = 0; c < C; c++)
+      if (masked_c<C, MB>(c, b)) { ps = fmaf(rk[c], z[c], ps); pt = fmaf(rk[2 * C + 1 + c], z[c], pt); }
+    float dps = 0.f, dpt = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; c++)
+      if (MB < 0 || !masked_c<C, MB>(c, b)) {
+        dps = fmaf(dsr[c], rk[C + 1 + c], dps);
+        dpt = fmaf(dtr[c], rk[3 * C + 2 + c], dpt);
+      }
+    dps = ps > 0.f ? dps : 0.f;
+    dpt = pt > 0.f ? dpt : 0.f;
+#pragma unroll
+    for (int c = 0; c < C; c++)
+      if (MB < 0 || masked_c<C, MB>(c, b)) dzm[c] = fmaf(dps, rk[c], fmaf(dpt, rk[2 * C + 1 + c], dzm[c]));
+  }
+}
+
+// warp-uniform dispatch on the flow's mask pattern (the alternating C = 2 patterns are compiled in; others run generic)
+#define AWB_FLOW_DISPATCH(C_, mb_, CALL)                 \
+  do {                                                   \
+    if ((C_) == 2 && (mb_) == 1) { CALL(1); }            \
+    else if ((C_) == 2 && (mb_) == 2) { CALL(2); }       \
+    else { CALL(-1); }                                   \
+  } while (0)
+
 template <int C>
 __global__ void __launch_bounds__(256) k_flow_fwd(FlowP p) {
   extern __shared__ __align__(16) float sp[];   // k-packed flow weights + [2C] linear
@@ -103,23 +174,12 @@ __global__ void __launch_bounds__(256) k_flow_fwd(FlowP p) {
 #pragma unroll
     for (int c = 0; c < C; c++) { b[c] = p.fc.masks[f * C + c] != 0; zm[c] = b[c] ? z[c] : 0.f; }
     float so[C], to[C];
+    int mb = 0;
 #pragma unroll
-    for (int c = 0; c < C; c++) { so[c] = tail[c]; to[c] = tail[C + c]; }
-#pragma unroll 4
-    for (int k = 0; k < m; k++) {
-      float rk[RK];
-#pragma unroll
-      for (int q4 = 0; q4 < RK / 4; q4++) *reinterpret_cast<float4*>(&rk[4 * q4]) = reinterpret_cast<const float4*>(wf + k * RK)[q4];
-      float ps = rk[C], pt = rk[3 * C + 1];
-#pragma unroll
-      for (int c = 0; c < C; c++) { ps = fmaf(rk[c], zm[c], ps); pt = fmaf(rk[2 * C + 1 + c], zm[c], pt); }
-      float hs = fmaxf(ps, 0.f), ht = fmaxf(pt, 0.f);
-#pragma unroll
-      for (int c = 0; c < C; c++) {
-        so[c] = fmaf(rk[C + 1 + c], hs, so[c]);
-        to[c] = fmaf(rk[3 * C + 2 + c], ht, to[c]);
-      }
-    }
+    for (int c = 0; c < C; c++) { so[c] = tail[c]; to[c] = tail[C + c]; mb |= b[c] ? 1 << c : 0; }
+#define AWB_CALL(MB) coupling_mlp_fwd<C, MB>(wf, m, zm, b, so, to)
+    AWB_FLOW_DISPATCH(C, mb, AWB_CALL);
+#undef AWB_CALL
 #pragma unroll
     for (int c = 0; c < C; c++) {
       float s_ = p.tanh_out ? tanhf(so[c]) : so[c];
@@ -237,23 +297,12 @@ __global__ void __launch_bounds__(1024) k_flow_bwd_px(FlowP p, float* __restrict
 #pragma unroll
       for (int c = 0; c < C; c++) { z[c] = zin[f * C + c]; b[c] = p.fc.masks[f * C + c] != 0; zm[c] = b[c] ? z[c] : 0.f; }
       float so[C], to[C];
+      int mb = 0;
 #pragma unroll
-      for (int c = 0; c < C; c++) { so[c] = tail[c]; to[c] = tail[C + c]; }
-#pragma unroll 4
-      for (int k = 0; k < m; k++) {
-        float rk[RK];
-#pragma unroll
-        for (int q4 = 0; q4 < RK / 4; q4++) *reinterpret_cast<float4*>(&rk[4 * q4]) = reinterpret_cast<const float4*>(wf + k * RK)[q4];
-        float ps = rk[C], pt = rk[3 * C + 1];
-#pragma unroll
-        for (int c = 0; c < C; c++) { ps = fmaf(rk[c], zm[c], ps); pt = fmaf(rk[2 * C + 1 + c], zm[c], pt); }
-        const float hs = fmaxf(ps, 0.f), ht = fmaxf(pt, 0.f);
-#pragma unroll
-        for (int c = 0; c < C; c++) {
-          so[c] = fmaf(rk[C + 1 + c], hs, so[c]);
-          to[c] = fmaf(rk[3 * C + 2 + c], ht, to[c]);
-        }
-      }
+      for (int c = 0; c < C; c++) { so[c] = tail[c]; to[c] = tail[C + c]; mb |= b[c] ? 1 << c : 0; }
+#define AWB_CALL(MB) coupling_mlp_fwd<C, MB>(wf, m, zm, b, so, to)
+      AWB_FLOW_DISPATCH(C, mb, AWB_CALL);
+#undef AWB_CALL
       float dsr[C], dtr[C], dzin[C];
 #pragma unroll
       for (int c = 0; c < C; c++) {
@@ -281,25 +330,9 @@ __global__ void __launch_bounds__(1024) k_flow_bwd_px(FlowP p, float* __restrict
       float dzm[C];
 #pragma unroll
       for (int c = 0; c < C; c++) dzm[c] = 0.f;
-#pragma unroll 4
-      for (int k = 0; k < m; k++) {
-        float rk[RK];
-#pragma unroll
-        for (int q4 = 0; q4 < RK / 4; q4++) *reinterpret_cast<float4*>(&rk[4 * q4]) = reinterpret_cast<const float4*>(wf + k * RK)[q4];
-        float ps = rk[C], pt = rk[3 * C + 1];
-#pragma unroll
-        for (int c = 0; c < C; c++) { ps = fmaf(rk[c], zm[c], ps); pt = fmaf(rk[2 * C + 1 + c], zm[c], pt); }
-        float dps = 0.f, dpt = 0.f;
-#pragma unroll
-        for (int c = 0; c < C; c++) {
-          dps = fmaf(dsr[c], rk[C + 1 + c], dps);
-          dpt = fmaf(dtr[c], rk[3 * C + 2 + c], dpt);
-        }
-        dps = ps > 0.f ? dps : 0.f;
-        dpt = pt > 0.f ? dpt : 0.f;
-#pragma unroll
-        for (int c = 0; c < C; c++) dzm[c] = fmaf(dps, rk[c], fmaf(dpt, rk[2 * C + 1 + c], dzm[c]));
-      }
+#define AWB_CALL(MB) coupling_mlp_bwd<C, MB>(wf, m, zm, b, dsr, dtr, dzm)
+      AWB_FLOW_DISPATCH(C, mb, AWB_CALL);
+#undef AWB_CALL
 #pragma unroll
       for (int c = 0; c < C; c++) dz[c] = dzin[c] + (b[c] ? dzm[c] : 0.f);
     }
@@ -364,37 +397,53 @@ __global__ void __launch_bounds__(256) k_flow_wgrad(FlowP p, const float* __rest
   const float* rp = rec + ((int64_t)o * p.N + r0 + warp) * (4 * FC) + f * 4 * C;
   const int64_t zstep = (int64_t)8 * FC, rstep = (int64_t)8 * 4 * FC;
   const int n_it = (int)((r1 - r0 - warp + 7) / 8);
+  // the mask pattern is a property of the flow (blockIdx.y): the whole block runs one instantiation of the pixel loop
+  auto pixel_loop = [&](auto mb_c) {
+    constexpr int MB = decltype(mb_c)::value;
 #pragma unroll 4
-  for (int it = 0; it < (n_it > 0 ? n_it : 0); it++, zp += zstep, rp += rstep) {
-    float zm[C], dsr[C], dtr[C];
-    if (C == 2) {
-      const float2 zz = *reinterpret_cast<const float2*>(zp);
-      const float4 r4 = *reinterpret_cast<const float4*>(rp);
-      zm[0] = b[0] ? zz.x : 0.f; zm[1] = b[1] ? zz.y : 0.f;
-      dsr[0] = r4.x; dsr[1] = r4.y; dtr[0] = r4.z; dtr[1] = r4.w;
-    } else {
+    for (int it = 0; it < (n_it > 0 ? n_it : 0); it++, zp += zstep, rp += rstep) {
+      float zm[C], dsr[C], dtr[C];
+      if (C == 2) {
+        const float2 zz = *reinterpret_cast<const float2*>(zp);
+        const float4 r4 = *reinterpret_cast<const float4*>(rp);
+        zm[0] = zz.x; zm[1] = zz.y;
+        dsr[0] = r4.x; dsr[1] = r4.y; dtr[0] = r4.z; dtr[1] = r4.w;
+      } else {
 #pragma unroll
-      for (int c = 0; c < C; c++) { zm[c] = b[c] ? zp[c] : 0.f; dsr[c] = rp[c]; dtr[c] = rp[C + c]; }
-    }
-    if (lane < 4 * C) a4 += rp[lane];
-    float ps = b1s, pt = b1t, dps = 0.f, dpt = 0.f;
+        for (int c = 0; c < C; c++) { zm[c] = zp[c]; dsr[c] = rp[c]; dtr[c] = rp[C + c]; }
+      }
+      if (lane < 4 * C) a4 += rp[lane];
+      float ps = b1s, pt = b1t, dps = 0.f, dpt = 0.f;
 #pragma unroll
-    for (int c = 0; c < C; c++) {
-      ps = fmaf(w1s[c], zm[c], ps); pt = fmaf(w1t[c], zm[c], pt);
-      dps = fmaf(dsr[c], w2s[c], dps); dpt = fmaf(dtr[c], w2t[c], dpt);
-    }
-    const float hs = fmaxf(ps, 0.f), ht = fmaxf(pt, 0.f);
-    dps = ps > 0.f ? dps : 0.f;
-    dpt = pt > 0.f ? dpt : 0.f;
+      for (int c = 0; c < C; c++) {
+        if (masked_c<C, MB>(c, b)) { ps = fmaf(w1s[c], zm[c], ps); pt = fmaf(w1t[c], zm[c], pt); }
+        if (MB < 0 || !masked_c<C, MB>(c, b)) { dps = fmaf(dsr[c], w2s[c], dps); dpt = fmaf(dtr[c], w2t[c], dpt); }
+      }
+      const float hs = fmaxf(ps, 0.f), ht = fmaxf(pt, 0.f);
+      dps = ps > 0.f ? dps : 0.f;
+      dpt = pt > 0.f ? dpt : 0.f;
 #pragma unroll
-    for (int c = 0; c < C; c++) {
-      acc[c] = fmaf(dps, zm[c], acc[c]);                               // d s.W1[k][c]
-      acc[C + 1 + c] = fmaf(dsr[c], hs, acc[C + 1 + c]);               // d s.W2[c][k]
-      acc[2 * C + 1 + c] = fmaf(dpt, zm[c], acc[2 * C + 1 + c]);       // d t.W1[k][c]
-      acc[3 * C + 2 + c] = fmaf(dtr[c], ht, acc[3 * C + 2 + c]);       // d t.W2[c][k]
+      for (int c = 0; c < C; c++) {
+        if (masked_c<C, MB>(c, b)) {
+          acc[c] = fmaf(dps, zm[c], acc[c]);                             // d s.W1[k][c]
+          acc[2 * C + 1 + c] = fmaf(dpt, zm[c], acc[2 * C + 1 + c]);     // d t.W1[k][c]
+        }
+        if (MB < 0 || !masked_c<C, MB>(c, b)) {
+          acc[C + 1 + c] = fmaf(dsr[c], hs, acc[C + 1 + c]);             // d s.W2[c][k]
+          acc[3 * C + 2 + c] = fmaf(dtr[c], ht, acc[3 * C + 2 + c]);     // d t.W2[c][k]
+        }
+      }
+      acc[C] += dps;                                                     // d s.b1[k]
+      acc[3 * C + 1] += dpt;                                             // d t.b1[k]
     }
-    acc[C] += dps;                                                     // d s.b1[k]
-    acc[3 * C + 1] += dpt;                                             // d t.b1[k]
+  };
+  {
+    int mb = 0;
+#pragma unroll
+    for (int c = 0; c < C; c++) mb |= b[c] ? 1 << c : 0;
+    if (C == 2 && mb == 1) pixel_loop(std::integral_constant<int, 1>{});
+    else if (C == 2 && mb == 2) pixel_loop(std::integral_constant<int, 2>{});
+    else pixel_loop(std::integral_constant<int, -1>{});
   }
 #pragma unroll
   for (int i = 0; i < NA; i++) red[warp][i][lane] = acc[i];
