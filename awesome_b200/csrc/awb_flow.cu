@@ -133,12 +133,17 @@ __device__ __forceinline__ void coupling_mlp_bwd(const float* __restrict__ wf, i
   }
 }
 
-// warp-uniform dispatch on the flow's mask pattern (the alternating C = 2 patterns are compiled in; others run generic)
-#define AWB_FLOW_DISPATCH(C_, mb_, CALL)                 \
-  do {                                                   \
-    if ((C_) == 2 && (mb_) == 1) { CALL(1); }            \
-    else if ((C_) == 2 && (mb_) == 2) { CALL(2); }       \
-    else { CALL(-1); }                                   \
+// warp-uniform dispatch on the flow's mask pattern: every pattern net_factory.py:86-99 produces (the binary codes
+// 1 .. 2^C - 2) is compiled in for C = 2 and C = 3; anything else runs the generic path
+#define AWB_FLOW_DISPATCH(C_, mb_, CALL)                                  \
+  do {                                                                    \
+    if ((mb_) == 1) { CALL(1); }                                          \
+    else if ((mb_) == 2) { CALL(2); }                                     \
+    else if ((C_) == 3 && (mb_) == 3) { CALL(3); }                        \
+    else if ((C_) == 3 && (mb_) == 4) { CALL(4); }                        \
+    else if ((C_) == 3 && (mb_) == 5) { CALL(5); }                        \
+    else if ((C_) == 3 && (mb_) == 6) { CALL(6); }                        \
+    else { CALL(-1); }                                                    \
   } while (0)
 
 template <int C>
@@ -441,9 +446,9 @@ __global__ void __launch_bounds__(256) k_flow_wgrad(FlowP p, const float* __rest
     int mb = 0;
 #pragma unroll
     for (int c = 0; c < C; c++) mb |= b[c] ? 1 << c : 0;
-    if (C == 2 && mb == 1) pixel_loop(std::integral_constant<int, 1>{});
-    else if (C == 2 && mb == 2) pixel_loop(std::integral_constant<int, 2>{});
-    else pixel_loop(std::integral_constant<int, -1>{});
+#define AWB_CALL(MB) pixel_loop(std::integral_constant<int, MB>{})
+    AWB_FLOW_DISPATCH(C, mb, AWB_CALL);
+#undef AWB_CALL
   }
 #pragma unroll
   for (int i = 0; i < NA; i++) red[warp][i][lane] = acc[i];
