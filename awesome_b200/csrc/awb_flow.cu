@@ -46,14 +46,32 @@ template <int C> struct FlowPack {
   static constexpr int RK = (4 * C + 2 + 3) / 4 * 4;       // 12 (C=2), 16 (C=3)
   __host__ __device__ static int flow_stride(int m) { return m * RK + 4 * C; }
 };
+// Flows whose mask pattern is one of the compiled-in ones (binary codes 1 .. 2^C - 2) get a COMPACT record in the first 8
+// floats: only what the pattern uses -- [w1s of the masked comps | b1s | w2s of the transformed comps | w1t masked | b1t |
+// w2t transformed] = 2C + 2 <= 8 floats = 2 LDS.128 per hidden unit instead of 3 (C = 2) / 4 (C = 3).
 template <int C>
-__device__ void stage_flow_packed(const float* __restrict__ par, int F, int m, int64_t per_flow, float* sp) {
+__device__ __forceinline__ bool flow_pattern_compiled(int mb) { return mb >= 1 && mb <= (1 << C) - 2; }
+template <int C>
+__device__ void stage_flow_packed(const float* __restrict__ par, int F, int m, int64_t per_flow, float* sp, const FlowConsts& fc) {
   constexpr int RK = FlowPack<C>::RK;
   const int half = 2 * m * C + m + C, FS = FlowPack<C>::flow_stride(m);
   for (int t = threadIdx.x; t < F * m; t += blockDim.x) {
     const int f = t / m, k = t - f * m;
     const float* w = par + (int64_t)f * per_flow;
     float* r = sp + f * FS + k * RK;
+    int mb = 0;
+#pragma unroll
+    for (int c = 0; c < C; c++) mb |= fc.masks[f * C + c] != 0 ? 1 << c : 0;
+    if (flow_pattern_compiled<C>(mb)) {
+      int pos = 0;
+      for (int c = 0; c < C; c++) if ((mb >> c) & 1) r[pos++] = w[k * C + c];                              // s.W1[k][c], masked c
+      r[pos++] = w[m * C + k];                                                                         // s.b1[k]
+      for (int c = 0; c < C; c++) if (!((mb >> c) & 1)) r[pos++] = w[m * C + m + c * m + k];               // s.W2[c][k], transformed c
+      for (int c = 0; c < C; c++) if ((mb >> c) & 1) r[pos++] = w[half + k * C + c];                       // t.W1[k][c]
+      r[pos++] = w[half + m * C + k];                                                                  // t.b1[k]
+      for (int c = 0; c < C; c++) if (!((mb >> c) & 1)) r[pos++] = w[half + m * C + m + c * m + k];        // t.W2[c][k]
+      continue;
+    }
 #pragma unroll
     for (int c = 0; c < C; c++) {
       r[c] = w[k * C + c];                               // s.W1[k][c]
@@ -81,25 +99,46 @@ template <int C, int MB>
 __device__ __forceinline__ bool masked_c(int c, const bool* b) { return MB < 0 ? b[c] : ((MB >> c) & 1) != 0; }
 
 // s / t pre-outputs of one coupling: so[c], to[c] for the transformed components (the others are left untouched)
+// record of hidden unit k: compact (8 floats) for a compiled-in pattern, the full RK floats otherwise
+template <int C, int MB>
+struct FlowRec {
+  static constexpr int NM = MB < 0 ? 0 : ((MB & 1) + ((MB >> 1) & 1) + ((MB >> 2) & 1));     // masked components
+  static constexpr int NU = C - NM;
+  static constexpr int N4 = MB < 0 ? FlowPack<C>::RK / 4 : 2;
+  float v[4 * N4];
+  __device__ __forceinline__ void load(const float* __restrict__ rec) {
+#pragma unroll
+    for (int q4 = 0; q4 < N4; q4++) *reinterpret_cast<float4*>(&v[4 * q4]) = reinterpret_cast<const float4*>(rec)[q4];
+  }
+  // rank of component c among the masked / the transformed ones (constant-folded after unrolling)
+  static __device__ __forceinline__ int rm(int c) { return __popc(MB & ((1 << c) - 1)); }
+  static __device__ __forceinline__ int ru(int c) { return c - rm(c); }
+  __device__ __forceinline__ float w1s(int c) const { return MB < 0 ? v[c] : v[rm(c)]; }
+  __device__ __forceinline__ float b1s() const { return MB < 0 ? v[C] : v[NM]; }
+  __device__ __forceinline__ float w2s(int c) const { return MB < 0 ? v[C + 1 + c] : v[NM + 1 + ru(c)]; }
+  __device__ __forceinline__ float w1t(int c) const { return MB < 0 ? v[2 * C + 1 + c] : v[NM + 1 + NU + rm(c)]; }
+  __device__ __forceinline__ float b1t() const { return MB < 0 ? v[3 * C + 1] : v[2 * NM + 1 + NU]; }
+  __device__ __forceinline__ float w2t(int c) const { return MB < 0 ? v[3 * C + 2 + c] : v[2 * NM + 2 + NU + ru(c)]; }
+};
+
 template <int C, int MB>
 __device__ __forceinline__ void coupling_mlp_fwd(const float* __restrict__ wf, int m, const float* z, const bool* b,
                                                  float* so, float* to) {
   constexpr int RK = FlowPack<C>::RK;
 #pragma unroll 4
   for (int k = 0; k < m; k++) {
-    float rk[RK];
-#pragma unroll
-    for (int q4 = 0; q4 < RK / 4; q4++) *reinterpret_cast<float4*>(&rk[4 * q4]) = reinterpret_cast<const float4*>(wf + k * RK)[q4];
-    float ps = rk[C], pt = rk[3 * C + 1];
+    FlowRec<C, MB> r;
+    r.load(wf + k * RK);
+    float ps = r.b1s(), pt = r.b1t();
 #pragma unroll
     for (int c = 0; c < C; c++)
-      if (masked_c<C, MB>(c, b)) { ps = fmaf(rk[c], z[c], ps); pt = fmaf(rk[2 * C + 1 + c], z[c], pt); }
+      if (masked_c<C, MB>(c, b)) { ps = fmaf(r.w1s(c), z[c], ps); pt = fmaf(r.w1t(c), z[c], pt); }
     const float hs = fmaxf(ps, 0.f), ht = fmaxf(pt, 0.f);
 #pragma unroll
     for (int c = 0; c < C; c++)
       if (MB < 0 || !masked_c<C, MB>(c, b)) {
-        so[c] = fmaf(rk[C + 1 + c], hs, so[c]);
-        to[c] = fmaf(rk[3 * C + 2 + c], ht, to[c]);
+        so[c] = fmaf(r.w2s(c), hs, so[c]);
+        to[c] = fmaf(r.w2t(c), ht, to[c]);
       }
   }
 }
@@ -111,25 +150,24 @@ __device__ __forceinline__ void coupling_mlp_bwd(const float* __restrict__ wf, i
   constexpr int RK = FlowPack<C>::RK;
 #pragma unroll 4
   for (int k = 0; k < m; k++) {
-    float rk[RK];
-#pragma unroll
-    for (int q4 = 0; q4 < RK / 4; q4++) *reinterpret_cast<float4*>(&rk[4 * q4]) = reinterpret_cast<const float4*>(wf + k * RK)[q4];
-    float ps = rk[C], pt = rk[3 * C + 1];
+    FlowRec<C, MB> r;
+    r.load(wf + k * RK);
+    float ps = r.b1s(), pt = r.b1t();
 #pragma unroll
     for (int c = 0; c < C; c++)
-      if (masked_c<C, MB>(c, b)) { ps = fmaf(rk[c], z[c], ps); pt = fmaf(rk[2 * C + 1 + c], z[c], pt); }
+      if (masked_c<C, MB>(c, b)) { ps = fmaf(r.w1s(c), z[c], ps); pt = fmaf(r.w1t(c), z[c], pt); }
     float dps = 0.f, dpt = 0.f;
 #pragma unroll
     for (int c = 0; c < C; c++)
       if (MB < 0 || !masked_c<C, MB>(c, b)) {
-        dps = fmaf(dsr[c], rk[C + 1 + c], dps);
-        dpt = fmaf(dtr[c], rk[3 * C + 2 + c], dpt);
+        dps = fmaf(dsr[c], r.w2s(c), dps);
+        dpt = fmaf(dtr[c], r.w2t(c), dpt);
       }
     dps = ps > 0.f ? dps : 0.f;
     dpt = pt > 0.f ? dpt : 0.f;
 #pragma unroll
     for (int c = 0; c < C; c++)
-      if (MB < 0 || masked_c<C, MB>(c, b)) dzm[c] = fmaf(dps, rk[c], fmaf(dpt, rk[2 * C + 1 + c], dzm[c]));
+      if (MB < 0 || masked_c<C, MB>(c, b)) dzm[c] = fmaf(dps, r.w1s(c), fmaf(dpt, r.w1t(c), dzm[c]));
   }
 }
 
@@ -153,7 +191,7 @@ __global__ void __launch_bounds__(256) k_flow_fwd(FlowP p) {
   const int o = blockIdx.y;
   const float* par = p.params + (int64_t)o * p.P + p.off_flow;
   const int m = p.m, FS = FlowPack<C>::flow_stride(m);
-  stage_flow_packed<C>(par, p.F, m, p.per_flow, sp);
+  stage_flow_packed<C>(par, p.F, m, p.per_flow, sp, p.fc);
   float* lin = sp + p.F * FS;
   if (threadIdx.x < 2 * C) lin[threadIdx.x] = par[p.P_flow + threadIdx.x];
   __syncthreads();
@@ -281,7 +319,7 @@ __global__ void __launch_bounds__(1024) k_flow_bwd_px(FlowP p, float* __restrict
   const float* par = p.params + (int64_t)o * p.P + p.off_flow;
   const int PF = (int)p.P_flow + 2 * C;
   const int m = p.m, FS = FlowPack<C>::flow_stride(m);
-  stage_flow_packed<C>(par, p.F, m, p.per_flow, sp);
+  stage_flow_packed<C>(par, p.F, m, p.per_flow, sp, p.fc);
   __syncthreads();
   const int64_t r0 = (int64_t)s * p.chunk, r1 = r0 + p.chunk < p.N ? r0 + p.chunk : p.N;
   float glw[C], glb[C];
