@@ -121,25 +121,30 @@ struct FlowRec {
   __device__ __forceinline__ float w2t(int c) const { return MB < 0 ? v[3 * C + 2 + c] : v[2 * NM + 2 + NU + ru(c)]; }
 };
 
-template <int C, int MB>
-__device__ __forceinline__ void coupling_mlp_fwd(const float* __restrict__ wf, int m, const float* z, const bool* b,
-                                                 float* so, float* to) {
+// P pixels per thread share every weight record: the per-pixel kernels are bound by the shared-memory loads of the
+// records (2 LDS.128 per ~6 FMAs with one pixel), not by the FMAs.
+template <int C, int MB, int P>
+__device__ __forceinline__ void coupling_mlp_fwd(const float* __restrict__ wf, int m, const float (*z)[C], const bool* b,
+                                                 float (*so)[C], float (*to)[C]) {
   constexpr int RK = FlowPack<C>::RK;
 #pragma unroll 4
   for (int k = 0; k < m; k++) {
     FlowRec<C, MB> r;
     r.load(wf + k * RK);
-    float ps = r.b1s(), pt = r.b1t();
 #pragma unroll
-    for (int c = 0; c < C; c++)
-      if (masked_c<C, MB>(c, b)) { ps = fmaf(r.w1s(c), z[c], ps); pt = fmaf(r.w1t(c), z[c], pt); }
-    const float hs = fmaxf(ps, 0.f), ht = fmaxf(pt, 0.f);
+    for (int q = 0; q < P; q++) {
+      float ps = r.b1s(), pt = r.b1t();
 #pragma unroll
-    for (int c = 0; c < C; c++)
-      if (MB < 0 || !masked_c<C, MB>(c, b)) {
-        so[c] = fmaf(r.w2s(c), hs, so[c]);
-        to[c] = fmaf(r.w2t(c), ht, to[c]);
-      }
+      for (int c = 0; c < C; c++)
+        if (masked_c<C, MB>(c, b)) { ps = fmaf(r.w1s(c), z[q][c], ps); pt = fmaf(r.w1t(c), z[q][c], pt); }
+      const float hs = fmaxf(ps, 0.f), ht = fmaxf(pt, 0.f);
+#pragma unroll
+      for (int c = 0; c < C; c++)
+        if (MB < 0 || !masked_c<C, MB>(c, b)) {
+          so[q][c] = fmaf(r.w2s(c), hs, so[q][c]);
+          to[q][c] = fmaf(r.w2t(c), ht, to[q][c]);
+        }
+    }
   }
 }
 
@@ -184,10 +189,12 @@ __device__ __forceinline__ void coupling_mlp_bwd(const float* __restrict__ wf, i
     else { CALL(-1); }                                                    \
   } while (0)
 
+constexpr int FLOW_FWD_P = 2;      // pixels per thread of k_flow_fwd
 template <int C>
 __global__ void __launch_bounds__(256) k_flow_fwd(FlowP p) {
   extern __shared__ __align__(16) float sp[];   // k-packed flow weights + [2C] linear
   constexpr int RK = FlowPack<C>::RK;
+  constexpr int P = FLOW_FWD_P;
   const int o = blockIdx.y;
   const float* par = p.params + (int64_t)o * p.P + p.off_flow;
   const int m = p.m, FS = FlowPack<C>::flow_stride(m);
@@ -195,51 +202,71 @@ __global__ void __launch_bounds__(256) k_flow_fwd(FlowP p) {
   float* lin = sp + p.F * FS;
   if (threadIdx.x < 2 * C) lin[threadIdx.x] = par[p.P_flow + threadIdx.x];
   __syncthreads();
-  int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= p.N) return;
-  float z[C];
+  // pixel q of this thread: consecutive threads take consecutive pixels within each of the block's P row groups
+  int64_t n[P];
+  bool ok[P];
+  float z[P][C];
 #pragma unroll
-  for (int c = 0; c < C; c++) {
-    float x = coord(p.g, n, c);
-    if (p.use_linear) x = x * lin[c] + lin[C + c];
-    z[c] = mm_fwd(x, p.fc.nmin[c], p.fc.nmax[c], p.fc.new_min, p.fc.new_max);
+  for (int q = 0; q < P; q++) {
+    const int64_t nq = ((int64_t)blockIdx.x * P + q) * blockDim.x + threadIdx.x;
+    ok[q] = nq < p.N;
+    n[q] = ok[q] ? nq : p.N - 1;          // padding threads recompute the last pixel and store nothing
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      float x = coord(p.g, n[q], c);
+      if (p.use_linear) x = x * lin[c] + lin[C + c];
+      z[q][c] = mm_fwd(x, p.fc.nmin[c], p.fc.nmax[c], p.fc.new_min, p.fc.new_max);
+    }
   }
-  float* zin = p.zin ? p.zin + ((int64_t)o * p.N + n) * (p.F * C) : nullptr;
+  if (!ok[0]) return;
   for (int f = 0; f < p.F; f++) {
     const float* wf = sp + f * FS;
     const float* tail = wf + m * RK;          // b2s[C] | b2t[C] | an_s[C] | an_t[C]
-    if (zin) {
-#pragma unroll
-      for (int c = 0; c < C; c++) zin[f * C + c] = z[c];
-    }
-    float zm[C];
     bool b[C];
-#pragma unroll
-    for (int c = 0; c < C; c++) { b[c] = p.fc.masks[f * C + c] != 0; zm[c] = b[c] ? z[c] : 0.f; }
-    float so[C], to[C];
     int mb = 0;
 #pragma unroll
-    for (int c = 0; c < C; c++) { so[c] = tail[c]; to[c] = tail[C + c]; mb |= b[c] ? 1 << c : 0; }
-#define AWB_CALL(MB) coupling_mlp_fwd<C, MB>(wf, m, zm, b, so, to)
+    for (int c = 0; c < C; c++) { b[c] = p.fc.masks[f * C + c] != 0; mb |= b[c] ? 1 << c : 0; }
+    float so[P][C], to[P][C];
+#pragma unroll
+    for (int q = 0; q < P; q++) {
+      if (p.zin && ok[q]) {
+        float* zin = p.zin + ((int64_t)o * p.N + n[q]) * (p.F * C);
+#pragma unroll
+        for (int c = 0; c < C; c++) zin[f * C + c] = z[q][c];
+      }
+#pragma unroll
+      for (int c = 0; c < C; c++) { so[q][c] = tail[c]; to[q][c] = tail[C + c]; }
+    }
+#define AWB_CALL(MB) coupling_mlp_fwd<C, MB, P>(wf, m, z, b, so, to)
     AWB_FLOW_DISPATCH(C, mb, AWB_CALL);
 #undef AWB_CALL
 #pragma unroll
-    for (int c = 0; c < C; c++) {
-      float s_ = p.tanh_out ? tanhf(so[c]) : so[c];
-      float t_ = p.tanh_out ? tanhf(to[c]) : to[c];
-      if (!isfinite(s_)) s_ = NAN;
-      if (!isfinite(t_)) t_ = NAN;
-      float zc = b[c] ? z[c] : fmaf(z[c], expf(s_), t_);
-      z[c] = fmaf(zc, expf(tail[2 * C + c]), tail[3 * C + c]);      // ActNorm
+    for (int q = 0; q < P; q++) {
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        float zc = z[q][c];
+        if (!b[c]) {
+          float s_ = p.tanh_out ? tanhf(so[q][c]) : so[q][c];
+          float t_ = p.tanh_out ? tanhf(to[q][c]) : to[q][c];
+          if (!isfinite(s_)) s_ = NAN;
+          if (!isfinite(t_)) t_ = NAN;
+          zc = fmaf(z[q][c], expf(s_), t_);
+        }
+        z[q][c] = fmaf(zc, expf(tail[2 * C + c]), tail[3 * C + c]);      // ActNorm
+      }
     }
   }
-  float xd[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-  for (int c = 0; c < C; c++) xd[c] = mm_fwd(z[c], p.fc.new_min, p.fc.new_max, p.fc.nmin[c], p.fc.nmax[c]);
-  *reinterpret_cast<float4*>(p.X + ((int64_t)o * p.N + n) * 4) = make_float4(xd[0], xd[1], xd[2], 1.f);
-  if (p.deformed) {
+  for (int q = 0; q < P; q++) {
+    if (!ok[q]) continue;
+    float xd[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int c = 0; c < C; c++) p.deformed[((int64_t)o * p.N + n) * C + c] = xd[c];
+    for (int c = 0; c < C; c++) xd[c] = mm_fwd(z[q][c], p.fc.new_min, p.fc.new_max, p.fc.nmin[c], p.fc.nmax[c]);
+    *reinterpret_cast<float4*>(p.X + ((int64_t)o * p.N + n[q]) * 4) = make_float4(xd[0], xd[1], xd[2], 1.f);
+    if (p.deformed) {
+#pragma unroll
+      for (int c = 0; c < C; c++) p.deformed[((int64_t)o * p.N + n[q]) * C + c] = xd[c];
+    }
   }
 }
 
@@ -343,7 +370,7 @@ __global__ void __launch_bounds__(1024) k_flow_bwd_px(FlowP p, float* __restrict
       int mb = 0;
 #pragma unroll
       for (int c = 0; c < C; c++) { so[c] = tail[c]; to[c] = tail[C + c]; mb |= b[c] ? 1 << c : 0; }
-#define AWB_CALL(MB) coupling_mlp_fwd<C, MB>(wf, m, zm, b, so, to)
+#define AWB_CALL(MB) coupling_mlp_fwd<C, MB, 1>(wf, m, reinterpret_cast<const float(*)[C]>(zm), b, reinterpret_cast<float(*)[C]>(so), reinterpret_cast<float(*)[C]>(to))
       AWB_FLOW_DISPATCH(C, mb, AWB_CALL);
 #undef AWB_CALL
       float dsr[C], dtr[C], dzin[C];
@@ -665,7 +692,7 @@ int flow_forward(const awb_prior* h, const float* params, const awb_grid_spec* g
   p.zin = ws.flowz;
   p.deformed = deformed;
   size_t smem = sizeof(float) * ((size_t)h->lay.F * (h->lay.C == 2 ? FlowPack<2>::flow_stride(h->lay.m) : FlowPack<3>::flow_stride(h->lay.m)) + 2 * h->lay.C);
-  dim3 grid((unsigned)((p.N + 255) / 256), h->desc.n_objects);
+  dim3 grid((unsigned)((p.N + 256 * FLOW_FWD_P - 1) / (256 * FLOW_FWD_P)), h->desc.n_objects);
   if (h->lay.C == 2) {
     AWB_CUDA(cudaFuncSetAttribute(k_flow_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AWB_LAUNCH(PK_FLOW_FWD, st, k_flow_fwd<2><<<grid, 256, smem, st>>>(p));
