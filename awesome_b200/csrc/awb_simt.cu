@@ -602,22 +602,18 @@ __global__ void __launch_bounds__(256) k_reduce_opt_aug(OptA a, int n_groups) {
   }
   grid_dep_wait();      // the partials and the loss sums are complete
   grid_dep_launch();
-  if (w == 0) {
-    float l = 0.f;
-    for (int s = lane; s < a.S; s += 32) l += a.lossp[s * a.O + o];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
-    if (lane == 0) s_loss = l;
-  }
-  __syncthreads();
-  const bool bad = !isfinite(s_loss);
-  if (!bad) {
+  // every warp's partial rows and warp 0's loss terms go out together: one L2 round trip and one barrier between the
+  // end of the fit kernel and the parameter update (this stretch is not hidden by anything)
+  float lsum = 0.f;
+  if (w == 0)
+    for (int s = lane; s < a.S; s += 32) lsum += __ldcg(a.lossp + s * a.O + o);
+  {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (g0 + 4 * lane < a.G) {
       const float4* src = reinterpret_cast<const float4*>(a.part + (int64_t)o * a.G + g0) + lane;
       const int64_t stride4 = a.sSplit / 4;
       const int s0 = (a.S * w) >> 3, s1 = (a.S * (w + 1)) >> 3;
-      // all of this warp's <= 19 partial rows in flight at once (one L2 round trip), summed in a fixed order
+      // all of this warp's <= 19 partial rows in flight at once, summed in a fixed order
       for (int sb = s0; sb < s1; sb += 20) {
         float4 tt[20];
 #pragma unroll
@@ -628,7 +624,15 @@ __global__ void __launch_bounds__(256) k_reduce_opt_aug(OptA a, int n_groups) {
       }
     }
     s_part[w][lane] = acc;
-    __syncthreads();
+  }
+  if (w == 0) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+    if (lane == 0) s_loss = lsum;
+  }
+  __syncthreads();
+  const bool bad = !isfinite(s_loss);
+  if (!bad) {
     if (gi >= 0) {
       float g = 0.f;
 #pragma unroll
