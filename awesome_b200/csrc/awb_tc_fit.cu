@@ -178,7 +178,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
   const float* wo = reinterpret_cast<const float*>(simg + L * W_B + WIN_B);
   const uint8_t* wo16 = simg + L * W_B + WIN_B + VEC_B;            // fp16 copy, 16 bytes per column chunk
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Hardware warp 0 issues the contractions; hardware warps 1..12 are the epilogue warps.  `warp` is their logical index
+  // 4 * column group + lane quadrant, with the quadrant = hardware warp % 4 (the TMEM lanes a warp may touch).
+  const int hwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = hwarp == 0 ? NEW : ((((hwarp - 1) >> 2) << 2) | (hwarp & 3));
   const int o = blockIdx.y;
   const bool issuer_warp = warp == NEW;
   // In-kernel timeline (clock64 stamps of one epilogue thread and of the issuer): compiled in only for the diagnostic
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
   int tr_n = 0;
 #define AWB_TR()                                                            \
   do {                                                                      \
-    if (trace && (threadIdx.x == 0 || threadIdx.x == NEW * 32) && tr_n < 120) \
+    if (trace && lane == 0 && (warp == 0 || issuer_warp) && tr_n < 120)        \
       trace[(issuer_warp ? TRACE_N / 2 : 0) + tr_n++] = clock64();          \
   } while (0)
 #else
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
 #define AWB_TR() do {} while (0)
 #endif
 
-  if (trace && threadIdx.x == 0) {                             // kernel entry (SM cycles and wall-clock ns)
+  if (trace && warp == 0 && lane == 0) {                       // kernel entry (SM cycles and wall-clock ns)
     trace[120] = clock64();
     unsigned long long ns;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
@@ -439,12 +442,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
       c6[0] = half_lo(cz.x); c6[1] = half_hi(cz.x); c6[2] = half_lo(cz.y); c6[3] = half_hi(cz.y); c6[4] = half_lo(cz.z); c6[5] = half_hi(cz.z);
     };
 
-    if (trace && threadIdx.x == 0) trace[121] = clock64();    // setup done
+    if (trace && warp == 0 && lane == 0) trace[121] = clock64();    // setup done
     fetch_tile(blockIdx.x);
     write_tx(0, x0n, x1n, x2n);
     stage_done();
     tc::mbar_wait(bar_w, 0);     // wo (read with plain loads below) has landed
-    if (trace && threadIdx.x == 0) trace[122] = clock64();    // weights landed: tile loop starts
+    if (trace && warp == 0 && lane == 0) trace[122] = clock64();    // weights landed: tile loop starts
 
     for (int it = 0; it < n_my; it++) {
       const int tile = blockIdx.x + it * gridDim.x;
@@ -675,13 +678,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
     tc::mbar_wait(bar_m2e, ph); ph ^= 1;
     tc::fence_after_sync();
     AWB_TR();
-    if (trace && threadIdx.x == 0) trace[123] = clock64();    // tile loop done
+    if (trace && warp == 0 && lane == 0) trace[123] = clock64();    // tile loop done
 
     // =========================================================== per-CTA partial write-out
     if (fit) {
       const float inv = 1.f / S;
       float* out = p.part + (int64_t)blockIdx.x * p.sSplit + (int64_t)o * p.G;
-      const int et = threadIdx.x;                         // 0..383
+      const int et = warp * 32 + lane;                    // 0..383
       // scalar / corner sums: fixed-order reduction through shared memory (scratch: the dead weight image)
       float* redS = reinterpret_cast<float*>(simg);       // [5][128]   per-row scalars of column group 0
       float* redC = redS + 5 * 128;                       // [L+1][4][16] lane-distributed corner sums of group 2
@@ -767,7 +770,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
       // the CTA may exit once the bulk stores have read their shared-memory source; kernel completion covers the writes
       if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
-    if (trace && threadIdx.x == 0) {                           // write-out done
+    if (trace && warp == 0 && lane == 0) {                     // write-out done
       trace[124] = clock64();
       unsigned long long ns;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
