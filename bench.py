@@ -474,7 +474,7 @@ def main():
             note = ("fp32 CUDA-core contraction (exact-parity path); reported against the sustained cuBLAS bf16 "
                     "tensor peak the north star names")
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r1_f16_tc_v11_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r1_f16_tc_v12_traffic.json")
         if dom == "tc_fused" and os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")      # from the committed ncu --set full capture
         ach = dom_flop / (per_class[dom]["ms_per_launch"] * 1e-3) / 1e12
