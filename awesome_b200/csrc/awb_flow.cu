@@ -231,8 +231,11 @@ __global__ void __launch_bounds__(256) k_flow_fwd(FlowP p) {
     for (int q = 0; q < P; q++) {
       if (p.zin && ok[q]) {
         float* zin = p.zin + ((int64_t)o * p.N + n[q]) * (p.F * C);
+        if (C == 2) *reinterpret_cast<float2*>(zin + f * C) = make_float2(z[q][0], z[q][1]);
+        else {
 #pragma unroll
-        for (int c = 0; c < C; c++) zin[f * C + c] = z[q][c];
+          for (int c = 0; c < C; c++) zin[f * C + c] = z[q][c];
+        }
       }
 #pragma unroll
       for (int c = 0; c < C; c++) { so[q][c] = tail[c]; to[q][c] = tail[C + c]; }
@@ -365,7 +368,14 @@ __global__ void __launch_bounds__(1024) k_flow_bwd_px(FlowP p, float* __restrict
       float z[C], zm[C];
       bool b[C];
 #pragma unroll
-      for (int c = 0; c < C; c++) { z[c] = zin[f * C + c]; b[c] = p.fc.masks[f * C + c] != 0; zm[c] = b[c] ? z[c] : 0.f; }
+      for (int c = 0; c < C; c++) b[c] = p.fc.masks[f * C + c] != 0;
+      if (C == 2) { const float2 zz = *reinterpret_cast<const float2*>(zin + f * C); z[0] = zz.x; z[1] = zz.y; }
+      else {
+#pragma unroll
+        for (int c = 0; c < C; c++) z[c] = zin[f * C + c];
+      }
+#pragma unroll
+      for (int c = 0; c < C; c++) zm[c] = b[c] ? z[c] : 0.f;
       float so[C], to[C];
       int mb = 0;
 #pragma unroll
@@ -373,7 +383,7 @@ __global__ void __launch_bounds__(1024) k_flow_bwd_px(FlowP p, float* __restrict
 #define AWB_CALL(MB) coupling_mlp_fwd<C, MB, 1>(wf, m, reinterpret_cast<const float(*)[C]>(zm), b, reinterpret_cast<float(*)[C]>(so), reinterpret_cast<float(*)[C]>(to))
       AWB_FLOW_DISPATCH(C, mb, AWB_CALL);
 #undef AWB_CALL
-      float dsr[C], dtr[C], dzin[C];
+      float dsr[C], dtr[C], dzin[C], rv[4 * C];
 #pragma unroll
       for (int c = 0; c < C; c++) {
         const float ea = expf(tail[2 * C + c]);
@@ -391,11 +401,15 @@ __global__ void __launch_bounds__(1024) k_flow_bwd_px(FlowP p, float* __restrict
           dtr[c] = p.tanh_out ? dzp * (1.f - tv * tv) : dzp;
           dzin[c] = dzp * e;
         }
-        rn[f * 4 * C + c] = dsr[c];
-        rn[f * 4 * C + C + c] = dtr[c];
-        rn[f * 4 * C + 2 * C + c] = das;      // d ActNorm.s
-        rn[f * 4 * C + 3 * C + c] = dz[c];    // d ActNorm.t
+        rv[c] = dsr[c];
+        rv[C + c] = dtr[c];
+        rv[2 * C + c] = das;                  // d ActNorm.s
+        rv[3 * C + c] = dz[c];                // d ActNorm.t
       }
+      // the record of this flow is 4C contiguous floats, 16-byte aligned: full-sector vector stores
+#pragma unroll
+      for (int q4 = 0; q4 < C; q4++)
+        reinterpret_cast<float4*>(rn + f * 4 * C)[q4] = make_float4(rv[4 * q4], rv[4 * q4 + 1], rv[4 * q4 + 2], rv[4 * q4 + 3]);
       // gradient reaching the masked inputs through the two MLPs
       float dzm[C];
 #pragma unroll
