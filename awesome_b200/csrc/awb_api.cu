@@ -83,9 +83,10 @@ Workspace carve(const awb_prior* h, int64_t N, bool training, void* base, bool f
   w.ZA = (float*)take(planes ? 4 * O * (L.L + 1) * N * L.ld : 0);
   w.D = (float*)take(training && planes ? 4 * O * 2 * N * L.ld : 0);
   w.logits = (float*)take(4 * O * N);
-  w.flowz = (float*)take(training ? 4 * O * N * (int64_t)L.F * L.C : 0);
+  const bool rnvp = h->desc.kind == AWB_KIND_FLOW_ICNN;
+  w.flowz = (float*)take(training ? 4 * O * N * (int64_t)L.F * (rnvp ? flow_save_floats(L.C) : L.C) : 0);
   if (!training || L.F == 0) w.flowz = nullptr;
-  w.flowg = (training && h->desc.kind == AWB_KIND_FLOW_ICNN) ? (float*)take(4 * O * N * (int64_t)L.F * 4 * L.C) : nullptr;
+  w.flowd = (training && rnvp && L.C == 3 && !flow_bwd_dz_in_smem(h, N)) ? (float*)take(4 * O * N * 4) : nullptr;
   w.tc = (h->desc.precision == AWB_PREC_F16 && tc_supported(h)) ? (void*)take(O * (int64_t)tc_image_bytes(L.L)) : nullptr;
   w.bytes = off;
   return w;

@@ -27,11 +27,15 @@ struct FlowP {
   int C, F, m, tanh_out, use_linear;
   int64_t N;
   float* X;              // [O][N][4]
-  float* zin;            // [O][N][F*C] or null
+  float* zin;            // [O][F][N][RW] saved coupling inputs / outputs (FlowSave), or null
   float* deformed;       // [O][N][C] or null
-  const float* dX;       // backward: [O][N][4]
+  float* dX;             // backward: [O][N][4] (overwritten in place when the range does not fit in shared memory)
   float* fpart;          // backward: [S][O][PF]
   int64_t chunk; int O;
+  int rounds;            // rounds of FLOW_P / FLOW_PB pixels per thread
+  int rounds1;           // backward: remainder rounds of one pixel per thread
+  int dz_smem;           // backward: the running coordinate gradient of the CTA's pixel range lives in shared memory
+  float* dzp_g;          // backward, C = 3, !dz_smem: [O][N][4] scratch for the partial gradient between unit passes
 };
 
 __device__ __forceinline__ float mm_fwd(float v, float vmin, float vmax, float nmin, float nmax) {
@@ -189,12 +193,40 @@ __device__ __forceinline__ void coupling_mlp_bwd(const float* __restrict__ wf, i
     else { CALL(-1); }                                                    \
   } while (0)
 
-constexpr int FLOW_FWD_P = 2;      // pixels per thread of k_flow_fwd
+// ---- launch geometry shared by the forward and the backward kernel: S = n_splits(N) pixel ranges of `chunk` rows (one
+// CTA each, per object), T threads per CTA, R rounds of P pixels per thread.  Pixel of (round r, slot q, thread t) =
+// r0 + (r * P + q) * T + t: consecutive threads touch consecutive pixels (coalesced), and T is chosen so that the last
+// round is as full as the others (2080 rows = 2 rounds x 4 pixels x 260 -> 288 threads, not 3 rounds of 256).
+struct FlowGeo { int S, T, R; int64_t chunk; };
+static FlowGeo flow_geo(int64_t N, int P, int maxT) {
+  FlowGeo g;
+  g.S = n_splits(N);
+  g.chunk = split_chunk(N);
+  const int64_t groups = (g.chunk + P - 1) / P;
+  int64_t R = (groups + 128) / 256;
+  if (R < 1) R = 1;
+  int64_t T = round_up((groups + R - 1) / R, 32);
+  if (T > maxT) { R = (groups + maxT - 1) / maxT; T = round_up((groups + R - 1) / R, 32); }
+  g.R = (int)R; g.T = (int)T;
+  return g;
+}
+
+// Saved per pixel and flow for the backward pass (training forward): the coupling's input z[C] and the post-activation
+// outputs s, t of its two MLPs for the transformed components -- RW floats, stored [O][F][N][RW] (pixel-contiguous:
+// full-sector vector stores / loads).  C = 2: (z0, z1, s, t); C = 3: (z0, z1, z2, s_a | s_b, t_a, t_b, -) with a, b the
+// transformed components in ascending order.
+template <int C> struct FlowSave { static constexpr int RW = C == 2 ? 4 : 8; };
+int flow_save_floats(int C) { return C == 2 ? 4 : 8; }
+
+constexpr int FLOW_P = 4;          // forward: pixels per thread and round: every weight record (2-3 LDS.128) feeds 4 pixels
+constexpr int FLOW_PB = 4;         // backward: same, bounded by the 128 accumulator registers beside them
+constexpr int FLOW_BWD_T = 256;    // 8 warps = 2 per scheduler: up to 255 registers per thread
 template <int C>
-__global__ void __launch_bounds__(256) k_flow_fwd(FlowP p) {
+__global__ void __launch_bounds__(512) k_flow_fwd(FlowP p) {
   extern __shared__ __align__(16) float sp[];   // k-packed flow weights + [2C] linear
   constexpr int RK = FlowPack<C>::RK;
-  constexpr int P = FLOW_FWD_P;
+  constexpr int P = FLOW_P;
+  constexpr int RW = FlowSave<C>::RW;
   const int o = blockIdx.y;
   const float* par = p.params + (int64_t)o * p.P + p.off_flow;
   const int m = p.m, FS = FlowPack<C>::flow_stride(m);
@@ -202,73 +234,78 @@ __global__ void __launch_bounds__(256) k_flow_fwd(FlowP p) {
   float* lin = sp + p.F * FS;
   if (threadIdx.x < 2 * C) lin[threadIdx.x] = par[p.P_flow + threadIdx.x];
   __syncthreads();
-  // pixel q of this thread: consecutive threads take consecutive pixels within each of the block's P row groups
-  int64_t n[P];
-  bool ok[P];
-  float z[P][C];
-#pragma unroll
-  for (int q = 0; q < P; q++) {
-    const int64_t nq = ((int64_t)blockIdx.x * P + q) * blockDim.x + threadIdx.x;
-    ok[q] = nq < p.N;
-    n[q] = ok[q] ? nq : p.N - 1;          // padding threads recompute the last pixel and store nothing
-#pragma unroll
-    for (int c = 0; c < C; c++) {
-      float x = coord(p.g, n[q], c);
-      if (p.use_linear) x = x * lin[c] + lin[C + c];
-      z[q][c] = mm_fwd(x, p.fc.nmin[c], p.fc.nmax[c], p.fc.new_min, p.fc.new_max);
-    }
-  }
-  if (!ok[0]) return;
-  for (int f = 0; f < p.F; f++) {
-    const float* wf = sp + f * FS;
-    const float* tail = wf + m * RK;          // b2s[C] | b2t[C] | an_s[C] | an_t[C]
-    bool b[C];
-    int mb = 0;
-#pragma unroll
-    for (int c = 0; c < C; c++) { b[c] = p.fc.masks[f * C + c] != 0; mb |= b[c] ? 1 << c : 0; }
-    float so[P][C], to[P][C];
+  const int T = blockDim.x;
+  const int64_t r0 = (int64_t)blockIdx.x * p.chunk, r1 = r0 + p.chunk < p.N ? r0 + p.chunk : p.N;
+  for (int r = 0; r < p.rounds; r++) {
+    int64_t n[P];
+    bool ok[P];
+    float z[P][C];
 #pragma unroll
     for (int q = 0; q < P; q++) {
-      if (p.zin && ok[q]) {
-        float* zin = p.zin + ((int64_t)o * p.N + n[q]) * (p.F * C);
-        if (C == 2) *reinterpret_cast<float2*>(zin + f * C) = make_float2(z[q][0], z[q][1]);
-        else {
-#pragma unroll
-          for (int c = 0; c < C; c++) zin[f * C + c] = z[q][c];
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < C; c++) { so[q][c] = tail[c]; to[q][c] = tail[C + c]; }
-    }
-#define AWB_CALL(MB) coupling_mlp_fwd<C, MB, P>(wf, m, z, b, so, to)
-    AWB_FLOW_DISPATCH(C, mb, AWB_CALL);
-#undef AWB_CALL
-#pragma unroll
-    for (int q = 0; q < P; q++) {
+      const int64_t nq = r0 + ((int64_t)r * P + q) * T + threadIdx.x;
+      ok[q] = nq < r1;
+      n[q] = ok[q] ? nq : (r1 > 0 ? r1 - 1 : 0);          // padding slots recompute the range's last pixel and store nothing
 #pragma unroll
       for (int c = 0; c < C; c++) {
-        float zc = z[q][c];
-        if (!b[c]) {
-          float s_ = p.tanh_out ? tanhf(so[q][c]) : so[q][c];
-          float t_ = p.tanh_out ? tanhf(to[q][c]) : to[q][c];
-          if (!isfinite(s_)) s_ = NAN;
-          if (!isfinite(t_)) t_ = NAN;
-          zc = fmaf(z[q][c], expf(s_), t_);
-        }
-        z[q][c] = fmaf(zc, expf(tail[2 * C + c]), tail[3 * C + c]);      // ActNorm
+        float x = coord(p.g, n[q], c);
+        if (p.use_linear) x = x * lin[c] + lin[C + c];
+        z[q][c] = mm_fwd(x, p.fc.nmin[c], p.fc.nmax[c], p.fc.new_min, p.fc.new_max);
       }
     }
-  }
+    if (!ok[0]) break;
+    for (int f = 0; f < p.F; f++) {
+      const float* wf = sp + f * FS;
+      const float* tail = wf + m * RK;          // b2s[C] | b2t[C] | an_s[C] | an_t[C]
+      bool b[C];
+      int mb = 0;
 #pragma unroll
-  for (int q = 0; q < P; q++) {
-    if (!ok[q]) continue;
-    float xd[3] = {0.f, 0.f, 0.f};
+      for (int c = 0; c < C; c++) { b[c] = p.fc.masks[f * C + c] != 0; mb |= b[c] ? 1 << c : 0; }
+      float so[P][C], to[P][C];
 #pragma unroll
-    for (int c = 0; c < C; c++) xd[c] = mm_fwd(z[q][c], p.fc.new_min, p.fc.new_max, p.fc.nmin[c], p.fc.nmax[c]);
-    *reinterpret_cast<float4*>(p.X + ((int64_t)o * p.N + n[q]) * 4) = make_float4(xd[0], xd[1], xd[2], 1.f);
-    if (p.deformed) {
+      for (int q = 0; q < P; q++) {
 #pragma unroll
-      for (int c = 0; c < C; c++) p.deformed[((int64_t)o * p.N + n[q]) * C + c] = xd[c];
+        for (int c = 0; c < C; c++) { so[q][c] = tail[c]; to[q][c] = tail[C + c]; }
+      }
+#define AWB_CALL(MB) coupling_mlp_fwd<C, MB, P>(wf, m, z, b, so, to)
+      AWB_FLOW_DISPATCH(C, mb, AWB_CALL);
+#undef AWB_CALL
+#pragma unroll
+      for (int q = 0; q < P; q++) {
+        float sv[2] = {0.f, 0.f}, tv[2] = {0.f, 0.f}, zi[3] = {0.f, 0.f, 0.f};
+        int u = 0;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          float zc = z[q][c];
+          zi[c] = zc;
+          if (!b[c]) {
+            float s_ = p.tanh_out ? tanhf(so[q][c]) : so[q][c];
+            float t_ = p.tanh_out ? tanhf(to[q][c]) : to[q][c];
+            if (!isfinite(s_)) s_ = NAN;
+            if (!isfinite(t_)) t_ = NAN;
+            zc = fmaf(z[q][c], expf(s_), t_);
+            if (u < 2) { sv[u] = s_; tv[u] = t_; }
+            u++;
+          }
+          z[q][c] = fmaf(zc, expf(tail[2 * C + c]), tail[3 * C + c]);      // ActNorm
+        }
+        if (p.zin && ok[q]) {
+          float4* rec = reinterpret_cast<float4*>(p.zin + (((int64_t)o * p.F + f) * p.N + n[q]) * RW);
+          if (C == 2) rec[0] = make_float4(zi[0], zi[1], sv[0], tv[0]);
+          else { rec[0] = make_float4(zi[0], zi[1], zi[2], sv[0]); rec[1] = make_float4(sv[1], tv[0], tv[1], 0.f); }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < P; q++) {
+      if (!ok[q]) continue;
+      float xd[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < C; c++) xd[c] = mm_fwd(z[q][c], p.fc.new_min, p.fc.new_max, p.fc.nmin[c], p.fc.nmax[c]);
+      *reinterpret_cast<float4*>(p.X + ((int64_t)o * p.N + n[q]) * 4) = make_float4(xd[0], xd[1], xd[2], 1.f);
+      if (p.deformed) {
+#pragma unroll
+        for (int c = 0; c < C; c++) p.deformed[((int64_t)o * p.N + n[q]) * C + c] = xd[c];
+      }
     }
   }
 }
@@ -333,105 +370,367 @@ __global__ void __launch_bounds__(256) k_flow_inv(FlowP p, float* out) {
 }
 
 // ---------------------------------------------------------------- backward
-// Two kernels, neither with a per-pixel cross-lane exchange:
-//  (A) k_flow_bwd_px: one thread per pixel walks the flows in reverse (recomputing each coupling from its stored
-//      input), propagates d loss / d z, and records per flow the 4C per-pixel factors every parameter gradient of
-//      that flow is linear in:  dsr, dtr (gradients at the pre-tanh outputs of the s / t nets) and the ActNorm terms.
-//      It also owns the 1x1-conv gradients (block reduction at the end).
-//  (B) k_flow_wgrad: grid = (pixel range, flow, object); lane k of every warp owns hidden unit k of that flow's two
-//      MLPs and accumulates its weight gradients in registers over the pixels of the range (broadcast loads of the
-//      per-pixel record, no shuffles, no atomics); the 8 warps are combined in a fixed order through shared memory.
+// ONE kernel, no per-pixel record through global memory.  A CTA owns a pixel range and walks the flows in reverse; the
+// running coordinate gradient dz of its pixels stays in shared memory between flows.  For one flow, every thread
+// visits its pixels (P at a time, sharing each weight record) and accumulates IN REGISTERS, per hidden unit k and net,
+// the masked sums every weight gradient of that unit is linear in:
+//     A[k][u]    = sum_px [pre_k > 0] * d_u            (d_u = gradient at the pre-activation output u of the net)
+//     B[k][u][c] = sum_px [pre_k > 0] * d_u * z_c      (c = masked input components)
+// because  d pre_k = [pre_k > 0] * sum_u d_u W2[u][k]  factors into a per-pixel and a per-unit part:
+//     dW1[k][c] = sum_u W2[u][k] B[k][u][c],  db1[k] = sum_u W2[u][k] A[k][u],
+//     dW2[u][k] = sum_px d_u relu(pre_k) = b1[k] A[k][u] + sum_c W1[k][c] B[k][u][c],
+// and the gradient reaching the masked inputs is  dz_c += sum_u d_u * (sum_k [pre_k > 0] W2[u][k] W1[k][c])  with the
+// products W2[u][k] W1[k][c] staged per unit.  Per (pixel, unit, net): one FMA per masked input, one compare and
+// 2 NU NM + NU predicated adds -- 10 instructions for C = 2 against 24 in the two-kernel version, and the cross-pixel
+// reduction happens once per flow and CTA (warp reduce-scatter + fixed-order combine), not per pixel.
+// The unit range is processed in blocks of KB units (32 for C = 2: one pass; 16 for C = 3: two passes over the pixels,
+// 128 accumulator registers either way).
+template <int C, int MB> struct FlowBwdCfg {
+  static constexpr int NM = (MB & 1) + ((MB >> 1) & 1) + ((MB >> 2) & 1), NU = C - NM;
+  static constexpr int NA1 = NU * (1 + NM);        // accumulators per unit and net
+  static constexpr int NACC = 2 * NA1;
+  static constexpr int KB = C == 2 ? 32 : 16;
+  static constexpr int NPASS = 32 / KB;
+  static __device__ __forceinline__ int rm(int c) { return __popc(MB & ((1 << c) - 1)); }   // rank among masked / transformed
+  static __device__ __forceinline__ int ru(int c) { return c - rm(c); }
+  static __device__ __forceinline__ bool masked(int c) { return ((MB >> c) & 1) != 0; }
+};
+template <int C> struct FlowBwdPack {
+  static constexpr int RKB = C == 2 ? 8 : 12;      // floats per unit: [w1s[NM] | b1s | vs[NU][NM] | w1t[NM] | b1t | vt[NU][NM]]
+  __host__ __device__ static int flow_stride() { return 32 * RKB + 4; }   // + exp(ActNorm.s)[C], pad
+};
+
 template <int C>
-__global__ void __launch_bounds__(1024) k_flow_bwd_px(FlowP p, float* __restrict__ rec) {
-  extern __shared__ __align__(16) float sp[];   // k-packed flow weights
-  constexpr int RK = FlowPack<C>::RK;
-  const int o = blockIdx.y, s = blockIdx.x;
+__device__ void stage_flow_bwd(const float* __restrict__ par, int F, int m, int64_t per_flow, float* sp, const FlowConsts& fc) {
+  constexpr int RKB = FlowBwdPack<C>::RKB;
+  const int half = 2 * m * C + m + C, FS = FlowBwdPack<C>::flow_stride();
+  for (int t = threadIdx.x; t < F * 32; t += blockDim.x) {
+    const int f = t >> 5, k = t & 31;
+    const float* w = par + (int64_t)f * per_flow;
+    float* r = sp + f * FS + k * RKB;
+    int mb = 0;
+#pragma unroll
+    for (int c = 0; c < C; c++) mb |= fc.masks[f * C + c] != 0 ? 1 << c : 0;
+#pragma unroll
+    for (int i = 0; i < RKB; i++) r[i] = 0.f;          // units k >= m: pre-activation 0 -> never active
+    if (k >= m) continue;
+    int pos = 0;
+    for (int net = 0; net < 2; net++) {
+      const float* wn = w + net * half;
+      for (int c = 0; c < C; c++) if ((mb >> c) & 1) r[pos++] = wn[k * C + c];                   // W1[k][c], masked c
+      r[pos++] = wn[m * C + k];                                                                  // b1[k]
+      for (int u = 0; u < C; u++) if (!((mb >> u) & 1))
+        for (int c = 0; c < C; c++) if ((mb >> c) & 1) r[pos++] = wn[m * C + m + u * m + k] * wn[k * C + c];   // W2[u][k] W1[k][c]
+    }
+  }
+  for (int t = threadIdx.x; t < F * 4; t += blockDim.x) {
+    const int f = t >> 2, c = t & 3;
+    const float* w = par + (int64_t)f * per_flow;
+    sp[f * FS + 32 * RKB + c] = c < C ? expf(w[2 * half + c]) : 0.f;
+  }
+}
+
+// Sum of v[i] over the 32 lanes for 32 values at once: afterwards lane l holds the total of value l (31 shuffles).
+__device__ __forceinline__ float warp_reduce_scatter32(float* v, int lane) {
+#pragma unroll
+  for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+    const bool up = lane & off;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      if (k < n / 2) {
+        const float send = up ? v[k] : v[k + n / 2];
+        const float keep = up ? v[k + n / 2] : v[k];
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+  }
+  return v[0];
+}
+
+struct FlowBwdShared {
+  float* wrec;     // staged weights (stage_flow_bwd)
+  float* dz;       // [C][chunk_pad] running coordinate gradient (or null: global, in place in dX)
+  float* dzp;      // partial masked-input gradient between unit passes (C = 3): [C][chunk] in shared memory or [n][4] global
+  int64_t dzp_cs, dzp_ps;
+  float* red;      // [warps][128] + [128] + [warps][16]
+};
+
+// one flow (mask pattern MB) of the CTA's pixel range
+template <int C, int MB>
+__device__ __forceinline__ void flow_bwd_one(const FlowP& p, const FlowBwdShared& sh, int f, int o, int64_t r0, int64_t r1,
+                                             float* dzg, int64_t dz_cs, int64_t dz_ps) {
+  using Cf = FlowBwdCfg<C, MB>;
+  constexpr int NM = Cf::NM, NU = Cf::NU, NA1 = Cf::NA1, NACC = Cf::NACC, KB = Cf::KB, NPASS = Cf::NPASS;
+  constexpr int RKB = FlowBwdPack<C>::RKB, RW = FlowSave<C>::RW;
+  constexpr int NSC = 2 * C + 2 * NU;      // per-thread scalar sums: d ActNorm.s[C], d ActNorm.t[C], d s.b2[NU], d t.b2[NU]
+  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+  const int m = p.m, half = 2 * m * C + m + C;
+  const float* wf = sh.wrec + f * FlowBwdPack<C>::flow_stride();
+  const float* eas = wf + 32 * RKB;
+  const float* zrec = p.zin + (((int64_t)o * p.F + f) * p.N) * RW;
+  const float* wglob = p.params + (int64_t)o * p.P + p.off_flow + (int64_t)f * p.per_flow;
+  float* out = p.fpart + ((int64_t)blockIdx.x * p.O + o) * (p.P_flow + 2 * C) + (int64_t)f * p.per_flow;
+  float ea[C];
+#pragma unroll
+  for (int c = 0; c < C; c++) ea[c] = eas[c];
+  float sc[NSC];
+#pragma unroll
+  for (int i = 0; i < NSC; i++) sc[i] = 0.f;
+
+#pragma unroll 1
+  for (int pass = 0; pass < NPASS; pass++) {
+    float acc[KB * NACC];
+#pragma unroll
+    for (int i = 0; i < KB * NACC; i++) acc[i] = 0.f;
+    const float* wk = wf + pass * KB * RKB;
+    // one round: P pixels of this thread starting at `base` (slot q -> pixel base + q * T + tid), all sharing the records
+    auto round = [&](auto p_c, int64_t base) -> bool {
+      constexpr int P = decltype(p_c)::value;
+      int64_t loc[P];
+      bool ok[P];
+      float zm[P][NM > 0 ? NM : 1], ds[P][NU], dt[P][NU], us[P][NU * NM > 0 ? NU * NM : 1], ut[P][NU * NM > 0 ? NU * NM : 1];
+      float Ds[P][NU * NM > 0 ? NU * NM : 1], Dt[P][NU * NM > 0 ? NU * NM : 1], dzo[P][C];
+#pragma unroll
+      for (int q = 0; q < P; q++) {
+        const int64_t n = base + (int64_t)q * T + tid;
+        ok[q] = n < r1;
+        loc[q] = ok[q] ? n - r0 : 0;
+        float z[C], s[NU], t[NU], dz[C];
+        if (ok[q]) {
+          const float4 a = *reinterpret_cast<const float4*>(zrec + n * RW);
+          if (C == 2) { z[0] = a.x; z[1] = a.y; s[0] = a.z; t[0] = a.w; }
+          else {
+            const float4 b4 = *reinterpret_cast<const float4*>(zrec + n * RW + 4);
+            z[0] = a.x; z[1] = a.y; z[C - 1] = a.z; s[0] = a.w;
+            if (NU == 2) { s[NU - 1] = b4.x; t[0] = b4.y; t[NU - 1] = b4.z; } else { t[0] = b4.y; }
+          }
+#pragma unroll
+          for (int c = 0; c < C; c++) dz[c] = dzg[c * dz_cs + loc[q] * dz_ps];
+        } else {
+#pragma unroll
+          for (int c = 0; c < C; c++) { z[c] = 0.f; dz[c] = 0.f; }
+#pragma unroll
+          for (int u = 0; u < NU; u++) { s[u] = 0.f; t[u] = 0.f; }
+        }
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          const float dzp = dz[c] * ea[c];
+          if (Cf::masked(c)) {
+            zm[q][Cf::rm(c)] = z[c];
+            dzo[q][c] = dzp;
+            if (pass == NPASS - 1) { sc[c] = fmaf(dz[c] * z[c], ea[c], sc[c]); sc[C + c] += dz[c]; }
+          } else {
+            const int u = Cf::ru(c);
+            const float e = expf(s[u]);
+            const float dsv = dzp * z[c] * e;
+            ds[q][u] = p.tanh_out ? dsv * (1.f - s[u] * s[u]) : dsv;
+            dt[q][u] = p.tanh_out ? dzp * (1.f - t[u] * t[u]) : dzp;
+            dzo[q][c] = dzp * e;
+            if (pass == NPASS - 1) {
+              sc[c] = fmaf(dz[c] * fmaf(z[c], e, t[u]), ea[c], sc[c]);
+              sc[C + c] += dz[c];
+              sc[2 * C + u] += ds[q][u];
+              sc[2 * C + NU + u] += dt[q][u];
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < NU; u++)
+#pragma unroll
+          for (int c = 0; c < NM; c++) { us[q][u * NM + c] = ds[q][u] * zm[q][c]; ut[q][u * NM + c] = dt[q][u] * zm[q][c]; Ds[q][u * NM + c] = 0.f; Dt[q][u * NM + c] = 0.f; }
+      }
+      if (!ok[0]) return false;       // slots are ordered: nothing left for this thread
+      // ---- unit loop: all KB units of this pass, every record shared by the P pixels
+#pragma unroll
+      for (int k = 0; k < KB; k++) {
+        float w[RKB];
+#pragma unroll
+        for (int i = 0; i < RKB / 4; i++) *reinterpret_cast<float4*>(&w[4 * i]) = reinterpret_cast<const float4*>(wk + k * RKB)[i];
+        constexpr int OT = NM + 1 + NU * NM;       // offset of the t net inside the record
+#pragma unroll
+        for (int q = 0; q < P; q++) {
+          float ps = w[NM], pt = w[OT + NM];
+#pragma unroll
+          for (int c = 0; c < NM; c++) { ps = fmaf(w[c], zm[q][c], ps); pt = fmaf(w[OT + c], zm[q][c], pt); }
+          float* a = &acc[k * NACC];
+          if (ps > 0.f) {
+#pragma unroll
+            for (int u = 0; u < NU; u++) {
+              a[u * (1 + NM)] += ds[q][u];
+#pragma unroll
+              for (int c = 0; c < NM; c++) { a[u * (1 + NM) + 1 + c] += us[q][u * NM + c]; Ds[q][u * NM + c] += w[NM + 1 + u * NM + c]; }
+            }
+          }
+          if (pt > 0.f) {
+#pragma unroll
+            for (int u = 0; u < NU; u++) {
+              a[NA1 + u * (1 + NM)] += dt[q][u];
+#pragma unroll
+              for (int c = 0; c < NM; c++) { a[NA1 + u * (1 + NM) + 1 + c] += ut[q][u * NM + c]; Dt[q][u * NM + c] += w[OT + NM + 1 + u * NM + c]; }
+            }
+          }
+        }
+      }
+      // ---- gradient reaching the inputs of this coupling
+#pragma unroll
+      for (int q = 0; q < P; q++) {
+        if (!ok[q]) continue;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          if (Cf::masked(c)) {
+            float g = 0.f;
+#pragma unroll
+            for (int u = 0; u < NU; u++) g = fmaf(ds[q][u], Ds[q][u * NM + Cf::rm(c)], fmaf(dt[q][u], Dt[q][u * NM + Cf::rm(c)], g));
+            if (NPASS > 1 && pass > 0) g += sh.dzp[c * sh.dzp_cs + loc[q] * sh.dzp_ps];
+            if (pass < NPASS - 1) sh.dzp[c * sh.dzp_cs + loc[q] * sh.dzp_ps] = g;
+            else dzg[c * dz_cs + loc[q] * dz_ps] = dzo[q][c] + g;
+          } else if (pass == NPASS - 1) {
+            dzg[c * dz_cs + loc[q] * dz_ps] = dzo[q][c];
+          }
+        }
+      }
+      return true;
+    };
+    {
+      int64_t base = r0;
+      bool more = true;
+#pragma unroll 1
+      for (int r = 0; r < p.rounds && more; r++, base += (int64_t)FLOW_PB * T) more = round(std::integral_constant<int, FLOW_PB>{}, base);
+#pragma unroll 1
+      for (int r = 0; r < p.rounds1 && more; r++, base += T) more = round(std::integral_constant<int, 1>{}, base);
+    }
+    // ---- cross-pixel reduction of this pass's KB units: warp reduce-scatter, fixed-order combine over the warps
+    float* red = sh.red;                       // [nwarps][KB * NACC]
+    float* tot = sh.red + 16 * 128;            // [KB * NACC]
+#pragma unroll
+    for (int b = 0; b < KB * NACC / 32; b++) red[warp * (KB * NACC) + b * 32 + lane] = warp_reduce_scatter32(&acc[b * 32], lane);
+    __syncthreads();
+    for (int i = tid; i < KB * NACC; i += T) {
+      float a = 0.f;
+      for (int w = 0; w < nwarps; w++) a += red[w * (KB * NACC) + i];
+      tot[i] = a;
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * KB; i += T) {
+      const int net = i / KB, k = i - net * KB, kk = pass * KB + k;
+      if (kk >= m) continue;
+      const float* wn = wglob + net * half;
+      const float* a = tot + k * NACC + net * NA1;
+      float* on = out + net * half;
+      float gb1 = 0.f, gw1[NM > 0 ? NM : 1];
+#pragma unroll
+      for (int c = 0; c < NM; c++) gw1[c] = 0.f;
+      const float b1 = wn[m * C + kk];
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        if (Cf::masked(c)) continue;
+        const int u = Cf::ru(c);
+        const float w2 = wn[m * C + m + c * m + kk];
+        gb1 = fmaf(w2, a[u * (1 + NM)], gb1);
+        float gw2 = b1 * a[u * (1 + NM)];
+#pragma unroll
+        for (int cc = 0; cc < C; cc++)
+          if (Cf::masked(cc)) {
+            gw1[Cf::rm(cc)] = fmaf(w2, a[u * (1 + NM) + 1 + Cf::rm(cc)], gw1[Cf::rm(cc)]);
+            gw2 = fmaf(wn[kk * C + cc], a[u * (1 + NM) + 1 + Cf::rm(cc)], gw2);
+          }
+        on[m * C + m + c * m + kk] = gw2;                                   // d W2[c][k], transformed c
+      }
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        if (Cf::masked(c)) { on[kk * C + c] = gw1[Cf::rm(c)]; on[m * C + m + c * m + kk] = 0.f; }   // d W1[k][c]; W2 rows of masked outputs are unused
+        else on[kk * C + c] = 0.f;                                           // W1 columns of transformed inputs see zm = 0
+      }
+      on[m * C + kk] = gb1;                                                  // d b1[k]
+    }
+    __syncthreads();
+  }
+  // ---- scalar sums of the flow: ActNorm pair and the output biases of s / t
+  float* red2 = sh.red + 16 * 128 + 128;       // [nwarps][16]
+#pragma unroll
+  for (int i = 0; i < NSC; i++) {
+    float a = sc[i];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+    if (lane == 0) red2[warp * 16 + i] = a;
+  }
+  __syncthreads();
+  if (tid < 4 * C) {
+    const int qd = tid / C, c = tid - qd * C;      // 0: s.b2, 1: t.b2, 2: ActNorm.s, 3: ActNorm.t
+    float a = 0.f;
+    if (qd >= 2) { for (int w = 0; w < nwarps; w++) a += red2[w * 16 + (qd - 2) * C + c]; }
+    else if (!Cf::masked(c)) { for (int w = 0; w < nwarps; w++) a += red2[w * 16 + 2 * C + qd * NU + Cf::ru(c)]; }
+    if (qd == 0) out[m * C + m + C * m + c] = a;
+    else if (qd == 1) out[half + m * C + m + C * m + c] = a;
+    else if (qd == 2) out[2 * half + c] = a;
+    else out[2 * half + C + c] = a;
+  }
+  __syncthreads();
+}
+
+template <int C>
+__global__ void __launch_bounds__(FLOW_BWD_T, 1) k_flow_bwd(FlowP p) {
+  extern __shared__ __align__(16) float sp[];
+  const int o = blockIdx.y, tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
   const float* par = p.params + (int64_t)o * p.P + p.off_flow;
   const int PF = (int)p.P_flow + 2 * C;
-  const int m = p.m, FS = FlowPack<C>::flow_stride(m);
-  stage_flow_packed<C>(par, p.F, m, p.per_flow, sp, p.fc);
-  __syncthreads();
-  const int64_t r0 = (int64_t)s * p.chunk, r1 = r0 + p.chunk < p.N ? r0 + p.chunk : p.N;
+  FlowBwdShared sh;
+  sh.wrec = sp;
+  sh.red = sp + p.F * FlowBwdPack<C>::flow_stride();
+  float* after = sh.red + 16 * 128 + 128 + 16 * 16;
+  sh.dz = p.dz_smem ? after : nullptr;
+  const int64_t r0 = (int64_t)blockIdx.x * p.chunk, r1 = r0 + p.chunk < p.N ? r0 + p.chunk : p.N;
+  sh.dzp = p.dz_smem ? after + C * p.chunk : p.dzp_g + ((int64_t)o * p.N + r0) * 4;   // C = 3 only (two unit passes)
+  sh.dzp_cs = p.dz_smem ? p.chunk : 1; sh.dzp_ps = p.dz_smem ? 1 : 4;
+  stage_flow_bwd<C>(par, p.F, p.m, p.per_flow, sp, p.fc);
+  float* outb = p.fpart + ((int64_t)blockIdx.x * p.O + o) * PF;
+  if (r0 >= p.N) {          // empty range (rounded-up chunk): its partial is all zeros
+    for (int i = tid; i < PF; i += T) outb[i] = 0.f;
+    return;
+  }
+  // running gradient: shared memory [C][chunk], or in place in dX ([n][4]) when the range is too large
+  float* dzg = p.dz_smem ? sh.dz : p.dX + ((int64_t)o * p.N + r0) * 4;
+  const int64_t dz_cs = p.dz_smem ? p.chunk : 1, dz_ps = p.dz_smem ? 1 : 4;
+  for (int64_t n = r0 + tid; n < r1; n += T) {
+    const float4 dx = *reinterpret_cast<const float4*>(p.dX + ((int64_t)o * p.N + n) * 4);
+    const float d3[3] = {dx.x, dx.y, dx.z};
+#pragma unroll
+    for (int c = 0; c < C; c++)
+      dzg[c * dz_cs + (n - r0) * dz_ps] = d3[c] * ((p.fc.nmax[c] - p.fc.nmin[c]) / (p.fc.new_max - p.fc.new_min));
+  }
+  __syncthreads();          // staged weights; (dz slots are thread-private: same pixel -> same thread in every flow)
+  // NOTE: the init loop above strides pixels by T, the flow loop by (r * P + q) * T + tid: both map pixel n to thread
+  // (n - r0) % T, so every dz slot is only ever touched by one thread.
+  for (int f = p.F - 1; f >= 0; f--) {
+    int mb = 0;
+#pragma unroll
+    for (int c = 0; c < C; c++) mb |= p.fc.masks[f * C + c] != 0 ? 1 << c : 0;
+#define AWB_CALL(MB) flow_bwd_one<C, MB>(p, sh, f, o, r0, r1, dzg, dz_cs, dz_ps)
+    if (mb == 1) { AWB_CALL(1); }
+    else if (mb == 2) { AWB_CALL(2); }
+    if constexpr (C == 3) {
+      if (mb == 3) { AWB_CALL(3); }
+      else if (mb == 4) { AWB_CALL(4); }
+      else if (mb == 5) { AWB_CALL(5); }
+      else if (mb == 6) { AWB_CALL(6); }
+    }
+#undef AWB_CALL
+  }
+  // ---- 1x1-conv gradients (path_connected_net.py:65,82): fixed-order block reduction
   float glw[C], glb[C];
 #pragma unroll
   for (int c = 0; c < C; c++) { glw[c] = 0.f; glb[c] = 0.f; }
-  for (int64_t n = r0 + threadIdx.x; n < r1; n += blockDim.x) {
-    float dz[C];
-    const float* dx = p.dX + ((int64_t)o * p.N + n) * 4;
-#pragma unroll
-    for (int c = 0; c < C; c++) dz[c] = dx[c] * ((p.fc.nmax[c] - p.fc.nmin[c]) / (p.fc.new_max - p.fc.new_min));
-    const float* zin = p.zin + ((int64_t)o * p.N + n) * (p.F * C);
-    float* rn = rec + ((int64_t)o * p.N + n) * (p.F * 4 * C);
-    for (int f = p.F - 1; f >= 0; f--) {
-      const float* wf = sp + f * FS;
-      const float* tail = wf + m * RK;
-      float z[C], zm[C];
-      bool b[C];
-#pragma unroll
-      for (int c = 0; c < C; c++) b[c] = p.fc.masks[f * C + c] != 0;
-      if (C == 2) { const float2 zz = *reinterpret_cast<const float2*>(zin + f * C); z[0] = zz.x; z[1] = zz.y; }
-      else {
-#pragma unroll
-        for (int c = 0; c < C; c++) z[c] = zin[f * C + c];
-      }
-#pragma unroll
-      for (int c = 0; c < C; c++) zm[c] = b[c] ? z[c] : 0.f;
-      float so[C], to[C];
-      int mb = 0;
-#pragma unroll
-      for (int c = 0; c < C; c++) { so[c] = tail[c]; to[c] = tail[C + c]; mb |= b[c] ? 1 << c : 0; }
-#define AWB_CALL(MB) coupling_mlp_fwd<C, MB, 1>(wf, m, reinterpret_cast<const float(*)[C]>(zm), b, reinterpret_cast<float(*)[C]>(so), reinterpret_cast<float(*)[C]>(to))
-      AWB_FLOW_DISPATCH(C, mb, AWB_CALL);
-#undef AWB_CALL
-      float dsr[C], dtr[C], dzin[C], rv[4 * C];
+  if (p.use_linear) {
+    for (int64_t n = r0 + tid; n < r1; n += T) {
 #pragma unroll
       for (int c = 0; c < C; c++) {
-        const float ea = expf(tail[2 * C + c]);
-        const float dzp = dz[c] * ea;
-        float das;
-        if (b[c]) {
-          das = dz[c] * z[c] * ea;            // masked component passes through the coupling
-          dsr[c] = 0.f; dtr[c] = 0.f; dzin[c] = dzp;
-        } else {
-          const float sv = p.tanh_out ? tanhf(so[c]) : so[c], tv = p.tanh_out ? tanhf(to[c]) : to[c];
-          const float e = expf(sv);
-          das = dz[c] * fmaf(z[c], e, tv) * ea;
-          const float ds = dzp * z[c] * e;
-          dsr[c] = p.tanh_out ? ds * (1.f - sv * sv) : ds;
-          dtr[c] = p.tanh_out ? dzp * (1.f - tv * tv) : dzp;
-          dzin[c] = dzp * e;
-        }
-        rv[c] = dsr[c];
-        rv[C + c] = dtr[c];
-        rv[2 * C + c] = das;                  // d ActNorm.s
-        rv[3 * C + c] = dz[c];                // d ActNorm.t
-      }
-      // the record of this flow is 4C contiguous floats, 16-byte aligned: full-sector vector stores
-#pragma unroll
-      for (int q4 = 0; q4 < C; q4++)
-        reinterpret_cast<float4*>(rn + f * 4 * C)[q4] = make_float4(rv[4 * q4], rv[4 * q4 + 1], rv[4 * q4 + 2], rv[4 * q4 + 3]);
-      // gradient reaching the masked inputs through the two MLPs
-      float dzm[C];
-#pragma unroll
-      for (int c = 0; c < C; c++) dzm[c] = 0.f;
-#define AWB_CALL(MB) coupling_mlp_bwd<C, MB>(wf, m, zm, b, dsr, dtr, dzm)
-      AWB_FLOW_DISPATCH(C, mb, AWB_CALL);
-#undef AWB_CALL
-#pragma unroll
-      for (int c = 0; c < C; c++) dz[c] = dzin[c] + (b[c] ? dzm[c] : 0.f);
-    }
-    if (p.use_linear) {
-#pragma unroll
-      for (int c = 0; c < C; c++) {
-        const float dxc = dz[c] * ((p.fc.new_max - p.fc.new_min) / (p.fc.nmax[c] - p.fc.nmin[c]));
+        const float dxc = dzg[c * dz_cs + (n - r0) * dz_ps] * ((p.fc.new_max - p.fc.new_min) / (p.fc.nmax[c] - p.fc.nmin[c]));
         glw[c] = fmaf(dxc, coord(p.g, n, c), glw[c]);     // linear.weight
         glb[c] += dxc;                                     // linear.bias
       }
     }
   }
-  // 1x1-conv gradients: fixed-order block reduction
-  __shared__ float red[32][2 * C];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* red2 = sh.red + 16 * 128 + 128;
 #pragma unroll
   for (int c = 0; c < C; c++) {
 #pragma unroll
@@ -439,122 +738,13 @@ __global__ void __launch_bounds__(1024) k_flow_bwd_px(FlowP p, float* __restrict
       glw[c] += __shfl_xor_sync(0xffffffffu, glw[c], off);
       glb[c] += __shfl_xor_sync(0xffffffffu, glb[c], off);
     }
-    if (lane == 0) { red[warp][c] = glw[c]; red[warp][C + c] = glb[c]; }
+    if (lane == 0) { red2[warp * 16 + c] = glw[c]; red2[warp * 16 + C + c] = glb[c]; }
   }
   __syncthreads();
-  if (threadIdx.x < 2 * C) {
+  if (tid < 2 * C) {
     float a = 0.f;
-    for (int i = 0; i < (int)(blockDim.x >> 5); i++) a += red[i][threadIdx.x];
-    p.fpart[((int64_t)s * p.O + o) * PF + p.P_flow + threadIdx.x] = p.use_linear ? a : 0.f;
-  }
-}
-
-template <int C>
-__global__ void __launch_bounds__(256) k_flow_wgrad(FlowP p, const float* __restrict__ rec) {
-  constexpr int NA = 2 * (2 * C + 1);      // per-lane accumulators: (W1[k][C], b1[k], W2[C][k]) x {s, t}
-  __shared__ float red[8][NA + 1][32];
-  __shared__ float red4[8][4 * C];
-  const int s = blockIdx.x, f = blockIdx.y, o = blockIdx.z;
-  const int m = p.m, half = 2 * m * C + m + C;
-  const float* w = p.params + (int64_t)o * p.P + p.off_flow + (int64_t)f * p.per_flow;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool act = lane < m;
-  const int k = act ? lane : 0;
-  float w1s[C], w1t[C], w2s[C], w2t[C];
-  bool b[C];
-#pragma unroll
-  for (int c = 0; c < C; c++) {
-    w1s[c] = w[k * C + c]; w1t[c] = w[half + k * C + c];
-    w2s[c] = w[m * C + m + c * m + k]; w2t[c] = w[half + m * C + m + c * m + k];
-    b[c] = p.fc.masks[f * C + c] != 0;
-  }
-  const float b1s = w[m * C + k], b1t = w[half + m * C + k];
-  float acc[NA];
-#pragma unroll
-  for (int i = 0; i < NA; i++) acc[i] = 0.f;
-  float a4 = 0.f;                          // lanes < 4C: output biases of s / t and the ActNorm pair
-  const int64_t r0 = (int64_t)s * p.chunk, r1 = r0 + p.chunk < p.N ? r0 + p.chunk : p.N;
-  const int FC = p.F * C;
-  // running pointers (8 pixels per step of the warp); the per-pixel record of this flow is 4C contiguous floats,
-  // 16-byte aligned: float4 loads; the coupling input pair is 8-byte aligned for C = 2
-  const float* zp = p.zin + ((int64_t)o * p.N + r0 + warp) * FC + f * C;
-  const float* rp = rec + ((int64_t)o * p.N + r0 + warp) * (4 * FC) + f * 4 * C;
-  const int64_t zstep = (int64_t)8 * FC, rstep = (int64_t)8 * 4 * FC;
-  const int n_it = (int)((r1 - r0 - warp + 7) / 8);
-  // the mask pattern is a property of the flow (blockIdx.y): the whole block runs one instantiation of the pixel loop
-  auto pixel_loop = [&](auto mb_c) {
-    constexpr int MB = decltype(mb_c)::value;
-#pragma unroll 4
-    for (int it = 0; it < (n_it > 0 ? n_it : 0); it++, zp += zstep, rp += rstep) {
-      float zm[C], dsr[C], dtr[C];
-      if (C == 2) {
-        const float2 zz = *reinterpret_cast<const float2*>(zp);
-        const float4 r4 = *reinterpret_cast<const float4*>(rp);
-        zm[0] = zz.x; zm[1] = zz.y;
-        dsr[0] = r4.x; dsr[1] = r4.y; dtr[0] = r4.z; dtr[1] = r4.w;
-      } else {
-#pragma unroll
-        for (int c = 0; c < C; c++) { zm[c] = zp[c]; dsr[c] = rp[c]; dtr[c] = rp[C + c]; }
-      }
-      if (lane < 4 * C) a4 += rp[lane];
-      float ps = b1s, pt = b1t, dps = 0.f, dpt = 0.f;
-#pragma unroll
-      for (int c = 0; c < C; c++) {
-        if (masked_c<C, MB>(c, b)) { ps = fmaf(w1s[c], zm[c], ps); pt = fmaf(w1t[c], zm[c], pt); }
-        if (MB < 0 || !masked_c<C, MB>(c, b)) { dps = fmaf(dsr[c], w2s[c], dps); dpt = fmaf(dtr[c], w2t[c], dpt); }
-      }
-      const float hs = fmaxf(ps, 0.f), ht = fmaxf(pt, 0.f);
-      dps = ps > 0.f ? dps : 0.f;
-      dpt = pt > 0.f ? dpt : 0.f;
-#pragma unroll
-      for (int c = 0; c < C; c++) {
-        if (masked_c<C, MB>(c, b)) {
-          acc[c] = fmaf(dps, zm[c], acc[c]);                             // d s.W1[k][c]
-          acc[2 * C + 1 + c] = fmaf(dpt, zm[c], acc[2 * C + 1 + c]);     // d t.W1[k][c]
-        }
-        if (MB < 0 || !masked_c<C, MB>(c, b)) {
-          acc[C + 1 + c] = fmaf(dsr[c], hs, acc[C + 1 + c]);             // d s.W2[c][k]
-          acc[3 * C + 2 + c] = fmaf(dtr[c], ht, acc[3 * C + 2 + c]);     // d t.W2[c][k]
-        }
-      }
-      acc[C] += dps;                                                     // d s.b1[k]
-      acc[3 * C + 1] += dpt;                                             // d t.b1[k]
-    }
-  };
-  {
-    int mb = 0;
-#pragma unroll
-    for (int c = 0; c < C; c++) mb |= b[c] ? 1 << c : 0;
-#define AWB_CALL(MB) pixel_loop(std::integral_constant<int, MB>{})
-    AWB_FLOW_DISPATCH(C, mb, AWB_CALL);
-#undef AWB_CALL
-  }
-#pragma unroll
-  for (int i = 0; i < NA; i++) red[warp][i][lane] = acc[i];
-  if (lane < 4 * C) red4[warp][lane] = a4;
-  __syncthreads();
-  const int PF = (int)p.P_flow + 2 * C;
-  float* out = p.fpart + ((int64_t)s * p.O + o) * PF + (int64_t)f * p.per_flow;
-  for (int t = threadIdx.x; t < NA * 32; t += blockDim.x) {
-    const int i = t >> 5, kk = t & 31;
-    if (kk >= m) continue;
-    float a = 0.f;
-    for (int ww = 0; ww < 8; ww++) a += red[ww][i][kk];
-    const int net = i / (2 * C + 1), j = i % (2 * C + 1);
-    int idx;
-    if (j < C) idx = kk * C + j;                                   // W1[k][c]
-    else if (j == C) idx = m * C + kk;                             // b1[k]
-    else idx = m * C + m + (j - C - 1) * m + kk;                   // W2[c][k]
-    out[net * half + idx] = a;
-  }
-  if (threadIdx.x < 4 * C) {
-    float a = 0.f;
-    for (int ww = 0; ww < 8; ww++) a += red4[ww][threadIdx.x];
-    const int q = threadIdx.x / C, c = threadIdx.x % C;
-    if (q == 0) out[m * C + m + C * m + c] = a;                    // s.b2[c]
-    else if (q == 1) out[half + m * C + m + C * m + c] = a;        // t.b2[c]
-    else if (q == 2) out[2 * half + c] = a;                        // ActNorm.s[c]
-    else out[2 * half + C + c] = a;                                // ActNorm.t[c]
+    for (int w = 0; w < nwarps; w++) a += red2[w * 16 + tid];
+    outb[p.P_flow + tid] = p.use_linear ? a : 0.f;
   }
 }
 
@@ -695,7 +885,7 @@ static FlowP make_p(const awb_prior* h, const float* params, const awb_grid_spec
   p.C = L.C; p.F = L.F; p.m = L.m; p.tanh_out = h->desc.flow_tanh; p.use_linear = 1;
   p.N = (int64_t)g->B * g->H * g->W;
   p.X = ws.X; p.zin = nullptr; p.deformed = nullptr; p.dX = ws.dX; p.fpart = ws.fpart;
-  p.chunk = split_chunk(p.N); p.O = h->desc.n_objects;
+  p.chunk = split_chunk(p.N); p.O = h->desc.n_objects; p.rounds = 1; p.rounds1 = 0; p.dz_smem = 0; p.dzp_g = nullptr;
   return p;
 }
 
@@ -705,14 +895,16 @@ int flow_forward(const awb_prior* h, const float* params, const awb_grid_spec* g
   p.use_linear = use_linear ? 1 : 0;
   p.zin = ws.flowz;
   p.deformed = deformed;
+  const FlowGeo geo = flow_geo(p.N, FLOW_P, 512);
+  p.chunk = geo.chunk; p.rounds = geo.R;
   size_t smem = sizeof(float) * ((size_t)h->lay.F * (h->lay.C == 2 ? FlowPack<2>::flow_stride(h->lay.m) : FlowPack<3>::flow_stride(h->lay.m)) + 2 * h->lay.C);
-  dim3 grid((unsigned)((p.N + 256 * FLOW_FWD_P - 1) / (256 * FLOW_FWD_P)), h->desc.n_objects);
+  dim3 grid(geo.S, h->desc.n_objects);
   if (h->lay.C == 2) {
     AWB_CUDA(cudaFuncSetAttribute(k_flow_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AWB_LAUNCH(PK_FLOW_FWD, st, k_flow_fwd<2><<<grid, 256, smem, st>>>(p));
+    AWB_LAUNCH(PK_FLOW_FWD, st, k_flow_fwd<2><<<grid, geo.T, smem, st>>>(p));
   } else {
     AWB_CUDA(cudaFuncSetAttribute(k_flow_fwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AWB_LAUNCH(PK_FLOW_FWD, st, k_flow_fwd<3><<<grid, 256, smem, st>>>(p));
+    AWB_LAUNCH(PK_FLOW_FWD, st, k_flow_fwd<3><<<grid, geo.T, smem, st>>>(p));
   }
   AWB_CUDA(cudaGetLastError());
   return AWB_OK;
@@ -735,24 +927,52 @@ int flow_inverse(const awb_prior* h, const float* params, const awb_grid_spec* g
   return AWB_OK;
 }
 
+// shared memory of k_flow_bwd without / with the running gradient of the CTA's pixel range
+static size_t flow_bwd_smem_base(const awb_prior* h) {
+  const int C = h->lay.C;
+  return sizeof(float) * ((size_t)h->lay.F * (C == 2 ? FlowBwdPack<2>::flow_stride() : FlowBwdPack<3>::flow_stride()) + 16 * 128 + 128 + 16 * 16);
+}
+bool flow_bwd_dz_in_smem(const awb_prior* h, int64_t N) {
+  const int C = h->lay.C;
+  const size_t dz = sizeof(float) * (size_t)split_chunk(N) * C * (C == 3 ? 2 : 1);
+  return flow_bwd_smem_base(h) + dz <= 200 * 1024;
+}
+
 int flow_backward(const awb_prior* h, const float* params, const awb_grid_spec* g, const Workspace& ws,
                   cudaStream_t st, bool use_linear) {
   FlowP p = make_p(h, params, g, ws);
   p.use_linear = use_linear ? 1 : 0;
   p.zin = ws.flowz;
-  if (!p.zin || !ws.flowg) { set_error("flow backward needs a training workspace"); return AWB_ERR_WORKSPACE; }
+  if (!p.zin) { set_error("flow backward needs a training workspace"); return AWB_ERR_WORKSPACE; }
   if (h->lay.m > 32) { set_error("flow MLP width must be <= 32"); return AWB_ERR_UNSUPPORTED; }
-  const size_t smem = sizeof(float) * ((size_t)h->lay.F * (h->lay.C == 2 ? FlowPack<2>::flow_stride(h->lay.m) : FlowPack<3>::flow_stride(h->lay.m)));
-  const int S = n_splits(p.N);
-  dim3 gridA(S, h->desc.n_objects), gridB(S, h->lay.F, h->desc.n_objects);
-  if (h->lay.C == 2) {
-    AWB_CUDA(cudaFuncSetAttribute(k_flow_bwd_px<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AWB_LAUNCH(PK_FLOW_BWD, st, k_flow_bwd_px<2><<<gridA, 1024, smem, st>>>(p, ws.flowg));
-    AWB_LAUNCH(PK_FLOW_BWD, st, k_flow_wgrad<2><<<gridB, 256, 0, st>>>(p, ws.flowg));
+  const int C = h->lay.C;
+  for (int f = 0; f < h->lay.F; f++) {
+    int mb = 0;
+    for (int c = 0; c < C; c++) mb |= h->fc.masks[f * C + c] != 0 ? 1 << c : 0;
+    if (mb < 1 || mb > (1 << C) - 2) {
+      set_error("flow %d has a degenerate coupling mask (all or no component masked): not trainable", f);
+      return AWB_ERR_UNSUPPORTED;
+    }
+  }
+  // T threads; full rounds of FLOW_PB pixels per thread, then the remainder of the range in rounds of one pixel per thread
+  // (2080 rows = 2 x 1024 + 32: a third full round for 32 pixels would cost its warp 50 %)
+  FlowGeo geo;
+  geo.S = n_splits(p.N); geo.chunk = split_chunk(p.N);
+  geo.T = (int)(geo.chunk < FLOW_BWD_T ? round_up(geo.chunk, 32) : FLOW_BWD_T);
+  geo.R = (int)(geo.chunk / ((int64_t)FLOW_PB * geo.T));
+  p.chunk = geo.chunk; p.rounds = geo.R;
+  p.rounds1 = (int)((geo.chunk - (int64_t)geo.R * FLOW_PB * geo.T + geo.T - 1) / geo.T);
+  p.dz_smem = flow_bwd_dz_in_smem(h, p.N) ? 1 : 0;
+  p.dzp_g = ws.flowd;
+  if (!p.dz_smem && C == 3 && !p.dzp_g) { set_error("flow backward: workspace lacks the pass scratch"); return AWB_ERR_WORKSPACE; }
+  const size_t smem = flow_bwd_smem_base(h) + (p.dz_smem ? sizeof(float) * (size_t)geo.chunk * C * (C == 3 ? 2 : 1) : 0);
+  dim3 grid(geo.S, h->desc.n_objects);
+  if (C == 2) {
+    AWB_CUDA(cudaFuncSetAttribute(k_flow_bwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AWB_LAUNCH(PK_FLOW_BWD, st, k_flow_bwd<2><<<grid, geo.T, smem, st>>>(p));
   } else {
-    AWB_CUDA(cudaFuncSetAttribute(k_flow_bwd_px<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AWB_LAUNCH(PK_FLOW_BWD, st, k_flow_bwd_px<3><<<gridA, 1024, smem, st>>>(p, ws.flowg));
-    AWB_LAUNCH(PK_FLOW_BWD, st, k_flow_wgrad<3><<<gridB, 256, 0, st>>>(p, ws.flowg));
+    AWB_CUDA(cudaFuncSetAttribute(k_flow_bwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AWB_LAUNCH(PK_FLOW_BWD, st, k_flow_bwd<3><<<grid, geo.T, smem, st>>>(p));
   }
   AWB_CUDA(cudaGetLastError());
   return AWB_OK;

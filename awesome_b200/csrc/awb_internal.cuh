@@ -103,8 +103,9 @@ struct Workspace {
   float* ZA;      // [O][L+1][N][ld]
   float* D;       // [O][2][N][ld]
   float* logits;  // [O][N]
-  float* flowz;   // [O][N][F*C] inputs of every coupling (training, flow priors)
-  float* flowg;   // [O][N][F*4C] per-pixel gradient factors of every coupling (RealNVP backward, phase A -> B)
+  float* flowz;   // training, flow priors: saved coupling inputs.  RealNVP: [O][F][N][RW] (input + s, t outputs of every
+                  // coupling, awb_flow.cu FlowSave); NormalizingFlow1D: [O][N][F*C]
+  float* flowd;   // RealNVP backward, C = 3, pixel ranges too large for shared memory: [O][N][4] scratch
   void* tc;       // tensor-core path scratch
   int64_t bytes;
 };
@@ -193,6 +194,8 @@ int flow_inverse(const awb_prior* h, const float* params, const awb_grid_spec* g
 int flow_identity_loss(const awb_prior* h, const awb_grid_spec* g, const Workspace& ws, cudaStream_t st);
 int flow_backward(const awb_prior* h, const float* params, const awb_grid_spec* g, const Workspace& ws,
                   cudaStream_t st, bool use_linear = true);
+int flow_save_floats(int C);                                     // floats saved per pixel and flow by the training forward
+bool flow_bwd_dz_in_smem(const awb_prior* h, int64_t N);         // the backward keeps its running gradient on the SM
 int flow_actnorm_init(const awb_prior* h, float* params, const awb_grid_spec* g, const Workspace& ws,
                       cudaStream_t st);
 

@@ -884,7 +884,7 @@ int simt_backward(const awb_prior* h, const float* params, const awb_grid_spec* 
   return AWB_OK;
 }
 
-static int n_groups_of(const awb_prior* h) { return h->desc.kind == AWB_KIND_FLOW_ICNN ? 3 : 3; }
+static int n_groups_of(const awb_prior*) { return AWB_MAX_GROUPS; }   // ReduceLROnPlateau reduces every param group (incl. the weight_g group 3)
 
 int simt_reduce_opt(const awb_prior* h, float* params, void* opt_state, const awb_opt_hyper* hy,
                     float* loss_out, const Workspace& ws, int64_t N, cudaStream_t st, int n_partials) {
