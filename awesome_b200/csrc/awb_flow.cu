@@ -56,7 +56,8 @@ template <int C> struct FlowPack {
 template <int C>
 __device__ __forceinline__ bool flow_pattern_compiled(int mb) { return mb >= 1 && mb <= (1 << C) - 2; }
 template <int C>
-__device__ void stage_flow_packed(const float* __restrict__ par, int F, int m, int64_t per_flow, float* sp, const FlowConsts& fc) {
+__device__ void stage_flow_packed(const float* __restrict__ par, int F, int m, int64_t per_flow, float* sp, const FlowConsts& fc,
+                                  bool exp_actnorm = false) {
   constexpr int RK = FlowPack<C>::RK;
   const int half = 2 * m * C + m + C, FS = FlowPack<C>::flow_stride(m);
   for (int t = threadIdx.x; t < F * m; t += blockDim.x) {
@@ -90,7 +91,7 @@ __device__ void stage_flow_packed(const float* __restrict__ par, int F, int m, i
     const int f = t / (4 * C), j = t - f * 4 * C, q = j / C, c = j - q * C;
     const float* w = par + (int64_t)f * per_flow;
     const float v = q == 0 ? w[m * C + m + C * m + c] : q == 1 ? w[half + m * C + m + C * m + c] : w[2 * half + (q - 2) * C + c];
-    sp[f * FS + m * RK + j] = v;
+    sp[f * FS + m * RK + j] = (exp_actnorm && q == 2) ? expf(v) : v;
   }
 }
 
@@ -193,24 +194,11 @@ __device__ __forceinline__ void coupling_mlp_bwd(const float* __restrict__ wf, i
     else { CALL(-1); }                                                    \
   } while (0)
 
-// ---- launch geometry shared by the forward and the backward kernel: S = n_splits(N) pixel ranges of `chunk` rows (one
-// CTA each, per object), T threads per CTA, R rounds of P pixels per thread.  Pixel of (round r, slot q, thread t) =
-// r0 + (r * P + q) * T + t: consecutive threads touch consecutive pixels (coalesced), and T is chosen so that the last
-// round is as full as the others (2080 rows = 2 rounds x 4 pixels x 260 -> 288 threads, not 3 rounds of 256).
+// ---- launch geometry of the forward and the backward kernel: S pixel ranges of `chunk` rows (one CTA each, per
+// object), T threads per CTA, R full rounds of P pixels per thread, then the remainder of the range in rounds of one
+// pixel per thread.  Pixel of (slot q, thread t) of a round starting at `base` = base + q * T + t: consecutive threads
+// touch consecutive pixels (coalesced).
 struct FlowGeo { int S, T, R; int64_t chunk; };
-static FlowGeo flow_geo(int64_t N, int P, int maxT) {
-  FlowGeo g;
-  g.S = n_splits(N);
-  g.chunk = split_chunk(N);
-  const int64_t groups = (g.chunk + P - 1) / P;
-  int64_t R = (groups + 128) / 256;
-  if (R < 1) R = 1;
-  int64_t T = round_up((groups + R - 1) / R, 32);
-  if (T > maxT) { R = (groups + maxT - 1) / maxT; T = round_up((groups + R - 1) / R, 32); }
-  g.R = (int)R; g.T = (int)T;
-  return g;
-}
-
 // Saved per pixel and flow for the backward pass (training forward): the coupling's input z[C] and the post-activation
 // outputs s, t of its two MLPs for the transformed components -- RW floats, stored [O][F][N][RW] (pixel-contiguous:
 // full-sector vector stores / loads).  C = 2: (z0, z1, s, t); C = 3: (z0, z1, z2, s_a | s_b, t_a, t_b, -) with a, b the
@@ -222,27 +210,28 @@ constexpr int FLOW_P = 4;          // forward: pixels per thread and round: ever
 constexpr int FLOW_PB = 4;         // backward: same, bounded by the 128 accumulator registers beside them
 constexpr int FLOW_BWD_T = 256;    // 8 warps = 2 per scheduler: up to 255 registers per thread
 template <int C>
-__global__ void __launch_bounds__(512) k_flow_fwd(FlowP p) {
+__global__ void __launch_bounds__(256) k_flow_fwd(FlowP p) {
   extern __shared__ __align__(16) float sp[];   // k-packed flow weights + [2C] linear
   constexpr int RK = FlowPack<C>::RK;
-  constexpr int P = FLOW_P;
   constexpr int RW = FlowSave<C>::RW;
   const int o = blockIdx.y;
   const float* par = p.params + (int64_t)o * p.P + p.off_flow;
   const int m = p.m, FS = FlowPack<C>::flow_stride(m);
-  stage_flow_packed<C>(par, p.F, m, p.per_flow, sp, p.fc);
+  stage_flow_packed<C>(par, p.F, m, p.per_flow, sp, p.fc, /*exp_actnorm=*/true);
   float* lin = sp + p.F * FS;
   if (threadIdx.x < 2 * C) lin[threadIdx.x] = par[p.P_flow + threadIdx.x];
   __syncthreads();
   const int T = blockDim.x;
   const int64_t r0 = (int64_t)blockIdx.x * p.chunk, r1 = r0 + p.chunk < p.N ? r0 + p.chunk : p.N;
-  for (int r = 0; r < p.rounds; r++) {
+  // one round: P pixels of this thread starting at `base` (slot q -> pixel base + q * T + tid) share every weight record
+  auto round = [&](auto p_c, int64_t base) -> bool {
+    constexpr int P = decltype(p_c)::value;
     int64_t n[P];
     bool ok[P];
     float z[P][C];
 #pragma unroll
     for (int q = 0; q < P; q++) {
-      const int64_t nq = r0 + ((int64_t)r * P + q) * T + threadIdx.x;
+      const int64_t nq = base + (int64_t)q * T + threadIdx.x;
       ok[q] = nq < r1;
       n[q] = ok[q] ? nq : (r1 > 0 ? r1 - 1 : 0);          // padding slots recompute the range's last pixel and store nothing
 #pragma unroll
@@ -252,10 +241,10 @@ __global__ void __launch_bounds__(512) k_flow_fwd(FlowP p) {
         z[q][c] = mm_fwd(x, p.fc.nmin[c], p.fc.nmax[c], p.fc.new_min, p.fc.new_max);
       }
     }
-    if (!ok[0]) break;
+    if (!ok[0]) return false;
     for (int f = 0; f < p.F; f++) {
       const float* wf = sp + f * FS;
-      const float* tail = wf + m * RK;          // b2s[C] | b2t[C] | an_s[C] | an_t[C]
+      const float* tail = wf + m * RK;          // b2s[C] | b2t[C] | exp(an_s)[C] | an_t[C]
       bool b[C];
       int mb = 0;
 #pragma unroll
@@ -283,10 +272,10 @@ __global__ void __launch_bounds__(512) k_flow_fwd(FlowP p) {
             if (!isfinite(s_)) s_ = NAN;
             if (!isfinite(t_)) t_ = NAN;
             zc = fmaf(z[q][c], expf(s_), t_);
-            if (u < 2) { sv[u] = s_; tv[u] = t_; }
+            if (u == 0) { sv[0] = s_; tv[0] = t_; } else { sv[1] = s_; tv[1] = t_; }
             u++;
           }
-          z[q][c] = fmaf(zc, expf(tail[2 * C + c]), tail[3 * C + c]);      // ActNorm
+          z[q][c] = fmaf(zc, tail[2 * C + c], tail[3 * C + c]);      // ActNorm: z * exp(s) + t, exp(s) staged once per CTA
         }
         if (p.zin && ok[q]) {
           float4* rec = reinterpret_cast<float4*>(p.zin + (((int64_t)o * p.F + f) * p.N + n[q]) * RW);
@@ -307,7 +296,14 @@ __global__ void __launch_bounds__(512) k_flow_fwd(FlowP p) {
         for (int c = 0; c < C; c++) p.deformed[((int64_t)o * p.N + n[q]) * C + c] = xd[c];
       }
     }
-  }
+    return true;
+  };
+  int64_t base = r0;
+  bool more = true;
+#pragma unroll 1
+  for (int r = 0; r < p.rounds && more; r++, base += (int64_t)FLOW_P * T) more = round(std::integral_constant<int, FLOW_P>{}, base);
+#pragma unroll 1
+  for (int r = 0; r < p.rounds1 && more; r++, base += T) more = round(std::integral_constant<int, 1>{}, base);
 }
 
 // ---------------------------------------------------------------- inverse (PathConnectedNet.inverse, path_connected_net.py:107-122)
@@ -385,15 +381,16 @@ __global__ void __launch_bounds__(256) k_flow_inv(FlowP p, float* out) {
 // reduction happens once per flow and CTA (warp reduce-scatter + fixed-order combine), not per pixel.
 // The unit range is processed in blocks of KB units (32 for C = 2: one pass; 16 for C = 3: two passes over the pixels,
 // 128 accumulator registers either way).
-template <int C, int MB> struct FlowBwdCfg {
-  static constexpr int NM = (MB & 1) + ((MB >> 1) & 1) + ((MB >> 2) & 1), NU = C - NM;
+// Everything held in registers is indexed by ROLE (i-th masked component, j-th transformed component), everything in
+// memory by component; which component plays which role is a run-time property of the flow.  One instantiation per number
+// of masked components NM therefore serves every mask pattern (C = 2: one body for both alternating masks -- the two
+// specialised copies did not fit the instruction cache together).
+template <int C, int NM> struct FlowBwdCfg {
+  static constexpr int NU = C - NM;
   static constexpr int NA1 = NU * (1 + NM);        // accumulators per unit and net
   static constexpr int NACC = 2 * NA1;
   static constexpr int KB = C == 2 ? 32 : 16;
   static constexpr int NPASS = 32 / KB;
-  static __device__ __forceinline__ int rm(int c) { return __popc(MB & ((1 << c) - 1)); }   // rank among masked / transformed
-  static __device__ __forceinline__ int ru(int c) { return c - rm(c); }
-  static __device__ __forceinline__ bool masked(int c) { return ((MB >> c) & 1) != 0; }
 };
 template <int C> struct FlowBwdPack {
   static constexpr int RKB = C == 2 ? 8 : 12;      // floats per unit: [w1s[NM] | b1s | vs[NU][NM] | w1t[NM] | b1t | vt[NU][NM]]
@@ -430,6 +427,12 @@ __device__ void stage_flow_bwd(const float* __restrict__ par, int F, int m, int6
   }
 }
 
+__device__ __forceinline__ float gate_gt0(float x) {      // x > 0 ? 1.0f : 0.0f  (FSET.BF.GT)
+  float g;
+  asm("set.gt.f32.f32 %0, %1, 0f00000000;" : "=f"(g) : "f"(x));
+  return g;
+}
+
 // Sum of v[i] over the 32 lanes for 32 values at once: afterwards lane l holds the total of value l (31 shuffles).
 __device__ __forceinline__ float warp_reduce_scatter32(float* v, int lane) {
 #pragma unroll
@@ -447,35 +450,83 @@ __device__ __forceinline__ float warp_reduce_scatter32(float* v, int lane) {
   return v[0];
 }
 
+template <int C> __device__ __forceinline__ float pick(const float* v, int c) {   // v[c] for a run-time c, v in registers
+  return C == 2 ? (c == 0 ? v[0] : v[1]) : (c == 0 ? v[0] : (c == 1 ? v[1] : v[2]));
+}
+
 struct FlowBwdShared {
   float* wrec;     // staged weights (stage_flow_bwd)
-  float* dz;       // [C][chunk_pad] running coordinate gradient (or null: global, in place in dX)
+  float* red;      // [16][128] + [128] + [16][16]
+  float* stage;    // [2][P][T] saved records of the next round, filled by cp.async (per-thread slots)
   float* dzp;      // partial masked-input gradient between unit passes (C = 3): [C][chunk] in shared memory or [n][4] global
   int64_t dzp_cs, dzp_ps;
-  float* red;      // [warps][128] + [128] + [warps][16]
 };
 
-// one flow (mask pattern MB) of the CTA's pixel range
-template <int C, int MB>
-__device__ __forceinline__ void flow_bwd_one(const FlowP& p, const FlowBwdShared& sh, int f, int o, int64_t r0, int64_t r1,
-                                             float* dzg, int64_t dz_cs, int64_t dz_ps) {
-  using Cf = FlowBwdCfg<C, MB>;
-  constexpr int NM = Cf::NM, NU = Cf::NU, NA1 = Cf::NA1, NACC = Cf::NACC, KB = Cf::KB, NPASS = Cf::NPASS;
+// the full rounds of the backward walk in execution order: flows in reverse, unit passes, rounds
+struct FlowStep {
+  int f, pass, r;
+  __device__ __forceinline__ bool valid() const { return f >= 0; }
+  __device__ __forceinline__ void next(int npass, int rounds) {
+    if (++r < rounds) return;
+    r = 0;
+    if (++pass < npass) return;
+    pass = 0;
+    --f;
+  }
+};
+
+// cp.async of this thread's P records of one round into its private slots of a staging buffer
+template <int C, int P>
+__device__ __forceinline__ void prefetch_round(const FlowP& p, float* stage_buf, const FlowStep& st, int o, int64_t r0, int64_t r1) {
+  constexpr int RW = FlowSave<C>::RW;
+  const int T = blockDim.x, tid = threadIdx.x;
+  const float* zrec = p.zin + (((int64_t)o * p.F + st.f) * p.N) * RW;
+#pragma unroll
+  for (int q = 0; q < P; q++) {
+    const int64_t n = r0 + ((int64_t)st.r * P + q) * T + tid;
+    if (n < r1) {
+#pragma unroll
+      for (int i = 0; i < RW / 4; i++) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stage_buf + ((q * (RW / 4) + i) * T + tid) * 4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(zrec + n * RW + 4 * i) : "memory");
+      }
+    }
+  }
+}
+
+// one flow with NM masked components (mask pattern mb) over the CTA's pixel range
+template <int C, int NM>
+__device__ __forceinline__ void flow_bwd_one(const FlowP& p, const FlowBwdShared& sh, int f, int mb, int o, int64_t r0, int64_t r1,
+                                             float* dzg, int64_t dz_cs, int64_t dz_ps, FlowStep& pre, int& buf) {
+  using Cf = FlowBwdCfg<C, NM>;
+  constexpr int NU = Cf::NU, NA1 = Cf::NA1, NACC = Cf::NACC, KB = Cf::KB, NPASS = Cf::NPASS;
   constexpr int RKB = FlowBwdPack<C>::RKB, RW = FlowSave<C>::RW;
-  constexpr int NSC = 2 * C + 2 * NU;      // per-thread scalar sums: d ActNorm.s[C], d ActNorm.t[C], d s.b2[NU], d t.b2[NU]
   const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
   const int m = p.m, half = 2 * m * C + m + C;
   const float* wf = sh.wrec + f * FlowBwdPack<C>::flow_stride();
-  const float* eas = wf + 32 * RKB;
   const float* zrec = p.zin + (((int64_t)o * p.F + f) * p.N) * RW;
   const float* wglob = p.params + (int64_t)o * p.P + p.off_flow + (int64_t)f * p.per_flow;
   float* out = p.fpart + ((int64_t)blockIdx.x * p.O + o) * (p.P_flow + 2 * C) + (int64_t)f * p.per_flow;
-  float ea[C];
+  // roles: mi[i] = i-th masked component, ui[j] = j-th transformed component (ascending)
+  int mi[NM], ui[NU];
+  {
+    int a = 0, b = 0;
 #pragma unroll
-  for (int c = 0; c < C; c++) ea[c] = eas[c];
-  float sc[NSC];
+    for (int c = 0; c < C; c++) {
+      if ((mb >> c) & 1) { if (a < NM) mi[a] = c; a++; } else { if (b < NU) ui[b] = c; b++; }
+    }
+  }
+  float ea_m[NM], ea_u[NU];
 #pragma unroll
-  for (int i = 0; i < NSC; i++) sc[i] = 0.f;
+  for (int i = 0; i < NM; i++) ea_m[i] = wf[32 * RKB + mi[i]];
+#pragma unroll
+  for (int j = 0; j < NU; j++) ea_u[j] = wf[32 * RKB + ui[j]];
+  // per-thread scalar sums: d ActNorm.s / .t of the masked and of the transformed components, d s.b2 / d t.b2
+  float sas_m[NM], sat_m[NM], sas_u[NU], sat_u[NU], sb2s[NU], sb2t[NU];
+#pragma unroll
+  for (int i = 0; i < NM; i++) { sas_m[i] = 0.f; sat_m[i] = 0.f; }
+#pragma unroll
+  for (int j = 0; j < NU; j++) { sas_u[j] = 0.f; sat_u[j] = 0.f; sb2s[j] = 0.f; sb2t[j] = 0.f; }
 
 #pragma unroll 1
   for (int pass = 0; pass < NPASS; pass++) {
@@ -483,61 +534,60 @@ __device__ __forceinline__ void flow_bwd_one(const FlowP& p, const FlowBwdShared
 #pragma unroll
     for (int i = 0; i < KB * NACC; i++) acc[i] = 0.f;
     const float* wk = wf + pass * KB * RKB;
-    // one round: P pixels of this thread starting at `base` (slot q -> pixel base + q * T + tid), all sharing the records
-    auto round = [&](auto p_c, int64_t base) -> bool {
+    const bool last_pass = pass == NPASS - 1;
+    // one round: P pixels of this thread starting at `base` (slot q -> pixel base + q * T + tid), all sharing the records;
+    // src: this thread's staged records (full rounds) or null (remainder rounds read global memory)
+    auto round = [&](auto p_c, int64_t base, const float* src) -> bool {
       constexpr int P = decltype(p_c)::value;
-      int64_t loc[P];
+      int loc[P];
       bool ok[P];
-      float zm[P][NM > 0 ? NM : 1], ds[P][NU], dt[P][NU], us[P][NU * NM > 0 ? NU * NM : 1], ut[P][NU * NM > 0 ? NU * NM : 1];
-      float Ds[P][NU * NM > 0 ? NU * NM : 1], Dt[P][NU * NM > 0 ? NU * NM : 1], dzo[P][C];
+      float zm[P][NM], ds[P][NU], dt[P][NU], us[P][NU * NM], ut[P][NU * NM], Ds[P][NU * NM], Dt[P][NU * NM];
+      float dzo_m[P][NM], dzo_u[P][NU];
 #pragma unroll
       for (int q = 0; q < P; q++) {
         const int64_t n = base + (int64_t)q * T + tid;
         ok[q] = n < r1;
-        loc[q] = ok[q] ? n - r0 : 0;
-        float z[C], s[NU], t[NU], dz[C];
+        loc[q] = ok[q] ? (int)(n - r0) : 0;
+        float z[3] = {0.f, 0.f, 0.f}, s[2] = {0.f, 0.f}, t[2] = {0.f, 0.f}, dz[3] = {0.f, 0.f, 0.f};
         if (ok[q]) {
-          const float4 a = *reinterpret_cast<const float4*>(zrec + n * RW);
-          if (C == 2) { z[0] = a.x; z[1] = a.y; s[0] = a.z; t[0] = a.w; }
-          else {
-            const float4 b4 = *reinterpret_cast<const float4*>(zrec + n * RW + 4);
-            z[0] = a.x; z[1] = a.y; z[C - 1] = a.z; s[0] = a.w;
-            if (NU == 2) { s[NU - 1] = b4.x; t[0] = b4.y; t[NU - 1] = b4.z; } else { t[0] = b4.y; }
+          float4 a, b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (src) {
+            a = *reinterpret_cast<const float4*>(src + ((q * (RW / 4)) * T + tid) * 4);
+            if (C == 3) b4 = *reinterpret_cast<const float4*>(src + ((q * (RW / 4) + (RW / 4 - 1)) * T + tid) * 4);
+          } else {
+            a = *reinterpret_cast<const float4*>(zrec + n * RW);
+            if (C == 3) b4 = *reinterpret_cast<const float4*>(zrec + n * RW + 4);
           }
+          if (C == 2) { z[0] = a.x; z[1] = a.y; s[0] = a.z; t[0] = a.w; }
+          else { z[0] = a.x; z[1] = a.y; z[2] = a.z; s[0] = a.w; s[1] = b4.x; t[0] = b4.y; t[1] = b4.z; }
 #pragma unroll
           for (int c = 0; c < C; c++) dz[c] = dzg[c * dz_cs + loc[q] * dz_ps];
-        } else {
-#pragma unroll
-          for (int c = 0; c < C; c++) { z[c] = 0.f; dz[c] = 0.f; }
-#pragma unroll
-          for (int u = 0; u < NU; u++) { s[u] = 0.f; t[u] = 0.f; }
         }
 #pragma unroll
-        for (int c = 0; c < C; c++) {
-          const float dzp = dz[c] * ea[c];
-          if (Cf::masked(c)) {
-            zm[q][Cf::rm(c)] = z[c];
-            dzo[q][c] = dzp;
-            if (pass == NPASS - 1) { sc[c] = fmaf(dz[c] * z[c], ea[c], sc[c]); sc[C + c] += dz[c]; }
-          } else {
-            const int u = Cf::ru(c);
-            const float e = expf(s[u]);
-            const float dsv = dzp * z[c] * e;
-            ds[q][u] = p.tanh_out ? dsv * (1.f - s[u] * s[u]) : dsv;
-            dt[q][u] = p.tanh_out ? dzp * (1.f - t[u] * t[u]) : dzp;
-            dzo[q][c] = dzp * e;
-            if (pass == NPASS - 1) {
-              sc[c] = fmaf(dz[c] * fmaf(z[c], e, t[u]), ea[c], sc[c]);
-              sc[C + c] += dz[c];
-              sc[2 * C + u] += ds[q][u];
-              sc[2 * C + NU + u] += dt[q][u];
-            }
+        for (int i = 0; i < NM; i++) {          // masked components pass through the coupling
+          const float zc = pick<C>(z, mi[i]), dzc = pick<C>(dz, mi[i]);
+          zm[q][i] = zc;
+          dzo_m[q][i] = dzc * ea_m[i];
+          if (last_pass) { sas_m[i] = fmaf(dzc * zc, ea_m[i], sas_m[i]); sat_m[i] += dzc; }
+        }
+#pragma unroll
+        for (int j = 0; j < NU; j++) {          // transformed components: z' = z exp(s) + t
+          const float zc = pick<C>(z, ui[j]), dzc = pick<C>(dz, ui[j]);
+          const float dzp = dzc * ea_u[j];
+          const float e = expf(s[j]);
+          const float dsv = dzp * zc * e;
+          ds[q][j] = p.tanh_out ? dsv * (1.f - s[j] * s[j]) : dsv;
+          dt[q][j] = p.tanh_out ? dzp * (1.f - t[j] * t[j]) : dzp;
+          dzo_u[q][j] = dzp * e;
+          if (last_pass) {
+            sas_u[j] = fmaf(dzc * fmaf(zc, e, t[j]), ea_u[j], sas_u[j]);
+            sat_u[j] += dzc;
+            sb2s[j] += ds[q][j];
+            sb2t[j] += dt[q][j];
           }
+#pragma unroll
+          for (int i = 0; i < NM; i++) { us[q][j * NM + i] = ds[q][j] * zm[q][i]; ut[q][j * NM + i] = dt[q][j] * zm[q][i]; Ds[q][j * NM + i] = 0.f; Dt[q][j * NM + i] = 0.f; }
         }
-#pragma unroll
-        for (int u = 0; u < NU; u++)
-#pragma unroll
-          for (int c = 0; c < NM; c++) { us[q][u * NM + c] = ds[q][u] * zm[q][c]; ut[q][u * NM + c] = dt[q][u] * zm[q][c]; Ds[q][u * NM + c] = 0.f; Dt[q][u * NM + c] = 0.f; }
       }
       if (!ok[0]) return false;       // slots are ordered: nothing left for this thread
       // ---- unit loop: all KB units of this pass, every record shared by the P pixels
@@ -552,21 +602,19 @@ __device__ __forceinline__ void flow_bwd_one(const FlowP& p, const FlowBwdShared
           float ps = w[NM], pt = w[OT + NM];
 #pragma unroll
           for (int c = 0; c < NM; c++) { ps = fmaf(w[c], zm[q][c], ps); pt = fmaf(w[OT + c], zm[q][c], pt); }
+          // gate = [pre > 0] as 1.0f / 0.0f (one FSET) and FMAs instead of predicated adds
           float* a = &acc[k * NACC];
-          if (ps > 0.f) {
+          const float gs = gate_gt0(ps), gt = gate_gt0(pt);
 #pragma unroll
-            for (int u = 0; u < NU; u++) {
-              a[u * (1 + NM)] += ds[q][u];
+          for (int u = 0; u < NU; u++) {
+            a[u * (1 + NM)] = fmaf(gs, ds[q][u], a[u * (1 + NM)]);
+            a[NA1 + u * (1 + NM)] = fmaf(gt, dt[q][u], a[NA1 + u * (1 + NM)]);
 #pragma unroll
-              for (int c = 0; c < NM; c++) { a[u * (1 + NM) + 1 + c] += us[q][u * NM + c]; Ds[q][u * NM + c] += w[NM + 1 + u * NM + c]; }
-            }
-          }
-          if (pt > 0.f) {
-#pragma unroll
-            for (int u = 0; u < NU; u++) {
-              a[NA1 + u * (1 + NM)] += dt[q][u];
-#pragma unroll
-              for (int c = 0; c < NM; c++) { a[NA1 + u * (1 + NM) + 1 + c] += ut[q][u * NM + c]; Dt[q][u * NM + c] += w[OT + NM + 1 + u * NM + c]; }
+            for (int c = 0; c < NM; c++) {
+              a[u * (1 + NM) + 1 + c] = fmaf(gs, us[q][u * NM + c], a[u * (1 + NM) + 1 + c]);
+              Ds[q][u * NM + c] = fmaf(gs, w[NM + 1 + u * NM + c], Ds[q][u * NM + c]);
+              a[NA1 + u * (1 + NM) + 1 + c] = fmaf(gt, ut[q][u * NM + c], a[NA1 + u * (1 + NM) + 1 + c]);
+              Dt[q][u * NM + c] = fmaf(gt, w[OT + NM + 1 + u * NM + c], Dt[q][u * NM + c]);
             }
           }
         }
@@ -576,17 +624,17 @@ __device__ __forceinline__ void flow_bwd_one(const FlowP& p, const FlowBwdShared
       for (int q = 0; q < P; q++) {
         if (!ok[q]) continue;
 #pragma unroll
-        for (int c = 0; c < C; c++) {
-          if (Cf::masked(c)) {
-            float g = 0.f;
+        for (int i = 0; i < NM; i++) {
+          float g = 0.f;
 #pragma unroll
-            for (int u = 0; u < NU; u++) g = fmaf(ds[q][u], Ds[q][u * NM + Cf::rm(c)], fmaf(dt[q][u], Dt[q][u * NM + Cf::rm(c)], g));
-            if (NPASS > 1 && pass > 0) g += sh.dzp[c * sh.dzp_cs + loc[q] * sh.dzp_ps];
-            if (pass < NPASS - 1) sh.dzp[c * sh.dzp_cs + loc[q] * sh.dzp_ps] = g;
-            else dzg[c * dz_cs + loc[q] * dz_ps] = dzo[q][c] + g;
-          } else if (pass == NPASS - 1) {
-            dzg[c * dz_cs + loc[q] * dz_ps] = dzo[q][c];
-          }
+          for (int u = 0; u < NU; u++) g = fmaf(ds[q][u], Ds[q][u * NM + i], fmaf(dt[q][u], Dt[q][u * NM + i], g));
+          if (NPASS > 1 && pass > 0) g += sh.dzp[mi[i] * sh.dzp_cs + loc[q] * sh.dzp_ps];
+          if (!last_pass) sh.dzp[mi[i] * sh.dzp_cs + loc[q] * sh.dzp_ps] = g;
+          else dzg[mi[i] * dz_cs + loc[q] * dz_ps] = dzo_m[q][i] + g;
+        }
+        if (last_pass) {
+#pragma unroll
+          for (int j = 0; j < NU; j++) dzg[ui[j] * dz_cs + loc[q] * dz_ps] = dzo_u[q][j];
         }
       }
       return true;
@@ -595,9 +643,18 @@ __device__ __forceinline__ void flow_bwd_one(const FlowP& p, const FlowBwdShared
       int64_t base = r0;
       bool more = true;
 #pragma unroll 1
-      for (int r = 0; r < p.rounds && more; r++, base += (int64_t)FLOW_PB * T) more = round(std::integral_constant<int, FLOW_PB>{}, base);
+      for (int r = 0; r < p.rounds; r++, base += (int64_t)FLOW_PB * T) {
+        // records of this round were requested one round ago; request the next full round (of whatever flow) now
+        float* cur = sh.stage + buf * (FLOW_PB * (RW / 4) * T * 4);
+        buf ^= 1;
+        pre.next(NPASS, p.rounds);
+        if (pre.valid()) prefetch_round<C, FLOW_PB>(p, sh.stage + buf * (FLOW_PB * (RW / 4) * T * 4), pre, o, r0, r1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        if (more) more = round(std::integral_constant<int, FLOW_PB>{}, base, cur);
+      }
 #pragma unroll 1
-      for (int r = 0; r < p.rounds1 && more; r++, base += T) more = round(std::integral_constant<int, 1>{}, base);
+      for (int r = 0; r < p.rounds1 && more; r++, base += T) more = round(std::integral_constant<int, 1>{}, base, nullptr);
     }
     // ---- cross-pixel reduction of this pass's KB units: warp reduce-scatter, fixed-order combine over the warps
     float* red = sh.red;                       // [nwarps][KB * NACC]
@@ -617,52 +674,57 @@ __device__ __forceinline__ void flow_bwd_one(const FlowP& p, const FlowBwdShared
       const float* wn = wglob + net * half;
       const float* a = tot + k * NACC + net * NA1;
       float* on = out + net * half;
-      float gb1 = 0.f, gw1[NM > 0 ? NM : 1];
+      float gb1 = 0.f, gw1[NM];
 #pragma unroll
       for (int c = 0; c < NM; c++) gw1[c] = 0.f;
       const float b1 = wn[m * C + kk];
 #pragma unroll
-      for (int c = 0; c < C; c++) {
-        if (Cf::masked(c)) continue;
-        const int u = Cf::ru(c);
-        const float w2 = wn[m * C + m + c * m + kk];
+      for (int c = 0; c < C; c++) { on[kk * C + c] = 0.f; on[m * C + m + c * m + kk] = 0.f; }   // W1 columns of transformed inputs / W2 rows of masked outputs
+#pragma unroll
+      for (int u = 0; u < NU; u++) {
+        const float w2 = wn[m * C + m + ui[u] * m + kk];
         gb1 = fmaf(w2, a[u * (1 + NM)], gb1);
         float gw2 = b1 * a[u * (1 + NM)];
 #pragma unroll
-        for (int cc = 0; cc < C; cc++)
-          if (Cf::masked(cc)) {
-            gw1[Cf::rm(cc)] = fmaf(w2, a[u * (1 + NM) + 1 + Cf::rm(cc)], gw1[Cf::rm(cc)]);
-            gw2 = fmaf(wn[kk * C + cc], a[u * (1 + NM) + 1 + Cf::rm(cc)], gw2);
-          }
-        on[m * C + m + c * m + kk] = gw2;                                   // d W2[c][k], transformed c
+        for (int c = 0; c < NM; c++) {
+          gw1[c] = fmaf(w2, a[u * (1 + NM) + 1 + c], gw1[c]);
+          gw2 = fmaf(wn[kk * C + mi[c]], a[u * (1 + NM) + 1 + c], gw2);
+        }
+        on[m * C + m + ui[u] * m + kk] = gw2;                                // d W2[u][k]
       }
 #pragma unroll
-      for (int c = 0; c < C; c++) {
-        if (Cf::masked(c)) { on[kk * C + c] = gw1[Cf::rm(c)]; on[m * C + m + c * m + kk] = 0.f; }   // d W1[k][c]; W2 rows of masked outputs are unused
-        else on[kk * C + c] = 0.f;                                           // W1 columns of transformed inputs see zm = 0
-      }
+      for (int c = 0; c < NM; c++) on[kk * C + mi[c]] = gw1[c];               // d W1[k][c]
       on[m * C + kk] = gb1;                                                  // d b1[k]
     }
     __syncthreads();
   }
-  // ---- scalar sums of the flow: ActNorm pair and the output biases of s / t
+  // ---- scalar sums of the flow: ActNorm pair and the output biases of s / t; red2 rows: [as(C) | at(C) | b2s(C) | b2t(C)]
   float* red2 = sh.red + 16 * 128 + 128;       // [nwarps][16]
-#pragma unroll
-  for (int i = 0; i < NSC; i++) {
-    float a = sc[i];
+  auto wsum = [&](float a) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-    if (lane == 0) red2[warp * 16 + i] = a;
+    return a;
+  };
+  if (lane < 16) red2[warp * 16 + lane] = 0.f;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < NM; i++) {
+    const float a = wsum(sas_m[i]), b = wsum(sat_m[i]);
+    if (lane == 0) { red2[warp * 16 + mi[i]] = a; red2[warp * 16 + C + mi[i]] = b; }
+  }
+#pragma unroll
+  for (int j = 0; j < NU; j++) {
+    const float a = wsum(sas_u[j]), b = wsum(sat_u[j]), c2 = wsum(sb2s[j]), d2 = wsum(sb2t[j]);
+    if (lane == 0) { red2[warp * 16 + ui[j]] = a; red2[warp * 16 + C + ui[j]] = b; red2[warp * 16 + 2 * C + ui[j]] = c2; red2[warp * 16 + 3 * C + ui[j]] = d2; }
   }
   __syncthreads();
   if (tid < 4 * C) {
-    const int qd = tid / C, c = tid - qd * C;      // 0: s.b2, 1: t.b2, 2: ActNorm.s, 3: ActNorm.t
+    const int qd = tid / C, c = tid - qd * C;      // 0: ActNorm.s, 1: ActNorm.t, 2: s.b2, 3: t.b2
     float a = 0.f;
-    if (qd >= 2) { for (int w = 0; w < nwarps; w++) a += red2[w * 16 + (qd - 2) * C + c]; }
-    else if (!Cf::masked(c)) { for (int w = 0; w < nwarps; w++) a += red2[w * 16 + 2 * C + qd * NU + Cf::ru(c)]; }
-    if (qd == 0) out[m * C + m + C * m + c] = a;
-    else if (qd == 1) out[half + m * C + m + C * m + c] = a;
-    else if (qd == 2) out[2 * half + c] = a;
+    for (int w = 0; w < nwarps; w++) a += red2[w * 16 + tid];
+    if (qd == 2) out[m * C + m + C * m + c] = a;
+    else if (qd == 3) out[half + m * C + m + C * m + c] = a;
+    else if (qd == 0) out[2 * half + c] = a;
     else out[2 * half + C + c] = a;
   }
   __syncthreads();
@@ -671,15 +733,17 @@ __device__ __forceinline__ void flow_bwd_one(const FlowP& p, const FlowBwdShared
 template <int C>
 __global__ void __launch_bounds__(FLOW_BWD_T, 1) k_flow_bwd(FlowP p) {
   extern __shared__ __align__(16) float sp[];
+  constexpr int RW = FlowSave<C>::RW;
   const int o = blockIdx.y, tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
   const float* par = p.params + (int64_t)o * p.P + p.off_flow;
   const int PF = (int)p.P_flow + 2 * C;
+  const int64_t r0 = (int64_t)blockIdx.x * p.chunk, r1 = r0 + p.chunk < p.N ? r0 + p.chunk : p.N;
   FlowBwdShared sh;
   sh.wrec = sp;
   sh.red = sp + p.F * FlowBwdPack<C>::flow_stride();
-  float* after = sh.red + 16 * 128 + 128 + 16 * 16;
-  sh.dz = p.dz_smem ? after : nullptr;
-  const int64_t r0 = (int64_t)blockIdx.x * p.chunk, r1 = r0 + p.chunk < p.N ? r0 + p.chunk : p.N;
+  sh.stage = sh.red + 16 * 128 + 128 + 16 * 16;
+  float* after = sh.stage + 2 * FLOW_PB * (RW / 4) * FLOW_BWD_T * 4;
+  float* dzs = p.dz_smem ? after : nullptr;
   sh.dzp = p.dz_smem ? after + C * p.chunk : p.dzp_g + ((int64_t)o * p.N + r0) * 4;   // C = 3 only (two unit passes)
   sh.dzp_cs = p.dz_smem ? p.chunk : 1; sh.dzp_ps = p.dz_smem ? 1 : 4;
   stage_flow_bwd<C>(par, p.F, p.m, p.per_flow, sp, p.fc);
@@ -688,8 +752,20 @@ __global__ void __launch_bounds__(FLOW_BWD_T, 1) k_flow_bwd(FlowP p) {
     for (int i = tid; i < PF; i += T) outb[i] = 0.f;
     return;
   }
+  // saved records of the first full round (last flow) are requested before anything else
+  constexpr int NPASS = FlowBwdCfg<C, 1>::NPASS;
+  FlowStep pre = {p.F - 1, 0, -1};
+  int buf = 0;
+  if (p.rounds > 0) {
+    pre.r = 0;
+    prefetch_round<C, FLOW_PB>(p, sh.stage, pre, o, r0, r1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  } else {
+    pre.f = -1;
+  }
+  (void)NPASS;
   // running gradient: shared memory [C][chunk], or in place in dX ([n][4]) when the range is too large
-  float* dzg = p.dz_smem ? sh.dz : p.dX + ((int64_t)o * p.N + r0) * 4;
+  float* dzg = p.dz_smem ? dzs : p.dX + ((int64_t)o * p.N + r0) * 4;
   const int64_t dz_cs = p.dz_smem ? p.chunk : 1, dz_ps = p.dz_smem ? 1 : 4;
   for (int64_t n = r0 + tid; n < r1; n += T) {
     const float4 dx = *reinterpret_cast<const float4*>(p.dX + ((int64_t)o * p.N + n) * 4);
@@ -698,23 +774,16 @@ __global__ void __launch_bounds__(FLOW_BWD_T, 1) k_flow_bwd(FlowP p) {
     for (int c = 0; c < C; c++)
       dzg[c * dz_cs + (n - r0) * dz_ps] = d3[c] * ((p.fc.nmax[c] - p.fc.nmin[c]) / (p.fc.new_max - p.fc.new_min));
   }
-  __syncthreads();          // staged weights; (dz slots are thread-private: same pixel -> same thread in every flow)
-  // NOTE: the init loop above strides pixels by T, the flow loop by (r * P + q) * T + tid: both map pixel n to thread
-  // (n - r0) % T, so every dz slot is only ever touched by one thread.
+  __syncthreads();          // staged weights; the dz slots are thread-private: pixel n is always handled by thread (n - r0) % T
   for (int f = p.F - 1; f >= 0; f--) {
     int mb = 0;
 #pragma unroll
     for (int c = 0; c < C; c++) mb |= p.fc.masks[f * C + c] != 0 ? 1 << c : 0;
-#define AWB_CALL(MB) flow_bwd_one<C, MB>(p, sh, f, o, r0, r1, dzg, dz_cs, dz_ps)
-    if (mb == 1) { AWB_CALL(1); }
-    else if (mb == 2) { AWB_CALL(2); }
+    const int nm = __popc(mb);
+    if (nm == 1) flow_bwd_one<C, 1>(p, sh, f, mb, o, r0, r1, dzg, dz_cs, dz_ps, pre, buf);
     if constexpr (C == 3) {
-      if (mb == 3) { AWB_CALL(3); }
-      else if (mb == 4) { AWB_CALL(4); }
-      else if (mb == 5) { AWB_CALL(5); }
-      else if (mb == 6) { AWB_CALL(6); }
+      if (nm == 2) flow_bwd_one<C, 2>(p, sh, f, mb, o, r0, r1, dzg, dz_cs, dz_ps, pre, buf);
     }
-#undef AWB_CALL
   }
   // ---- 1x1-conv gradients (path_connected_net.py:65,82): fixed-order block reduction
   float glw[C], glb[C];
@@ -895,8 +964,26 @@ int flow_forward(const awb_prior* h, const float* params, const awb_grid_spec* g
   p.use_linear = use_linear ? 1 : 0;
   p.zin = ws.flowz;
   p.deformed = deformed;
-  const FlowGeo geo = flow_geo(p.N, FLOW_P, 512);
+  // The forward has no per-CTA partials, so the number of CTAs is free: k CTAs of 128 threads per SM (latency hiding: the
+  // kernel needs 47 registers), each with one or two full rounds of FLOW_P pixels per thread and a one-pixel remainder
+  // round, sized so that every SM gets the same number of pixels.
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  FlowGeo geo;
+  geo.T = 128;
+  int64_t per_sm = (p.N * h->desc.n_objects + sms - 1) / sms;
+  int k = (int)((per_sm + FLOW_P * geo.T / 2) / (FLOW_P * geo.T));
+  if (k < 1) k = 1;
+  if (k > 8) k = 8;
+  int64_t n_cta = (int64_t)sms * k / h->desc.n_objects;
+  if (n_cta < 1) n_cta = 1;
+  geo.chunk = (p.N + n_cta - 1) / n_cta;
+  if (geo.chunk < 32) geo.chunk = 32;
+  geo.S = (int)((p.N + geo.chunk - 1) / geo.chunk);
+  if (geo.chunk < geo.T) geo.T = (int)round_up(geo.chunk, 32);
+  geo.R = (int)(geo.chunk / ((int64_t)FLOW_P * geo.T));
   p.chunk = geo.chunk; p.rounds = geo.R;
+  p.rounds1 = (int)((geo.chunk - (int64_t)geo.R * FLOW_P * geo.T + geo.T - 1) / geo.T);
   size_t smem = sizeof(float) * ((size_t)h->lay.F * (h->lay.C == 2 ? FlowPack<2>::flow_stride(h->lay.m) : FlowPack<3>::flow_stride(h->lay.m)) + 2 * h->lay.C);
   dim3 grid(geo.S, h->desc.n_objects);
   if (h->lay.C == 2) {
@@ -930,7 +1017,8 @@ int flow_inverse(const awb_prior* h, const float* params, const awb_grid_spec* g
 // shared memory of k_flow_bwd without / with the running gradient of the CTA's pixel range
 static size_t flow_bwd_smem_base(const awb_prior* h) {
   const int C = h->lay.C;
-  return sizeof(float) * ((size_t)h->lay.F * (C == 2 ? FlowBwdPack<2>::flow_stride() : FlowBwdPack<3>::flow_stride()) + 16 * 128 + 128 + 16 * 16);
+  return sizeof(float) * ((size_t)h->lay.F * (C == 2 ? FlowBwdPack<2>::flow_stride() : FlowBwdPack<3>::flow_stride()) + 16 * 128 + 128 + 16 * 16 +
+                          2 * (size_t)FLOW_PB * flow_save_floats(C) * FLOW_BWD_T);
 }
 bool flow_bwd_dz_in_smem(const awb_prior* h, int64_t N) {
   const int C = h->lay.C;
