@@ -346,7 +346,8 @@ int awb_prior_fit_step(awb_handle h, float* params, void* opt_state, const awb_g
       // deformed coordinates X, the fused kernel returns d loss / d X, the flow backward consumes it.
       rc = any_flow_forward(h, params, g, w, nullptr, st);
       if (rc) return rc;
-      rc = tc_fit_forward_backward(h, params, g, target, loss, nullptr, 1, w, &n_part, st, false, w.X, w.dX);
+      rc = tc_fit_forward_backward(h, params, g, target, loss, nullptr, 1, w, &n_part, st,
+                                   (flags & AWB_FIT_REUSE_PACKED) != 0 && hy->active_groups == 0, w.X, w.dX);
       if (rc) return rc;
       rc = any_flow_backward(h, params, g, w, st);
       if (rc) return rc;

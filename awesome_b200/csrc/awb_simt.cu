@@ -562,6 +562,8 @@ struct OptA {
   awb_opt_hyper hy;
   float* loss_out;
   uint8_t* img; int64_t img_stride, vec_off; const int32_t* aug2img;
+  // flow priors: blocks nb_aug .. gridDim.x - 1 own 128 consecutive flow / linear parameters each (state_dict order)
+  const float* fpart; int64_t sFSplit, off_flow, PF; int SF, nb_aug;
 };
 
 __global__ void __launch_bounds__(256) k_reduce_opt_aug(OptA a, int n_groups) {
@@ -582,12 +584,23 @@ __global__ void __launch_bounds__(256) k_reduce_opt_aug(OptA a, int n_groups) {
     if (g == 0) s_bc2s = (float)sqrt(1.0 - pow((double)a.hy.beta2, (double)step1));
   }
   const int t = threadIdx.x;
+  const bool flow_blk = (int)blockIdx.x >= a.nb_aug && a.nb_aug > 0;
+  const int64_t fj0 = flow_blk ? ((int64_t)blockIdx.x - a.nb_aug) * 128 : 0;     // first flow / linear parameter of the block
   const int64_t aug = g0 + t;
   int64_t gi = -1;
   int grp = 0, e = -1;
   bool do_clamp = false;
   float p = 0.f, m = 0.f, v = 0.f;
-  if (t < 128 && aug < a.G) {
+  if (flow_blk) {
+    if (t < 128 && fj0 + t < a.PF) {
+      const int64_t i = a.off_flow + fj0 + t;
+      grp = a.group[i];
+      if (!(a.hy.active_groups && !((a.hy.active_groups >> grp) & 1))) {
+        gi = (int64_t)o * a.P + i;
+        p = a.params[gi]; m = a.m[gi]; v = a.v[gi];
+      }
+    }
+  } else if (t < 128 && aug < a.G) {
     const int32_t li = a.imap[aug];
     if (li >= 0) {
       const int64_t i = a.off_icnn + li;
@@ -607,7 +620,21 @@ __global__ void __launch_bounds__(256) k_reduce_opt_aug(OptA a, int n_groups) {
   float lsum = 0.f;
   if (w == 0)
     for (int s = lane; s < a.S; s += 32) lsum += __ldcg(a.lossp + s * a.O + o);
-  {
+  if (flow_blk) {
+    // flow / linear partials [SF][O][PF]: lane owns columns lane + 32 k of the block (rows need not be 16-byte aligned)
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* src = a.fpart + (int64_t)o * a.PF + fj0;
+    const int s0 = (a.SF * w) >> 3, s1 = (a.SF * (w + 1)) >> 3;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (fj0 + lane + 32 * k < a.PF) {
+#pragma unroll 4
+        for (int sb = s0; sb < s1; sb++) acc[k] += __ldcg(src + (int64_t)sb * a.sFSplit + lane + 32 * k);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) reinterpret_cast<float*>(&s_part[w][0])[lane + 32 * k] = acc[k];
+  } else {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (g0 + 4 * lane < a.G) {
       const float4* src = reinterpret_cast<const float4*>(a.part + (int64_t)o * a.G + g0) + lane;
@@ -644,7 +671,7 @@ __global__ void __launch_bounds__(256) k_reduce_opt_aug(OptA a, int n_groups) {
       if (a.img) {   // keep the tensor path's fp16 weight image in step
         uint8_t* base = a.img + (int64_t)o * a.img_stride;
         if (e >= 0) reinterpret_cast<__half*>(base)[e] = __float2half_rn(p);
-        if (aug >= a.aug_out) {
+        if (!flow_blk && aug >= a.aug_out) {
           const int k = (int)(aug - a.aug_out);
           reinterpret_cast<float*>(base + a.vec_off)[k] = p;
           reinterpret_cast<__half*>(base + a.vec_off + 4 * 144)[k] = __float2half_rn(p);
@@ -901,7 +928,10 @@ int simt_reduce_opt(const awb_prior* h, float* params, void* opt_state, const aw
   a.map = h->d_map; a.clamp = h->d_clamp; a.group = h->d_group;
   a.P = L.P; a.off_icnn = L.off_icnn; a.P_icnn = L.P_icnn; a.off_flow = L.off_flow; a.G = L.G;
   a.O = O; a.hy = *hy; a.loss_out = loss_out;
-  if (h->desc.kind == AWB_KIND_ICNN) {
+  // augmented-space kernel (programmatic dependent launch, fp16 weight image kept in step): plain ICNN priors, and flow
+  // priors whose optimizer owns every group (the flow / linear parameters then ride in extra blocks of the same launch)
+  const bool flow_aug = has_flow(h) && hy->active_groups == 0;
+  if (h->desc.kind == AWB_KIND_ICNN || flow_aug) {
     OptA b = {};
     b.params = params; b.m = a.m; b.v = a.v; b.scal = a.scal;
     b.part = a.part; b.sSplit = a.sSplit; b.S = a.S; b.lossp = a.lossp;
@@ -911,8 +941,12 @@ int simt_reduce_opt(const awb_prior* h, float* params, void* opt_state, const aw
     if (ws.tc && h->d_aug2img) {
       b.img = (uint8_t*)ws.tc; b.img_stride = tc_image_bytes(L.L); b.vec_off = tc_vec_offset_bytes(L.L); b.aug2img = h->d_aug2img;
     }
-    AWB_LAUNCH(PK_OPT, st, AWB_CUDA(launch_ex(k_reduce_opt_aug, dim3((unsigned)((L.G + 127) / 128), O), dim3(256), 0, st, true,
-                                              b, n_groups_of(h))));
+    unsigned nb = (unsigned)((L.G + 127) / 128);
+    if (flow_aug) {
+      b.fpart = a.fpart; b.sFSplit = a.sFSplit; b.off_flow = L.off_flow; b.PF = a.PF; b.SF = a.SF; b.nb_aug = (int)nb;
+      nb += (unsigned)((a.PF + 127) / 128);
+    }
+    AWB_LAUNCH(PK_OPT, st, AWB_CUDA(launch_ex(k_reduce_opt_aug, dim3(nb, O), dim3(256), 0, st, true, b, n_groups_of(h))));
   } else {
     AWB_LAUNCH(PK_OPT, st, k_reduce_opt<<<dim3((unsigned)((L.P + 31) / 32), O), 256, 0, st>>>(a, n_groups_of(h), 1));
   }
