@@ -11,6 +11,8 @@ from .optim import FusedAdam, FusedAdamax  # noqa: F401
 from .pretrain import (FitSchedule, FrameResult, fit_frames, fit_frames_grouped, fit_sequence, mask_iou,  # noqa: F401
                        noisy_unaries)
 from .prior_cache import DevicePriorCache, PriorManager  # noqa: F401
+from .sharded_fit import fit_sequence_sharded, plan_segments, segments_of_rank  # noqa: F401
+from . import synth  # noqa: F401
 from .joint import GradBucket, JointTrainer  # noqa: F401
 from . import image, measures  # noqa: F401
 from .model import (ConvexDiffeomorphismNet, ConvexNet, ConvexNextNet, MinMax, NoisyPathConnectedNet, NormNet, NumberBasedMultiPriorModule, PathConnectedNet,  # noqa: F401

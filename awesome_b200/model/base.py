@@ -39,10 +39,12 @@ class Affine(nn.Module):
 
 class _PriorFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, spec, grid_tensor, *params):
+    def forward(ctx, module, spec, needs_grad, grid_tensor, *params):
+        """``needs_grad`` is decided by the caller (grad mode is always off inside ``Function.forward`` and
+        ``ctx.needs_input_grad`` ignores ``torch.no_grad()``): a forward under ``no_grad`` takes the exact fp32 inference
+        path (mode 0) on the cached workspace, whatever ``requires_grad`` says."""
         prior = module._prior_for(params[0].device)
         arena = module._arena
-        needs_grad = any(ctx.needs_input_grad[2:])
         if needs_grad:
             ws = prior.new_workspace(spec.n_pixels, True, arena.device)   # private: several forwards may precede backward
         else:
@@ -51,15 +53,20 @@ class _PriorFunction(torch.autograd.Function):
         # with the upstream gradient.  Inference (no grad) always takes the exact fp32 path.
         mode = (3 if module.precision == "f16" else 1) if needs_grad else 0
         logits, _ = prior.forward(arena, spec, mode, ws)
-        ctx.module, ctx.spec, ctx.ws, ctx.prior = module, spec, ws, prior
+        ctx.module, ctx.spec, ctx.ws, ctx.prior = module, spec, (ws if needs_grad else None), prior
         ctx.shapes = [p.shape for p in params]
+        ctx.rows_input = grid_tensor is not None and grid_tensor.dim() == 2
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
         module, spec, prior = ctx.module, ctx.spec, ctx.prior
-        want_dgrid = ctx.needs_input_grad[2]
+        if ctx.ws is None:
+            raise RuntimeError("backward through an awesome_b200 prior needs a forward that ran with grad enabled")
+        want_dgrid = ctx.needs_input_grad[3]
         grads, dgrid = prior.backward(module._arena, spec, dlogits.contiguous().float(), ctx.ws, want_dgrid)
+        if dgrid is not None and ctx.rows_input:      # pixel rows [N,C] went in as [1,C,1,N]: hand their gradient back as [N,C]
+            dgrid = dgrid.reshape(dgrid.shape[1], -1).t().contiguous()
         ctx.ws = None
         outs, off = [], 0
         flat = grads.reshape(-1)
@@ -69,7 +76,7 @@ class _PriorFunction(torch.autograd.Function):
                 n *= s
             outs.append(flat[off:off + n].view(shp))
             off += n
-        return (None, None, dgrid) + tuple(outs)
+        return (None, None, None, dgrid) + tuple(outs)
 
 
 class ArenaPriorModule(nn.Module):
@@ -167,8 +174,10 @@ class ArenaPriorModule(nn.Module):
         self._ensure_flat()
         params = self._arena_params()
         self._prior_for(self._arena.device)       # raises loudly on a non-CUDA device
+        needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params)
+                                                  or (grid_tensor is not None and grid_tensor.requires_grad))
         with torch.cuda.device(self._arena.device):
-            return _PriorFunction.apply(self, spec, grid_tensor, *params)
+            return _PriorFunction.apply(self, spec, needs_grad, grid_tensor, *params)
 
     def _forward_any(self, x: torch.Tensor, n_channels: int) -> torch.Tensor:
         """Accepts ``[B,C,H,W]`` (-> ``[B,1,H,W]``), ``[C,H,W]`` (-> ``[1,H,W]``) or pixel rows ``[N,C]``

@@ -223,6 +223,17 @@ class PathConnectedNet(ArenaPriorModule):
     def enforce_convexity(self) -> None:
         super().enforce_convexity()
 
+    def make_fitter(self, grid, target, loss=None, optim=None, **kw):
+        """Fused fit loop on this prior; un-initialised ActNorms get their data-dependent init from ``grid`` first, as the
+        reference's first training forward would do (normflows ``ActNorm.forward``)."""
+        if isinstance(grid, torch.Tensor):
+            grid = GridSpecHost.from_tensor(grid)
+        self._ensure_flat()
+        r = self._rnvp
+        if not all(float(r.flows[2 * f + 1].data_dep_init_done) > 0 for f in range(r.n_flows)):
+            self.actnorm_init(grid, use_linear=True)
+        return super().make_fitter(grid, target, loss, optim, **kw)
+
     def get_deformation(self, x: torch.Tensor) -> torch.Tensor:
         """``path_connected_net.py:125-129``: 1x1 conv -> NormNet(flow).  ``[B,C,H,W] -> [B,C,H,W]``."""
         squeeze = x.dim() == 3

@@ -75,6 +75,7 @@ class FrameResult:
     steps: int = 0
     final_loss: float = float("nan")
     state: Optional[torch.Tensor] = None      # the fitted arena (device), one row
+    mask_fg: Optional[torch.Tensor] = None    # fitted foreground mask (bool, device, flat), when ``keep_masks``
 
 
 def _as_grid(grid, device) -> GridSpecHost:
@@ -96,7 +97,8 @@ def mask_iou(pred_prob: torch.Tensor, target_prob: torch.Tensor) -> float:
 
 def fit_frames(model, grids: Sequence, unaries: Sequence[torch.Tensor], schedule: Optional[FitSchedule] = None,
                on_frame: Optional[Callable[[FrameResult], None]] = None, frame_indices: Optional[Sequence[int]] = None,
-               warm_start_hook: Optional[Callable[[Any, torch.Tensor, Any], None]] = None) -> List[FrameResult]:
+               warm_start_hook: Optional[Callable[[Any, torch.Tensor, Any], None]] = None,
+               keep_masks: bool = False) -> List[FrameResult]:
     """Fit ``model`` (ConvexNextNet or PathConnectedNet drop-in) to every frame in turn.  ``grids[i]`` is a
     ``[1,C,H,W]`` tensor or ``GridSpecHost``; ``unaries[i]`` the frame's soft segmentation (any shape with H*W
     elements; convention fg = 0, bg = 1 like the reference).  The model ends holding the last proper state."""
@@ -156,6 +158,8 @@ def fit_frames(model, grids: Sequence, unaries: Sequence[torch.Tensor], schedule
             with torch.no_grad():
                 prob = torch.sigmoid(model(spec.materialize(getattr(model, "in_channels", getattr(model, "in_features", 2)), dev)))
             res.iou = mask_iou(prob.reshape(1, -1), un)
+            if keep_masks:
+                res.mask_fg = (prob.reshape(-1) <= 0.5)
             proper = res.iou >= s.proper_prior_fit_threshold
             if not proper and res.retries < s.proper_prior_fit_retrys:
                 logging.info("Prior fit not proper on image index: %s. Retrying. Metric: %s", idx, res.iou)
@@ -177,7 +181,7 @@ def fit_frames(model, grids: Sequence, unaries: Sequence[torch.Tensor], schedule
 
 def fit_frames_grouped(multi, grid, unaries: Sequence[torch.Tensor], schedule: Optional[FitSchedule] = None,
                        on_frame: Optional[Callable[[FrameResult], None]] = None,
-                       frame_indices: Optional[Sequence[int]] = None) -> List[FrameResult]:
+                       frame_indices: Optional[Sequence[int]] = None, keep_masks: bool = False) -> List[FrameResult]:
     """``fit_frames`` for frames that are fitted WITHOUT chaining inside a group: ``multi`` (a
     ``NumberBasedMultiPriorModule`` of G equal priors) takes G frames per fused launch, one prior per frame -- the
     execution that ``bench.py`` measures (G = 4: one wave of 37 persistent CTAs per frame).
@@ -214,7 +218,13 @@ def fit_frames_grouped(multi, grid, unaries: Sequence[torch.Tensor], schedule: O
                 on_frame(results[-1])
         else:
             todo.append((idx, un))
-    fitter: Optional[PriorFitter] = None
+    # the fitter (workspace, optimizer state, captured CUDA graphs) is kept on the container between calls: a rank that
+    # fits one segment of the sequence after the other pays for the capture once
+    fkey = tuple(getattr(spec, a, None) for a in ("mode", "B", "H", "W", "t0", "t_step")) + (
+        id(getattr(spec, "grid", None)), big.data_ptr(), s.optimizer, s.lr, s.plateau, s.steps_per_graph, s.criterion.kind,
+        s.criterion.mode)
+    cached = getattr(multi, "_grouped_fitter", None)
+    fitter: Optional[PriorFitter] = cached[1] if cached is not None and cached[0] == fkey else None
     C_in = getattr(multi.priors[0], "in_channels", getattr(multi.priors[0], "in_features", 2))
     for g0 in range(0, len(todo), G):
         chunk = todo[g0:g0 + G]
@@ -226,6 +236,7 @@ def fit_frames_grouped(multi, grid, unaries: Sequence[torch.Tensor], schedule: O
             big.copy_((previous if warm else entry).unsqueeze(0).expand_as(big))
         if fitter is None:
             fitter = multi.make_fitter(spec, tg, s.criterion, s.optim(False), steps_per_graph=s.steps_per_graph)
+            multi._grouped_fitter = (fkey, fitter)
         else:
             fitter.set_target(tg, s.criterion)
         epochs = s.reuse_state_epochs if warm else s.num_epochs
@@ -241,6 +252,8 @@ def fit_frames_grouped(multi, grid, unaries: Sequence[torch.Tensor], schedule: O
             inter, pf, tf = int(cnts[k, 0]), int(cnts[k, 1]), int(cnts[k, 2])
             res.iou = 0.0 if tf == 0 else inter / float(pf + tf - inter)
             res.proper_fit = res.iou >= s.proper_prior_fit_threshold
+            if keep_masks:
+                res.mask_fg = logits.reshape(G, -1)[k] <= 0
             if not res.proper_fit and s.proper_prior_fit_retrys > 0:
                 # the reference's retry: reset_parameters, full schedule -- per frame, through the one-frame path
                 logging.info("Prior fit not proper on image index: %s. Retrying. Metric: %s", idx, res.iou)
@@ -250,10 +263,12 @@ def fit_frames_grouped(multi, grid, unaries: Sequence[torch.Tensor], schedule: O
                 import dataclasses
                 again = fit_frames(pk, [spec], [un], dataclasses.replace(s, reuse_state=False,
                                                                          proper_prior_fit_retrys=s.proper_prior_fit_retrys - 1),
-                                   frame_indices=[idx])[0]
+                                   frame_indices=[idx], keep_masks=keep_masks)[0]
                 multi._arena_all = None                       # the one-frame path may have re-pointed the prior's arena
                 big = multi._group_arena()
                 fitter = None
+                multi._grouped_fitter = None
+                res.mask_fg = again.mask_fg
                 res.retries = 1 + again.retries
                 res.steps += again.steps
                 res.iou, res.proper_fit, res.final_loss = again.iou, again.proper_fit, again.final_loss

@@ -44,13 +44,22 @@ WORKLOAD = "convexity ICNN prior fit per frame, synthetic FBMS-shaped 640x480 fr
 
 def synth_unaries(seed: int, t: float = 0.0):
     """Soft UNet-like unaries in (0,1): blob on a Lissajous path with breathing axes."""
-    import torch
-    g = torch.Generator().manual_seed(seed)
-    yy, xx = torch.meshgrid(torch.linspace(0, 1, H), torch.linspace(0, 1, W), indexing="ij")
-    cx, cy = 0.5 + 0.2 * torch.sin(torch.tensor(2.0 * t)), 0.5 + 0.15 * torch.sin(torch.tensor(3.0 * t + 0.5))
-    rx, ry = 0.22 * (1 + 0.2 * torch.sin(torch.tensor(5.0 * t))), 0.28 * (1 + 0.2 * torch.cos(torch.tensor(4.0 * t)))
-    sdf = torch.sqrt(((xx - cx) / rx) ** 2 + ((yy - cy) / ry) ** 2) - 1
-    return torch.sigmoid((sdf + 0.05 * torch.randn(H, W, generator=g)) / 0.08).float()
+    from awesome_b200 import synth
+    return synth.c2_unaries(H, W, seed=seed, t=t)
+
+
+def workload_config(G: int, precision: str) -> dict:
+    """The ``config`` object of the JSON line -- ONE definition for both arms (``--impl ours`` and ``--impl reference``
+    describe the same workload; what differs between them is reported outside ``config``)."""
+    n_groups = (POOL_FRAMES + G - 1) // G
+    return {"workload": WORKLOAD, "prior": f"ConvexNextNet(h={HID},L={LAYERS},C={CH})",
+            "loss": "MSE(sigmoid(y), unaries)", "optimizer": "Adam lr=1e-3 + enforce_convexity",
+            "frame": f"{W}x{H}", "pixels_per_frame": N_PIX, "frames_per_step_per_gpu": G,
+            "pixels_per_step_per_gpu": G * N_PIX, "precision": precision,
+            "grouping": f"{G} independent frames of the rank's share of the sequence per fused launch "
+                        "(one prior, optimizer state and loss per frame)",
+            "l2": f"each step reads its unaries from a rotating pool of {n_groups * G} distinct frames "
+                  f"({n_groups * G * N_PIX * 4 / 1e6:.0f} MB > 126 MB L2); no explicit flush"}
 
 
 _JSON_OUT = None
@@ -105,7 +114,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
@@ -116,6 +125,10 @@ class ClockSampler:
                         continue
                     sm.append(float(f[1]))
                     mx.append(float(f[2]))
+                    try:
+                        pw.append(float(f[3]))
+                    except ValueError:
+                        pass
                 except ValueError:
                     continue
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
@@ -125,18 +138,54 @@ class ClockSampler:
         except Exception:
             pass
         if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w=statistics.median(pw) if pw else None)
         return out
 
 
-def cpu_oracle_throughput(steps: int, warmup: int, budget_s: float = 60.0):
-    """The reference's CPU implementation of one fit step, restated by the oracle port (same ATen ops as the
-    reference modules), on all host cores.  Each step is a bounded sample of the workload: a horizontal band
-    of the 640x480 frame sized so that warmup+steps finish within ``budget_s``."""
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def _reference_fit_step():
+    """One fit step of the BASELINE configs[1] workload with the UNMODIFIED reference package installed in
+    ``baseline/_ref`` (``baseline/install_reference.py``): ``awesome.model.convex_net.ConvexNextNet``,
+    ``UnariesWeightedLoss(SE("mean"))``, ``torch.optim.Adam`` and ``enforce_convexity`` exactly as the reference's per-frame
+    loop runs them (``awesome/model/path_connected_net.py:939-953``).  Returns (step(rows) -> loss, kind)."""
     import torch
+    if not os.path.isdir(os.path.join(REF_DIR, "awesome")) and os.path.isdir("/root/reference/awesome"):
+        import subprocess as sp                                     # build container: install it now
+        sp.run([sys.executable, os.path.join(ROOT, "baseline", "install_reference.py")], stdout=sp.DEVNULL, stderr=sp.DEVNULL)
+    if os.path.isdir(os.path.join(REF_DIR, "awesome")):
+        from oracle import ref_shim                                 # stubs for the non-numeric packages missing offline
+        ref_shim.REFERENCE_ROOT = REF_DIR
+        ref_shim.install()
+        from awesome.dataset.transformator import Transformator
+        from awesome.measures.se import SE
+        from awesome.measures.unaries_weighted_loss import UnariesWeightedLoss
+        from awesome.model.convex_net import ConvexNextNet
+        from awesome.run.runner import seed_all
+        seed_all(42)
+        model = ConvexNextNet(n_hidden=HID, in_features=CH, n_hidden_layers=LAYERS)
+        model.train()
+        x_full = Transformator.get_positional_matrices(W, H)[None]
+        un_full = synth_unaries(42)[None, None]
+        crit = UnariesWeightedLoss(SE("mean"))
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+
+        def step(n_rows: int) -> float:
+            h = n_rows // W                                         # a horizontal band of the frame (h == H: the full frame)
+            x, un = x_full[:, :, :h], un_full[:, :, :h]
+            opt.zero_grad()
+            loss = crit(torch.sigmoid(model(x)), un)
+            loss.backward()
+            opt.step()
+            model.enforce_convexity()
+            return float(loss.detach())
+        return step, "reference"
+    # no installed reference: the oracle port (same ATen op sequence)
     from oracle import prior_oracle as O
     torch.manual_seed(42)
-    lin = torch.nn.Linear  # reference initialisation order (ConvexNextNet.__init__)
+    lin = torch.nn.Linear
     p = {}
     l = lin(CH, HID); p["input.weight"], p["input.bias"] = l.weight.detach(), l.bias.detach()
     for i in range(LAYERS):
@@ -147,25 +196,39 @@ def cpu_oracle_throughput(steps: int, warmup: int, budget_s: float = 60.0):
     p = O.clone_params(p)
     rows_full = O.pixelize(O.grid_linspace(H, W)[None])
     un_full = synth_unaries(42).reshape(-1)
-    # calibrate on 1/16 of the frame
-    n_cal = N_PIX // 16
+
+    def step(n_rows: int) -> float:
+        O.fit_icnn(p, rows_full[:n_rows], un_full[:n_rows], steps=1, optimizer="adam", lr=1e-3)
+        return 0.0
+    return step, "port"
+
+
+def cpu_reference_throughput(steps: int, warmup: int, budget_s: float = 240.0):
+    """The reference's own CPU implementation of one fit step on ALL host cores (torchrun pins OMP_NUM_THREADS=1: reset).
+    Each step fits the FULL 640x480 frame; only when warmup+steps full-frame steps would not end within ``budget_s`` is the
+    sample cut to a horizontal band of the frame (and said so in ``sample``)."""
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    step, kind = _reference_fit_step()
     t0 = time.perf_counter()
-    O.fit_icnn(O.clone_params(p), rows_full[:n_cal], un_full[:n_cal], steps=1, optimizer="adam", lr=1e-3)
-    t_cal = time.perf_counter() - t0
-    per_px = t_cal / n_cal
+    step(N_PIX)                                                     # calibration = first warm-up step, full frame
+    t_full = time.perf_counter() - t0
     frac = 1.0
-    while frac > 1 / 64 and per_px * N_PIX * frac * (steps + warmup) > budget_s:
+    while frac > 1 / 64 and t_full * frac * (steps + warmup) > budget_s:
         frac /= 2
-    n = int(N_PIX * frac)
-    rows, un = rows_full[:n].contiguous(), un_full[:n].contiguous()
-    O.fit_icnn(p, rows, un, steps=max(1, warmup), optimizer="adam", lr=1e-3)
+    n = int(H * frac) * W
+    for _ in range(max(0, warmup - 1)):
+        step(n)
     t0 = time.perf_counter()
-    O.fit_icnn(p, rows, un, steps=steps, optimizer="adam", lr=1e-3)
+    for _ in range(steps):
+        step(n)
     dt = time.perf_counter() - t0
     cores = torch.get_num_threads()
-    sample = f"{steps} fit steps on the first {n} of {N_PIX} pixel rows of the frame ({frac:g} frame), torch CPU fp32, " \
-             f"{cores} threads (os.cpu_count()={os.cpu_count()})"
-    return n * steps / dt, dt / steps * 1e3, cores, sample
+    what = "the full 640x480 frame" if frac == 1.0 else f"the top {n} of {N_PIX} pixel rows of the frame ({frac:g} frame)"
+    impl = ("reference package (baseline/_ref): awesome.model.convex_net.ConvexNextNet + UnariesWeightedLoss(SE) + "
+            "torch.optim.Adam + enforce_convexity" if kind == "reference" else "oracle port of the reference's loop")
+    sample = f"{steps} fit steps on {what}, {impl}, torch CPU fp32, {cores} threads (os.cpu_count()={os.cpu_count()})"
+    return n * steps / dt, dt / steps * 1e3, cores, sample, kind
 
 
 def _time_fitter(fitter, steps: int) -> float:
@@ -179,6 +242,86 @@ def _time_fitter(fitter, steps: int) -> float:
     torch.cuda.synchronize()
     fitter.raise_if_nonfinite()
     return e0.elapsed_time(e1) / steps
+
+
+def sustained_leg(fitter, pool, dev, gpu_index: int, G: int, seconds: float = 10.0):
+    """The headline loop, unchanged, for >= ``seconds`` of device time: ms per step with the clocks settled, median SM
+    clock, power and clock-event reasons sampled over the whole region (nvidia-smi, 20 ms period)."""
+    import torch
+    fitter.set_target_pool(pool)
+    fitter.run(200, record=False)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); fitter.run(1000, record=False); e1.record()
+    torch.cuda.synchronize(dev)
+    n_steps = max(2000, int(seconds * 1e3 / (e0.elapsed_time(e1) / 1000.0)))
+    sampler = ClockSampler(gpu_index)
+    sampler.query_power = True
+    sampler.start()
+    time.sleep(0.3)
+    t0 = time.time()
+    e0.record()
+    done = 0
+    while done < n_steps:
+        k = min(2000, n_steps - done)
+        fitter.run(k, record=False)
+        done += k
+    e1.record()
+    torch.cuda.synchronize(dev)
+    t1 = time.time()
+    clk = sampler.stop(t0, t1)
+    ms = e0.elapsed_time(e1)
+    fitter.raise_if_nonfinite()
+    return {"seconds": ms * 1e-3, "steps": n_steps, "ms_per_step": ms / n_steps,
+            "pixel_samples_per_s": G * N_PIX * n_steps / (ms * 1e-3), "sm_mhz_median": clk["sm_mhz"],
+            "sm_max_mhz": clk["sm_max_mhz"], "power_w_median": clk.get("power_w"), "reasons": clk["reasons"],
+            "clock_samples": clk["samples"]}
+
+
+def frames_per_s_leg(A, dev, rank: int, world: int, G: int, precision: str, barrier, n_frames: int = 60, n_segments: int = 8):
+    """The second half of BASELINE's metric, MEASURED: wall-clock frames/s of fitting the whole synthetic 60-frame 640x480
+    sequence (configs[1]) with ``awesome_b200.fit_sequence_sharded`` -- 8 fixed segments over the ranks, 4000 cold / 400 warm
+    steps, G frames per fused launch, CUDA-graph step loops, no-foreground skip, IoU check + retry, every frame's unaries
+    copied from pinned host memory, masks / states / IoUs gathered on every rank at the end.  Time = barrier to barrier,
+    max over ranks.  ``digest`` hashes every fitted state: it is the same for any number of GPUs."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    from awesome_b200 import synth
+    segs = A.plan_segments(n_frames, n_segments)
+    mine = [i for si in A.segments_of_rank(len(segs), rank, world) for i in segs[si]]
+    host = {i: synth.c2_unaries(H, W, seed=42 + i, t=0.1 * i).pin_memory() for i in mine}     # outside the timed region
+    sched = A.FitSchedule(num_epochs=4000, reuse_state_epochs=400, optimizer="adam", plateau=False, lr=1e-3,
+                          steps_per_graph=50, proper_prior_fit_retrys=1)
+    grid = A.GridSpecHost("linspace", 1, H, W)
+    args = dict(n_hidden=HID, in_features=CH, n_hidden_layers=LAYERS, precision=precision)
+    # warm-up: library / graph-capture costs of a first call are not part of a sequence fit's steady state
+    A.fit_sequence_sharded(A.ConvexNextNet, args, grid, lambda i: host[mine[0]], G, A.FitSchedule(
+        num_epochs=100, reuse_state_epochs=50, optimizer="adam", plateau=False, lr=1e-3, steps_per_graph=50), n_segments=1,
+        group=G, rank=0, world=1, device=dev, gather=False, keep_states=False)
+    barrier()
+    t0 = time.perf_counter()
+    res = A.fit_sequence_sharded(A.ConvexNextNet, args, grid, lambda i: host[i], n_frames, sched, n_segments=n_segments,
+                                 group=G, rank=rank, world=world, device=dev, gather=True)
+    barrier()
+    wall = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([wall], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t[0])
+    h = hashlib.sha256()
+    for i in sorted(res):
+        if res[i]["state"] is not None:
+            h.update(res[i]["state"].numpy().tobytes())
+    fitted = [r for r in res.values() if not r["skipped"]]
+    return {"value": n_frames / wall, "unit": "frames/s", "measured": True, "frames": n_frames, "wall_s": wall,
+            "segments": n_segments, "frames_per_launch": G, "schedule": "4000 steps cold (first group of a segment) / 400 warm, Adam 1e-3",
+            "steps_total_per_rank_max": max(sum(4000 if k == 0 else 400 for k in range((len(sg) + G - 1) // G))
+                                            for sg in segs) * len(A.segments_of_rank(len(segs), 0, world)),
+            "mean_iou": sum(r["iou"] for r in fitted) / max(1, len(fitted)), "min_iou": min(r["iou"] for r in fitted),
+            "proper_fits": sum(1 for r in fitted if r["proper_fit"]), "retries": sum(r["retries"] for r in fitted),
+            "skipped": sum(1 for r in res.values() if r["skipped"]), "digest": h.hexdigest()[:16],
+            "includes": "H2D of every frame's unaries, skip check, fit, IoU check / retry, mask packing, D2H + gather of results"}
 
 
 def secondary_workloads(A, dev, unaries640):
@@ -308,18 +451,17 @@ def eager_gpu_throughput(dev, steps: int = 10):
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
-    import torch
-    torch.set_num_threads(os.cpu_count() or 1)      # torchrun pins OMP_NUM_THREADS=1: the CPU arm uses every host core
-    thr, ms, cores, sample = cpu_oracle_throughput(args.steps, args.warmup, budget_s=120.0)
+    thr, ms, cores, sample, kind = cpu_reference_throughput(args.steps, max(1, args.warmup), budget_s=240.0)
+    G = max(1, args.frames_per_step)
     line = {
         "impl": "reference", "metric": "prior-fit pixel-samples/sec (fwd+bwd+step)", "value": thr,
-        "unit": "pixel-samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "unit": "pixel-samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": max(1, args.warmup),
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "prior": f"ConvexNextNet(h={HID},L={LAYERS},C={CH})",
-                                        "loss": "MSE(sigmoid(y), unaries)", "optimizer": "Adam lr=1e-3"},
-        "cpu_baseline": {"value": thr, "unit": "pixel-samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "data": "synthetic", "config": workload_config(G, args.precision),
+        "cpu_baseline": {"value": thr, "unit": "pixel-samples/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": thr, "unit": "pixel-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "one CPU process on rank 0 (the reference fits one frame at a time); value does not grow with --gpus",
     }
     emit(line)
 
@@ -335,6 +477,9 @@ def main():
                     help="independent frames of the rank's share of the sequence fitted together per fused launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short runs of BASELINE configs 0, 2, 3")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 10 s leg behind roofline.sustained")
+    ap.add_argument("--no-frames", action="store_true", help="skip the measured frames/s leg (60-frame sharded sequence fit)")
+    ap.add_argument("--sustained-seconds", type=float, default=10.0)
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON: everything any library prints to file descriptor 1 (NCCL's version
     # banner, warnings of child processes) is sent to stderr, and the JSON line is written to the saved descriptor.
@@ -363,7 +508,7 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("AWB_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # NCCL_DEBUG is left to the caller (stdout carries only the JSON line either way: fd 1 is redirected above)
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     sampler = ClockSampler(local_rank)
@@ -431,12 +576,26 @@ def main():
         raise SystemExit("e2e: non-finite loss read back from the host-frame fit")
     fitter.raise_if_nonfinite()
 
+    # ---- frames/s over the sharded 60-frame sequence, measured (every rank takes part)
+    frames_leg = None
+    if not args.no_frames:
+        fitter.set_target_pool(None)
+        frames_leg = frames_per_s_leg(A, dev, rank, world, G, args.precision, barrier)
+
+    # ---- the same loop for >= 10 s: earns (or not) the sustained-clock reading of the roofline (N = 1 only)
+    sustained = None
+    if rank == 0 and world == 1 and not args.no_sustained:
+        sustained = sustained_leg(fitter, pool, dev, local_rank, G, seconds=args.sustained_seconds)
+        fitter.set_target_pool(None)
+
     # ---- the other BASELINE configs, briefly (N = 1 only; device-timed, not part of `value`)
     secondary = None
     if rank == 0 and world == 1 and not args.no_secondary:
         secondary = secondary_workloads(A, dev, unaries[0])
 
-    # ---- roofline of the dominant kernel: hidden-layer contraction launches, timed live with CUDA events
+    # ---- per-kernel timing of the step, live with CUDA events on the launch stream (profile mode brackets every launch
+    # with events, which removes the programmatic-dependent-launch overlap: used for SHARES, not for the roofline)
+    fitter.set_target_pool(pool)
     n_cls = lib.awb_profile_classes()
     lib.awb_profile_enable(1)
     fitter.run(6, record=False)
@@ -462,58 +621,81 @@ def main():
         units = world * G * N_PIX * args.steps
         value = units / (ms_total * 1e-3)
         e2e_val = units / (t_e2e * 1e-3)
+        ms_step = ms_total / args.steps
+        burst, sust = pk["bf16_tflops"], pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
         if args.precision == "f16" and "tc_fused" in per_class:
             dom, dom_flop = "tc_fused", FLOP_PER_PX_STEP * N_PIX * G
-            peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
-            note = "fused fit kernel: all layer contractions of one step; peak = sustained cuBLAS bf16"
+            # The fused kernel IS the step (one launch per step; the optimizer kernel overlaps its tail through programmatic
+            # dependent launch), and a kernel cannot take longer than the step that contains it: the launch duration used
+            # for `achieved` is the device-timed step.  The timed region is short (K steps of ~0.36 ms), so the applicable
+            # peak is the BURST figure; `sustained` below repeats the measurement over >= 10 s against the sustained one.
+            ms_launch = ms_step
+            note = ("fused fit kernel = all layer contractions of one step; achieved = algorithmic FLOP per step / device-timed "
+                    "ms_per_step; peak = measured cuBLAS bf16 burst (short timed region)")
         else:
             gemm = [k for k in ("gemm_fwd", "gemm_wgrad", "gemm_dgrad") if k in per_class]
             dom = max(gemm, key=lambda k: per_class[k]["ms_per_step"])
             dom_flop = GEMM_FLOP_PER_PX_LAUNCH * N_PIX * G
-            peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
-            note = ("fp32 CUDA-core contraction (exact-parity path); reported against the sustained cuBLAS bf16 "
-                    "tensor peak the north star names")
+            ms_launch = per_class[dom]["ms_per_launch"]
+            note = ("fp32 CUDA-core contraction (exact-parity path); reported against the cuBLAS bf16 tensor peak the north "
+                    "star names")
         traffic = None
         tp = os.path.join(ROOT, "profiles", "r1_f16_tc_v12_traffic.json")
         if dom == "tc_fused" and os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")      # from the committed ncu --set full capture
-        ach = dom_flop / (per_class[dom]["ms_per_launch"] * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": ach / peak_tf, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
-                    "algorithmic_flop_per_launch": dom_flop, "peak_source": pk_src,
-                    "ms_per_launch": per_class[dom]["ms_per_launch"],
-                    "share_of_step": per_class[dom]["ms_per_step"] / step_ms_prof,
-                    "whole_step_tflops": FLOP_PER_PX_STEP * N_PIX * G / (ms_total / args.steps * 1e-3) / 1e12,
+        ach = dom_flop / (ms_launch * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": burst, "unit": "TFLOP/s",
+                    "frac": ach / burst, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
+                    "peaks": {"bf16_tflops_burst": burst, "bf16_tflops_sustained": sust, "source": pk_src},
+                    "frac_of_burst": ach / burst, "frac_of_sustained": ach / sust,
+                    "algorithmic_flop_per_launch": dom_flop, "ms_per_launch": ms_launch,
+                    "ms_per_launch_event_bracketed": per_class[dom]["ms_per_launch"],
+                    "share_of_step_event_bracketed": per_class[dom]["ms_per_step"] / step_ms_prof,
                     "note": note, "per_class_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in per_class.items()}}
+        if sustained is not None:
+            roofline["sustained"] = {
+                **sustained, "achieved": FLOP_PER_PX_STEP * N_PIX * G / (sustained["ms_per_step"] * 1e-3) / 1e12,
+                "peak": sust, "frac": FLOP_PER_PX_STEP * N_PIX * G / (sustained["ms_per_step"] * 1e-3) / 1e12 / sust}
+        # HBM-bound kernels of the step (north star item 4): the optimizer pass
+        roofline_hbm = None
+        if "reduce_opt" in per_class:
+            P_prior = int(sum(p.numel() for p in model.priors[0].parameters()))
+            n_part = min(148 // G if G <= 148 else 1, (N_PIX + 127) // 128) if args.precision == "f16" else min(148, (N_PIX + 255) // 256)
+            G_aug = 4 * HID + LAYERS * HID * 136 + 136
+            alg = 28 * P_prior * G + (2 * P_prior * G if args.precision == "f16" else 0)      # p, m, v read + written, g read (+ fp16 image)
+            moved = alg + 4 * n_part * G * G_aug                                                  # + the per-CTA gradient partials it reduces
+            us = per_class["reduce_opt"]["ms_per_launch"] * 1e3
+            roofline_hbm = {"kernel": "k_reduce_opt_aug (cross-CTA gradient reduction + Adam + clamp + fp16 image)",
+                            "bound": "hbm", "unit": "GB/s", "peak": pk["hbm_gbs"], "us_per_launch": us,
+                            "algorithmic_bytes_per_launch": alg, "achieved": alg / us / 1e3, "frac": alg / us / 1e3 / pk["hbm_gbs"],
+                            "bytes_moved_per_launch": moved, "moved_GBps": moved / us / 1e3,
+                            "moved_frac_of_peak": moved / us / 1e3 / pk["hbm_gbs"], "partials_per_object": n_part,
+                            "share_of_step": per_class["reduce_opt"]["ms_per_step"] / step_ms_prof,
+                            "note": "latency bound: 28 B/parameter of optimizer traffic (+ the L2-resident gradient partials); "
+                                    "runs in the shadow of the next fit kernel's prologue (PDL), < 5 % of the step"}
         cpu, eager = None, None
         if not args.no_cpu_baseline:
             try:
                 eager = eager_gpu_throughput(dev)
             except Exception as e:       # a baseline leg must never take the bench line down
                 eager = {"unavailable": repr(e)[:200]}
-            thr, ms_cpu, cores, sample = cpu_oracle_throughput(steps=8, warmup=1, budget_s=20.0)
-            cpu = {"value": thr, "unit": "pixel-samples/s", "cores": cores, "kind": "port", "sample": sample,
+            thr, ms_cpu, cores, sample, kind = cpu_reference_throughput(steps=8, warmup=1, budget_s=30.0)
+            cpu = {"value": thr, "unit": "pixel-samples/s", "cores": cores, "kind": kind, "sample": sample,
                    "ms_per_step_sample": ms_cpu}
         line = {
             "metric": "prior-fit pixel-samples/sec (fwd+bwd+step)", "value": value, "unit": "pixel-samples/s",
-            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_total / args.steps,
+            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == "fp32" else "f16 operands / f32 accumulate", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "prior": f"ConvexNextNet(h={HID},L={LAYERS},C={CH})",
-                       "loss": "MSE(sigmoid(y), unaries)", "optimizer": "Adam lr=1e-3 + enforce_convexity",
-                       "frames_per_step_per_gpu": G, "pixels_per_step_per_gpu": G * N_PIX, "precision": args.precision,
-                       "grouping": f"{G} independent frames of the rank's share of the sequence per fused launch "
-                                   "(one prior, optimizer state and loss per frame)",
-                       "l2": f"each step reads its unaries from a rotating pool of {n_groups * G} distinct frames "
-                             f"({n_groups * G * N_PIX * 4 / 1e6:.0f} MB > 126 MB L2); no explicit flush",
-                       "frames_per_s_at_400_steps_per_frame": value / N_PIX / 400.0,
-                       "frames_per_s_at_4000_steps_per_frame": value / N_PIX / 4000.0},
+            "config": workload_config(G, args.precision),
             "e2e": {"value": e2e_val, "unit": "pixel-samples/s", "h2d_bytes_per_step": 4 * N_PIX * G,
                     "d2h_bytes_per_step": 4 * G, "ms_per_step": t_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "samples": clocks["samples"]},
+            "frames_per_s": frames_leg,
             "roofline": roofline,
+            "roofline_hbm": roofline_hbm,
             "cpu_baseline": cpu,
             "eager_gpu_baseline": eager,
             "secondary": secondary,

@@ -365,3 +365,46 @@ def test_grouped_frames_one_wave_at_frame_size_matches_single_frame_fits(A):
     for p, st in zip(multi.priors, grouped):
         for name, b in p.state_dict().items():
             assert torch.equal(st[name], b), name
+
+
+def test_no_grad_forward_is_exact_fp32_on_cached_workspace(A):
+    """A forward under ``torch.no_grad()`` of a module whose parameters require grad takes the inference path: exact fp32
+    logits (also for precision="f16") on the cached workspace, no training-sized allocation."""
+    torch.manual_seed(0)
+    m32 = A.ConvexNextNet(n_hidden_layers=2).to(DEV)
+    m16 = A.ConvexNextNet(n_hidden_layers=2, precision="f16")
+    m16.load_state_dict(m32.state_dict())
+    m16 = m16.to(DEV)
+    x = A.GridSpecHost("linspace", 1, 40, 56).materialize(2, DEV)
+    with torch.no_grad():
+        y32, y16 = m32(x), m16(x)
+        ws = m16._prior._ws_cache
+        assert len(ws) == 1 and list(ws.keys())[0][1] is False          # inference workspace, cached
+        y16b = m16(x)
+        assert len(m16._prior._ws_cache) == 1
+    assert torch.equal(y32, y16) and torch.equal(y16, y16b)               # bit-identical: same fp32 kernels
+    assert not y16.requires_grad
+    y_train = m16(x)                                                     # grad enabled: tensor-path logits, differentiable
+    assert y_train.requires_grad
+    assert float((y_train - y32).abs().max()) < 2e-2
+
+
+def test_pixel_row_input_gradient_shape_and_values(A):
+    """``forward([N,C])`` with ``requires_grad`` rows: the input gradient comes back as ``[N,C]`` and equals the
+    ``[B,C,H,W]`` path's (``model_input_requires_grad`` configs)."""
+    torch.manual_seed(1)
+    m = A.ConvexNextNet(n_hidden_layers=2).to(DEV)
+    H, W = 12, 20
+    x4 = A.GridSpecHost("linspace", 1, H, W).materialize(2, DEV).clone().requires_grad_(True)
+    rows = x4.detach().permute(0, 2, 3, 1).reshape(-1, 2).clone().requires_grad_(True)
+    wgt = torch.linspace(-1, 1, H * W, device=DEV)
+    (m(x4).reshape(-1) * wgt).sum().backward()
+    y = m(rows)
+    assert y.shape == (H * W, 1)
+    (y.reshape(-1) * wgt).sum().backward()
+    assert rows.grad.shape == rows.shape
+    torch.testing.assert_close(rows.grad, x4.grad.permute(0, 2, 3, 1).reshape(-1, 2), rtol=1e-5, atol=1e-7)
+    p = O.clone_params({k: v.detach().cpu() for k, v in m.state_dict().items()})
+    r = rows.detach().cpu().clone().requires_grad_(True)
+    (O.icnn_forward(p, r).reshape(-1) * wgt.cpu()).sum().backward()
+    torch.testing.assert_close(rows.grad.cpu(), r.grad, rtol=1e-4, atol=1e-6)

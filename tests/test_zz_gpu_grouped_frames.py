@@ -57,3 +57,35 @@ def test_fit_frames_grouped_matches_independent_frame_fits(A):
     res2 = A.fit_frames_grouped(multi, grid, frames[2:4], hard)
     assert [r.retries for r in res2] == [1, 1] and not any(r.proper_fit for r in res2)
     assert [r.steps for r in res2] == [120, 120]
+
+
+def test_sharded_sequence_fit_is_independent_of_the_number_of_ranks(A):
+    """fit_sequence_sharded: the segmentation is fixed, so the per-frame results of a 1-rank run and of a 2-rank run
+    (simulated: rank 0 and rank 1 one after the other, results merged) are bit-identical -- states, masks, IoUs."""
+    from awesome_b200 import synth
+    from awesome_b200.sharding import merge_by_unit
+    T, H, W = 10, 60, 80
+    frames = [blob(H, W, cx=0.40 + 0.02 * i, cy=0.5, rx=0.2, ry=0.25) for i in range(T)]
+    frames[6] = torch.ones(H, W)                      # one frame without foreground -> skipped
+    grid = A.GridSpecHost("linspace", 1, H, W)
+    sched = A.FitSchedule(num_epochs=300, reuse_state_epochs=80, optimizer="adam", plateau=False, lr=2e-3, steps_per_graph=20)
+    args = dict(n_hidden_layers=2, precision="f16")
+    kw = dict(n_segments=4, group=2, device=DEV, seed=7)
+    one = A.fit_sequence_sharded(A.ConvexNextNet, args, grid, frames, T, sched, rank=0, world=1, **kw)
+    two = merge_by_unit([A.fit_sequence_sharded(A.ConvexNextNet, args, grid, frames, T, sched, rank=r, world=2, gather=False, **kw)
+                         for r in range(2)])
+    assert sorted(one) == sorted(two) == list(range(T))
+    assert A.plan_segments(T, 4) == [[0, 1, 2], [3, 4, 5], [6, 7], [8, 9]]
+    for i in range(T):
+        a, b = one[i], two[i]
+        assert a["skipped"] == b["skipped"] == (i == 6)
+        assert a["segment"] == b["segment"] and b["rank"] == a["segment"] % 2
+        if a["skipped"]:
+            continue
+        assert torch.equal(a["state"], b["state"]) and torch.equal(a["mask_fg_packed"], b["mask_fg_packed"]), i
+        assert a["iou"] == b["iou"] and a["steps"] == b["steps"]
+        assert a["proper_fit"] and a["iou"] > 0.9
+        fg = synth.unpack_mask(a["mask_fg_packed"], H, W)
+        assert abs(synth.fg_iou(fg, frames[i] < 0.5) - a["iou"]) < 2e-3
+    # first group of a segment is cold, the following groups warm
+    assert [one[i]["steps"] for i in (0, 1, 2, 3, 7, 8, 9)] == [300, 300, 80, 300, 300, 300, 300]
