@@ -145,6 +145,60 @@ class _FusedBase(torch.optim.Optimizer):
         self._plan = None
         self._inner = None
 
+    # ---- checkpointing: the agent saves ``optimizer.state_dict()`` (torch_agent.py:1009) and, with keep_device=False,
+    # frees and recreates the optimizer around every best-model save (``_free_optimizer`` / ``_get_optimizer`` +
+    # ``load_state_dict``, torch_agent.py:356, 808, 836).  The moments live outside ``self.state`` (stock optimizer of the
+    # non-arena parameters, native blob per arena module), so both are carried in an extra key.
+    def _flat_index(self) -> Dict[int, int]:
+        out, i = {}, 0
+        for g in self.param_groups:
+            for p in g["params"]:
+                out[id(p)] = i
+                i += 1
+        return out
+
+    def state_dict(self):
+        sd = super().state_dict()
+        extra = {"kind": self._kind, "inner": None, "native": []}
+        if self._plan is not None:
+            idx = self._flat_index()
+            if self._inner is not None:
+                import copy
+                extra["inner"] = copy.deepcopy(self._inner.state_dict())     # a snapshot, like the native blob below
+            for ent in self._plan["native"]:
+                first = ent["module"]._arena_params()[0]
+                blob = ent["state"].detach().cpu().clone() if ent["state"] is not None else None
+                extra["native"].append({"first_param": idx[id(first)], "n_params": len(ent["module"]._arena_params()),
+                                        "blob": blob})
+        sd["awb_fused"] = extra
+        return sd
+
+    def load_state_dict(self, state_dict):
+        extra = state_dict.get("awb_fused") if isinstance(state_dict, dict) else None
+        super().load_state_dict({k: v for k, v in state_dict.items() if k != "awb_fused"})
+        self._plan, self._inner = None, None
+        if not extra:
+            return
+        if extra.get("kind") != self._kind:
+            raise ValueError(f"optimizer state of kind {extra.get('kind')!r} loaded into {self._kind!r}")
+        self._build_plan()
+        if extra.get("inner") is not None:
+            if self._inner is None:
+                raise ValueError("saved state holds non-arena parameters, this optimizer has none")
+            self._inner.load_state_dict(extra["inner"])
+        idx = self._flat_index()
+        saved = {e["first_param"]: e for e in extra.get("native", [])}
+        for ent in self._plan["native"]:
+            m = ent["module"]
+            e = saved.get(idx[id(m._arena_params()[0])])
+            if e is None or e["blob"] is None:
+                continue
+            arena = m._ensure_flat()
+            prior = m._prior_for(arena.device)
+            if e["blob"].numel() != prior.opt_state_bytes() or e["n_params"] != len(m._arena_params()):
+                raise ValueError("saved native optimizer state does not match this prior's layout")
+            ent["state"] = e["blob"].to(arena.device).clone()
+
 
 class FusedAdam(_FusedBase):
     """``torch.optim.Adam`` (single-tensor arithmetic) + fused non-negativity clamp for prior arenas."""

@@ -125,3 +125,42 @@ def fg_iou(pred_fg: torch.Tensor, target_fg: torch.Tensor) -> float:
     inter = int((p & t).sum())
     union = int((p | t).sum())
     return inter / union if union else 0.0
+
+
+def stock_unet(in_chn: int = 4, out_chn: int = 1):
+    """A plain PyTorch U-Net of the reference segmentation net's size (``awesome/model/unet.py``: widths 64-128-256-512-512,
+    two 3x3 conv + BatchNorm + ReLU per level, 2x max-pool down, bilinear 2x up + skip concatenation, 1x1 output conv;
+    13 395 905 parameters for ``in_chn=4``) -- the frozen / jointly trained segmentation side of BASELINE configs[4].  Stock
+    cuDNN work and NOT part of the prior path: it exists so that the joint step and its gradient all-reduce are measured at
+    the reference's message size (53.6 MB)."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    def double(i, o):
+        return nn.Sequential(nn.Conv2d(i, o, 3, padding=1), nn.BatchNorm2d(o), nn.ReLU(inplace=True),
+                             nn.Conv2d(o, o, 3, padding=1), nn.BatchNorm2d(o), nn.ReLU(inplace=True))
+
+    class UNet(nn.Module):
+        def __init__(self):
+            super().__init__()
+            w = (64, 128, 256, 512, 512)
+            self.enc = nn.ModuleList([double(in_chn, w[0])] + [double(w[i], w[i + 1]) for i in range(4)])
+            self.dec = nn.ModuleList([double(w[4] + w[3], 256), double(256 + w[2], 128), double(128 + w[1], 64),
+                                      double(64 + w[0], 64)])
+            self.head = nn.Conv2d(64, out_chn, 1)
+
+        def forward(self, x):
+            skips = []
+            for i, e in enumerate(self.enc):
+                x = e(x if i == 0 else F.max_pool2d(x, 2))
+                skips.append(x)
+            x = skips.pop()
+            for d in self.dec:
+                s = skips.pop()
+                x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+                dy, dx = s.shape[2] - x.shape[2], s.shape[3] - x.shape[3]
+                if dy or dx:
+                    x = F.pad(x, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))
+                x = d(torch.cat([s, x], dim=1))
+            return self.head(x)
+    return UNet()

@@ -324,6 +324,92 @@ def frames_per_s_leg(A, dev, rank: int, world: int, G: int, precision: str, barr
             "includes": "H2D of every frame's unaries, skip check, fit, IoU check / retry, mask packing, D2H + gather of results"}
 
 
+def joint_leg(A, dev, rank: int, world: int, barrier, precision: str, steps: int = 10):
+    """BASELINE configs[4] on hardware: the data-parallel joint UNet + (x, y, t) prior step of the spatio-temporal configs
+    (``awesome/agent/torch_agent.py:428-551``) -- a stock U-Net of the reference's size (13 395 905 parameters), the
+    RealNVP(18 flows, m = 32) o ICNN(L = 2) prior on the tensor path, ``FBMSJointLoss``, Adam 1e-4, 2 frames of 640x480 per
+    GPU and step, ONE exchange step: the all-reduce of the 53.8 MB flat gradient bucket between ``backward`` and
+    ``optimizer.step`` (``:489-492``).  Timed three ways (CUDA events, max over ranks): bucketed all-reduce overlapped with
+    the backward pass (the product), one all-reduce after backward, no exchange; plus the collective alone.  Replicas are
+    checked bit-identical after the overlapped run."""
+    import torch
+    import torch.distributed as dist
+    from awesome_b200 import measures as M
+    from awesome_b200 import synth
+    B, T = 2, 200
+    torch.manual_seed(42)
+    seg = synth.stock_unet(4).to(dev)
+    pri = A.real_nvp_path_connected_net(channels=3, hidden_units=32, flow_n_flows=18, flow_output_fn="tanh", norm="minmax",
+                                        convex_net_hidden_units=130, convex_net_hidden_layers=2, precision=precision).to(dev)
+    g = torch.Generator().manual_seed(1000 + rank)
+    img = torch.randn(B, 4, H, W, generator=g).to(dev)                       # random RGB + edge channel
+    grid = A.GridSpecHost("linspace", B, H, W, t0=rank * B / (T - 1), t_step=1.0 / (T - 1)).materialize(3, dev)
+    lab = torch.full((B, 1, H, W), 2.0)                                      # sparse weak labels: 0 fg, 1 bg, 2 none
+    lab[torch.rand(B, 1, H, W, generator=g) < 0.05] = 0.0
+    lab[torch.rand(B, 1, H, W, generator=g) < 0.10] = 1.0
+    lab = lab.to(dev)
+    with torch.no_grad():
+        pri(grid)                                                            # ActNorm data-dependent init
+    init = ({k: v.clone() for k, v in seg.state_dict().items()}, {k: v.clone() for k, v in pri.state_dict().items()})
+    out = {"workload": "joint UNet + spatio-temporal prior step (BASELINE configs[4])", "frames_per_gpu_per_step": B,
+           "frames_per_step": world * B, "unet_params": sum(p.numel() for p in seg.parameters()),
+           "prior_params": sum(p.numel() for p in pri.parameters()), "n_gpus": world}
+
+    def run(mode):
+        seg.load_state_dict(init[0]); pri.load_state_dict(init[1])
+        tr = A.JointTrainer(seg, pri, M.FBMSJointLoss(), optimizer_args=dict(lr=1e-4), n_buckets=4, comm=mode)
+        tr.broadcast_parameters(0)
+        for _ in range(3):
+            tr.step(img, grid, lab)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = tr.step(img, grid, lab)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        tr.bucket.remove_hooks()
+        return tr, ms, float(loss)
+
+    tr, ms_overlap, loss = run("overlap")
+    out.update(bucket_bytes=tr.bucket.nbytes, n_buckets=tr.bucket.n_buckets, ms_per_step=ms_overlap,
+               frames_per_s=world * B / ms_overlap * 1e3, final_loss=loss)
+    if world > 1:
+        flat = torch.cat([p.detach().reshape(-1) for p in list(seg.parameters()) + list(pri.parameters())])
+        ref = flat.clone()
+        dist.broadcast(ref, src=0)
+        same = torch.tensor([float(torch.equal(ref, flat))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        out["replicas_bit_identical"] = bool(same.item() > 0)
+        del tr
+        tr, ms_after, _ = run("after")
+        buf = tr.bucket.flat
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            dist.all_reduce(buf, op=dist.ReduceOp.AVG)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ar = float(t[0])
+        del tr
+        _, ms_off, _ = run("off")
+        hidden = (ms_after - ms_overlap) / ar if ar > 0 else None
+        out.update(ms_per_step_allreduce_after_backward=ms_after, ms_per_step_no_exchange=ms_off, allreduce_ms_alone=ar,
+                   allreduce_busbw_GBps=2 * (world - 1) / world * buf.numel() * 4 / (ar * 1e-3) / 1e9,
+                   exposed_comm_ms=ms_overlap - ms_off, overlapped_fraction=None if hidden is None else max(0.0, min(1.0, hidden)))
+    del seg, pri
+    torch.cuda.empty_cache()
+    return out
+
+
 def secondary_workloads(A, dev, unaries640):
     """Short device-timed runs of the other BASELINE configs (ms per fused fit step, pixel-samples/s):
     configs[0] 256x256 ICNN(L=1) notebook fit, configs[2] RealNVP path-connectedness fit, configs[3] 8 objects per
@@ -478,6 +564,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short runs of BASELINE configs 0, 2, 3")
     ap.add_argument("--no-sustained", action="store_true", help="skip the >= 10 s leg behind roofline.sustained")
+    ap.add_argument("--no-joint", action="store_true", help="skip the joint UNet + prior step leg (BASELINE configs[4])")
     ap.add_argument("--no-frames", action="store_true", help="skip the measured frames/s leg (60-frame sharded sequence fit)")
     ap.add_argument("--sustained-seconds", type=float, default=10.0)
     args = ap.parse_args()
@@ -581,6 +668,14 @@ def main():
     if not args.no_frames:
         fitter.set_target_pool(None)
         frames_leg = frames_per_s_leg(A, dev, rank, world, G, args.precision, barrier)
+
+    # ---- configs[4]: joint UNet + prior step with its gradient all-reduce (every rank takes part)
+    joint = None
+    if not args.no_joint:
+        try:
+            joint = joint_leg(A, dev, rank, world, barrier, args.precision)
+        except Exception as e:           # a secondary leg must never take the bench line down
+            joint = {"unavailable": repr(e)[:300]}
 
     # ---- the same loop for >= 10 s: earns (or not) the sustained-clock reading of the roofline (N = 1 only)
     sustained = None
@@ -694,6 +789,7 @@ def main():
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "samples": clocks["samples"]},
             "frames_per_s": frames_leg,
+            "joint_unet_prior": joint,
             "roofline": roofline,
             "roofline_hbm": roofline_hbm,
             "cpu_baseline": cpu,

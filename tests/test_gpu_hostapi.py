@@ -408,3 +408,48 @@ def test_pixel_row_input_gradient_shape_and_values(A):
     r = rows.detach().cpu().clone().requires_grad_(True)
     (O.icnn_forward(p, r).reshape(-1) * wgt.cpu()).sum().backward()
     torch.testing.assert_close(rows.grad.cpu(), r.grad, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("cls_name", ["FusedAdam", "FusedAdamax"])
+def test_fused_optimizer_state_dict_round_trip(A, cls_name):
+    """save -> recreate -> load_state_dict -> the next step is bit-equal to the uninterrupted run, for the arena parameters
+    (native moments blob) and for ordinary parameters (stock inner optimizer) -- what the agent does around every
+    best-model save (torch_agent.py:356, 808, 836)."""
+    cls = getattr(A, cls_name)
+    x = A.GridSpecHost("linspace", 1, 24, 32).materialize(2, DEV)
+    tgt = blob(24, 32).to(DEV)[None, None]
+
+    def make():
+        torch.manual_seed(5)
+        prior = A.ConvexNextNet(n_hidden_layers=2).to(DEV)
+        other = torch.nn.Linear(3, 2).to(DEV)
+        opt = cls([dict(params=list(other.parameters())), dict(params=list(prior.parameters()))], lr=2e-3)
+        return prior, other, opt
+
+    def one_step(prior, other, opt):
+        opt.zero_grad()
+        loss = ((torch.sigmoid(prior(x)) - tgt) ** 2).mean() + other(torch.ones(1, 3, device=DEV)).pow(2).sum()
+        loss.backward()
+        opt.step()
+        prior.enforce_convexity()
+
+    pa, oa, opta = make()
+    for _ in range(3):
+        one_step(pa, oa, opta)
+    sd = opta.state_dict()
+    assert sd["awb_fused"]["native"][0]["blob"] is not None and sd["awb_fused"]["inner"] is not None
+    weights = ({k: v.clone() for k, v in pa.state_dict().items()}, {k: v.clone() for k, v in oa.state_dict().items()})
+    one_step(pa, oa, opta)                                   # uninterrupted 4th step
+    pb, ob, optb = make()                                    # fresh objects, as after _free_optimizer / _get_optimizer
+    pb.load_state_dict(weights[0]); ob.load_state_dict(weights[1])
+    optb.load_state_dict(sd)
+    one_step(pb, ob, optb)
+    for (k, a), b in zip(pa.state_dict().items(), pb.state_dict().values()):
+        assert torch.equal(a, b), k
+    for (k, a), b in zip(oa.state_dict().items(), ob.state_dict().values()):
+        assert torch.equal(a, b), k
+    # without the saved moments the step differs (the test would be vacuous otherwise)
+    pc, oc, optc = make()
+    pc.load_state_dict(weights[0]); oc.load_state_dict(weights[1])
+    one_step(pc, oc, optc)
+    assert not torch.equal(pa.state_dict()["input.weight"], pc.state_dict()["input.weight"])

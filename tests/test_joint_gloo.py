@@ -75,20 +75,20 @@ def _data(n, seed):
             (torch.rand(n, 1, 12, 16, generator=g) > 0.5).float())
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, comm="overlap"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         import awesome_b200 as A
         seg, pri = _make(seed=100 + rank)           # replicas start different: broadcast must fix that
-        tr = A.JointTrainer(seg, pri, _mse_joint, optimizer_cls=torch.optim.Adam, optimizer_args=dict(lr=1e-2))
+        tr = A.JointTrainer(seg, pri, _mse_joint, optimizer_cls=torch.optim.Adam, optimizer_args=dict(lr=1e-2), n_buckets=3, comm=comm)
         tr.broadcast_parameters(0)
         img, grid, lab = _data(4, seed=7)
         sl = slice(rank * 2, rank * 2 + 2)           # 2 frames per rank
         losses = [float(tr.step(img[sl], grid[sl], lab[sl])) for _ in range(3)]
         flat = torch.cat([p.detach().reshape(-1) for p in list(seg.parameters()) + list(pri.parameters())])
-        ret[rank] = (flat, losses, tr.bucket.nbytes)
+        ret[rank] = (flat, losses, tr.bucket.nbytes, tr.bucket.n_buckets)
     finally:
         dist.destroy_process_group()
 
@@ -100,8 +100,9 @@ def test_joint_step_two_ranks_equals_single_process_on_concatenated_batch():
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
-    flat0, _, nbytes = ret[0]
-    flat1, _, _ = ret[1]
+    flat0, _, nbytes, nb = ret[0]
+    flat1 = ret[1][0]
+    assert nb == 3                                    # bucketed: three collectives launched from the backward hooks
     assert torch.equal(flat0, flat1), "replicas diverged"
     # single process, whole batch, same initial weights as rank 0
     seg, pri = _make(seed=100)
@@ -126,3 +127,18 @@ def test_grad_bucket_views_survive_zero_grad():
         p.grad = None                                 # e.g. zero_grad(set_to_none=True) by foreign code
     b.zero()
     assert float(b.flat.abs().sum()) == 0 and all(p.grad is not None for p in seg.parameters())
+
+
+def test_overlapped_buckets_equal_one_allreduce_after_backward():
+    """comm="overlap" (bucket collectives launched from autograd hooks during backward) and comm="after" (one collective
+    after backward) are the same arithmetic: bit-identical replicas and bit-identical results between the two modes."""
+    world = 2
+    mgr = mp.Manager()
+    res = {}
+    for i, comm in enumerate(("overlap", "after")):
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(world, 29700 + (os.getpid() % 1000) + 7 * i, ret, comm), nprocs=world, join=True)
+        assert torch.equal(ret[0][0], ret[1][0])
+        res[comm] = ret[0]
+    assert torch.equal(res["overlap"][0], res["after"][0]) and res["overlap"][1] == res["after"][1]
+    assert res["overlap"][3] == 3 and res["after"][3] == 1
