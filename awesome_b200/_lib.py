@@ -73,6 +73,7 @@ SYMBOLS = [
     ("awb_opt_state_bytes", C.c_int64, [_P]),
     ("awb_prior_set_flow_consts", C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
                                             C.c_float, C.POINTER(C.c_uint8)]),
+    ("awb_prior_set_flow_output_scale", C.c_int, [_P, C.c_float]),
     ("awb_prior_forward", C.c_int, [_P, _P, C.POINTER(GridSpec), _P, _P, C.c_int32, _P, C.c_size_t, _P]),
     ("awb_prior_flow_inverse", C.c_int, [_P, _P, C.POINTER(GridSpec), _P, _P]),
     ("awb_prior_backward", C.c_int, [_P, _P, C.POINTER(GridSpec), _P, _P, _P, _P, C.c_size_t, _P]),
@@ -91,6 +92,7 @@ SYMBOLS = [
     ("awb_star_fit_step", C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.POINTER(LossSpec), C.POINTER(OptHyper), _P, _P,
                                     C.c_size_t, _P]),
     ("awb_opt_set_lr", C.c_int, [_P, _P, C.POINTER(C.c_double), _P]),
+    ("awb_opt_plateau_step", C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(OptHyper), _P]),
     ("awb_opt_read_scalars", C.c_int, [_P, _P, C.c_int32, C.POINTER(OptScalars), _P]),
     ("awb_prior_actnorm_init", C.c_int, [_P, _P, C.POINTER(GridSpec), _P, C.c_size_t, _P]),
     ("awb_mask_iou_counts", C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),

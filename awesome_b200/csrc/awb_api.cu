@@ -1,5 +1,6 @@
 // extern "C" entry points of libawb.so (declared in include/awb.h) and the host-side
 // bookkeeping behind them: handle, parameter-arena layout, workspace carving, error state.
+#include <math.h>
 #include <stdarg.h>
 #include <string.h>
 
@@ -132,6 +133,7 @@ int awb_prior_create(const awb_desc* d, awb_handle* out) {
     h->lay.P_icnn = 0; h->lay.off_flow = 0; h->lay.P_flow = 0; h->lay.off_lin = h->lay.P;
   }
   h->fc_set = false;
+  h->fc.out_scale = 1.f;
   h->d_map = nullptr; h->d_clamp = nullptr; h->d_group = nullptr; h->d_tcmap = nullptr; h->d_imap = nullptr; h->d_aug2img = nullptr;
   const Layout& L = h->lay;
   // arena (state_dict order) -> augmented index; clamp mask; optimizer groups
@@ -244,6 +246,14 @@ int awb_prior_set_flow_consts(awb_handle h, const float* nmin, const float* nmax
   h->fc.new_min = new_min; h->fc.new_max = new_max;
   memcpy(h->fc.masks, masks, (size_t)h->lay.F * h->lay.C);
   h->fc_set = true;
+  return AWB_OK;
+}
+
+int awb_prior_set_flow_output_scale(awb_handle h, float scale) {
+  if (!h) { set_error("null argument"); return AWB_ERR_INVALID; }
+  if (h->desc.kind != AWB_KIND_FLOW_ICNN) { set_error("not a flow prior"); return AWB_ERR_INVALID; }
+  if (!(scale > 0.f) || !isfinite(scale)) { set_error("output_scale must be a positive finite number"); return AWB_ERR_INVALID; }
+  h->fc.out_scale = scale;
   return AWB_OK;
 }
 
@@ -482,6 +492,13 @@ int awb_star_fit_step(awb_handle h, float* params, void* opt_state, const float*
 int awb_opt_set_lr(awb_handle h, void* opt_state, const double* lr, void* stream) {
   if (!h || !opt_state || !lr) { set_error("null argument"); return AWB_ERR_INVALID; }
   return opt_set_lr(h, opt_state, lr, (cudaStream_t)stream);
+}
+
+int awb_opt_plateau_step(awb_handle h, void* opt_state, const float* loss, int32_t loss_stride, const awb_opt_hyper* hy,
+                         void* stream) {
+  if (!h || !opt_state || !loss || !hy) { set_error("null argument"); return AWB_ERR_INVALID; }
+  if (loss_stride != 0 && loss_stride != 1) { set_error("loss_stride must be 0 (shared scalar) or 1 ([O])"); return AWB_ERR_INVALID; }
+  return plateau_step(h, opt_state, loss, loss_stride, hy, (cudaStream_t)stream);
 }
 
 int awb_opt_read_scalars(awb_handle h, const void* opt_state, int32_t obj, awb_opt_scalars* out, void* stream) {

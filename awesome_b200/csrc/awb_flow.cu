@@ -25,6 +25,7 @@ struct FlowP {
   const float* params;   // arena, object 0
   int64_t P, off_flow, P_flow, per_flow, off_lin;
   int C, F, m, tanh_out, use_linear;
+  float out_scale;       // normflows MLP output_scale: s, t = out_scale * tanh(.) (1 when unset; only with an output_fn)
   int64_t N;
   float* X;              // [O][N][4]
   float* zin;            // [O][F][N][RW] saved coupling inputs / outputs (FlowSave), or null
@@ -274,11 +275,11 @@ __global__ void __launch_bounds__(256) k_flow_fwd(FlowP p) {
           float zc = z[q][c];
           zi[c] = zc;
           if (!b[c]) {
-            float s_ = p.tanh_out ? tanh_sfu(so[q][c]) : so[q][c];
-            float t_ = p.tanh_out ? tanh_sfu(to[q][c]) : to[q][c];
+            float s_ = p.tanh_out ? p.out_scale * tanh_sfu(so[q][c]) : so[q][c];
+            float t_ = p.tanh_out ? p.out_scale * tanh_sfu(to[q][c]) : to[q][c];
             if (!isfinite(s_)) s_ = NAN;
             if (!isfinite(t_)) t_ = NAN;
-            zc = fmaf(z[q][c], p.tanh_out ? exp_sfu(s_) : expf(s_), t_);
+            zc = fmaf(z[q][c], (p.tanh_out && p.out_scale == 1.f) ? exp_sfu(s_) : expf(s_), t_);
             if (u == 0) { sv[0] = s_; tv[0] = t_; } else { sv[1] = s_; tv[1] = t_; }
             u++;
           }
@@ -358,8 +359,8 @@ __global__ void __launch_bounds__(256) k_flow_inv(FlowP p, float* out) {
     }
 #pragma unroll
     for (int c = 0; c < C; c++) {
-      float s_ = p.tanh_out ? tanhf(so[c]) : so[c];
-      float t_ = p.tanh_out ? tanhf(to[c]) : to[c];
+      float s_ = p.tanh_out ? p.out_scale * tanhf(so[c]) : so[c];
+      float t_ = p.tanh_out ? p.out_scale * tanhf(to[c]) : to[c];
       if (!isfinite(s_)) s_ = NAN;
       if (!isfinite(t_)) t_ = NAN;
       if (!b[c]) z[c] = (z[c] - t_) * expf(-s_);
@@ -581,10 +582,11 @@ __device__ __forceinline__ void flow_bwd_one(const FlowP& p, const FlowBwdShared
         for (int j = 0; j < NU; j++) {          // transformed components: z' = z exp(s) + t
           const float zc = pick<C>(z, ui[j]), dzc = pick<C>(dz, ui[j]);
           const float dzp = dzc * ea_u[j];
-          const float e = p.tanh_out ? exp_sfu(s[j]) : expf(s[j]);      // the same function as the forward
+          const float e = (p.tanh_out && p.out_scale == 1.f) ? exp_sfu(s[j]) : expf(s[j]);      // the same function as the forward
+          const float isc = 1.f / p.out_scale;
           const float dsv = dzp * zc * e;
-          ds[q][j] = p.tanh_out ? dsv * (1.f - s[j] * s[j]) : dsv;
-          dt[q][j] = p.tanh_out ? dzp * (1.f - t[j] * t[j]) : dzp;
+          ds[q][j] = p.tanh_out ? dsv * p.out_scale * (1.f - (s[j] * isc) * (s[j] * isc)) : dsv;     // d (c tanh a) / da = c (1 - tanh^2)
+          dt[q][j] = p.tanh_out ? dzp * p.out_scale * (1.f - (t[j] * isc) * (t[j] * isc)) : dzp;
           dzo_u[q][j] = dzp * e;
           if (last_pass) {
             sas_u[j] = fmaf(dzc * fmaf(zc, e, t[j]), ea_u[j], sas_u[j]);
@@ -874,7 +876,7 @@ __global__ void __launch_bounds__(256) k_flow_init_pass(FlowP p, int f, double* 
     }
 #pragma unroll
     for (int c = 0; c < C; c++) {
-      float s = p.tanh_out ? tanhf(so[c]) : so[c], t = p.tanh_out ? tanhf(to[c]) : to[c];
+      float s = p.tanh_out ? p.out_scale * tanhf(so[c]) : so[c], t = p.tanh_out ? p.out_scale * tanhf(to[c]) : to[c];
       zc[c] = b[c] ? z[c] : fmaf(z[c], expf(s), t);
     }
     *reinterpret_cast<float4*>(p.X + n * 4) = make_float4(zc[0], zc[1], C > 2 ? zc[2] : 0.f, 1.f);
@@ -958,7 +960,7 @@ static FlowP make_p(const awb_prior* h, const float* params, const awb_grid_spec
   p.fc = h->fc;
   p.params = params; p.P = L.P; p.off_flow = L.off_flow; p.P_flow = L.P_flow; p.per_flow = L.per_flow;
   p.off_lin = L.off_lin;
-  p.C = L.C; p.F = L.F; p.m = L.m; p.tanh_out = h->desc.flow_tanh; p.use_linear = 1;
+  p.C = L.C; p.F = L.F; p.m = L.m; p.tanh_out = h->desc.flow_tanh; p.use_linear = 1; p.out_scale = h->fc.out_scale;
   p.N = (int64_t)g->B * g->H * g->W;
   p.X = ws.X; p.zin = nullptr; p.deformed = nullptr; p.dX = ws.dX; p.fpart = ws.fpart;
   p.chunk = split_chunk(p.N); p.O = h->desc.n_objects; p.rounds = 1; p.rounds1 = 0; p.dz_smem = 0; p.dzp_g = nullptr;

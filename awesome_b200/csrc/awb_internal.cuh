@@ -52,6 +52,7 @@ struct OptScal {  // per object, device resident
 struct FlowConsts {
   float nmin[4], nmax[4];
   float new_min, new_max;
+  float out_scale;        // output_scale of the coupling MLPs (1 when unset)
   uint8_t masks[64 * 4];  // [F][C]
 };
 
@@ -163,6 +164,7 @@ int simt_dgrid(const awb_prior* h, const awb_grid_spec* g, float* dgrid, const W
 int optim_step(const awb_prior* h, float* params, const float* grads, void* opt_state,
                const awb_opt_hyper* hy, cudaStream_t st);
 int clamp_only(const awb_prior* h, float* params, cudaStream_t st);
+int plateau_step(const awb_prior* h, void* opt_state, const float* loss, int stride, const awb_opt_hyper* hy, cudaStream_t st);
 // reduce [S][P] plain (state_dict order) gradient partials + [S] loss partials, then the optimizer step
 int reduce_opt_plain(const awb_prior* h, float* params, void* opt_state, const awb_opt_hyper* hy, float* loss_out,
                      const float* partials, int S, const float* lossp, cudaStream_t st);

@@ -1005,6 +1005,35 @@ int optim_step(const awb_prior* h, float* params, const float* grads, void* opt_
   return AWB_OK;
 }
 
+// ReduceLROnPlateau.step(loss) without an optimizer step (one thread per object)
+__global__ void k_plateau_step(OptScal* scal, const float* loss, int stride, awb_opt_hyper hy, int n_groups, int O) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= O) return;
+  OptScal& s = scal[o];
+  const double cur = (double)loss[(int64_t)o * stride];
+  if (!isfinite(cur)) { s.nonfinite = 1; return; }
+  if (cur < s.best * (1.0 - (double)hy.threshold)) { s.best = cur; s.num_bad = 0; }
+  else s.num_bad += 1;
+  if (s.num_bad > hy.patience) {
+    for (int g = 0; g < n_groups; g++) {
+      double nl = s.lr[g] * (double)hy.factor;
+      if (nl < (double)hy.min_lr) nl = (double)hy.min_lr;
+      if (s.lr[g] - nl > (double)hy.plateau_eps) s.lr[g] = nl;
+    }
+    s.num_bad = 0;
+  }
+}
+
+int plateau_step(const awb_prior* h, void* opt_state, const float* loss, int stride, const awb_opt_hyper* hy, cudaStream_t st) {
+  float *m, *v;
+  OptScal* scal;
+  opt_ptrs(h, opt_state, &m, &v, &scal);
+  const int O = h->desc.n_objects;
+  AWB_LAUNCH(PK_OPT, st, k_plateau_step<<<(O + 31) / 32, 32, 0, st>>>(scal, loss, stride, *hy, n_groups_of(h), O));
+  AWB_CUDA(cudaGetLastError());
+  return AWB_OK;
+}
+
 int clamp_only(const awb_prior* h, float* params, cudaStream_t st) {
   AWB_LAUNCH(PK_OPT, st, k_clamp<<<dim3((unsigned)((h->lay.P + 255) / 256), h->desc.n_objects), 256, 0, st>>>(params, h->d_clamp, h->lay.P));
   AWB_CUDA(cudaGetLastError());

@@ -127,3 +127,161 @@ class NumberBasedMultiPriorModule(nn.Module):
                 p._maybe_actnorm_init(x)
         return PriorFitter(self._group_prior, big.reshape(-1), grid, target.reshape(len(self.priors), -1),
                            loss or LossConfig(), optim or OptimConfig(), **kw)
+
+
+class BatchSizeMultiPriorModule(NumberBasedMultiPriorModule):
+    """``awesome/model/batch_size_multi_prior_module.py:13-18``: one prior per batch item; ``forward(..., batch_size=B)``
+    evaluates ``B`` priors on the same arguments and stacks them on dim 1."""
+
+    def forward(self, *args, batch_size: int, **kwargs) -> torch.Tensor:       # noqa: D401
+        return super().forward(*args, num_priors=batch_size, **kwargs)
+
+
+class MultipleObjectsAwarePathConnectedNet(NumberBasedMultiPriorModule):
+    """``awesome/model/multiple_object_aware_path_connected_net.py``: one path-connectedness prior per object of a frame.
+
+    The reference's loop (``:186-367``) is experimental and not runnable as written; the semantics kept are
+    the ones its structure spells out: ``n_priors = unaries.shape[1] - 1`` (channel 0 is the background, ``:186-192``),
+    object ``k`` is fitted against unaries channel ``k + 1``, every object carries its OWN warm-start chain from frame to
+    frame (``previous_image_object_states``, ``:206-219``), fresh optimizer per object and attempt (``:289-298``), IoU check
+    and retry per object (``:330-355``), checkpoints ``pretrain_checkpoint_{i}_{k}.pth`` holding the OBJECT's prior
+    (``:220-229, 364-367``).  The O objects of a frame are independent, so a frame is ONE grouped launch per kernel whenever
+    its objects need the same number of steps (all cold or all warm); otherwise object by object."""
+
+    def pretrain_load_state(self, train_set, test_set, device, agent, state, use_progress_bar: bool = True,
+                            wrapper_module=None, **kwargs):
+        agent.training_dataset.__prior_cache__.set_state(state)
+
+    def pretrain(self, train_set, test_set=None, device=None, agent=None, use_progress_bar: bool = True,
+                 do_pretrain_checkpoints: bool = False, use_pretrain_checkpoints: bool = False,
+                 pretrain_checkpoint_dir: Optional[str] = None, wrapper_module=None, **kwargs) -> Any:
+        from .. import pretrain as P
+        ds = getattr(agent, "training_dataset", None)
+        cache = getattr(ds, "__prior_cache__", None)
+        if cache is None or not bool(getattr(ds, "has_prior", getattr(ds, "__has_prior__", False))):
+            raise NotImplementedError("Fixed pretraining not implemented.")
+        if wrapper_module is None:
+            raise ValueError("Wrapper model must be provided for pretraining.")
+        sched = P.FitSchedule.from_pretrain_args(kwargs)
+        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        was = wrapper_module.training
+        wrapper_module.eval()
+        try:
+            _, grids, uns, keys = P.collect_unaries(wrapper_module, agent, train_set, dev, sched.unet_batch_size)
+
+            def keep(i, _results):
+                state = {k: v.detach().clone() for k, v in self.state_dict().items()}
+                if hasattr(cache, "__setitem__"):
+                    cache[keys[i]] = state
+            self.fit_frames_multi_object(grids, uns, sched, on_frame=keep, do_pretrain_checkpoints=do_pretrain_checkpoints,
+                                         use_pretrain_checkpoints=use_pretrain_checkpoints,
+                                         pretrain_checkpoint_dir=pretrain_checkpoint_dir)
+            return cache.get_state()
+        finally:
+            wrapper_module.train(was)
+
+    def fit_frames_multi_object(self, grids, unaries, schedule=None, on_frame=None, do_pretrain_checkpoints: bool = False,
+                                use_pretrain_checkpoints: bool = False, pretrain_checkpoint_dir: Optional[str] = None):
+        """``unaries[i]``: ``[1, O+1, H, W]`` (or ``[1,1,H,W]``: one object).  Returns ``results[i][k]`` (``FrameResult`` of
+        object k in frame i, or ``None`` for a skipped frame)."""
+        import dataclasses
+        import logging
+        import os
+        from .. import pretrain as P
+        from ..core import iou_counts, target_counts
+        s = schedule or P.FitSchedule()
+        if do_pretrain_checkpoints:
+            if pretrain_checkpoint_dir is None:
+                raise ValueError("Pretrain checkpoint dir must be provided.")
+            os.makedirs(pretrain_checkpoint_dir, exist_ok=True)
+        all_results = []
+        prev: dict = {}                     # object -> state (device row) of the previous frame, when its fit was proper
+        prev_frame = -2
+        for i, (grid, un) in enumerate(zip(grids, unaries)):
+            dev = next(self.parameters()).device if len(self.priors) else torch.device("cuda")
+            un = un.detach().float()
+            if un.dim() == 3:
+                un = un.unsqueeze(0)
+            O_ = un.shape[1] - 1 if un.shape[1] > 1 else 1
+            self.assure_prior_count(O_)
+            dev = next(self.parameters()).device
+            un = un.to(dev)
+            obj_un = un[0, 1:] if un.shape[1] > 1 else un[0]                 # [O,H,W]: channel 0 is the background
+            cnt = target_counts(un.reshape(1, -1), L.AWB_CLS_UNARY_LT_HALF).cpu()[0]
+            if int(cnt[0]) == 0 or int(cnt[1]) == 0:                          # torch.unique(unaries >= 0.5) has one value
+                logging.warning("Unaries of segmentation model contain no foreground. Skipping image. %s", i)
+                all_results.append(None)
+                continue
+            if prev_frame != i - 1:
+                prev = {}                                                      # only the last image's states are kept (:209-212)
+            spec = P._as_grid(grid, dev)
+            x = spec.materialize(self.priors[0].in_channels, dev)
+            results: List[Any] = [None] * O_
+            todo = list(range(O_))
+            if use_pretrain_checkpoints and pretrain_checkpoint_dir:
+                for k in list(todo):
+                    path = os.path.join(pretrain_checkpoint_dir, f"pretrain_checkpoint_{i}_{k}.pth")
+                    if os.path.exists(path) and P.load_pretrain_checkpoint(self.priors[k], path, device=dev):
+                        results[k] = P.FrameResult(index=i, proper_fit=True, state=self.priors[k]._ensure_flat().detach().clone())
+                        todo.remove(k)
+            warm = {k: (s.reuse_state and k in prev) for k in todo}
+            for k in todo:
+                pk = self.priors[k]
+                if warm[k]:
+                    with torch.no_grad():
+                        pk._ensure_flat().copy_(prev[k])
+                else:
+                    if s.prefit_flow_net_identity:
+                        pk.learn_flow_identity(x, lr=s.prefit_flow_net_identity_lr, weight_decay=s.prefit_flow_net_identity_weight_decay,
+                                               max_iter=s.prefit_flow_net_identity_num_epochs, use_progress_bar=False)
+                    if s.prefit_convex_net:
+                        pk.learn_convex_net(x, obj_un[k][None, None], lr=s.prefit_convex_net_lr,
+                                            weight_decay=s.prefit_convex_net_weight_decay,
+                                            max_iter=s.prefit_convex_net_num_epochs, use_progress_bar=False)
+            grouped = len(todo) == O_ and O_ > 1 and len({warm[k] for k in todo}) == 1
+            if grouped:
+                epochs = s.reuse_state_epochs if warm[0] else s.num_epochs
+                fitter = self.make_fitter(spec, obj_un.reshape(O_, -1), s.criterion, s.optim(True), steps_per_graph=s.steps_per_graph)
+                hist = fitter.run(epochs)
+                fitter.raise_if_nonfinite()
+                with torch.no_grad():
+                    logits = self(x, num_priors=O_)
+                cnts = iou_counts(logits.reshape(O_, -1), obj_un.reshape(O_, -1), pred_is_logit=True, n_objects=O_).cpu()
+                for k in range(O_):
+                    inter, pf, tf = int(cnts[k, 0]), int(cnts[k, 1]), int(cnts[k, 2])
+                    r = P.FrameResult(index=i, steps=epochs, final_loss=float(hist[-1, k]) if epochs > 0 else float("nan"))
+                    r.iou = 0.0 if tf == 0 else inter / float(pf + tf - inter)
+                    r.proper_fit = r.iou >= s.proper_prior_fit_threshold
+                    results[k] = r
+                redo = [k for k in range(O_) if not results[k].proper_fit and s.proper_prior_fit_retrys > 0]
+            else:
+                redo = list(todo)
+            for k in redo:                     # per-object path: mixed cold / warm frames, and the reset + refit retry
+                pk = self.priors[k]
+                first_try = results[k] is None
+                if not first_try:
+                    logging.info("Prior fit not proper on image index: %s object %s. Retrying. Metric: %s", i, k, results[k].iou)
+                    pk.reset_parameters()
+                    pk._ensure_flat()
+                sch_k = dataclasses.replace(s, prefit_flow_net_identity=False, prefit_convex_net=False, reuse_state=True,
+                                            proper_prior_fit_retrys=s.proper_prior_fit_retrys - (0 if first_try else 1))
+                init_prev = pk._ensure_flat().detach().clone() if (first_try and warm.get(k, False)) else None
+                again = P.fit_frames(pk, [spec], [obj_un[k]], sch_k, frame_indices=[i], initial_previous=init_prev)[0]
+                if not first_try:
+                    again.retries += 1
+                    again.steps += results[k].steps
+                results[k] = again
+                self._arena_all = None
+            for k in range(O_):
+                results[k].state = self.priors[k]._ensure_flat().detach().clone()
+                if s.reuse_state and results[k].proper_fit:
+                    prev[k] = results[k].state
+                elif k in prev:
+                    del prev[k]
+                if do_pretrain_checkpoints and k in todo:
+                    P.save_pretrain_checkpoint(self.priors[k], os.path.join(pretrain_checkpoint_dir, f"pretrain_checkpoint_{i}_{k}.pth"))
+            prev_frame = i
+            all_results.append(results)
+            if on_frame:
+                on_frame(i, results)
+        return all_results

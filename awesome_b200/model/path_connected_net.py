@@ -23,7 +23,7 @@ from .convex_net import ConvexNextNet
 class _MLP(nn.Module):
     """Parameter holder with the keys of normflows ``nets.MLP([C,m,C])``: ``net.0.*``, ``net.2.*``."""
 
-    def __init__(self, channels: int, hidden: int, init_zeros: bool = True):
+    def __init__(self, channels: int, hidden: int, init_zeros: bool = True, output_scale: Optional[float] = None):
         super().__init__()
         l0 = nn.Linear(channels, hidden)
         l2 = nn.Linear(hidden, channels)
@@ -32,6 +32,14 @@ class _MLP(nn.Module):
             nn.init.zeros_(l2.bias)
         self.net = nn.ModuleDict({"0": Affine(l0.weight.detach().clone(), l0.bias.detach().clone()),
                                   "2": Affine(l2.weight.detach().clone(), l2.bias.detach().clone())})
+        if output_scale is not None:          # normflows ConstScaleLayer behind Linear, LeakyReLU, Linear, Tanh: key ``net.4.scale``
+            self.net["4"] = _ConstScale(output_scale)
+
+
+class _ConstScale(nn.Module):
+    def __init__(self, scale: float):
+        super().__init__()
+        self.register_buffer("scale", torch.tensor(float(scale)))
 
 
 class _MaskedAffineFlow(nn.Module):
@@ -53,16 +61,21 @@ class _ActNorm(nn.Module):
 class RealNVP(nn.Module):
     """Holder for ``nf.NormalizingFlow(q0, flows, q0)`` built by ``init_realnvp``."""
 
-    def __init__(self, channels: int, hidden_units: int, n_flows: int, output_fn: Optional[str]):
+    def __init__(self, channels: int, hidden_units: int, n_flows: int, output_fn: Optional[str],
+                 output_scale: Optional[float] = None):
         super().__init__()
         if output_fn not in (None, "tanh"):
             raise ValueError("the fused flow supports output_fn in (None, 'tanh')")
+        if output_scale is not None and not (float(output_scale) > 0):
+            raise ValueError("output_scale must be positive")
         self.channels, self.hidden_units, self.n_flows, self.output_fn = channels, hidden_units, n_flows, output_fn
+        # normflows nets.MLP appends ConstScaleLayer(output_scale) behind the output_fn (and only when there is one)
+        self.output_scale = float(output_scale) if (output_scale is not None and output_fn is not None) else None
         masks = realnvp_masks(channels, n_flows)
         flows = []
         for i in range(n_flows):
-            s = _MLP(channels, hidden_units)
-            t = _MLP(channels, hidden_units)
+            s = _MLP(channels, hidden_units, output_scale=self.output_scale)
+            t = _MLP(channels, hidden_units, output_scale=self.output_scale)
             flows += [_MaskedAffineFlow(masks[i], t, s), _ActNorm(channels)]
         self.flows = nn.ModuleList(flows)
 
@@ -84,9 +97,7 @@ def realnvp_masks(channels: int, n_flows: int) -> torch.Tensor:
 def init_realnvp(channels: int, height: int = 0, width: int = 0, hidden_units: int = 8, n_flows: int = 6,
                  output_fn: Optional[str] = None, output_scale: Optional[float] = None) -> RealNVP:
     """Same signature as ``net_factory.init_realnvp`` (``net_factory.py:70-114``)."""
-    if output_scale is not None:
-        raise ValueError("output_scale is not supported by the fused flow (no reference config sets it)")
-    return RealNVP(channels, hidden_units, n_flows, output_fn)
+    return RealNVP(channels, hidden_units, n_flows, output_fn, output_scale)
 
 
 class PixelizeNet(nn.Module):
@@ -120,10 +131,30 @@ class MinMax(nn.Module):
         self.min, self.max = mn, mx
 
 
-def get_norm(norm: Literal["minmax"], **kwargs) -> MinMax:
+class MeanStd(nn.Module):
+    """``awesome/transforms/mean_std.py``: buffers ``mean, std``; ``(x - mean) / std`` and back.  The kernels evaluate it as
+    the MinMax map from [mean, mean + std] onto [0, 1] (same formula, ``(mean + std) - mean`` instead of ``std``: 1 ulp)."""
+
+    def __init__(self, dim=None):
+        super().__init__()
+        self.register_buffer("mean", torch.zeros(1))
+        self.register_buffer("std", torch.ones(1))
+        self.dim = dim
+        self.fitted = False
+
+    def fit(self, x: torch.Tensor) -> None:
+        self.fitted = True
+        self.mean = x.mean(dim=self.dim, keepdim=True)
+        self.std = x.std(dim=self.dim, keepdim=True)
+
+
+def get_norm(norm: Literal["minmax", "meanstd"], **kwargs):
+    """``net_factory.get_norm`` (``net_factory.py:116-122``)."""
     if norm == "minmax":
         return MinMax(**kwargs)
-    raise ValueError("Invalid norm (the fused flow supports 'minmax', as every reference config)")
+    if norm == "meanstd":
+        return MeanStd(**kwargs)
+    raise ValueError("Invalid norm")
 
 
 class NormNet(nn.Module):
@@ -151,8 +182,8 @@ class PathConnectedNet(ArenaPriorModule):
         if not isinstance(convex_net, ConvexNextNet):
             raise TypeError("convex_net must be an awesome_b200 ConvexNextNet")
         if not isinstance(flow_net, NormNet) or not isinstance(flow_net.net, PixelizeNet) \
-                or not isinstance(flow_net.net.network, RealNVP) or not isinstance(flow_net.norm, MinMax):
-            raise TypeError("flow_net must be NormNet(PixelizeNet(init_realnvp(...)), MinMax)")
+                or not isinstance(flow_net.net.network, RealNVP) or not isinstance(flow_net.norm, (MinMax, MeanStd)):
+            raise TypeError("flow_net must be NormNet(PixelizeNet(init_realnvp(...)), MinMax | MeanStd)")
         if convex_net.in_features != in_channels or flow_net.net.network.channels != in_channels:
             raise ValueError("channel mismatch between convex_net, flow_net and in_channels")
         self.in_channels = in_channels
@@ -183,13 +214,23 @@ class PathConnectedNet(ArenaPriorModule):
     def _push_consts(self, prior: Prior) -> None:
         norm = self.flow_net.norm
         C_ = self.in_channels
-        mn = norm.min.detach().float().reshape(-1).cpu()
-        mx = norm.max.detach().float().reshape(-1).cpu()
-        mn = mn.expand(C_) if mn.numel() == 1 else mn
-        mx = mx.expand(C_) if mx.numel() == 1 else mx
+        if isinstance(norm, MeanStd):       # (x - mean) / std  ==  MinMax from [mean, mean + std] onto [0, 1]
+            mn = norm.mean.detach().float().reshape(-1).cpu()
+            sd = norm.std.detach().float().reshape(-1).cpu()
+            mn = mn.expand(C_) if mn.numel() == 1 else mn
+            mx = mn + (sd.expand(C_) if sd.numel() == 1 else sd)
+            new_min, new_max = 0.0, 1.0
+        else:
+            mn = norm.min.detach().float().reshape(-1).cpu()
+            mx = norm.max.detach().float().reshape(-1).cpu()
+            mn = mn.expand(C_) if mn.numel() == 1 else mn
+            mx = mx.expand(C_) if mx.numel() == 1 else mx
+            new_min, new_max = float(norm.new_min), float(norm.new_max)
         masks = torch.stack([self._rnvp.flows[2 * f].b.reshape(-1) for f in range(self._rnvp.n_flows)])
-        prior.set_flow_consts(mn.tolist(), mx.tolist(), float(norm.new_min), float(norm.new_max),
+        prior.set_flow_consts(mn.tolist(), mx.tolist(), new_min, new_max,
                               masks.reshape(-1).to(torch.uint8).cpu().tolist())
+        if self._rnvp.output_scale is not None:
+            L.check(prior.lib.awb_prior_set_flow_output_scale(prior.handle, self._rnvp.output_scale))
 
     def load_state_dict(self, state_dict, *args, **kwargs):
         out = super().load_state_dict(state_dict, *args, **kwargs)
@@ -299,25 +340,49 @@ class PathConnectedNet(ArenaPriorModule):
     def learn_flow_identity(self, x: torch.Tensor, lr: float = 1e-2, weight_decay: float = 1e-5,
                             max_iter: int = 1000, device: Optional[torch.device] = None, zoo: Any = None,
                             use_progress_bar: bool = True, batch_size: int = 1) -> torch.Tensor:
-        """``path_connected_net.py:155-250``: regress the NormNet-wrapped flow onto its own input with
-        SE("mean") and Adamax(lr, weight_decay) for ``max_iter`` steps.  The reference iterates a shuffled
-        DataLoader with ``batch_size`` frames per step; the fused version takes all frames per step (equal
-        for a single frame, the case of every per-frame config)."""
+        """``path_connected_net.py:155-250``: regress the NormNet-wrapped flow onto its own input with SE("mean") and
+        Adamax(lr, weight_decay).  Like the reference, ``max_iter`` passes over a shuffled ``DataLoader`` of the frames of
+        ``x`` with ``batch_size`` frames per optimizer step (the frame order comes from the same sampler, hence the same
+        global-RNG stream); ``loss_hist[i]`` is the loss of the last batch of pass ``i``.  One frame (every per-frame
+        config) or one batch per pass: the whole fit is replayed from CUDA graphs."""
         from ..fit import OptimConfig, FlowIdentityFitter
         if x.dim() == 3:
             x = x.unsqueeze(0)
         if device is not None and self._ensure_flat().device != torch.device(device):
             self.to(device)
         arena = self._ensure_flat()
-        grid = GridSpecHost.from_tensor(x.to(arena.device))
+        x = x.to(arena.device)
+        T = x.shape[0]
+        bs = max(1, int(batch_size))
         r = self._rnvp
-        if not all(float(r.flows[2 * f + 1].data_dep_init_done) > 0 for f in range(r.n_flows)):
-            self.actnorm_init(grid, use_linear=False)
-        fitter = FlowIdentityFitter(self._prior_for(arena.device), arena, grid,
-                                    OptimConfig("adamax", lr=lr, weight_decay=[weight_decay, 0.0, 0.0, 0.0]))
-        hist = fitter.run(max_iter)
-        fitter.raise_if_nonfinite()
-        return hist.reshape(-1)
+        cfg = OptimConfig("adamax", lr=lr, weight_decay=[weight_decay, 0.0, 0.0, 0.0])
+        if T <= bs:                                       # a single batch per pass: frame order inside it is immaterial
+            grid = GridSpecHost.from_tensor(x)
+            if not all(float(r.flows[2 * f + 1].data_dep_init_done) > 0 for f in range(r.n_flows)):
+                self.actnorm_init(grid, use_linear=False)
+            fitter = FlowIdentityFitter(self._prior_for(arena.device), arena, grid, cfg)
+            hist = fitter.run(max_iter)
+            fitter.raise_if_nonfinite()
+            return hist.reshape(-1)
+        from torch.utils.data import DataLoader, TensorDataset
+        loader = DataLoader(TensorDataset(torch.arange(T)), batch_size=bs, shuffle=True)
+        prior = self._prior_for(arena.device)
+        fitters, stage = {}, {}
+        hist = torch.full((max_iter,), float("nan"), device=arena.device)
+        for i in range(max_iter):
+            for (idx,) in loader:
+                nb = int(idx.numel())
+                if nb not in fitters:
+                    stage[nb] = torch.empty((nb,) + tuple(x.shape[1:]), dtype=torch.float32, device=arena.device)
+                    fitters[nb] = FlowIdentityFitter(prior, arena, GridSpecHost.from_tensor(stage[nb]), cfg, use_graph=False)
+                    if len(fitters) > 1:                  # every batch size steps the same optimizer
+                        fitters[nb].opt_state = next(iter(fitters.values())).opt_state
+                torch.index_select(x, 0, idx.to(arena.device), out=stage[nb])
+                if not all(float(r.flows[2 * f + 1].data_dep_init_done) > 0 for f in range(r.n_flows)):
+                    self.actnorm_init(GridSpecHost.from_tensor(stage[nb]), use_linear=False)   # first batch the flow ever sees
+                hist[i] = fitters[nb].run(1)[0, 0]
+        next(iter(fitters.values())).raise_if_nonfinite()
+        return hist
 
     def learn_convex_net(self, x: torch.Tensor, unaries: torch.Tensor, mode: Literal["circle", "unaries"] = "unaries",
                          use_deformed_grid: bool = True, lr: float = 1e-3, weight_decay: float = 0,
@@ -325,19 +390,49 @@ class PathConnectedNet(ArenaPriorModule):
                          use_progress_bar: bool = True) -> torch.Tensor:
         """``path_connected_net.py:307-390``: fit the ICNN alone (Adam, SE) on the deformed grid."""
         from ..fit import LossConfig, OptimConfig
-        if mode != "unaries":
-            raise NotImplementedError("only mode='unaries' is fused (the mode used by the pretrain loops)")
+        if mode not in ("circle", "unaries"):
+            raise ValueError("Mode must be either 'circle' or 'unaries'!")
         if x.dim() == 3:
             x = x.unsqueeze(0)
+        if unaries.dim() != 4:
+            unaries = unaries.unsqueeze(0)
         arena = self._ensure_flat()
         x = x.to(arena.device)
         if use_deformed_grid:
             x = self.get_deformation(x)
+        if mode == "circle":
+            unaries = 1 - self.get_unary_circle_approximation(1 - unaries[0])[None, ...].float()
         fitter = self.convex_net.make_fitter(x, unaries.to(arena.device), LossConfig("mse"),
                                              OptimConfig("adam", lr=lr, weight_decay=weight_decay))
         hist = fitter.run(max_iter)
         fitter.raise_if_nonfinite()
         return hist.reshape(-1)
+
+    def create_circle(self, grid_shape: Tuple[int, ...], radius: float, center) -> torch.Tensor:
+        """``path_connected_net.py:298-305``, as written there: ``create_coordinate_grid`` returns (x, y) planes and the
+        reference unpacks them as ``yy, xx`` -- the centre's row is compared with the column plane.  Kept bit for bit."""
+        grid = PathConnectedNet.create_coordinate_grid(grid_shape)
+        yy, xx = grid
+        return ((yy - center[0]) ** 2 + (xx - center[1]) ** 2) <= radius ** 2
+
+    def get_unary_circle_approximation(self, unaries: torch.Tensor) -> torch.Tensor:
+        """``path_connected_net.py:143-152``: disc of the mask's area around its centre of mass."""
+        import math
+        area = unaries.sum()
+        com = torch.argwhere(unaries.squeeze() > 0.).to(dtype=torch.float32).mean(dim=0).cpu()
+        radius = math.sqrt(float(area) / math.pi)
+        circle = self.create_circle(tuple(unaries.shape[-2:]), radius, com).to(unaries.device)
+        if unaries.dim() == 3:
+            circle = circle.unsqueeze(0)
+        return circle
+
+    def save_state(self, path: str) -> None:
+        import os
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+        torch.save(self.state_dict(), path)
+
+    def load_state(self, path: str) -> None:
+        self.load_state_dict(torch.load(path))
 
     def pretrain(self, *args, **kwargs):
         """``PretrainableModule.pretrain`` (``path_connected_net.py:472-509``), see ``awesome_b200/pretrain.py``."""
@@ -379,7 +474,7 @@ class NoisyPathConnectedNet(PathConnectedNet):
 
 def real_nvp_path_connected_net(channels: int = 2, hidden_units: int = 130, flow_n_flows: int = 6,
                                 flow_output_fn: Optional[str] = None, flow_output_scale: Optional[float] = None,
-                                norm: Literal["minmax"] = "minmax", spatial_shape: tuple = (1000, 1000),
+                                norm: Literal["minmax", "meanstd"] = "minmax", spatial_shape: tuple = (1000, 1000),
                                 convex_net_hidden_units: int = 130, convex_net_hidden_layers: int = 2,
                                 dtype: torch.dtype = torch.float32, network_type: Optional[type] = None,
                                 network_args: Optional[Dict[str, Any]] = None, precision: str = "fp32",
@@ -394,9 +489,26 @@ def real_nvp_path_connected_net(channels: int = 2, hidden_units: int = 130, flow
                         output_scale=flow_output_scale, n_flows=flow_n_flows,
                         height=spatial_shape[0], width=spatial_shape[1])
     nrm = get_norm(norm, dim=(0, 2, 3))
-    nrm.fitted = True
-    nrm.min = torch.zeros(1, channels, 1, 1)
-    nrm.max = torch.ones(1, channels, 1, 1)
+    if isinstance(nrm, MeanStd):
+        # fitted like the reference on the normalised coordinate grid of ``spatial_shape`` (net_factory.py:159-165); the grid
+        # factorises per axis, so mean / unbiased std per channel follow from the 1-D coordinate vectors (fp64, then fp32)
+        dims = tuple(spatial_shape)[::-1][:channels] if channels == 2 else (spatial_shape[-1], spatial_shape[-2], spatial_shape[0])
+        total = 1
+        for d_ in spatial_shape:
+            total *= int(d_)
+        means, stds = [], []
+        for n_c in dims:
+            v = torch.arange(int(n_c), dtype=torch.float64) / max(1, int(n_c) - 1)
+            mu = v.mean()
+            var = ((v - mu) ** 2).mean() * total / max(1, total - 1)
+            means.append(float(mu)); stds.append(float(var.sqrt()))
+        nrm.fitted = True
+        nrm.mean = torch.tensor(means, dtype=torch.float32).view(1, channels, 1, 1)
+        nrm.std = torch.tensor(stds, dtype=torch.float32).view(1, channels, 1, 1)
+    else:
+        nrm.fitted = True
+        nrm.min = torch.zeros(1, channels, 1, 1)
+        nrm.max = torch.ones(1, channels, 1, 1)
     norm_flow = NormNet(net=PixelizeNet(flow), norm=nrm)
     return network_type(convex_net=ConvexNextNet(n_hidden=convex_net_hidden_units,
                                                  n_hidden_layers=convex_net_hidden_layers,

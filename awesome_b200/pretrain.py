@@ -33,7 +33,9 @@ class FitSchedule:
     reuse_state: bool = True
     reuse_state_epochs: int = 200
     batch_size: int = 1
+    dataloader_shuffle: bool = False     # spatio-temporal loop: shuffled frame batches per epoch (:550, :654)
     noisy_percentage: float = 0.0        # NoisyPathConnectedNet (noisy_path_connected_net.py:87): frames with noise unaries
+    unet_batch_size: int = 8             # N1: frames per frozen-UNet inference call when collecting the unaries
     prefit_flow_net_identity: bool = False
     prefit_flow_net_identity_lr: float = 1e-2
     prefit_flow_net_identity_weight_decay: float = 1e-5
@@ -48,6 +50,9 @@ class FitSchedule:
     weight_decay_on_weight_g: float = 0.0    # ConvexDiffeomorphismNet.pretrain decays only the weight-norm gains
     optimizer: str = "adamax"            # the pretrain loops use Adamax + plateau(200, 0.5) (:929-933)
     plateau: bool = True
+    plateau_patience: int = 200          # ReduceLROnPlateau(patience=200, factor=0.5) in every pretrain loop (:644, :932)
+    plateau_factor: float = 0.5
+    plateau_threshold: float = 1e-4      # torch default (rel)
     steps_per_graph: int = 50
 
     @classmethod
@@ -62,7 +67,8 @@ class FitSchedule:
 
     def optim(self, has_flow: bool) -> OptimConfig:
         wd = [self.flow_weight_decay if has_flow else 0.0, 0.0, 0.0, self.weight_decay_on_weight_g]
-        return OptimConfig(self.optimizer, lr=self.lr, weight_decay=wd, plateau=self.plateau, patience=200, factor=0.5)
+        return OptimConfig(self.optimizer, lr=self.lr, weight_decay=wd, plateau=self.plateau, patience=self.plateau_patience,
+                           factor=self.plateau_factor, threshold=self.plateau_threshold)
 
 
 @dataclass
@@ -98,7 +104,7 @@ def mask_iou(pred_prob: torch.Tensor, target_prob: torch.Tensor) -> float:
 def fit_frames(model, grids: Sequence, unaries: Sequence[torch.Tensor], schedule: Optional[FitSchedule] = None,
                on_frame: Optional[Callable[[FrameResult], None]] = None, frame_indices: Optional[Sequence[int]] = None,
                warm_start_hook: Optional[Callable[[Any, torch.Tensor, Any], None]] = None,
-               keep_masks: bool = False) -> List[FrameResult]:
+               keep_masks: bool = False, initial_previous: Optional[torch.Tensor] = None) -> List[FrameResult]:
     """Fit ``model`` (ConvexNextNet or PathConnectedNet drop-in) to every frame in turn.  ``grids[i]`` is a
     ``[1,C,H,W]`` tensor or ``GridSpecHost``; ``unaries[i]`` the frame's soft segmentation (any shape with H*W
     elements; convention fg = 0, bg = 1 like the reference).  The model ends holding the last proper state."""
@@ -108,7 +114,7 @@ def fit_frames(model, grids: Sequence, unaries: Sequence[torch.Tensor], schedule
     has_flow = hasattr(model, "flow_net")
     flow_group = has_flow or hasattr(model, "diffeo_net")
     results: List[FrameResult] = []
-    previous: Optional[torch.Tensor] = None
+    previous: Optional[torch.Tensor] = initial_previous      # a proper state carried in from an earlier call / a checkpoint
     fitter: Optional[PriorFitter] = None
     fitter_key = None
     for k, (grid, un) in enumerate(zip(grids, unaries)):
@@ -302,12 +308,28 @@ def noisy_unaries(unaries: torch.Tensor, noisy_percentage: float, seed: Optional
     return out, idx
 
 
+def _plateau_hyper(s: FitSchedule, has_flow: bool):
+    o = s.optim(has_flow)
+    o.plateau = True
+    return o.to_c()
+
+
 def fit_sequence(model, n_frames: int, H: int, W: int, unaries: torch.Tensor, schedule: Optional[FitSchedule] = None,
-                 grid_mode: str = "linspace") -> torch.Tensor:
-    """Spatio-temporal fit (``_non_prior_based_pretrain``, ``path_connected_net.py:652-719``): one (x, y, t) prior,
-    ``num_epochs`` passes over the ``ceil(T / batch_size)`` frame batches in order.  ``unaries`` ``[T,H,W]``;
-    frame ``i`` has ``t = i / (T - 1)`` (``awesome/dataset/transformator.py:54-60``).  Returns the loss history
-    ``[num_epochs * n_batches]`` (device)."""
+                 grid_mode: str = "linspace", first_last_unaries: Optional[torch.Tensor] = None,
+                 lr_trace: Optional[list] = None) -> torch.Tensor:
+    """Spatio-temporal fit (``_non_prior_based_pretrain``, ``path_connected_net.py:511-728``): ONE (x, y, t) prior for all
+    frames.  ``unaries`` ``[T,H,W]``; frame ``i`` has ``t = i / (T - 1)`` (``awesome/dataset/transformator.py:54-60``).
+
+    * prefits (``:577-631``): ``learn_flow_identity`` on the normalised ``(T, 3, H, W)`` grid in shuffled batches of
+      ``batch_size`` frames, then ``learn_convex_net`` on the first and the last frame stacked (their unaries:
+      ``first_last_unaries`` ``[2,H,W]``, default ``unaries[[0, -1]]``);
+    * main loop (``:633-719``): ONE optimizer (Adamax, flow weight decay) for all epochs, ``num_epochs`` passes over the
+      ``ceil(T / batch_size)`` frame batches (in order, or shuffled with ``dataloader_shuffle``), one fused fit step per
+      batch; ``ReduceLROnPlateau.step`` ONCE PER EPOCH on the epoch-mean loss (``:719``) -- the batch steps run with the
+      scheduler off and the epoch end calls ``awb_opt_plateau_step``.
+    Returns the per-step loss history ``[num_epochs * n_batches]`` (device)."""
+    import ctypes as C
+    import dataclasses
     s = schedule or FitSchedule()
     arena = model._ensure_flat()
     dev = arena.device
@@ -317,25 +339,171 @@ def fit_sequence(model, n_frames: int, H: int, W: int, unaries: torch.Tensor, sc
     if s.noisy_percentage > 0:
         un, _ = noisy_unaries(un, s.noisy_percentage)
     has_flow = hasattr(model, "flow_net")
+    C_in = getattr(model, "in_channels", getattr(model, "in_features", 2))
+    full = GridSpecHost(grid_mode, T, H, W, t0=0.0, t_step=t_step)
+    if has_flow and s.prefit_flow_net_identity:
+        model.learn_flow_identity(full.materialize(C_in, dev), lr=s.prefit_flow_net_identity_lr,
+                                  weight_decay=s.prefit_flow_net_identity_weight_decay,
+                                  max_iter=s.prefit_flow_net_identity_num_epochs, use_progress_bar=False, batch_size=bs)
+    if has_flow and s.prefit_convex_net:
+        fl = first_last_unaries if first_last_unaries is not None else un[[0, T - 1]]
+        g2 = torch.stack([GridSpecHost(grid_mode, 1, H, W, t0=0.0).materialize(C_in, dev)[0],
+                          GridSpecHost(grid_mode, 1, H, W, t0=(T - 1) * t_step).materialize(C_in, dev)[0]])
+        model.learn_convex_net(g2, fl.detach().to(dev).float().reshape(2, 1, H, W), mode="unaries", use_deformed_grid=True,
+                               lr=s.prefit_convex_net_lr, weight_decay=s.prefit_convex_net_weight_decay,
+                               max_iter=s.prefit_convex_net_num_epochs, use_progress_bar=False)
     if has_flow:
-        model._maybe_actnorm_init(GridSpecHost(grid_mode, T, H, W, t0=0.0, t_step=t_step).materialize(model.in_channels, dev))
-    fitters = []
-    for b0 in range(0, T, bs):
-        nb = min(bs, T - b0)
-        spec = GridSpecHost(grid_mode, nb, H, W, t0=b0 * t_step, t_step=t_step)
-        f = model.make_fitter(spec, un[b0:b0 + nb].reshape(1, -1), s.criterion, s.optim(has_flow), use_graph=False)
-        fitters.append(f)
-    # all batches share ONE optimizer state (the reference builds the optimizer once, outside the loops: :642-645)
-    for f in fitters[1:]:
-        f.opt_state = fitters[0].opt_state
-        if f.ws.numel() == fitters[0].ws.numel():
-            f.ws = fitters[0].ws                     # batches run one after the other: one scratch area
-    hist = []
-    for _ in range(s.num_epochs):
-        for f in fitters:
-            hist.append(f.run(1)[0, 0])
-    fitters[0].raise_if_nonfinite()
+        model._maybe_actnorm_init(full.materialize(C_in, dev)[:min(bs, T)])     # first batch the full prior ever sees
+    # batch steps never advance the scheduler; the epoch end does
+    step_optim = dataclasses.replace(s.optim(has_flow), plateau=False)
+    plateau_hy = _plateau_hyper(s, has_flow)
+    n_batches = (T + bs - 1) // bs
+    hist: List[torch.Tensor] = []
+    first: Optional[PriorFitter] = None
+
+    def share(f: PriorFitter) -> PriorFitter:
+        nonlocal first
+        if first is None:
+            first = f
+        else:                       # the reference builds the optimizer once, outside the loops (:633-645)
+            f.opt_state = first.opt_state
+            if f.ws.numel() == first.ws.numel():
+                f.ws = first.ws     # batches run one after the other: one scratch area
+        return f
+
+    def end_of_epoch(losses: List[torch.Tensor]) -> None:
+        if not s.plateau:
+            return
+        mean = torch.stack(losses).mean().reshape(1)
+        L.check(first.lib.awb_opt_plateau_step(first.prior.handle, first.opt_state.data_ptr(), mean.data_ptr(), 0,
+                                               C.byref(plateau_hy), L.stream_ptr()))
+        first._keep = mean          # the kernel reads it asynchronously
+        if lr_trace is not None:    # diagnostics / tests: the learning rates after this epoch's scheduler step (synchronises)
+            lr_trace.append(list(first.scalars(0).lr))
+
+    if not s.dataloader_shuffle:
+        fitters = []
+        for b0 in range(0, T, bs):
+            nb = min(bs, T - b0)
+            spec = GridSpecHost(grid_mode, nb, H, W, t0=b0 * t_step, t_step=t_step)
+            fitters.append(share(model.make_fitter(spec, un[b0:b0 + nb].reshape(1, -1), s.criterion, step_optim,
+                                                   use_graph=False)))
+        for _ in range(s.num_epochs):
+            ep = [f.run(1)[0, 0] for f in fitters]
+            hist += ep
+            end_of_epoch(ep)
+    else:
+        # shuffled batches (the reference's DataLoader(shuffle=True): same sampler, same global-RNG stream): the frames of a
+        # batch are not equidistant in t, so the batch grid is gathered into a staging tensor
+        from torch.utils.data import DataLoader, TensorDataset
+        gfull = full.materialize(C_in, dev)
+        stage_g, stage_u, fitters_by = {}, {}, {}
+        for _ in range(s.num_epochs):
+            ep = []
+            for (idx,) in DataLoader(TensorDataset(torch.arange(T)), batch_size=bs, shuffle=True):
+                nb = int(idx.numel())
+                if nb not in fitters_by:
+                    stage_g[nb] = torch.empty((nb, C_in, H, W), dtype=torch.float32, device=dev)
+                    stage_u[nb] = torch.empty((1, nb * H * W), dtype=torch.float32, device=dev)
+                    fitters_by[nb] = share(model.make_fitter(GridSpecHost.from_tensor(stage_g[nb]), stage_u[nb], s.criterion,
+                                                             step_optim, use_graph=False))
+                di = idx.to(dev)
+                torch.index_select(gfull, 0, di, out=stage_g[nb])
+                fitters_by[nb].set_target(torch.index_select(un, 0, di).reshape(1, -1))
+                ep.append(fitters_by[nb].run(1)[0, 0])
+            hist += ep
+            end_of_epoch(ep)
+    if first is not None:
+        first.raise_if_nonfinite()
     return torch.stack(hist) if hist else torch.empty(0, device=dev)
+
+
+# ------------------------------------------------------------------ pretrain checkpoints (reference format)
+def save_pretrain_checkpoint(model, path: str) -> bool:
+    """``path_connected_net.py:45-51``: ``torch.save(model.state_dict(), path)``."""
+    try:
+        torch.save({k: v.detach().cpu() for k, v in model.state_dict().items()}, path)
+        return True
+    except Exception as e:          # the reference logs and carries on
+        logging.error("Could not save pretrain checkpoint to %s. Error: %s", path, e)
+        return False
+
+
+def load_pretrain_checkpoint(model, path: str, device=None) -> bool:
+    """``path_connected_net.py:33-43``: ``model.load_state_dict(torch.load(path, map_location=device))``."""
+    try:
+        model.load_state_dict(torch.load(path, map_location=device))
+        return True
+    except Exception as e:
+        logging.error("Could not load pretrain checkpoint from %s. Error: %s", path, e)
+        return False
+
+
+# ------------------------------------------------------------------ N1: unaries of the frozen segmentation net, batched
+def _cat_inputs(items: Sequence[Any]):
+    """Stack the per-frame inputs (each a tensor or a list / tuple of tensors with leading batch dimension 1)."""
+    first = items[0]
+    if torch.is_tensor(first):
+        return [torch.cat(list(items), dim=0)]
+    return [torch.cat([it[j] for it in items], dim=0) if torch.is_tensor(first[j]) else first[j] for j in range(len(first))]
+
+
+def collect_unaries(wrapper_module, agent, train_set, device, unet_batch_size: int = 8):
+    """The UNet side of the pretrain loops (``path_connected_net.py:672-676, 832-836``): the reference evaluates the frozen
+    segmentation net once per frame and loop iteration (per EPOCH in the spatio-temporal loop).  Here every frame is
+    evaluated once, ``unet_batch_size`` frames per call (the net is in eval mode: BatchNorm uses its running statistics, so a
+    frame's unaries do not depend on its batch mates), and the unaries stay on the device for all epochs.
+    Returns (inputs per frame, grids ``[1,C,H,W]`` per frame, unaries ``[1,1,H,W]`` per frame, prior keys)."""
+    from torch.utils.data import DataLoader
+    loader = DataLoader(train_set, batch_size=1, shuffle=False)
+    dec = [agent._decompose_training_item(item) for item in loader]
+    ins = [d[0] if isinstance(d[0], (list, tuple)) else [d[0]] for d in dec]
+    keys = [int(d[3][0]) if d[3] is not None else i for i, d in enumerate(dec)]
+    grids, uns, dev_ins = [], [], []
+    old = getattr(wrapper_module, "evaluate_prior", True)
+    wrapper_module.evaluate_prior = False
+    try:
+        bs = max(1, int(unet_batch_size))
+        for b0 in range(0, len(ins), bs):
+            chunk = ins[b0:b0 + bs]
+            batch = [x.to(device) if torch.is_tensor(x) else x for x in _cat_inputs(chunk)]
+            with torch.no_grad():
+                u = wrapper_module(*batch)
+            for k in range(len(chunk)):
+                one = [x[k:k + 1] if torch.is_tensor(x) else x for x in batch]
+                pa, _ = wrapper_module.get_prior_args(one[0], *one[1:], segm=u[k])
+                g = pa[0].detach()
+                grids.append(g if g.dim() == 4 else g.unsqueeze(0))
+                uns.append(u[k:k + 1].detach())
+                dev_ins.append(one)
+    finally:
+        wrapper_module.evaluate_prior = old
+    return dev_ins, grids, uns, keys
+
+
+def evaluate_frames(wrapper_module, agent, dataset, device, prior_cache=None, unet_batch_size: int = 8) -> List[torch.Tensor]:
+    """Evaluation path of ``get_result`` (``awesome/run/functions.py:2111-2151``) over a whole dataset: segmentation net
+    batched over frames, the prior evaluated per frame with that frame's weights swapped in from ``prior_cache``
+    (``PriorManager``, ``awesome/dataset/prior_dataset.py:70-110``).  Returns per frame ``cat([sigmoid(seg), sigmoid(prior)], 1)``
+    on the host -- what ``WrapperModule.forward`` returns for ``evaluate_prior=True`` (``wrapper_module.py:157-228``)."""
+    was = wrapper_module.training
+    wrapper_module.eval()
+    try:
+        _, grids, uns, keys = collect_unaries(wrapper_module, agent, dataset, device, unet_batch_size)
+        prior = wrapper_module.prior_module
+        out = []
+        with torch.no_grad():
+            for g, u, key in zip(grids, uns, keys):
+                if prior_cache is not None and hasattr(prior_cache, "load_into"):
+                    prior_cache.load_into(prior, key)
+                elif prior_cache is not None:
+                    prior.load_state_dict(prior_cache[key])
+                p = prior(g.to(device))
+                p = torch.sigmoid(p) if getattr(wrapper_module, "use_prior_sigmoid", True) else p
+                out.append(torch.cat([u, p.reshape(u.shape)], dim=1).cpu())
+        return out
+    finally:
+        wrapper_module.train(was)
 
 
 # ------------------------------------------------------------------ PretrainableModule protocol (duck-typed)
@@ -345,42 +513,69 @@ def pretrain(self, train_set, test_set=None, device=None, agent=None, use_progre
     """``PathConnectedNet.pretrain`` (``path_connected_net.py:472-509``) with the reference's arguments.  The agent,
     dataset and wrapper module are the reference's objects (this module is plugged into ``scripts/run.py``):
     ``agent._decompose_training_item`` splits a dataset item, ``wrapper_module(...)`` with ``evaluate_prior=False``
-    yields the UNet unaries, ``wrapper_module.get_prior_args`` the coordinate grid."""
+    yields the UNet unaries, ``wrapper_module.get_prior_args`` the coordinate grid.
+
+    Per-frame mode (dataset with a prior cache): ``fit_frames`` per frame; ``pretrain_checkpoint_{i}.pth`` (the frame's
+    ``state_dict``, ``torch.save``) is written after every fitted frame with ``do_pretrain_checkpoints`` and, with
+    ``use_pretrain_checkpoints``, an existing file is loaded instead of fitting -- the loaded state counts as a proper fit
+    and becomes the warm start of the next frame (``:857-870, 996-998``).  Otherwise the spatio-temporal ``fit_sequence``."""
+    import os
     if wrapper_module is None:
         raise ValueError("Wrapper model must be provided for pretraining.")
+    if do_pretrain_checkpoints:
+        if pretrain_checkpoint_dir is None:
+            raise ValueError("Pretrain checkpoint dir must be provided.")
+        os.makedirs(pretrain_checkpoint_dir, exist_ok=True)
     sched = FitSchedule.from_pretrain_args(kwargs)
     device = torch.device(device) if device is not None else self._ensure_flat().device
     ds = getattr(agent, "training_dataset", None)
     cache = getattr(ds, "__prior_cache__", None)
     per_frame = cache is not None and bool(getattr(ds, "has_prior", getattr(ds, "__has_prior__", False)))
-    from torch.utils.data import DataLoader
-    loader = DataLoader(train_set, batch_size=1, shuffle=False)
     was_training = wrapper_module.training
     wrapper_module.eval()
-    grids, uns, keys = [], [], []
     try:
-        for i, item in enumerate(loader):
-            inputs, labels, indices, prior_state = agent._decompose_training_item(item)
-            dev_in = [x.to(device) if torch.is_tensor(x) else x for x in (inputs if isinstance(inputs, (list, tuple)) else [inputs])]
-            old = getattr(wrapper_module, "evaluate_prior", True)
-            wrapper_module.evaluate_prior = False
-            try:
-                with torch.no_grad():
-                    u = wrapper_module(*dev_in)
-            finally:
-                wrapper_module.evaluate_prior = old
-            pa, _ = wrapper_module.get_prior_args(dev_in[0], *dev_in[1:], segm=u[0, ...])
-            grids.append(pa[0].detach())
-            uns.append(u.detach())
-            keys.append(int(prior_state[0]) if prior_state is not None else i)
+        _, grids, uns, keys = collect_unaries(wrapper_module, agent, train_set, device, sched.unet_batch_size)
         if per_frame:
             def keep(res: FrameResult):
-                if not res.skipped and hasattr(cache, "store_from"):
+                if res.skipped:
+                    return
+                if hasattr(cache, "store_from"):
                     cache.store_from(self, res.index)
-                elif not res.skipped:
+                else:
                     cache[res.index] = {k: v.detach().clone() for k, v in self.state_dict().items()}
-            fit_frames(self, [g if g.dim() == 4 else g.unsqueeze(0) for g in grids], uns, sched, on_frame=keep,
-                       frame_indices=keys, warm_start_hook=kwargs.get("_warm_start_hook"))
+
+            pos_of = {k: i for i, k in enumerate(keys)}
+            run: List[int] = []            # consecutive frames without a checkpoint: one fit_frames call (keeps the chain)
+            previous_from_ckpt = [None]
+
+            def flush():
+                if not run:
+                    return
+                def on_frame(res: FrameResult):
+                    keep(res)
+                    if do_pretrain_checkpoints and not res.skipped:
+                        # on_frame runs right after the frame's fit: the module holds exactly this frame's state (:996-998)
+                        save_pretrain_checkpoint(self, os.path.join(pretrain_checkpoint_dir,
+                                                                    f"pretrain_checkpoint_{pos_of[res.index]}.pth"))
+                if previous_from_ckpt[0] is not None:
+                    self.load_state_dict(previous_from_ckpt[0])
+                fit_frames(self, [grids[i] for i in run], [uns[i] for i in run], sched, on_frame=on_frame,
+                           frame_indices=[keys[i] for i in run], warm_start_hook=kwargs.get("_warm_start_hook"),
+                           initial_previous=self._ensure_flat().detach().clone() if previous_from_ckpt[0] is not None else None)
+                previous_from_ckpt[0] = {k: v.detach().clone() for k, v in self.state_dict().items()}
+                run.clear()
+
+            for i in range(len(grids)):
+                path = os.path.join(pretrain_checkpoint_dir, f"pretrain_checkpoint_{i}.pth") if pretrain_checkpoint_dir else None
+                if use_pretrain_checkpoints and path and os.path.exists(path):
+                    flush()
+                    if load_pretrain_checkpoint(self, path, device=device):
+                        logging.info("Loaded pretrain checkpoint from %s. Continuing with next image.", path)
+                        keep(FrameResult(index=keys[i], proper_fit=True))
+                        previous_from_ckpt[0] = {k: v.detach().clone() for k, v in self.state_dict().items()}
+                        continue
+                run.append(i)
+            flush()
             return cache.get_state()
         T = len(grids)
         H, W = grids[0].shape[-2:]

@@ -376,9 +376,11 @@ def joint_leg(A, dev, rank: int, world: int, barrier, precision: str, steps: int
         tr.bucket.remove_hooks()
         return tr, ms, float(loss)
 
-    tr, ms_overlap, loss = run("overlap")
-    out.update(bucket_bytes=tr.bucket.nbytes, n_buckets=tr.bucket.n_buckets, ms_per_step=ms_overlap,
-               frames_per_s=world * B / ms_overlap * 1e3, final_loss=loss)
+    # default mode of JointTrainer: ONE all-reduce of the flat bucket between backward and optimizer.step (measured faster than
+    # the bucketed overlap on NVSwitch: the collective takes ~0.5 % of the step, the hooks and the concurrent NCCL kernels cost more)
+    tr, ms_after, loss = run("after")
+    out.update(bucket_bytes=tr.bucket.nbytes, ms_per_step=ms_after, frames_per_s=world * B / ms_after * 1e3, final_loss=loss,
+               exchange="one NCCL all-reduce (AVG) of the flat fp32 gradient bucket after backward")
     if world > 1:
         flat = torch.cat([p.detach().reshape(-1) for p in list(seg.parameters()) + list(pri.parameters())])
         ref = flat.clone()
@@ -386,8 +388,6 @@ def joint_leg(A, dev, rank: int, world: int, barrier, precision: str, steps: int
         same = torch.tensor([float(torch.equal(ref, flat))], device=dev)
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         out["replicas_bit_identical"] = bool(same.item() > 0)
-        del tr
-        tr, ms_after, _ = run("after")
         buf = tr.bucket.flat
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -400,11 +400,16 @@ def joint_leg(A, dev, rank: int, world: int, barrier, precision: str, steps: int
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ar = float(t[0])
         del tr
+        tr, ms_overlap, _ = run("overlap")
+        nb = tr.bucket.n_buckets
+        del tr
         _, ms_off, _ = run("off")
-        hidden = (ms_after - ms_overlap) / ar if ar > 0 else None
-        out.update(ms_per_step_allreduce_after_backward=ms_after, ms_per_step_no_exchange=ms_off, allreduce_ms_alone=ar,
+        hidden = (ms_after - ms_overlap) / ar if ar > 0 else 0.0
+        out.update(ms_per_step_bucketed_overlap=ms_overlap, n_buckets_overlap=nb, ms_per_step_no_exchange=ms_off,
+                   allreduce_ms_alone=ar, allreduce_share_of_step=ar / ms_after,
                    allreduce_busbw_GBps=2 * (world - 1) / world * buf.numel() * 4 / (ar * 1e-3) / 1e9,
-                   exposed_comm_ms=ms_overlap - ms_off, overlapped_fraction=None if hidden is None else max(0.0, min(1.0, hidden)))
+                   exposed_comm_ms=ms_after - ms_off, overlap_gain_ms=ms_after - ms_overlap,
+                   overlapped_fraction=max(0.0, min(1.0, hidden)))
     del seg, pri
     torch.cuda.empty_cache()
     return out

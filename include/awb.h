@@ -137,6 +137,10 @@ int64_t awb_opt_state_bytes(awb_handle h);
 int awb_prior_set_flow_consts(awb_handle h, const float* norm_min, const float* norm_max,
                               float new_min, float new_max, const uint8_t* masks);
 
+/* output_scale of the coupling MLPs (normflows nets.MLP(..., output_fn, output_scale), net_factory.py:104-105): s, t =
+ * scale * tanh(.).  Only applied with an output_fn (flow_tanh == 1), like normflows; default 1. */
+int awb_prior_set_flow_output_scale(awb_handle h, float scale);
+
 /* forward(grid) -> raw logits [O][N]  (ConvexNextNet.forward convex_net.py:205-214;
  * PathConnectedNet.forward path_connected_net.py:79-85).  Leaves activations in the
  * workspace for awb_prior_backward when training != 0.  deformed (optional, [O][N][C])
@@ -204,6 +208,12 @@ int awb_opt_state_init(awb_handle h, void* opt_state, const double* lr_per_group
 /* Overwrite the learning rates only (torch lr schedulers mutate param_group["lr"] between steps:
  * awesome/agent/torch_agent.py:308-325); moments, step counter and plateau state are kept. */
 int awb_opt_set_lr(awb_handle h, void* opt_state, const double* lr_per_group, void* stream);
+/* lr_scheduler.step(loss) alone: ReduceLROnPlateau on a caller-provided loss (device pointer, [O] or one scalar shared by
+ * all objects when loss_stride == 0), without an optimizer step.  The spatio-temporal pretrain loop steps its scheduler
+ * once per EPOCH on the epoch-mean loss (awesome/model/path_connected_net.py:719), not once per batch: its batch steps run
+ * with hyper->plateau_enabled == 0 and the epoch end calls this. */
+int awb_opt_plateau_step(awb_handle h, void* opt_state, const float* loss, int32_t loss_stride, const awb_opt_hyper* hyper,
+                         void* stream);
 /* synchronises the stream and copies the scalars of object obj to the host. */
 int awb_opt_read_scalars(awb_handle h, const void* opt_state, int32_t obj, awb_opt_scalars* out,
                          void* stream);

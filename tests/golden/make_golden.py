@@ -209,6 +209,76 @@ def gen_pcn(channels, n_flows, T=None):
     return out
 
 
+def gen_variants():
+    """Round-2 rows: meanstd norm + output_scale, circle prefit, shuffled-batch flow-identity prefit and the
+    spatio-temporal main loop with its once-per-epoch scheduler -- all run by the reference's modules."""
+    H, W, T = 14, 18, 5
+    out = {"H": H, "W": W, "T": T}
+    # (1) meanstd + output_scale through the reference factory
+    seed_all(21)
+    m = real_nvp_path_connected_net(channels=2, hidden_units=16, flow_n_flows=4, flow_output_fn="tanh", flow_output_scale=0.5,
+                                    norm="meanstd", spatial_shape=(H, W), convex_net_hidden_units=130, convex_net_hidden_layers=1)
+    x = Transformator.get_positional_matrices(W, H)[None]
+    un = blob_unaries(H, W, soft=True, seed=4)[None, None]
+    g = torch.Generator().manual_seed(3)
+    m.train()
+    m(x)                                              # ActNorm data-dependent init
+    with torch.no_grad():                             # move off the zero-initialised couplings, or scale / tanh are invisible
+        for k_, p_ in m.flow_net.named_parameters():
+            p_.add_(0.2 * torch.randn(p_.shape, generator=g))
+    m.zero_grad()
+    y = m(x)
+    loss = UnariesWeightedLoss(SE("mean"))(torch.sigmoid(y), un)
+    loss.backward()
+    out["ms"] = {"state": sd(m), "grid": x, "unaries": un, "logits": y.detach().clone(), "loss": loss.detach().clone(),
+                 "grads": grads(m), "deformation": m.get_deformation(x).detach().clone()}
+    # (2) circle approximation + learn_convex_net(mode="circle")
+    seed_all(22)
+    m2 = real_nvp_path_connected_net(channels=2, hidden_units=16, flow_n_flows=4, flow_output_fn="tanh", norm="minmax",
+                                     convex_net_hidden_units=130, convex_net_hidden_layers=1)
+    hard = blob_unaries(H, W, soft=False, seed=5, cx=0.4, cy=0.6, rx=0.2, ry=0.3)[None, None]
+    m2.train()
+    m2(x)
+    out["circle"] = {"state": sd(m2), "unaries": hard, "circle": m2.get_unary_circle_approximation(1 - hard[0]).clone()}
+    hist = m2.learn_convex_net(x, hard, mode="circle", use_deformed_grid=True, lr=1e-3, max_iter=3, device=torch.device("cpu"),
+                               use_progress_bar=False)
+    out["circle"]["hist"], out["circle"]["after"] = hist.detach().clone(), sd(m2)
+    # (3) spatio-temporal: flow identity prefit in shuffled batches, then the main loop (path_connected_net.py:633-719)
+    seed_all(23)
+    m3 = real_nvp_path_connected_net(channels=3, hidden_units=16, flow_n_flows=6, flow_output_fn="tanh", norm="minmax",
+                                     convex_net_hidden_units=130, convex_net_hidden_layers=1)
+    xs = torch.stack([Transformator.get_positional_matrices(W, H, t=t, t_max=T - 1) for t in range(T)])
+    uns = torch.stack([blob_unaries(H, W, soft=True, seed=30 + t, cx=0.35 + 0.07 * t)[None] for t in range(T)])
+    out["st"] = {"init": sd(m3), "grid": xs, "unaries": uns}
+    seed_all(24)                                       # the DataLoader's shuffle draws from the global RNG
+    ih = m3.learn_flow_identity(PathConnectedNet.create_normalized_grid((T, H, W)), lr=1e-2, weight_decay=1e-5, max_iter=3,
+                                device=torch.device("cpu"), use_progress_bar=False, batch_size=2)
+    out["st"]["identity_hist"], out["st"]["after_identity"] = ih.detach().clone(), sd(m3)
+    groups = [dict(params=m3.flow_net.parameters(), weight_decay=1e-5), dict(params=m3.convex_net.parameters()),
+              dict(params=m3.linear.parameters())]
+    opt = torch.optim.Adamax(groups, lr=1e-3)
+    sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, patience=1, factor=0.5, threshold=0.9)
+    crit = UnariesWeightedLoss(SE("mean"))
+    bs, step_hist, lrs = 2, [], []
+    m3.train()
+    for epoch in range(5):
+        ep, n_steps = torch.tensor(0.), (T + bs - 1) // bs
+        for b0 in range(0, T, bs):
+            opt.zero_grad()
+            o = torch.sigmoid(m3(xs[b0:b0 + bs]))
+            l = crit(o, uns[b0:b0 + bs])
+            l.backward()
+            opt.step()
+            m3.enforce_convexity()
+            step_hist.append(float(l))
+            ep += (1 / n_steps) * l.item()
+        sched.step(ep)
+        lrs.append(opt.param_groups[0]["lr"])
+    out["st"].update(step_hist=torch.tensor(step_hist), lrs=torch.tensor(lrs), final=sd(m3),
+                     plateau_args=dict(patience=1, factor=0.5, threshold=0.9))
+    return out
+
+
 def gen_diffeo():
     """a6: ConvexDiffeomorphismNet (NormalizingFlow1D + ConvexNextNet)."""
     H, W = 16, 20
@@ -299,6 +369,7 @@ def main():
         "icnn_c2.pt": gen_icnn_c2,
         "pcn_c3.pt": lambda: gen_pcn(2, 12),
         "pcn_c5.pt": lambda: gen_pcn(3, 18, T=2),
+        "variants.pt": gen_variants,
         "diffeo.pt": gen_diffeo,
         "star.pt": gen_star,
         "losses.pt": gen_losses,
