@@ -19,4 +19,8 @@ from .model import (BatchSizeMultiPriorModule, ConvexDiffeomorphismNet, ConvexNe
                     MultipleObjectsAwarePathConnectedNet, NoisyPathConnectedNet, NormNet, NumberBasedMultiPriorModule, PathConnectedNet,
                     PixelizeNet, StarFitter, StarShapedNet, get_norm, init_realnvp, real_nvp_path_connected_net)
 
-__version__ = "0.1.0"
+from .reference_bridge import integrate_with_reference  # noqa: F401,E402
+
+integrate_with_reference()          # no-op unless the reference package is already imported in this process
+
+__version__ = "0.2.0"

@@ -93,6 +93,8 @@ class ArenaPriorModule(nn.Module):
         self._prior_device = None
         from ..optim import _ARENA_MODULES
         _ARENA_MODULES.add(self)
+        from ..reference_bridge import integrate_with_reference
+        integrate_with_reference()
 
     def _optimizer_group_ids(self) -> List[int]:
         """Native optimizer group of every arena parameter (0 flow_net, 1 convex_net, 2 linear), in arena order."""

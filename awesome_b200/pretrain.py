@@ -448,6 +448,24 @@ def _cat_inputs(items: Sequence[Any]):
     return [torch.cat([it[j] for it in items], dim=0) if torch.is_tensor(first[j]) else first[j] for j in range(len(first))]
 
 
+def _segmentation_unaries(wrapper_module, batch):
+    """Unaries ``[k,1,H,W]`` of ``k`` stacked frames.  The reference ``WrapperModule.forward`` loops over the batch items and
+    calls the segmentation net once per image (``wrapper_module.py:196-239``); for a real reference wrapper the net is called
+    ONCE on the stacked frames with the wrapper's own argument selection and output processing
+    (``get_segmentation_module_args`` ``:141-155``, ``process_segmentation_output`` ``:248-262``: sigmoid, inversion -- both
+    elementwise).  Duck-typed wrappers are simply called."""
+    seg = getattr(wrapper_module, "segmentation_module", None)
+    if seg is None or not hasattr(wrapper_module, "get_segmentation_module_args") or not hasattr(wrapper_module, "process_segmentation_output"):
+        return wrapper_module(*batch)
+    primary, args, kwargs = wrapper_module.get_segmentation_module_args(batch[0], tuple(batch[1:]), {}, targets=None)
+    out = seg(primary, *args, **kwargs)
+    k = out.shape[0]
+    u = wrapper_module.process_segmentation_output(out)
+    if k == 1 and u.dim() == out.dim() - 1:        # the wrapper drops a batch dimension of one
+        u = u[None]
+    return u
+
+
 def collect_unaries(wrapper_module, agent, train_set, device, unet_batch_size: int = 8):
     """The UNet side of the pretrain loops (``path_connected_net.py:672-676, 832-836``): the reference evaluates the frozen
     segmentation net once per frame and loop iteration (per EPOCH in the spatio-temporal loop).  Here every frame is
@@ -468,7 +486,7 @@ def collect_unaries(wrapper_module, agent, train_set, device, unet_batch_size: i
             chunk = ins[b0:b0 + bs]
             batch = [x.to(device) if torch.is_tensor(x) else x for x in _cat_inputs(chunk)]
             with torch.no_grad():
-                u = wrapper_module(*batch)
+                u = _segmentation_unaries(wrapper_module, batch)
             for k in range(len(chunk)):
                 one = [x[k:k + 1] if torch.is_tensor(x) else x for x in batch]
                 pa, _ = wrapper_module.get_prior_args(one[0], *one[1:], segm=u[k])
