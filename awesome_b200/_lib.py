@@ -79,6 +79,8 @@ SYMBOLS = [
     ("awb_prior_backward", C.c_int, [_P, _P, C.POINTER(GridSpec), _P, _P, _P, _P, C.c_size_t, _P]),
     ("awb_prior_fit_step", C.c_int, [_P, _P, _P, C.POINTER(GridSpec), _P, C.POINTER(LossSpec),
                                      C.POINTER(OptHyper), _P, _P, C.c_size_t, C.c_int32, _P]),
+    ("awb_prior_fit_steps", C.c_int, [_P, _P, _P, C.POINTER(GridSpec), C.POINTER(_P), C.c_int32, C.c_int32, C.c_int32,
+                                      C.POINTER(LossSpec), C.POINTER(OptHyper), _P, _P, C.c_size_t, C.c_int32, _P]),
     ("awb_prior_fit_host_frames", C.c_int, [_P, _P, _P, C.POINTER(GridSpec), C.POINTER(_P), C.c_int32, C.c_int32,
                                             C.POINTER(LossSpec), C.POINTER(OptHyper), _P, _P, _P, C.c_size_t,
                                             C.c_int32, _P]),

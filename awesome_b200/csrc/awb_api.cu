@@ -374,6 +374,22 @@ int awb_prior_fit_step(awb_handle h, float* params, void* opt_state, const awb_g
   return simt_reduce_opt(h, params, opt_state, hy, loss_out, w, N, st);
 }
 
+int awb_prior_fit_steps(awb_handle h, float* params, void* opt_state, const awb_grid_spec* g, const float* const* targets,
+                        int32_t n_targets, int32_t first, int32_t n_steps, const awb_loss_spec* loss, const awb_opt_hyper* hy,
+                        float* loss_out, void* ws, size_t ws_bytes, int32_t flags, void* stream) {
+  if (!targets || n_targets < 1 || n_steps < 0 || first < 0) { set_error("bad target list"); return AWB_ERR_INVALID; }
+  for (int i = 0; i < n_targets; i++)
+    if (!targets[i]) { set_error("targets[%d] is null", i); return AWB_ERR_INVALID; }
+  const int O = h ? h->desc.n_objects : 1;
+  for (int s = 0; s < n_steps; s++) {
+    int rc = awb_prior_fit_step(h, params, opt_state, g, targets[(first + s) % n_targets], loss, hy,
+                                loss_out ? loss_out + (size_t)s * O : nullptr, ws, ws_bytes,
+                                (s > 0 || (flags & AWB_FIT_REUSE_PACKED)) ? AWB_FIT_REUSE_PACKED : 0, stream);
+    if (rc) return rc;
+  }
+  return AWB_OK;
+}
+
 int awb_prior_fit_host_frames(awb_handle h, float* params, void* opt_state, const awb_grid_spec* g,
                               const float* const* host_targets, int32_t n_host, int32_t n_steps, const awb_loss_spec* loss,
                               const awb_opt_hyper* hy, float* loss_host, float* staging, void* ws, size_t ws_bytes,

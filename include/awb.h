@@ -178,6 +178,14 @@ int awb_prior_fit_step(awb_handle h, float* params, void* opt_state, const awb_g
                        const float* target, const awb_loss_spec* loss, const awb_opt_hyper* hyper,
                        float* loss_out, void* workspace, size_t workspace_bytes, int32_t flags, void* stream);
 
+/* n_steps fused fit steps in one call, step s fitting the DEVICE target targets[(first + s) % n_targets] ([O][N] each): the
+ * reference's step loop (path_connected_net.py:939-953) without a host round trip per step.  loss_out (optional, device):
+ * [n_steps][O].  Asynchronous. */
+int awb_prior_fit_steps(awb_handle h, float* params, void* opt_state, const awb_grid_spec* grid,
+                        const float* const* targets, int32_t n_targets, int32_t first, int32_t n_steps,
+                        const awb_loss_spec* loss, const awb_opt_hyper* hyper, float* loss_out, void* workspace,
+                        size_t workspace_bytes, int32_t flags, void* stream);
+
 /* The same loop with HOST inputs: n_steps fused fit steps, step s fitting the host frame host_targets[s % n_host]
  * ([O][N] fp32 unaries; the reference moves the frame's inputs to the device and evaluates them per frame,
  * path_connected_net.py:812-840, before the loop of :939-953; pretrain_unaries does `(1 - unaries).to(device)`, :439).  The host->device copy of frame s+1 runs on a copy stream
