@@ -277,6 +277,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
       auto mma_k144 = [&](uint32_t dcol, uint32_t a, uint32_t b, bool b_mn) { issue_k144(dcol, prep_k144(a, b, b_mn)); };
       // MN-major A window [0,128) x MN-major B, K = 128 pixels (8 steps); b_sbo = byte distance of B's 2nd N chunk
       auto mma_px = [&](uint32_t dcol, uint32_t a, uint32_t b, uint32_t b_sbo, int N, bool acc) {
+#ifdef AWB_TC_NO_STRIPS
+        if (N == 16) return;      // timing experiment only (wrong gradients): upper bound of what the N = 16 strips cost
+#endif
         const uint32_t idesc = tc::make_idesc(128, N, 1, 1);
         const tc::DescLH a0 = tc::make_desc_lh(a, 128, 2048), b0 = tc::make_desc_lh(b, 128, b_sbo);
 #pragma unroll
