@@ -740,9 +740,11 @@ def main():
             note = ("fp32 CUDA-core contraction (exact-parity path); reported against the cuBLAS bf16 tensor peak the north "
                     "star names")
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r1_f16_tc_v12_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r2_headline_f16_tc_traffic.json")     # from the committed ncu --set full capture
         if dom == "tc_fused" and os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")      # from the committed ncu --set full capture
+            for name, rec in json.load(open(tp)).get("kernels", {}).items():
+                if "k_icnn_fit_tc" in name:
+                    traffic = rec.get("dram_bytes_per_launch")
         ach = dom_flop / (ms_launch * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": burst, "unit": "TFLOP/s",
                     "frac": ach / burst, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",

@@ -17,6 +17,7 @@ from awesome_b200 import synth
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 MIOU_TOL = 1e-3          # 0.1 points
+TC_LOGIT_BOUND = 2e-2    # stated per-pixel bound of tensor-path logits, |d| / max(1, |y|) (include/awb.h)
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -194,6 +195,20 @@ def test_c2_per_frame_cold_4000_then_warm_400(A, golden, precision):
         ref_fg = synth.unpack_mask(fr["mask_fg_packed"], H, W)
         direct = _compare(f"c2 frame {k} {precision}", fg, ref_fg, un < 0.5, fr["iou_vs_unaries"])
         assert direct > 0.99
+        if precision == "f16" and k == 0:
+            # The stated bound of the tensor-path logits (awb_prior_forward training = 2 / 3; include/awb.h): on the weights of
+            # a finished 4000-step fit at 640x480, against the exact fp32 forward of the same weights.
+            prior = m._prior_for(torch.device(DEV))
+            with torch.no_grad():
+                exact = m(x).reshape(-1)
+                ws = prior.new_workspace(spec.n_pixels, True, torch.device(DEV))
+                tp = prior.forward_tensor_path(m._ensure_flat(), spec, ws).reshape(-1)
+            per_px = float(((tp - exact).abs() / exact.abs().clamp(min=1.0)).max())
+            normwise = float((tp - exact).norm() / exact.norm())
+            flips = int(((tp < 0) != (exact < 0)).sum())
+            print(f"[c2 tensor-path logits after 4000 steps] per-pixel |d|/max(1,|y|) max {per_px:.2e}, normwise {normwise:.2e}, "
+                  f"{flips} of {exact.numel()} mask pixels differ")
+            assert per_px <= TC_LOGIT_BOUND and normwise <= 1e-3 and flips <= 40
 
 
 @pytest.mark.parametrize("precision", ["fp32", "f16"])
