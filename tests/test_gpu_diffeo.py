@@ -82,3 +82,23 @@ def test_fused_fit_step_fp32_and_tensor_path(A, golden):
     moved16 = torch.cat([(res["f16"][1][k] - g["pert"][k].to(DEV)).reshape(-1) for k in g["pert"]])
     big = moved32.abs() > 5e-4
     assert float((torch.sign(moved16[big]) == torch.sign(moved32[big])).float().mean()) > 0.995
+
+
+def test_plateau_reduces_every_group_including_weight_g(A, golden):
+    """ReduceLROnPlateau halves EVERY param group, also the weight-norm gains' own group 3
+    (convex_diffeomorphism_net.py:399-400; ADVICE r1: the scheduler loop used to stop at group 2)."""
+    g = golden("diffeo.pt")
+    H, W = 24, 32
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, H), torch.linspace(0, 1, W), indexing="ij")
+    un = torch.sigmoid((torch.sqrt(((xx - 0.5) / 0.3) ** 2 + ((yy - 0.45) / 0.25) ** 2) - 1) / 0.1).to(DEV)
+    m = make(A, g, "pert")
+    # lr = 0: the loss cannot improve, so the scheduler (patience 2) must fire after 4 steps
+    opt = A.OptimConfig("adam", lr=[1e-9, 2e-9, 3e-9, 4e-9], weight_decay=[0, 0, 0, 5e-5], plateau=True, patience=2, factor=0.5,
+                        threshold=0.5, plateau_eps=0.0)
+    f = m.make_fitter(A.GridSpecHost("linspace", 1, H, W), un, A.LossConfig("mse"), opt, use_graph=False)
+    f.run(3)
+    before = list(f.scalars(0).lr)
+    f.run(3)
+    after = list(f.scalars(0).lr)
+    assert before == pytest.approx([1e-9, 2e-9, 3e-9, 4e-9])
+    assert after == pytest.approx([0.5e-9, 1e-9, 1.5e-9, 2e-9]), after

@@ -59,3 +59,17 @@ def test_gather_world2_gloo():
 def test_merge_rejects_double_ownership():
     with pytest.raises(ValueError):
         merge_by_unit([{0: 1}, {0: 2}])
+
+
+def test_fixed_segmentation_is_independent_of_world_size():
+    """fit_sequence_sharded's plan: the segments of the sequence are fixed; ranks only choose which of them they fit."""
+    from awesome_b200.sharded_fit import plan_segments, segments_of_rank
+    segs = plan_segments(60, 8)
+    assert [len(s) for s in segs] == [8, 8, 8, 8, 7, 7, 7, 7] and [i for s in segs for i in s] == list(range(60))
+    for world in (1, 2, 4, 8):
+        owned = [segments_of_rank(len(segs), r, world) for r in range(world)]
+        assert sorted(s for o in owned for s in o) == list(range(8))
+        assert max(len(o) for o in owned) == 8 // world
+    assert plan_segments(3, 8) == [[0], [1], [2]] and plan_segments(0, 4) == [[]]
+    with pytest.raises(ValueError):
+        segments_of_rank(8, 2, 2)
