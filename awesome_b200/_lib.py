@@ -74,6 +74,7 @@ SYMBOLS = [
     ("awb_prior_set_flow_consts", C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
                                             C.c_float, C.POINTER(C.c_uint8)]),
     ("awb_prior_set_flow_output_scale", C.c_int, [_P, C.c_float]),
+    ("awb_prior_set_flow_eval", C.c_int, [_P, C.c_int32]),
     ("awb_prior_forward", C.c_int, [_P, _P, C.POINTER(GridSpec), _P, _P, C.c_int32, _P, C.c_size_t, _P]),
     ("awb_prior_flow_inverse", C.c_int, [_P, _P, C.POINTER(GridSpec), _P, _P]),
     ("awb_prior_backward", C.c_int, [_P, _P, C.POINTER(GridSpec), _P, _P, _P, _P, C.c_size_t, _P]),

@@ -120,6 +120,11 @@ class Prior:
         m = (C.c_uint8 * len(masks))(*masks)
         L.check(self.lib.awb_prior_set_flow_consts(self._h, a, b, new_min, new_max, m))
 
+    def set_flow_eval(self, mode: int) -> None:
+        """RealNVP coupling MLPs: 0 auto, 1 unit loops (reference order of operations), 2 segment tables (C = 2);
+        see ``awb_prior_set_flow_eval`` in ``include/awb.h``."""
+        L.check(self.lib.awb_prior_set_flow_eval(self._h, int(mode)))
+
     # ---- kernels
     def forward(self, params: torch.Tensor, grid: GridSpecHost, training, ws: torch.Tensor,
                 want_deformed: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:

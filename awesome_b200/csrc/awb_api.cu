@@ -88,6 +88,8 @@ Workspace carve(const awb_prior* h, int64_t N, bool training, void* base, bool f
   w.flowz = (float*)take(training ? 4 * O * N * (int64_t)L.F * (rnvp ? flow_save_floats(L.C) : L.C) : 0);
   if (!training || L.F == 0) w.flowz = nullptr;
   w.flowd = (training && rnvp && L.C == 3 && !flow_bwd_dz_in_smem(h, N)) ? (float*)take(4 * O * N * 4) : nullptr;
+  w.flowtab = (rnvp && flow_tab_floats(h) > 0) ? (float*)take(4 * flow_tab_floats(h)) : nullptr;
+  w.flowseg = (training && rnvp && flow_seg_scratch_floats(h, S) > 0) ? (float*)take(4 * flow_seg_scratch_floats(h, S)) : nullptr;
   w.tc = (h->desc.precision == AWB_PREC_F16 && tc_supported(h)) ? (void*)take(O * (int64_t)tc_image_bytes(L.L)) : nullptr;
   w.bytes = off;
   return w;
@@ -134,6 +136,7 @@ int awb_prior_create(const awb_desc* d, awb_handle* out) {
   }
   h->fc_set = false;
   h->fc.out_scale = 1.f;
+  h->flow_eval = 0;
   h->d_map = nullptr; h->d_clamp = nullptr; h->d_group = nullptr; h->d_tcmap = nullptr; h->d_imap = nullptr; h->d_aug2img = nullptr;
   const Layout& L = h->lay;
   // arena (state_dict order) -> augmented index; clamp mask; optimizer groups
@@ -254,6 +257,15 @@ int awb_prior_set_flow_output_scale(awb_handle h, float scale) {
   if (h->desc.kind != AWB_KIND_FLOW_ICNN) { set_error("not a flow prior"); return AWB_ERR_INVALID; }
   if (!(scale > 0.f) || !isfinite(scale)) { set_error("output_scale must be a positive finite number"); return AWB_ERR_INVALID; }
   h->fc.out_scale = scale;
+  return AWB_OK;
+}
+
+int awb_prior_set_flow_eval(awb_handle h, int32_t mode) {
+  if (!h) { set_error("null argument"); return AWB_ERR_INVALID; }
+  if (h->desc.kind != AWB_KIND_FLOW_ICNN) { set_error("not a flow prior"); return AWB_ERR_INVALID; }
+  if (mode < 0 || mode > 2) { set_error("flow_eval must be 0 (auto), 1 (unit loops) or 2 (segment tables), got %d", mode); return AWB_ERR_INVALID; }
+  if (mode == 2 && !flow_seg_capable(h)) { set_error("segment tables need C = 2 and m <= 32"); return AWB_ERR_UNSUPPORTED; }
+  h->flow_eval = mode;
   return AWB_OK;
 }
 

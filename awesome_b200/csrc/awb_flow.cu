@@ -38,6 +38,8 @@ struct FlowP {
   int rounds1;           // backward: remainder rounds of one pixel per thread
   int dz_smem;           // backward: the running coordinate gradient of the CTA's pixel range lives in shared memory
   float* dzp_g;          // backward, C = 3, !dz_smem: [O][N][4] scratch for the partial gradient between unit passes
+  float* tab;            // C = 2: [O][F][2][FLOW_TAB] segment tables of the coupling MLPs (k_flow_tables), or null
+  float* segscr;         // C = 2 backward: [S][O][F][8 warps][FLOW_SEG_RS] per-warp histogram sums
 };
 
 // tanh and exp of the coupling outputs on the special-function unit: tanh(a) = 1 - 2 / (exp(2a) + 1) with ex2.approx /
@@ -809,6 +811,501 @@ __global__ void __launch_bounds__(FLOW_BWD_T, 1) k_flow_bwd(FlowP p) {
   }
 }
 
+// ======================================================================= C = 2: segment tables
+// With two coordinates every coupling masks exactly one of them, so both of its MLPs are functions of ONE scalar:
+//     net(z) = b2 + sum_k W2[k] relu(W1[k] z + b1[k])
+// is piecewise linear in z with (at most) m breakpoints beta_k = -b1[k] / W1[k].  k_flow_tables sorts the breakpoints of every
+// (flow, net) once per forward and tabulates slope and intercept of each of the m + 1 segments (sums in double, a unit that
+// is active nowhere contributes an exact 0); the per-pixel work is then a 6-step branch-free search and ONE FMA per net
+// instead of m (compare, max, FMA) triples, and the backward pass replaces the 4 m masked sums per pixel by 4 additions
+// into the pixel's segment of a thread-private histogram in shared memory:
+//     H0[j] = sum_{px in segment j} g,   H1[j] = sum_{px in segment j} g z        (g = gradient at the net's output)
+// from which the masked sums of unit k follow as the sum over the segments where the unit is active (a suffix of the sorted
+// segments for W1[k] > 0, a prefix for W1[k] < 0) -- summed as such, never as a difference of totals: a unit without active
+// pixels gets an exactly zero gradient, as in the reference (Adam / Adamax would amplify any rounding residue to a full
+// step).  No atomics: fixed summation order, results independent of the launch geometry of other objects.
+// Table of one (flow, net): beta[32] sorted ascending (+inf padding) | (slope, intercept)[33] | info[32]: per UNIT its rank
+// among the breakpoints | type << 8 (0: active above its breakpoint, 1: active below), -1 for k >= m | 2 pad.
+constexpr int FLOW_TAB = 132;
+constexpr int FLOW_TAB_FWD = 98;        // what the forward stages
+constexpr int FLOW_SEG_ROWS = 132;      // histogram rows: (net, segment 0..32, {g, g z})
+
+__global__ void __launch_bounds__(32) k_flow_tables(FlowP p) {
+  const unsigned full = 0xffffffffu;
+  const int f = blockIdx.x >> 1, net = blockIdx.x & 1, o = blockIdx.y, lane = threadIdx.x;
+  const int m = p.m, half = 4 * m + m + 2;
+  const float* wn = p.params + (int64_t)o * p.P + p.off_flow + (int64_t)f * p.per_flow + net * half;
+  const int cm = p.fc.masks[f * 2] != 0 ? 0 : 1, cu = 1 - cm;
+  float w = 0.f, b = 0.f, v = 0.f;
+  if (lane < m) { w = wn[lane * 2 + cm]; b = wn[2 * m + lane]; v = wn[2 * m + m + cu * m + lane]; }
+  const float c0 = wn[2 * m + m + 2 * m + cu];
+  // breakpoint and type; W1 = 0: a constant unit (always active for b1 > 0: "below +inf"; never otherwise: "above +inf")
+  float beta = INFINITY;
+  int type = 0;
+  if (w > 0.f) { beta = -b / w; }
+  else if (w < 0.f) { beta = -b / w; type = 1; }
+  else if (b > 0.f) { type = 1; }
+  if (!(beta == beta)) beta = INFINITY;
+  if (lane >= m) { type = 0; v = 0.f; }
+  // bitonic sort of (beta, unit) across the warp
+  float kb = beta;
+  int ki = lane;
+#pragma unroll
+  for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      const float ob = __shfl_xor_sync(full, kb, j);
+      const int oi = __shfl_xor_sync(full, ki, j);
+      const bool asc = (lane & k2) == 0, lower = (lane & j) == 0;
+      const bool other_less = ob < kb || (ob == kb && oi < ki);
+      if ((lower == asc) ? other_less : !other_less) { kb = ob; ki = oi; }
+    }
+  }
+  // lane r now holds the r-th smallest breakpoint and its unit
+  const float ws_ = __shfl_sync(full, w, ki), bs_ = __shfl_sync(full, b, ki), vs_ = __shfl_sync(full, v, ki);
+  const int ts_ = __shfl_sync(full, type, ki);
+  const double a = (double)vs_ * (double)ws_, d = (double)vs_ * (double)bs_;
+  double pa = ts_ == 0 ? a : 0.0, pd = ts_ == 0 ? d : 0.0;        // inclusive prefix over the "above" units
+  double na = ts_ == 1 ? a : 0.0, nd = ts_ == 1 ? d : 0.0;        // inclusive suffix over the "below" units
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const double ua = __shfl_up_sync(full, pa, off), ud = __shfl_up_sync(full, pd, off);
+    const double da = __shfl_down_sync(full, na, off), dd = __shfl_down_sync(full, nd, off);
+    if (lane >= off) { pa += ua; pd += ud; }
+    if (lane + off < 32) { na += da; nd += dd; }
+  }
+  // segment j = number of breakpoints below z: "above" units of rank < j and "below" units of rank >= j are active
+  double ea = __shfl_up_sync(full, pa, 1), ed = __shfl_up_sync(full, pd, 1);
+  if (lane == 0) { ea = 0.0; ed = 0.0; }
+  float* tab = p.tab + (((int64_t)o * p.F + f) * 2 + net) * FLOW_TAB;
+  tab[lane] = kb;
+  tab[32 + 2 * lane] = (float)(ea + na);
+  tab[33 + 2 * lane] = (float)((double)c0 + ed + nd);
+  if (lane == 31) { tab[32 + 64] = (float)pa; tab[33 + 64] = (float)((double)c0 + pd); }
+  __shared__ int rank_of[32];
+  rank_of[ki] = lane;
+  __syncwarp();
+  reinterpret_cast<int*>(tab)[FLOW_TAB_FWD + lane] = lane < m ? (rank_of[lane] | (type << 8)) : -1;
+}
+
+// number of breakpoints below z (0 .. 32) TIMES 4 (the byte offset of the segment's float): lower bound over beta[0..30]
+// in five dependent steps, beta[31] on its own.  `tab`: shared-space address of the table (ld.shared with an immediate
+// offset per step: load, compare, predicated add).
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float2 lds_f32x2(uint32_t a) { float2 v; asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t seg_find4(uint32_t tab, float z) {
+  uint32_t o = lds_f32(tab + 15 * 4) < z ? 64u : 0u;
+  const uint32_t top = lds_f32(tab + 31 * 4) < z ? 4u : 0u;
+  o += lds_f32(tab + o + 7 * 4) < z ? 32u : 0u;
+  o += lds_f32(tab + o + 3 * 4) < z ? 16u : 0u;
+  o += lds_f32(tab + o + 1 * 4) < z ? 8u : 0u;
+  o += lds_f32(tab + o) < z ? 4u : 0u;
+  return o + top;
+}
+__device__ __forceinline__ int seg_find(const float* __restrict__ beta, float z) {
+  return (int)(seg_find4((uint32_t)__cvta_generic_to_shared(beta), z) >> 2);
+}
+
+// tanh / exp of the segment kernels: ex2.approx.ftz / rcp.approx.ftz without the denormal fix-ups of __expf / __fdividef
+// (5 + 2 instructions; tanh(0) = 0 exactly, saturates to +-1, NaN propagates; forward and backward use the same two)
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float tanh_seg(float a) { return fmaf(-2.f, rcp_ftz(ex2_ftz(a * 2.885390081777927f) + 1.f), 1.f); }
+__device__ __forceinline__ float exp_seg(float s) { return ex2_ftz(s * 1.4426950408889634f); }
+
+// forward: k_flow_fwd<2> with the two MLP loops replaced by the table lookups; same launch geometry, same saved records
+__global__ void __launch_bounds__(256) k_flow_fwd_seg(FlowP p) {
+  extern __shared__ __align__(16) float sp[];   // [F][2][FLOW_TAB_FWD] tables | [F][4] exp(an_s)[2], an_t[2] | [4] linear
+  const int o = blockIdx.y, T = blockDim.x;
+  const float* par = p.params + (int64_t)o * p.P + p.off_flow;
+  const int m = p.m, half = 4 * m + m + 2;
+  {
+    const float* tg = p.tab + (int64_t)o * p.F * 2 * FLOW_TAB;
+    for (int i = threadIdx.x; i < p.F * 2 * FLOW_TAB_FWD; i += T) {
+      const int fn = i / FLOW_TAB_FWD, j = i - fn * FLOW_TAB_FWD;
+      sp[i] = tg[fn * FLOW_TAB + j];
+    }
+    float* an = sp + p.F * 2 * FLOW_TAB_FWD;
+    for (int i = threadIdx.x; i < p.F * 4; i += T) {
+      const int f = i >> 2, q = i & 3;
+      const float v = par[(int64_t)f * p.per_flow + 2 * half + q];
+      an[i] = q < 2 ? expf(v) : v;
+    }
+    if (threadIdx.x < 4) an[p.F * 4 + threadIdx.x] = par[p.P_flow + threadIdx.x];
+  }
+  __syncthreads();
+  const float* ans = sp + p.F * 2 * FLOW_TAB_FWD;
+  const float* lin = ans + p.F * 4;
+  const int64_t r0 = (int64_t)blockIdx.x * p.chunk, r1 = r0 + p.chunk < p.N ? r0 + p.chunk : p.N;
+  const bool save = p.zin != nullptr;
+  auto round = [&](auto p_c, int64_t base) -> bool {
+    constexpr int P = decltype(p_c)::value;
+    int64_t n[P];
+    bool ok[P];
+    float z0[P], z1[P];
+    float4* rec[P];
+#pragma unroll
+    for (int q = 0; q < P; q++) {
+      const int64_t nq = base + (int64_t)q * T + threadIdx.x;
+      ok[q] = nq < r1;
+      n[q] = ok[q] ? nq : (r1 > 0 ? r1 - 1 : 0);
+      float x0 = coord(p.g, n[q], 0), x1 = coord(p.g, n[q], 1);
+      if (p.use_linear) { x0 = x0 * lin[0] + lin[2]; x1 = x1 * lin[1] + lin[3]; }
+      z0[q] = mm_fwd(x0, p.fc.nmin[0], p.fc.nmax[0], p.fc.new_min, p.fc.new_max);
+      z1[q] = mm_fwd(x1, p.fc.nmin[1], p.fc.nmax[1], p.fc.new_min, p.fc.new_max);
+      rec[q] = reinterpret_cast<float4*>(p.zin) + ((int64_t)o * p.F * p.N + n[q]);
+    }
+    if (!ok[0]) return false;
+    // one coupling + ActNorm; zm: the masked coordinate (feeds the MLPs, passes through), zu: the transformed one
+    auto couple = [&](uint32_t ts, uint32_t tt, float& zm, float& zu, float am, float bm, float au, float bu, float4* r, bool st,
+                      bool m_first) {
+      const uint32_t js = seg_find4(ts, zm), jt = seg_find4(tt, zm);
+      const float2 cs = lds_f32x2(ts + 128 + 2 * js), ct = lds_f32x2(tt + 128 + 2 * jt);      // (slope, intercept) of the segment
+      const float s_ = tanh_seg(fmaf(cs.x, zm, cs.y)), t_ = tanh_seg(fmaf(ct.x, zm, ct.y));      // finite or NaN
+      if (st) *r = m_first ? make_float4(zm, zu, s_, t_) : make_float4(zu, zm, s_, t_);
+      zu = fmaf(fmaf(zu, exp_seg(s_), t_), au, bu);
+      zm = fmaf(zm, am, bm);
+    };
+#pragma unroll 1
+    for (int f = 0; f < p.F; f++) {
+      const uint32_t ts = (uint32_t)__cvta_generic_to_shared(sp + f * 2 * FLOW_TAB_FWD), tt = ts + FLOW_TAB_FWD * 4;
+      const float4 an = *reinterpret_cast<const float4*>(ans + f * 4);      // exp(s0), exp(s1), t0, t1
+      if (p.fc.masks[f * 2] != 0) {          // component 0 is the masked one
+#pragma unroll
+        for (int q = 0; q < P; q++) couple(ts, tt, z0[q], z1[q], an.x, an.z, an.y, an.w, rec[q], save && ok[q], true);
+      } else {
+#pragma unroll
+        for (int q = 0; q < P; q++) couple(ts, tt, z1[q], z0[q], an.y, an.w, an.x, an.z, rec[q], save && ok[q], false);
+      }
+#pragma unroll
+      for (int q = 0; q < P; q++) rec[q] += p.N;
+    }
+#pragma unroll
+    for (int q = 0; q < P; q++) {
+      if (!ok[q]) continue;
+      const float xa = mm_fwd(z0[q], p.fc.new_min, p.fc.new_max, p.fc.nmin[0], p.fc.nmax[0]);
+      const float xb = mm_fwd(z1[q], p.fc.new_min, p.fc.new_max, p.fc.nmin[1], p.fc.nmax[1]);
+      *reinterpret_cast<float4*>(p.X + ((int64_t)o * p.N + n[q]) * 4) = make_float4(xa, xb, 0.f, 1.f);
+      if (p.deformed) { p.deformed[((int64_t)o * p.N + n[q]) * 2] = xa; p.deformed[((int64_t)o * p.N + n[q]) * 2 + 1] = xb; }
+    }
+    return true;
+  };
+  int64_t base = r0;
+  bool more = true;
+#pragma unroll 1
+  for (int r = 0; r < p.rounds && more; r++, base += (int64_t)FLOW_P * T) more = round(std::integral_constant<int, FLOW_P>{}, base);
+#pragma unroll 1
+  for (int r = 0; r < p.rounds1 && more; r++, base += T) more = round(std::integral_constant<int, 1>{}, base);
+}
+
+// Sum over the 32 lanes of N values at once (N = 32, 16, ...): afterwards every lane holds the total of value
+// (lane >> log2(32 / N)); N - 1 + log2(32 / N) shuffles.
+template <int N>
+__device__ __forceinline__ float warp_reduce_scatter(float* v, int lane) {
+  int off = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1, off >>= 1) {
+    const bool up = lane & off;
+#pragma unroll
+    for (int k = 0; k < N / 2; k++) {
+      if (k < n / 2) {
+        const float send = up ? v[k] : v[k + n / 2];
+        const float keep = up ? v[k + n / 2] : v[k];
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+  }
+#pragma unroll
+  for (; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+  return v[0];
+}
+
+// backward: like k_flow_bwd<2> a CTA owns a pixel range, keeps the running gradient in shared memory, walks the flows in
+// reverse and prefetches the saved records one round ahead with cp.async -- but the unit loop is the segment histogram, and
+// the warps never meet inside the flow loop: histogram columns, gradient slots and staged records are thread-private, every
+// warp sums ITS 32 columns after each flow (warp reduce-scatter, 32 rows at a time) and parks the 138 sums in an L2-resident
+// scratch.  One block barrier after the last flow, then the warps' sums are added in a fixed order and converted into the
+// gradients of all flows at once.
+// Shared memory: tables [F][2][FLOW_TAB] | exp(an_s) [F][4] | 64 floats | staged records [2][P][T][4] | histogram [132][T]
+// (afterwards: summed rows [F][FLOW_SEG_RS]) | running gradient [2][chunk] (DZS)
+constexpr int FLOW_SEG_RS = 144;      // scratch floats per (flow, warp): 132 histogram rows | 6 scalar sums | pad
+template <bool DZS>
+__global__ void __launch_bounds__(FLOW_BWD_T, 1) k_flow_bwd_seg(FlowP p) {
+  extern __shared__ __align__(16) float sp[];
+  constexpr int C = 2, RW = 4, P = FLOW_PB, T = FLOW_BWD_T;      // always 256 threads: strides are immediates
+  constexpr int nwarps = T / 32;
+  const unsigned full = 0xffffffffu;
+  const int o = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* par = p.params + (int64_t)o * p.P + p.off_flow;
+  const int PF = (int)p.P_flow + 2 * C;
+  const int m = p.m, half = 4 * m + m + 2;
+  const int64_t r0 = (int64_t)blockIdx.x * p.chunk, r1 = r0 + p.chunk < p.N ? r0 + p.chunk : p.N;
+  float* tabs = sp;
+  float* eas = tabs + p.F * 2 * FLOW_TAB;
+  float* red2 = eas + p.F * 4;
+  float* stage = red2 + 64;
+  float* hist = stage + 2 * P * T * 4;
+  float* dzs = hist + FLOW_SEG_ROWS * T;
+  {
+    const float* tg = p.tab + (int64_t)o * p.F * 2 * FLOW_TAB;
+    for (int i = tid; i < p.F * 2 * FLOW_TAB; i += T) tabs[i] = tg[i];
+    for (int i = tid; i < p.F * 4; i += T) {
+      const int f = i >> 2, c = i & 3;
+      eas[i] = c < C ? expf(par[(int64_t)f * p.per_flow + 2 * half + c]) : 0.f;
+    }
+#pragma unroll 4
+    for (int i = 0; i < FLOW_SEG_ROWS; i++) hist[i * T + tid] = 0.f;
+  }
+  float* outb = p.fpart + ((int64_t)blockIdx.x * p.O + o) * PF;
+  if (r0 >= p.N) {
+    for (int i = tid; i < PF; i += T) outb[i] = 0.f;
+    return;
+  }
+  const int len = (int)(r1 - r0);
+  // Every warp owns a CONTIGUOUS block of the range (slot i of a lane = pixel wbase + 32 i + lane): its pixels are
+  // neighbours in the image, so they fall into few segments and the per-flow reduction below touches few rows.
+  const int wl_full = (len + nwarps - 1) / nwarps;
+  const int wbase = warp * wl_full;
+  const int wlen = len - wbase < wl_full ? (len - wbase > 0 ? len - wbase : 0) : wl_full;
+  const int n_rounds = p.rounds;
+  auto prefetch = [&](float* stage_buf, int f, int r) {
+    const float* zrec = p.zin + ((((int64_t)o * p.F + f) * p.N) + r0 + wbase) * RW;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(stage_buf);
+#pragma unroll
+    for (int q = 0; q < P; q++) {
+      const int li = (r * P + q) * 32 + lane;
+      if (li < wlen)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + (uint32_t)((q * T + tid) * 16)), "l"(zrec + (uint32_t)(li * RW)) : "memory");
+    }
+  };
+  int pre_f = p.F - 1, pre_r = 0, buf = 0;
+  if (n_rounds > 0) prefetch(stage, pre_f, 0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  // running gradient: shared memory [2][chunk], or in place in dX ([n][4]) when the range is too large
+  float* dzg = DZS ? dzs : p.dX + ((int64_t)o * p.N + r0) * 4;
+  const int dz_cs = DZS ? (int)p.chunk : 1;
+  constexpr int dz_ps = DZS ? 1 : 4;
+  for (int n = tid; n < len; n += T) {
+    const float4 dx = *reinterpret_cast<const float4*>(p.dX + ((int64_t)o * p.N + r0 + n) * 4);
+    dzg[n * dz_ps] = dx.x * ((p.fc.nmax[0] - p.fc.nmin[0]) / (p.fc.new_max - p.fc.new_min));
+    dzg[dz_cs + n * dz_ps] = dx.y * ((p.fc.nmax[1] - p.fc.nmin[1]) / (p.fc.new_max - p.fc.new_min));
+  }
+  __syncthreads();          // tables, initial gradient; from here on gradient slots, histogram columns and staged records are thread-private
+  float* hmine = hist + tid;
+  float* scr_w = p.segscr + ((((int64_t)blockIdx.x * p.O + o) * p.F) * 8 + warp) * FLOW_SEG_RS;
+#pragma unroll 1
+  for (int f = p.F - 1; f >= 0; f--) {
+    const bool m0 = p.fc.masks[f * 2] != 0;
+    const int cmi = m0 ? 0 : 1, cui = 1 - cmi;
+    const uint32_t ts = (uint32_t)__cvta_generic_to_shared(tabs + f * 2 * FLOW_TAB), tt = ts + FLOW_TAB * 4;
+    const float ea_m = eas[f * 4 + cmi], ea_u = eas[f * 4 + cui];
+    float* dzm_p = dzg + cmi * dz_cs + wbase * dz_ps;
+    float* dzu_p = dzg + cui * dz_cs + wbase * dz_ps;
+    float sas_m = 0.f, sat_m = 0.f, sas_u = 0.f, sat_u = 0.f, sb2s = 0.f, sb2t = 0.f;
+    uint32_t lo_s = 0xffffu, hi_s = 0u, lo_t = 0xffffu, hi_t = 0u;      // touched segments (x 4), per net
+    const float* zrec_w = p.zin + ((((int64_t)o * p.F + f) * p.N) + r0 + wbase) * RW;
+    // one round: slots i0 .. i0 + PP - 1 of this lane.  Branch-free (the PP pixels interleave): a slot past the warp's block
+    // computes on zeros and stores nothing.
+    // records of the first remainder slot: requested now, consumed after the full rounds
+    const int li_rem = n_rounds * P * 32 + lane;
+    float4 rec_rem = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.rounds1 > 0 && li_rem < wlen) rec_rem = __ldcg(reinterpret_cast<const float4*>(zrec_w + (uint32_t)(li_rem * RW)));
+    auto round = [&](auto p_c, auto all_c, int i0, const float* src, const float4* reg) {
+      constexpr int PP = decltype(p_c)::value;
+      constexpr bool ALL = decltype(all_c)::value;      // every slot of the round holds a pixel for every lane: no predicates
+      bool ok[PP];
+      float gs[PP], gt[PP], zmv[PP];
+      uint32_t js[PP], jt[PP];          // 4 x segment index
+#pragma unroll
+      for (int q = 0; q < PP; q++) {
+        const int li = (i0 + q) * 32 + lane;
+        ok[q] = ALL || li < wlen;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        float dzm = 0.f, dzu = 0.f;
+        if (reg) a = *reg;
+        else if (src) { if (ok[q]) a = *reinterpret_cast<const float4*>(src + (q * T + tid) * 4); }
+        else if (ok[q]) a = *reinterpret_cast<const float4*>(zrec_w + (uint32_t)(li * RW));
+        if (ok[q]) { dzm = dzm_p[li * dz_ps]; dzu = dzu_p[li * dz_ps]; }
+        const float zm = m0 ? a.x : a.y, zu = m0 ? a.y : a.x, s = a.z, t = a.w;
+        const float dzp = dzu * ea_u;
+        const float e = exp_seg(s);                      // s = tanh(.), the same function as the forward
+        const float dsv = dzp * zu * e;
+        const float g_s = dsv * (1.f - s * s);           // d tanh(a) / da = 1 - tanh^2
+        const float g_t = dzp * (1.f - t * t);
+        sas_m = fmaf(dzm * zm, ea_m, sas_m); sat_m += dzm;
+        sas_u = fmaf(dzu * fmaf(zu, e, t), ea_u, sas_u); sat_u += dzu;
+        sb2s += g_s; sb2t += g_t;
+        const uint32_t j_s = seg_find4(ts, zm), j_t = seg_find4(tt, zm);
+        const float Ss = lds_f32(ts + 128 + 2 * j_s), St = lds_f32(tt + 128 + 2 * j_t);      // slopes of the segments
+        if (ok[q]) {
+          dzm_p[li * dz_ps] = fmaf(dzm, ea_m, fmaf(g_s, Ss, g_t * St));
+          dzu_p[li * dz_ps] = dzp * e;
+          lo_s = min(lo_s, j_s); hi_s = max(hi_s, j_s); lo_t = min(lo_t, j_t); hi_t = max(hi_t, j_t);
+        }
+        gs[q] = g_s; gt[q] = g_t; zmv[q] = zm; js[q] = j_s; jt[q] = j_t;
+      }
+#pragma unroll
+      for (int q = 0; q < PP; q++) {
+        float* hs = hmine + (js[q] >> 1) * T;                  // rows 2 j, 2 j + 1
+        float* ht = hmine + (66 + (jt[q] >> 1)) * T;
+        if (ok[q]) {
+          hs[0] += gs[q];
+          hs[T] = fmaf(gs[q], zmv[q], hs[T]);
+          ht[0] += gt[q];
+          ht[T] = fmaf(gt[q], zmv[q], ht[T]);
+        }
+      }
+    };
+#pragma unroll 1
+    for (int r = 0; r < n_rounds; r++) {
+      // records of this round were requested one round ago; request the next full round (of whatever flow) now
+      float* cur = stage + buf * (P * T * 4);
+      buf ^= 1;
+      if (++pre_r == n_rounds) { pre_r = 0; --pre_f; }
+      if (pre_f >= 0) prefetch(stage + buf * (P * T * 4), pre_f, pre_r);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      if ((r * P + P) * 32 <= wlen) round(std::integral_constant<int, P>{}, std::true_type{}, r * P, cur, nullptr);
+      else round(std::integral_constant<int, P>{}, std::false_type{}, r * P, cur, nullptr);
+    }
+    if (p.rounds1 > 0) round(std::integral_constant<int, 1>{}, std::false_type{}, n_rounds * P, nullptr, &rec_rem);
+#pragma unroll 1
+    for (int r = 1; r < p.rounds1; r++) round(std::integral_constant<int, 1>{}, std::false_type{}, n_rounds * P + r, nullptr, nullptr);
+    // ---- this warp's 32 histogram columns -> row sums + 6 scalar sums in the scratch.  Only the segments some lane of the
+    // warp touched in this flow (a contiguous range per net) are summed and zeroed again, four segments = 8 rows per
+    // reduce-scatter; everything else is written as 0.  Fixed order (lane tree), no other warp involved.
+    float* scr = scr_w + (int64_t)f * 8 * FLOW_SEG_RS;
+#pragma unroll
+    for (int i = 0; i < FLOW_SEG_RS; i += 32) if (i + lane < FLOW_SEG_RS) scr[i + lane] = 0.f;
+    __syncwarp();
+    {
+      float v[8] = {sas_m, sat_m, sas_u, sat_u, sb2s, sb2t, 0.f, 0.f};
+      const float a = warp_reduce_scatter<8>(v, lane);
+      if ((lane & 3) == 0 && lane < 24) scr[132 + (lane >> 2)] = a;
+    }
+#pragma unroll 1
+    for (int net = 0; net < 2; net++) {
+      const int lo = (int)(__reduce_min_sync(full, net ? lo_t : lo_s) >> 2), hi = (int)(__reduce_max_sync(full, net ? hi_t : hi_s) >> 2);
+#pragma unroll 1
+      for (int j = lo & ~3; j <= hi; j += 4) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int row = 2 * j + i;          // within the net: rows 0 .. 65
+          v[i] = 0.f;
+          if (row < 66) { v[i] = hmine[(net * 66 + row) * T]; hmine[(net * 66 + row) * T] = 0.f; }
+        }
+        const float a = warp_reduce_scatter<8>(v, lane);
+        const int row = 2 * j + (lane >> 2);
+        if ((lane & 3) == 0 && row < 66) scr[net * 66 + row] = a;
+      }
+    }
+  }
+  __syncthreads();          // every warp's gradient slots and scratch rows are written; the histogram is dead
+  // ---- 1x1-conv gradients: fixed-order block reduction
+  float glw[C] = {0.f, 0.f}, glb[C] = {0.f, 0.f};
+  if (p.use_linear) {
+    for (int n = tid; n < len; n += T) {
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        const float dxc = dzg[c * dz_cs + n * dz_ps] * ((p.fc.new_max - p.fc.new_min) / (p.fc.nmax[c] - p.fc.nmin[c]));
+        glw[c] = fmaf(dxc, coord(p.g, r0 + n, c), glw[c]);
+        glb[c] += dxc;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; c++) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      glw[c] += __shfl_xor_sync(full, glw[c], off);
+      glb[c] += __shfl_xor_sync(full, glb[c], off);
+    }
+    if (lane == 0) { red2[warp * 4 + c] = glw[c]; red2[warp * 4 + C + c] = glb[c]; }
+  }
+  // ---- rows of all flows: the warps' sums in ascending warp order (read from L2)
+  float* Hs = hist;
+  {
+    const float* scr_cta = p.segscr + (((int64_t)blockIdx.x * p.O + o) * p.F) * 8 * FLOW_SEG_RS;
+    const int items = p.F * FLOW_SEG_RS;
+#pragma unroll 2
+    for (int i = tid; i < items; i += T) {
+      const int f = i / FLOW_SEG_RS, row = i - f * FLOW_SEG_RS;
+      const float* src = scr_cta + (int64_t)f * 8 * FLOW_SEG_RS + row;
+      float v[nwarps];
+#pragma unroll
+      for (int w = 0; w < nwarps; w++) v[w] = __ldcg(src + w * FLOW_SEG_RS);
+      float a = v[0];
+#pragma unroll
+      for (int w = 1; w < nwarps; w++) a += v[w];
+      Hs[i] = a;
+    }
+  }
+  __syncthreads();
+  if (tid < 2 * C) {
+    float a = 0.f;
+    for (int w = 0; w < nwarps; w++) a += red2[w * 4 + tid];
+    outb[p.P_flow + tid] = p.use_linear ? a : 0.f;
+  }
+  // ---- masked sums of every hidden unit = sum over the segments where it is active (a prefix or a suffix of the sorted
+  // segments: warp scans, lane = segment, then lane = unit picks the entry of its rank), then the gradients.  A warp per
+  // (flow, net).
+#pragma unroll 1
+  for (int pr = warp; pr < p.F * 2; pr += nwarps) {
+    const int f = pr >> 1, net = pr & 1;
+    const int cmi = p.fc.masks[f * 2] != 0 ? 0 : 1, cui = 1 - cmi;
+    const float* hr = Hs + f * FLOW_SEG_RS + net * 66;
+    const float* wn = par + (int64_t)f * p.per_flow + net * half;
+    float* on = outb + (int64_t)f * p.per_flow + net * half;
+    const int k = lane;
+    float w1 = 0.f, b1 = 0.f, w2 = 0.f;
+    int info = -1;
+    if (k < m) {
+      w1 = wn[k * 2 + cmi]; b1 = wn[2 * m + k]; w2 = wn[2 * m + m + cui * m + k];
+      info = reinterpret_cast<const int*>(tabs + pr * FLOW_TAB)[FLOW_TAB_FWD + k];
+    }
+    const float2 h = *reinterpret_cast<const float2*>(hr + 2 * lane);          // segment `lane`
+    const float2 e = *reinterpret_cast<const float2*>(hr + 64);                // segment 32
+    float p0 = h.x, p1 = h.y, s0 = h.x, s1 = h.y;      // inclusive prefix / suffix over segments 0 .. 31
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const float u0 = __shfl_up_sync(full, p0, off), u1 = __shfl_up_sync(full, p1, off);
+      const float d0 = __shfl_down_sync(full, s0, off), d1 = __shfl_down_sync(full, s1, off);
+      if (lane >= off) { p0 += u0; p1 += u1; }
+      if (lane + off < 32) { s0 += d0; s1 += d1; }
+    }
+    s0 += e.x; s1 += e.y;                                // ... and segment 32
+    const int rank = info & 0xff, type = info >> 8;
+    // "above" units (type 0) are active in the segments rank + 1 .. 32, "below" units in 0 .. rank
+    const int srcl = type == 0 ? (rank < 31 ? rank + 1 : 31) : rank;
+    const float fs0 = __shfl_sync(full, s0, srcl & 31), fs1 = __shfl_sync(full, s1, srcl & 31);
+    const float fp0 = __shfl_sync(full, p0, srcl & 31), fp1 = __shfl_sync(full, p1, srcl & 31);
+    float a0 = type == 0 ? (rank < 31 ? fs0 : e.x) : fp0;
+    float a1 = type == 0 ? (rank < 31 ? fs1 : e.y) : fp1;
+    if (k < m) {
+      on[k * 2 + cmi] = w2 * a1;                       // d W1[k][masked]
+      on[k * 2 + cui] = 0.f;
+      on[2 * m + k] = w2 * a0;                         // d b1[k]
+      on[2 * m + m + cui * m + k] = fmaf(w1, a1, b1 * a0);   // d W2[transformed][k]
+      on[2 * m + m + cmi * m + k] = 0.f;
+    }
+    if (net == 0 && lane < 8) {
+      // 0,1: ActNorm.s[c]; 2,3: ActNorm.t[c]; 4,5: s.b2[c]; 6,7: t.b2[c]      scalar sums: [sas_m sat_m sas_u sat_u sb2s sb2t]
+      const float* rs = Hs + f * FLOW_SEG_RS;
+      float* out = outb + (int64_t)f * p.per_flow;
+      const int qd = lane >> 1, c = lane & 1;
+      const bool masked = c == cmi;
+      const int src = qd == 0 ? (masked ? 0 : 2) : qd == 1 ? (masked ? 1 : 3) : qd == 2 ? 4 : 5;
+      float a = rs[132 + src];
+      if (qd >= 2 && masked) a = 0.f;
+      if (qd == 2) out[2 * m + m + 2 * m + c] = a;
+      else if (qd == 3) out[half + 2 * m + m + 2 * m + c] = a;
+      else if (qd == 0) out[2 * half + c] = a;
+      else out[2 * half + C + c] = a;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- ActNorm data-dependent init
 // z state lives in X[n] (pre-ActNorm output of the previous coupling).  One pass per flow.
 template <int C>
@@ -947,7 +1444,31 @@ static FlowP make_p(const awb_prior* h, const float* params, const awb_grid_spec
   p.N = (int64_t)g->B * g->H * g->W;
   p.X = ws.X; p.zin = nullptr; p.deformed = nullptr; p.dX = ws.dX; p.fpart = ws.fpart;
   p.chunk = split_chunk(p.N); p.O = h->desc.n_objects; p.rounds = 1; p.rounds1 = 0; p.dz_smem = 0; p.dzp_g = nullptr;
+  p.tab = ws.flowtab; p.segscr = nullptr;
   return p;
+}
+
+// C = 2 priors can run the segment-table kernels.  Default (awb_prior_set_flow_eval mode 0): tensor-path handles do, fp32
+// handles keep the unit loops -- the fp32 path is the parity anchor and evaluates the MLPs in the reference's order of
+// operations; the tables reassociate the sums (differences at the 1e-7 level, tests/test_gpu_flow.py).
+static size_t flow_seg_bwd_smem(const awb_prior* h, int T, int64_t chunk_in_smem) {
+  const size_t hist = (size_t)FLOW_SEG_ROWS * T, rows = (size_t)h->lay.F * FLOW_SEG_RS;      // the region is reused for the summed rows
+  return sizeof(float) * ((size_t)h->lay.F * (2 * FLOW_TAB + 4) + 64 + 2 * (size_t)FLOW_PB * T * 4 + (hist > rows ? hist : rows) +
+                          2 * (size_t)chunk_in_smem);
+}
+bool flow_seg_capable(const awb_prior* h) {
+  return h->desc.kind == AWB_KIND_FLOW_ICNN && h->lay.C == 2 && h->lay.m <= 32 && flow_seg_bwd_smem(h, FLOW_BWD_T, 0) <= 220 * 1024;
+}
+bool flow_seg_path(const awb_prior* h) {
+  // (the segment kernels are specialised for the standard couplings s, t = tanh(MLP); anything else keeps the unit loops)
+  if (!flow_seg_capable(h) || h->flow_eval == 1 || !h->desc.flow_tanh || h->fc.out_scale != 1.f) return false;
+  return h->flow_eval == 2 || h->desc.precision == AWB_PREC_F16;
+}
+int64_t flow_seg_scratch_floats(const awb_prior* h, int S) {
+  return flow_seg_capable(h) ? (int64_t)S * h->desc.n_objects * h->lay.F * 8 * FLOW_SEG_RS : 0;
+}
+int64_t flow_tab_floats(const awb_prior* h) {
+  return flow_seg_capable(h) ? (int64_t)h->desc.n_objects * h->lay.F * 2 * FLOW_TAB : 0;
 }
 
 int flow_forward(const awb_prior* h, const float* params, const awb_grid_spec* g, const Workspace& ws,
@@ -978,7 +1499,12 @@ int flow_forward(const awb_prior* h, const float* params, const awb_grid_spec* g
   p.rounds1 = (int)((geo.chunk - (int64_t)geo.R * FLOW_P * geo.T + geo.T - 1) / geo.T);
   size_t smem = sizeof(float) * ((size_t)h->lay.F * (h->lay.C == 2 ? FlowPack<2>::flow_stride(h->lay.m) : FlowPack<3>::flow_stride(h->lay.m)) + 2 * h->lay.C);
   dim3 grid(geo.S, h->desc.n_objects);
-  if (h->lay.C == 2) {
+  if (flow_seg_path(h) && p.tab) {
+    smem = sizeof(float) * ((size_t)h->lay.F * (2 * FLOW_TAB_FWD + 4) + 4);
+    AWB_LAUNCH(PK_FLOW_FWD, st, k_flow_tables<<<dim3(2 * h->lay.F, h->desc.n_objects), 32, 0, st>>>(p));
+    AWB_CUDA(cudaFuncSetAttribute(k_flow_fwd_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AWB_LAUNCH(PK_FLOW_FWD, st, k_flow_fwd_seg<<<grid, geo.T, smem, st>>>(p));
+  } else if (h->lay.C == 2) {
     AWB_CUDA(cudaFuncSetAttribute(k_flow_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AWB_LAUNCH(PK_FLOW_FWD, st, k_flow_fwd<2><<<grid, geo.T, smem, st>>>(p));
   } else {
@@ -1045,9 +1571,26 @@ int flow_backward(const awb_prior* h, const float* params, const awb_grid_spec* 
   p.dz_smem = flow_bwd_dz_in_smem(h, p.N) ? 1 : 0;
   p.dzp_g = ws.flowd;
   if (!p.dz_smem && C == 3 && !p.dzp_g) { set_error("flow backward: workspace lacks the pass scratch"); return AWB_ERR_WORKSPACE; }
-  const size_t smem = flow_bwd_smem_base(h) + (p.dz_smem ? sizeof(float) * (size_t)geo.chunk * C * (C == 3 ? 2 : 1) : 0);
+  size_t smem = flow_bwd_smem_base(h) + (p.dz_smem ? sizeof(float) * (size_t)geo.chunk * C * (C == 3 ? 2 : 1) : 0);
   dim3 grid(geo.S, h->desc.n_objects);
-  if (C == 2) {
+  if (flow_seg_path(h) && p.tab) {
+    geo.T = FLOW_BWD_T;          // the segment kernel always runs 256 threads (idle ones for tiny ranges)
+    const int64_t wl = (geo.chunk + FLOW_BWD_T / 32 - 1) / (FLOW_BWD_T / 32);      // pixels of one warp's block
+    geo.R = (int)(wl / (32 * FLOW_PB));
+    p.rounds = geo.R;
+    p.rounds1 = (int)((wl - (int64_t)geo.R * 32 * FLOW_PB + 31) / 32);
+    p.dz_smem = flow_seg_bwd_smem(h, geo.T, geo.chunk) <= 220 * 1024 ? 1 : 0;
+    smem = flow_seg_bwd_smem(h, geo.T, p.dz_smem ? geo.chunk : 0);
+    p.segscr = ws.flowseg;
+    if (!p.segscr) { set_error("flow backward: workspace lacks the segment scratch"); return AWB_ERR_WORKSPACE; }
+    if (p.dz_smem) {
+      AWB_CUDA(cudaFuncSetAttribute(k_flow_bwd_seg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      AWB_LAUNCH(PK_FLOW_BWD, st, k_flow_bwd_seg<true><<<grid, geo.T, smem, st>>>(p));
+    } else {
+      AWB_CUDA(cudaFuncSetAttribute(k_flow_bwd_seg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      AWB_LAUNCH(PK_FLOW_BWD, st, k_flow_bwd_seg<false><<<grid, geo.T, smem, st>>>(p));
+    }
+  } else if (C == 2) {
     AWB_CUDA(cudaFuncSetAttribute(k_flow_bwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AWB_LAUNCH(PK_FLOW_BWD, st, k_flow_bwd<2><<<grid, geo.T, smem, st>>>(p));
   } else {

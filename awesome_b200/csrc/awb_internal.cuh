@@ -69,6 +69,7 @@ struct awb_prior {
   int32_t* d_aug2img; // tensor path: [G] augmented index -> fp16 element of the weight image (or -1)
   awb::FlowConsts fc;
   bool fc_set;
+  int flow_eval;      // RealNVP coupling MLPs: 0 auto, 1 unit loops, 2 segment tables (awb_prior_set_flow_eval)
   int device;
   // awb_prior_fit_host_frames: copy stream + staging-buffer events, created on first use
   cudaStream_t copy_stream;
@@ -107,6 +108,8 @@ struct Workspace {
   float* flowz;   // training, flow priors: saved coupling inputs.  RealNVP: [O][F][N][RW] (input + s, t outputs of every
                   // coupling, awb_flow.cu FlowSave); NormalizingFlow1D: [O][N][F*C]
   float* flowd;   // RealNVP backward, C = 3, pixel ranges too large for shared memory: [O][N][4] scratch
+  float* flowtab; // RealNVP, C = 2: [O][F][2][132] segment tables of the coupling MLPs, rebuilt by every forward
+  float* flowseg; // RealNVP, C = 2, training: [S][O][F][8][144] per-warp histogram sums of the segment backward
   void* tc;       // tensor-core path scratch
   int64_t bytes;
 };
@@ -197,6 +200,10 @@ int flow_identity_loss(const awb_prior* h, const awb_grid_spec* g, const Workspa
 int flow_backward(const awb_prior* h, const float* params, const awb_grid_spec* g, const Workspace& ws,
                   cudaStream_t st, bool use_linear = true);
 int flow_save_floats(int C);                                     // floats saved per pixel and flow by the training forward
+bool flow_seg_capable(const awb_prior* h);                        // C = 2, m <= 32: segment-table kernels exist (awb_flow.cu)
+bool flow_seg_path(const awb_prior* h);                           // ... and are the ones this handle runs
+int64_t flow_tab_floats(const awb_prior* h);                      // size of Workspace.flowtab
+int64_t flow_seg_scratch_floats(const awb_prior* h, int S);       // size of Workspace.flowseg
 bool flow_bwd_dz_in_smem(const awb_prior* h, int64_t N);         // the backward keeps its running gradient on the SM
 int flow_actnorm_init(const awb_prior* h, float* params, const awb_grid_spec* g, const Workspace& ws,
                       cudaStream_t st);

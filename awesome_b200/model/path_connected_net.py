@@ -231,6 +231,7 @@ class PathConnectedNet(ArenaPriorModule):
                               masks.reshape(-1).to(torch.uint8).cpu().tolist())
         if self._rnvp.output_scale is not None:
             L.check(prior.lib.awb_prior_set_flow_output_scale(prior.handle, self._rnvp.output_scale))
+        prior.set_flow_eval(int(getattr(self, "flow_eval", 0)))     # 0 auto / 1 unit loops / 2 segment tables (awb.h)
 
     def load_state_dict(self, state_dict, *args, **kwargs):
         out = super().load_state_dict(state_dict, *args, **kwargs)

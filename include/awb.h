@@ -141,6 +141,18 @@ int awb_prior_set_flow_consts(awb_handle h, const float* norm_min, const float* 
  * scale * tanh(.).  Only applied with an output_fn (flow_tanh == 1), like normflows; default 1. */
 int awb_prior_set_flow_output_scale(awb_handle h, float scale);
 
+/* How the coupling MLPs s, t = MLP([C, m, C]) of a RealNVP prior are evaluated (net_factory.py:101-113):
+ *   1  unit loops: sum_k W2[k] relu(W1[k] z + b1[k]) in the reference's order of operations;
+ *   2  segment tables (C = 2 and m <= 32 only): with two coordinates every coupling feeds ONE scalar into its MLPs, which
+ *      are then piecewise linear with m breakpoints; the breakpoints are sorted once per forward and each pixel costs a
+ *      6-step search and one FMA per net (backward: 4 histogram updates instead of 4 m masked sums).  Same function, the
+ *      sums reassociated: outputs agree with mode 1 to ~1e-6, a hidden unit that is active nowhere still gets an exactly
+ *      zero gradient;
+ *   0  (default) mode 2 on tensor-path (AWB_PREC_F16) handles that support it, mode 1 otherwise -- the fp32 path stays
+ *      the arithmetic-order parity anchor.
+ * Set before the first forward of a fit; forward and backward of one step must use the same mode. */
+int awb_prior_set_flow_eval(awb_handle h, int32_t mode);
+
 /* forward(grid) -> raw logits [O][N]  (ConvexNextNet.forward convex_net.py:205-214;
  * PathConnectedNet.forward path_connected_net.py:79-85).  Leaves activations in the
  * workspace for awb_prior_backward when training != 0.  deformed (optional, [O][N][C])

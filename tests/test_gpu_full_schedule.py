@@ -53,12 +53,20 @@ def _run_traced(fitter, model, grid, target_fg, steps):
     return torch.cat(hist).reshape(-1).cpu(), torch.tensor(trace)
 
 
-def _compare_trace(name, trace, ref_trace):
-    med, ref_med = float(trace.median()), float(ref_trace.median())
-    print(f"[{name}] median mIoU over the last {TRACE_LAST} steps: device {100 * med:.3f}  reference {100 * ref_med:.3f}  "
-          f"(delta {100 * (med - ref_med):+.3f} points); step-to-step spread: device {100 * float(trace.min()):.2f}.."
+def _compare_trace(name, trace, ref_trace, replicas=None):
+    """Median mIoU over the last 200 steps within 0.1 points of the reference's.  Where the fixture holds REPLICAS of the
+    reference fit (the reference's own modules, same schedule, parameters perturbed by one part in 10^7: the fit is chaotic
+    at the level of an fp32 rounding, see ``make_golden_full.py:gen_c3nb_replicas``), the reference is the band its own
+    runs span, not one trajectory."""
+    med = float(trace.median())
+    ref_meds = [float(ref_trace.median())] + ([float(r.median()) for r in replicas] if replicas is not None else [])
+    lo, hi = min(ref_meds), max(ref_meds)
+    ref_txt = f"{100 * lo:.3f}" if len(ref_meds) == 1 else f"{100 * lo:.3f}..{100 * hi:.3f} over {len(ref_meds)} runs"
+    delta = med - hi if med > hi else (med - lo if med < lo else 0.0)
+    print(f"[{name}] median mIoU over the last {TRACE_LAST} steps: device {100 * med:.3f}  reference {ref_txt}  "
+          f"(delta {100 * delta:+.3f} points); step-to-step spread: device {100 * float(trace.min()):.2f}.."
           f"{100 * float(trace.max()):.2f}, reference {100 * float(ref_trace.min()):.2f}..{100 * float(ref_trace.max()):.2f}")
-    assert abs(med - ref_med) <= MIOU_TOL, (name, med, ref_med)
+    assert abs(delta) <= MIOU_TOL, (name, med, ref_meds)
 
 
 def _fitted_fg(model, grid):
@@ -137,7 +145,10 @@ def test_c3_path_connectedness_notebook_2000_steps(A, golden, precision):
     # This fit (Adamax at a constant 1e-3 / 2e-3) ends with an oscillating loss: the IoU of one particular step moves by
     # up to half a point from step to step -- in the reference's own run as well (fixture trace) -- so the criterion is
     # the median over the last 200 steps; the last step's mask must lie inside the reference's own step-to-step spread.
-    _compare_trace(f"c3nb {precision}", trace, g["iou_trace"])
+    # It is also chaotic at the level of one fp32 rounding: three more runs of the reference itself, from parameters
+    # perturbed by 1e-7, end 0.10-0.12 points away from the first (fixture "replica_traces") -- the band those runs span
+    # is the reference here.
+    _compare_trace(f"c3nb {precision}", trace, g["iou_trace"], g.get("replica_traces"))
     fg = _fitted_fg(m, x)
     ref_fg = synth.unpack_mask(g["mask_fg_packed"], H, W)
     iou_last = synth.fg_iou(fg, un < 0.5)
