@@ -9,6 +9,8 @@
 // rows-first symmetric summation of the float64 filter): bit-identical to cv2 (tests/test_gpu_image.py against outputs of
 // OpenCV itself, tests/golden/make_image_golden.py).  Byte / integer work, HBM bound: 12 B read + 12 B (4 B) written per pixel;
 // one fused kernel per function, every intermediate image lives in shared memory.
+#include <stdint.h>
+
 #include "awb_internal.cuh"
 
 namespace awb {
@@ -166,6 +168,214 @@ __global__ void __launch_bounds__(256) k_image_edge_map(const float* __restrict_
   else edge_tile<true>(img, out, H, W, m);
 }
 
+// ======================================================================= streaming versions (W % 4 == 0, W >= 128, H >= 8)
+// The tiled kernels above spend their time on index arithmetic and byte-wide shared-memory traffic (21 % / 7 % of the HBM
+// roofline).  These walk the image top to bottom instead: a lane owns 4 neighbouring pixels (one LDG.128 per channel and
+// row, packed to one 32-bit word of 4 uint8), the horizontal taps come from the neighbouring lanes' words (2 shuffles per
+// row and stage), the vertical taps from a register ring of the last 3 / 5 filtered rows -- no shared memory apart from
+// the 256-entry division tables, no barrier in the row loop.  A warp covers a window of 128 columns, of which the outer
+// lanes are the horizontal halo (4 pixels per side: the sum of the stages' radii), i.e. 120 output columns.
+// Borders: every stage of the OpenCV chain extends ITS input by BORDER_REFLECT_101.  All kernels of the chain are symmetric
+// (or antisymmetric with an absolute value behind them), so an intermediate image of the reflect-extended source is itself
+// reflect-symmetric: reflecting once, at the source fetch (virtual rows / columns outside the image read pixel reflect101(.)),
+// reproduces the per-stage extension exactly -- the row loop has no border cases at all.
+constexpr int ST_COLS = 120;      // output columns per warp
+// reflect101 without the loop: one reflection per side is enough for -n < i < 2n - 1 (the streaming kernels run on images of
+// at least 8 x 128 pixels, where their halo rows and the columns of the last window stay inside that range)
+__device__ __forceinline__ int reflect1(int i, int n) {
+  i = i < 0 ? -i : i;
+  return i >= n ? 2 * n - 2 - i : i;
+}
+__device__ __forceinline__ float4 load_raw4(const float* __restrict__ row, int xv, int W) {
+  if (xv >= 0 && xv + 3 < W) return __ldg(reinterpret_cast<const float4*>(row + xv));
+  return make_float4(row[reflect1(xv, W)], row[reflect1(xv + 1, W)], row[reflect1(xv + 2, W)], row[reflect1(xv + 3, W)]);
+}
+__device__ __forceinline__ uint32_t pack_u8x4(float4 v) {
+  return (uint32_t)to_u8(v.x) | ((uint32_t)to_u8(v.y) << 8) | ((uint32_t)to_u8(v.z) << 16) | ((uint32_t)to_u8(v.w) << 24);
+}
+// the 8 pixels x-2 .. x+5 around a lane's word from its neighbours' words
+__device__ __forceinline__ void neighbours(uint32_t w, int* p) {
+  const uint32_t l = __shfl_up_sync(0xffffffffu, w, 1), r = __shfl_down_sync(0xffffffffu, w, 1);
+  p[0] = (l >> 16) & 255; p[1] = l >> 24;
+  p[2] = w & 255; p[3] = (w >> 8) & 255; p[4] = (w >> 16) & 255; p[5] = w >> 24;
+  p[6] = r & 255; p[7] = (r >> 8) & 255;
+}
+
+// _process_image: grid (windows, bands / 4, frames * 3); a warp = one band of R rows of one channel
+__global__ void __launch_bounds__(128) k_image_process_stream(const float* __restrict__ img, float* __restrict__ out, int H, int W,
+                                                              int R, int bgr) {
+  __shared__ float lut[256];
+  for (int i = threadIdx.x; i < 256; i += 128) lut[i] = (float)i / 255.0f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int yb = (blockIdx.y * 4 + warp) * R;
+  if (yb >= H) return;
+  const int f = blockIdx.z / 3, c = blockIdx.z % 3;
+  const int64_t hw = (int64_t)H * W;
+  const float* src = img + ((int64_t)f * 3 + c) * hw;
+  float* dst = out + ((int64_t)f * 3 + (bgr ? 2 - c : c)) * hw;
+  const int xv = (int)blockIdx.x * ST_COLS - 4 + lane * 4;          // first of this lane's 4 (virtual) columns
+  const bool store = lane >= 1 && lane <= 30 && xv < W;
+  const int y_end = yb + R < H ? yb + R : H;
+  int ring[4][4];                                                   // horizontally filtered rows v-4 .. v-1
+#pragma unroll
+  for (int k = 0; k < 4; k++) { ring[k][0] = ring[k][1] = ring[k][2] = ring[k][3] = 0; }
+  // rows v+1 .. v+3 are in flight (raw, converted only when their turn comes) while row v is filtered
+  constexpr int DEPTH = 3;
+  float4 raw[DEPTH];
+#pragma unroll
+  for (int k = 0; k < DEPTH; k++) raw[k] = load_raw4(src + (int64_t)reflect1(yb - 2 + k, H) * W, xv, W);
+#pragma unroll 4      // the ring of 4 rows turns into register renaming
+  for (int v = yb - 2; v < y_end + 2; v++) {
+    const uint32_t w = pack_u8x4(raw[0]);
+#pragma unroll
+    for (int k = 0; k + 1 < DEPTH; k++) raw[k] = raw[k + 1];
+    raw[DEPTH - 1] = load_raw4(src + (int64_t)reflect1(v + DEPTH, H) * W, xv, W);
+    int p[8], h[4];
+    neighbours(w, p);
+#pragma unroll
+    for (int i = 0; i < 4; i++) h[i] = p[i] + 4 * p[i + 1] + 6 * p[i + 2] + 4 * p[i + 3] + p[i + 4];      // [1 4 6 4 1], exact
+    const int y = v - 2;
+    if (y >= yb && store) {
+      float o[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int acc = ring[0][i] + 4 * ring[1][i] + 6 * ring[2][i] + 4 * ring[3][i] + h[i];
+        o[i] = lut[(acc + 128) >> 8];                               // the one rounding (half up), then / 255
+      }
+      *reinterpret_cast<float4*>(dst + (int64_t)y * W + xv) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { ring[0][i] = ring[1][i]; ring[1][i] = ring[2][i]; ring[2][i] = ring[3][i]; ring[3][i] = h[i]; }
+  }
+}
+
+// create_edge_map: grid (windows, bands / 4, frames); a warp = one band of R output rows
+__global__ void __launch_bounds__(128, 4) k_image_edge_stream(const float* __restrict__ img, float* __restrict__ out, int H, int W, int R) {
+  __shared__ double lutd[256];
+  for (int i = threadIdx.x; i < 256; i += 128) lutd[i] = (double)i / 255.0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int yb = (blockIdx.y * 4 + warp) * R;
+  if (yb >= H) return;
+  const int64_t hw = (int64_t)H * W;
+  const float* src = img + (int64_t)blockIdx.z * 3 * hw;
+  float* dst = out + (int64_t)blockIdx.z * hw;
+  const int xv = (int)blockIdx.x * ST_COLS - 4 + lane * 4;
+  const bool store = lane >= 1 && lane <= 30 && xv < W;
+  const int y_end = yb + R < H ? yb + R : H;
+  const double k0 = 0.375, k1 = 0.25, k2 = 0.0625;
+  // rings, newest last.  A: [1 2 1]-filtered source rows (3 channels), G: gray rows with their x-1 / x+4 neighbours,
+  // D: row-filtered float64 gradient rows
+  int ra[2][3][4];
+  int rg[2][6];
+  double rd[4][4];
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) rg[k][i] = 0;
+#pragma unroll
+    for (int cc = 0; cc < 3; cc++) { ra[k][cc][0] = ra[k][cc][1] = ra[k][cc][2] = ra[k][cc][3] = 0; }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) { rd[k][0] = rd[k][1] = rd[k][2] = rd[k][3] = 0.0; }
+  constexpr int DEPTH = 2;                              // source rows in flight (raw), 3 channels each
+  float4 raw[DEPTH][3];
+#pragma unroll
+  for (int k = 0; k < DEPTH; k++) {
+    const int64_t ro = (int64_t)reflect1(yb - 4 + k, H) * W;
+#pragma unroll
+    for (int cc = 0; cc < 3; cc++) raw[k][cc] = load_raw4(src + cc * hw + ro, xv, W);
+  }
+#pragma unroll 2      // the rings of 2 rows turn into register renaming (4 iterations would spill under 128 registers)
+  for (int v = yb - 4; v < y_end + 4; v++) {            // source row v -> blurred / gray row v-1 -> gradient row v-2 -> output row v-4
+    uint32_t w[3];
+#pragma unroll
+    for (int cc = 0; cc < 3; cc++) w[cc] = pack_u8x4(raw[0][cc]);
+    {
+      const int64_t ro = (int64_t)reflect1(v + DEPTH, H) * W;
+#pragma unroll
+      for (int cc = 0; cc < 3; cc++) {
+#pragma unroll
+        for (int k = 0; k + 1 < DEPTH; k++) raw[k][cc] = raw[k + 1][cc];
+        raw[DEPTH - 1][cc] = load_raw4(src + cc * hw + ro, xv, W);
+      }
+    }
+    // stage 1: GaussianBlur 3x3 per channel (rows of [1 2 1] now, columns from the ring), RGB2GRAY
+    int ha[3][4];
+#pragma unroll
+    for (int cc = 0; cc < 3; cc++) {
+      int p[8];
+      neighbours(w[cc], p);
+#pragma unroll
+      for (int i = 0; i < 4; i++) ha[cc][i] = p[i + 1] + 2 * p[i + 2] + p[i + 3];
+    }
+    uint32_t gw = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int ch[3];
+#pragma unroll
+      for (int cc = 0; cc < 3; cc++) ch[cc] = (ra[0][cc][i] + 2 * ra[1][cc][i] + ha[cc][i] + 8) >> 4;
+      gw |= (uint32_t)((ch[0] * 9798 + ch[1] * 19235 + ch[2] * 3735 + 16384) >> 15) << (8 * i);
+    }
+#pragma unroll
+    for (int cc = 0; cc < 3; cc++) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) { ra[0][cc][i] = ra[1][cc][i]; ra[1][cc][i] = ha[cc][i]; }
+    }
+    // gray row v-1 with its neighbours: g[0] = x-1, g[1..4] = x .. x+3, g[5] = x+4
+    int g[6];
+    {
+      int p[8];
+      neighbours(gw, p);
+#pragma unroll
+      for (int i = 0; i < 6; i++) g[i] = p[i + 1];
+    }
+    // stage 2: Sobel on gray rows v-3, v-2, v-1 -> gradient row v-2
+    uint32_t dw = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int a = rg[0][i], b = rg[0][i + 1], cq = rg[0][i + 2];
+      const int d = rg[1][i], fq = rg[1][i + 2];
+      const int gq = g[i], hq = g[i + 1], kq = g[i + 2];
+      int gx = (cq + 2 * fq + kq) - (a + 2 * d + gq), gy = (gq + 2 * hq + kq) - (a + 2 * b + cq);
+      gx = gx < 0 ? -gx : gx; gy = gy < 0 ? -gy : gy;
+      const int sm = (gx > 255 ? 255 : gx) + (gy > 255 ? 255 : gy);
+      dw |= (uint32_t)(sm / 2 + ((sm & 1) & ((sm / 2) & 1))) << (8 * i);      // addWeighted(.5, .5): round half to even
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) { rg[0][i] = rg[1][i]; rg[1][i] = g[i]; }
+    // stage 3: float64 GaussianBlur 5x5 of gradient / 255: row v-2 filtered now, columns from the ring -> output row v-4
+    double hd[4];
+    {
+      int p[8];
+      neighbours(dw, p);
+      double q[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) q[i] = lutd[p[i]];
+#pragma unroll
+      for (int i = 0; i < 4; i++) hd[i] = k0 * q[i + 2] + k1 * (q[i + 1] + q[i + 3]) + k2 * (q[i] + q[i + 4]);
+    }
+    const int y = v - 4;
+    if (y >= yb && store) {
+      float o[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) o[i] = (float)(k0 * rd[2][i] + k1 * (rd[1][i] + rd[3][i]) + k2 * (rd[0][i] + hd[i]));
+      *reinterpret_cast<float4*>(dst + (int64_t)y * W + xv) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { rd[0][i] = rd[1][i]; rd[1][i] = rd[2][i]; rd[2][i] = rd[3][i]; rd[3][i] = hd[i]; }
+  }
+}
+
+// rows per warp: long bands amortise the 4 / 8 halo rows, short ones keep a small batch spread over the SMs
+static int stream_band_rows(int H, int W, int n_frames, int planes, int min_warps) {
+  const int64_t windows = (W + ST_COLS - 1) / ST_COLS;
+  int R = 128;
+  while (R > 8 && windows * ((H + R - 1) / R) * n_frames * planes < min_warps) R >>= 1;
+  return R;
+}
+
 }  // namespace awb
 
 using namespace awb;
@@ -177,6 +387,13 @@ int awb_image_process(const float* image, float* out, int32_t n_frames, int32_t 
   if (!image || !out || image == out) { set_error("image / out must be distinct non-null device pointers"); return AWB_ERR_INVALID; }
   if (H < 1 || W < 1 || n_frames < 1 || n_frames > 65535) { set_error("bad batch %d x %dx%d", n_frames, H, W); return AWB_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (do_blur && W % 4 == 0 && W >= 128 && H >= 8 && ((uintptr_t)image & 15) == 0 && ((uintptr_t)out & 15) == 0 && n_frames * 3 <= 65535) {
+    const int R = stream_band_rows(H, W, n_frames, 3, 148 * 48);
+    dim3 sgrid((W + ST_COLS - 1) / ST_COLS, ((H + R - 1) / R + 3) / 4, n_frames * 3);
+    AWB_LAUNCH(PK_MISC, st, k_image_process_stream<<<sgrid, 128, 0, st>>>(image, out, H, W, R, bgr));
+    AWB_CUDA(cudaGetLastError());
+    return AWB_OK;
+  }
   dim3 grid((W + PT_W - 1) / PT_W, (H + PT_H - 1) / PT_H, n_frames);
   AWB_LAUNCH(PK_MISC, st, k_image_process<<<grid, 256, 0, st>>>(image, out, H, W, do_blur, bgr));
   AWB_CUDA(cudaGetLastError());
@@ -187,6 +404,13 @@ int awb_image_edge_map(const float* image, float* out, int32_t n_frames, int32_t
   if (!image || !out) { set_error("null argument"); return AWB_ERR_INVALID; }
   if (H < 1 || W < 1 || n_frames < 1 || n_frames > 65535) { set_error("bad batch %d x %dx%d", n_frames, H, W); return AWB_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (W % 4 == 0 && W >= 128 && H >= 8 && ((uintptr_t)image & 15) == 0 && ((uintptr_t)out & 15) == 0) {
+    const int R = stream_band_rows(H, W, n_frames, 1, 148 * 24);
+    dim3 sgrid((W + ST_COLS - 1) / ST_COLS, ((H + R - 1) / R + 3) / 4, n_frames);
+    AWB_LAUNCH(PK_MISC, st, k_image_edge_stream<<<sgrid, 128, 0, st>>>(image, out, H, W, R));
+    AWB_CUDA(cudaGetLastError());
+    return AWB_OK;
+  }
   dim3 grid((W + ET_W - 1) / ET_W, (H + ET_H - 1) / ET_H, n_frames);
   AWB_LAUNCH(PK_MISC, st, k_image_edge_map<<<grid, 256, 0, st>>>(image, out, H, W));
   AWB_CUDA(cudaGetLastError());

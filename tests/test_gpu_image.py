@@ -36,7 +36,8 @@ def test_kernels_match_opencv_golden_bit_for_bit(A):
         assert torch.equal(A.image.process_image(img, do_image_blurring=False), img)
 
 
-@pytest.mark.parametrize("H,W", [(480, 640), (481, 643), (31, 33), (17, 129), (16, 32), (7, 3)])
+@pytest.mark.parametrize("H,W", [(480, 640), (481, 643), (31, 33), (17, 129), (16, 32), (7, 3),
+                                 (8, 128), (37, 260), (130, 132), (200, 1000)])      # streaming kernels: W % 4 == 0, W >= 128, H >= 8
 def test_kernels_match_oracle_on_random_frames(A, H, W):
     rng = np.random.default_rng(H * 1000 + W)
     img = rng.random((3, H, W), dtype=np.float32)
@@ -54,6 +55,12 @@ def test_properties_and_errors(A):
     batch = torch.rand(5, 3, 33, 47, device="cuda")                           # a batch == its frames one by one
     assert torch.equal(A.image.process_image(batch), torch.stack([A.image.process_image(f) for f in batch]))
     assert torch.equal(A.image.create_edge_map(batch), torch.stack([A.image.create_edge_map(f) for f in batch]))
+    wide = torch.rand(7, 3, 70, 256, device="cuda")                           # the same through the streaming kernels
+    assert torch.equal(A.image.process_image(wide), torch.stack([A.image.process_image(f) for f in wide]))
+    assert torch.equal(A.image.process_image(wide, image_channel_format="bgr"), A.image.process_image(wide).flip(1))
+    assert torch.equal(A.image.create_edge_map(wide), torch.stack([A.image.create_edge_map(f) for f in wide]))
+    assert torch.equal(A.image.create_edge_map(wide.flip(3)), A.image.create_edge_map(wide).flip(3))
+    assert torch.equal(A.image.create_edge_map(wide.flip(2)), A.image.create_edge_map(wide).flip(2))
     flipped = A.image.process_image(t.flip(2))                                # reflect-101 borders are mirror symmetric
     assert torch.equal(flipped, A.image.process_image(t).flip(2))
     with pytest.raises(ValueError):
