@@ -916,6 +916,7 @@ __device__ __forceinline__ float exp_seg(float s) { return ex2_ftz(s * 1.4426950
 // forward: k_flow_fwd<2> with the two MLP loops replaced by the table lookups; same launch geometry, same saved records
 __global__ void __launch_bounds__(256) k_flow_fwd_seg(FlowP p) {
   extern __shared__ __align__(16) float sp[];   // [F][2][FLOW_TAB_FWD] tables | [F][4] exp(an_s)[2], an_t[2] | [4] linear
+  grid_dep_launch();      // plain launch (nothing to wait for); the next kernel's own griddepcontrol.wait orders it after this one
   const int o = blockIdx.y, T = blockDim.x;
   const float* par = p.params + (int64_t)o * p.P + p.off_flow;
   const int m = p.m, half = 4 * m + m + 2;
@@ -1047,15 +1048,19 @@ __global__ void __launch_bounds__(FLOW_BWD_T, 1) k_flow_bwd_seg(FlowP p) {
   float* hist = stage + 2 * P * T * 4;
   float* dzs = hist + FLOW_SEG_ROWS * T;
   {
+    // launched with programmatic stream serialization behind the fused ICNN kernel: everything here depends on kernels
+    // further back in the stream only (the tables and the parameters of this step), dX is read after the wait
+#pragma unroll 4
+    for (int i = 0; i < FLOW_SEG_ROWS; i++) hist[i * T + tid] = 0.f;
     const float* tg = p.tab + (int64_t)o * p.F * 2 * FLOW_TAB;
     for (int i = tid; i < p.F * 2 * FLOW_TAB; i += T) tabs[i] = tg[i];
     for (int i = tid; i < p.F * 4; i += T) {
       const int f = i >> 2, c = i & 3;
       eas[i] = c < C ? expf(par[(int64_t)f * p.per_flow + 2 * half + c]) : 0.f;
     }
-#pragma unroll 4
-    for (int i = 0; i < FLOW_SEG_ROWS; i++) hist[i * T + tid] = 0.f;
   }
+  grid_dep_wait();
+  grid_dep_launch();
   float* outb = p.fpart + ((int64_t)blockIdx.x * p.O + o) * PF;
   if (r0 >= p.N) {
     for (int i = tid; i < PF; i += T) outb[i] = 0.f;
@@ -1585,10 +1590,10 @@ int flow_backward(const awb_prior* h, const float* params, const awb_grid_spec* 
     if (!p.segscr) { set_error("flow backward: workspace lacks the segment scratch"); return AWB_ERR_WORKSPACE; }
     if (p.dz_smem) {
       AWB_CUDA(cudaFuncSetAttribute(k_flow_bwd_seg<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      AWB_LAUNCH(PK_FLOW_BWD, st, k_flow_bwd_seg<true><<<grid, geo.T, smem, st>>>(p));
+      AWB_LAUNCH(PK_FLOW_BWD, st, AWB_CUDA(launch_ex(k_flow_bwd_seg<true>, grid, dim3(geo.T), smem, st, true, p)));
     } else {
       AWB_CUDA(cudaFuncSetAttribute(k_flow_bwd_seg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      AWB_LAUNCH(PK_FLOW_BWD, st, k_flow_bwd_seg<false><<<grid, geo.T, smem, st>>>(p));
+      AWB_LAUNCH(PK_FLOW_BWD, st, AWB_CUDA(launch_ex(k_flow_bwd_seg<false>, grid, dim3(geo.T), smem, st, true, p)));
     }
   } else if (C == 2) {
     AWB_CUDA(cudaFuncSetAttribute(k_flow_bwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
