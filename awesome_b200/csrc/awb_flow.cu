@@ -38,7 +38,7 @@ struct FlowP {
   int rounds1;           // backward: remainder rounds of one pixel per thread
   int dz_smem;           // backward: the running coordinate gradient of the CTA's pixel range lives in shared memory
   float* dzp_g;          // backward, C = 3, !dz_smem: [O][N][4] scratch for the partial gradient between unit passes
-  float* tab;            // C = 2: [O][F][2][FLOW_TAB] segment tables of the coupling MLPs (k_flow_tables), or null
+  float* tab;            // C = 2: [O][F][FLOW_TAB] segment tables of the coupling MLPs (k_flow_tables), or null
   float* segscr;         // C = 2 backward: [S][O][F][8 warps][FLOW_SEG_RS] per-warp histogram sums
 };
 
@@ -826,16 +826,27 @@ __global__ void __launch_bounds__(FLOW_BWD_T, 1) k_flow_bwd(FlowP p) {
 // step).  No atomics: fixed summation order, results independent of the launch geometry of other objects.
 // Table of one (flow, net): beta[32] sorted ascending (+inf padding) | (slope, intercept)[33] | info[32]: per UNIT its rank
 // among the breakpoints | type << 8 (0: active above its breakpoint, 1: active below), -1 for k >= m | 2 pad.
-constexpr int FLOW_TAB = 132;
-constexpr int FLOW_TAB_FWD = 98;        // what the forward stages
+// Table of one FLOW (both nets), FLOW_TAB floats:
+//   [0, 64)      gamma: the breakpoints of both nets merged and sorted ascending (+inf padding) -- ONE search serves both nets
+//   [64, 324)    per merged segment J = 0 .. 64: (slope_s, slope_t, intercept_s, intercept_t)
+//   [324, 389)   per merged segment: 4 j_s | (4 j_t) << 16 -- the segment of each net (number of ITS breakpoints below z)
+//   [392, 456)   per unit (net 0: 32, net 1: 32): rank among its net's breakpoints | type << 8 (0: active above its breakpoint,
+//                1: active below), -1 for k >= m
+constexpr int FLOW_TAB = 456;
+constexpr int FLOW_TAB_FWD = 324;       // what the forward stages
+constexpr int FLOW_TAB_SEG = 64;        // offset of the per-segment coefficients
+constexpr int FLOW_TAB_JJ = 324;
+constexpr int FLOW_TAB_INFO = 392;
 constexpr int FLOW_SEG_ROWS = 132;      // histogram rows: (net, segment 0..32, {g, g z})
 
-__global__ void __launch_bounds__(32) k_flow_tables(FlowP p) {
+__global__ void __launch_bounds__(64) k_flow_tables(FlowP p) {
   const unsigned full = 0xffffffffu;
-  const int f = blockIdx.x >> 1, net = blockIdx.x & 1, o = blockIdx.y, lane = threadIdx.x;
+  const int f = blockIdx.x, o = blockIdx.y, lane = threadIdx.x & 31, net = threadIdx.x >> 5;
   const int m = p.m, half = 4 * m + m + 2;
   const float* wn = p.params + (int64_t)o * p.P + p.off_flow + (int64_t)f * p.per_flow + net * half;
   const int cm = p.fc.masks[f * 2] != 0 ? 0 : 1, cu = 1 - cm;
+  __shared__ float sb[2][32], sS[2][33], sI[2][33];
+  __shared__ int rank_of[2][32], flag[64];
   float w = 0.f, b = 0.f, v = 0.f;
   if (lane < m) { w = wn[lane * 2 + cm]; b = wn[2 * m + lane]; v = wn[2 * m + m + cu * m + lane]; }
   const float c0 = wn[2 * m + m + 2 * m + cu];
@@ -847,7 +858,7 @@ __global__ void __launch_bounds__(32) k_flow_tables(FlowP p) {
   else if (b > 0.f) { type = 1; }
   if (!(beta == beta)) beta = INFINITY;
   if (lane >= m) { type = 0; v = 0.f; }
-  // bitonic sort of (beta, unit) across the warp
+  // bitonic sort of (beta, unit) across the warp (one warp per net)
   float kb = beta;
   int ki = lane;
 #pragma unroll
@@ -861,7 +872,7 @@ __global__ void __launch_bounds__(32) k_flow_tables(FlowP p) {
       if ((lower == asc) ? other_less : !other_less) { kb = ob; ki = oi; }
     }
   }
-  // lane r now holds the r-th smallest breakpoint and its unit
+  // lane r now holds the r-th smallest breakpoint of its net and the unit it belongs to
   const float ws_ = __shfl_sync(full, w, ki), bs_ = __shfl_sync(full, b, ki), vs_ = __shfl_sync(full, v, ki);
   const int ts_ = __shfl_sync(full, type, ki);
   const double a = (double)vs_ * (double)ws_, d = (double)vs_ * (double)bs_;
@@ -874,36 +885,54 @@ __global__ void __launch_bounds__(32) k_flow_tables(FlowP p) {
     if (lane >= off) { pa += ua; pd += ud; }
     if (lane + off < 32) { na += da; nd += dd; }
   }
-  // segment j = number of breakpoints below z: "above" units of rank < j and "below" units of rank >= j are active
+  // segment j of the net = number of its breakpoints below z: "above" units of rank < j and "below" units of rank >= j are active
   double ea = __shfl_up_sync(full, pa, 1), ed = __shfl_up_sync(full, pd, 1);
   if (lane == 0) { ea = 0.0; ed = 0.0; }
-  float* tab = p.tab + (((int64_t)o * p.F + f) * 2 + net) * FLOW_TAB;
-  tab[lane] = kb;
-  tab[32 + 2 * lane] = (float)(ea + na);
-  tab[33 + 2 * lane] = (float)((double)c0 + ed + nd);
-  if (lane == 31) { tab[32 + 64] = (float)pa; tab[33 + 64] = (float)((double)c0 + pd); }
-  __shared__ int rank_of[32];
-  rank_of[ki] = lane;
-  __syncwarp();
-  reinterpret_cast<int*>(tab)[FLOW_TAB_FWD + lane] = lane < m ? (rank_of[lane] | (type << 8)) : -1;
+  sb[net][lane] = kb;
+  sS[net][lane] = (float)(ea + na);
+  sI[net][lane] = (float)((double)c0 + ed + nd);
+  if (lane == 31) { sS[net][32] = (float)pa; sI[net][32] = (float)((double)c0 + pd); }
+  rank_of[net][ki] = lane;
+  __syncthreads();
+  float* tab = p.tab + ((int64_t)o * p.F + f) * FLOW_TAB;
+  reinterpret_cast<int*>(tab)[FLOW_TAB_INFO + net * 32 + lane] = lane < m ? (rank_of[net][lane] | (type << 8)) : -1;
+  // merge: position of this breakpoint among all 64 (ties: net 0 first), then the segment of either net per merged segment
+  int cnt = 0;
+#pragma unroll 8
+  for (int i = 0; i < 32; i++) cnt += net == 0 ? (sb[1][i] < kb ? 1 : 0) : (sb[0][i] <= kb ? 1 : 0);
+  const int pos = lane + cnt;
+  tab[pos] = kb;
+  flag[pos] = net;
+  __syncthreads();
+  for (int J = threadIdx.x; J <= 64; J += 64) {
+    int js = 0;
+    for (int i = 0; i < J; i++) js += flag[i] == 0 ? 1 : 0;
+    const int jt = J - js;
+    *reinterpret_cast<float4*>(tab + FLOW_TAB_SEG + 4 * J) = make_float4(sS[0][js], sS[1][jt], sI[0][js], sI[1][jt]);
+    reinterpret_cast<int*>(tab)[FLOW_TAB_JJ + J] = (4 * js) | ((4 * jt) << 16);
+  }
 }
 
-// number of breakpoints below z (0 .. 32) TIMES 4 (the byte offset of the segment's float): lower bound over beta[0..30]
-// in five dependent steps, beta[31] on its own.  `tab`: shared-space address of the table (ld.shared with an immediate
-// offset per step: load, compare, predicated add).
+// number of merged breakpoints below z (0 .. 64) TIMES 4: lower bound over gamma[0..62] in six dependent steps, gamma[63] on
+// its own.  `tab`: shared-space address of the table (ld.shared with an immediate offset per step: load, compare,
+// predicated add).
 __device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ float2 lds_f32x2(uint32_t a) { float2 v; asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ uint32_t seg_find4(uint32_t tab, float z) {
-  uint32_t o = lds_f32(tab + 15 * 4) < z ? 64u : 0u;
-  const uint32_t top = lds_f32(tab + 31 * 4) < z ? 4u : 0u;
+  uint32_t o = lds_f32(tab + 31 * 4) < z ? 128u : 0u;
+  const uint32_t top = lds_f32(tab + 63 * 4) < z ? 4u : 0u;
+  o += lds_f32(tab + o + 15 * 4) < z ? 64u : 0u;
   o += lds_f32(tab + o + 7 * 4) < z ? 32u : 0u;
   o += lds_f32(tab + o + 3 * 4) < z ? 16u : 0u;
   o += lds_f32(tab + o + 1 * 4) < z ? 8u : 0u;
   o += lds_f32(tab + o) < z ? 4u : 0u;
   return o + top;
-}
-__device__ __forceinline__ int seg_find(const float* __restrict__ beta, float z) {
-  return (int)(seg_find4((uint32_t)__cvta_generic_to_shared(beta), z) >> 2);
 }
 
 // tanh / exp of the segment kernels: ex2.approx.ftz / rcp.approx.ftz without the denormal fix-ups of __expf / __fdividef
@@ -915,18 +944,18 @@ __device__ __forceinline__ float exp_seg(float s) { return ex2_ftz(s * 1.4426950
 
 // forward: k_flow_fwd<2> with the two MLP loops replaced by the table lookups; same launch geometry, same saved records
 __global__ void __launch_bounds__(256) k_flow_fwd_seg(FlowP p) {
-  extern __shared__ __align__(16) float sp[];   // [F][2][FLOW_TAB_FWD] tables | [F][4] exp(an_s)[2], an_t[2] | [4] linear
+  extern __shared__ __align__(16) float sp[];   // [F][FLOW_TAB_FWD] tables | [F][4] exp(an_s)[2], an_t[2] | [4] linear
   grid_dep_launch();      // plain launch (nothing to wait for); the next kernel's own griddepcontrol.wait orders it after this one
   const int o = blockIdx.y, T = blockDim.x;
   const float* par = p.params + (int64_t)o * p.P + p.off_flow;
   const int m = p.m, half = 4 * m + m + 2;
   {
-    const float* tg = p.tab + (int64_t)o * p.F * 2 * FLOW_TAB;
-    for (int i = threadIdx.x; i < p.F * 2 * FLOW_TAB_FWD; i += T) {
-      const int fn = i / FLOW_TAB_FWD, j = i - fn * FLOW_TAB_FWD;
-      sp[i] = tg[fn * FLOW_TAB + j];
+    const float* tg = p.tab + (int64_t)o * p.F * FLOW_TAB;
+    for (int i = threadIdx.x; i < p.F * (FLOW_TAB_FWD / 4); i += T) {
+      const int fn = i / (FLOW_TAB_FWD / 4), j = i - fn * (FLOW_TAB_FWD / 4);
+      reinterpret_cast<float4*>(sp)[i] = reinterpret_cast<const float4*>(tg + fn * FLOW_TAB)[j];
     }
-    float* an = sp + p.F * 2 * FLOW_TAB_FWD;
+    float* an = sp + p.F * FLOW_TAB_FWD;
     for (int i = threadIdx.x; i < p.F * 4; i += T) {
       const int f = i >> 2, q = i & 3;
       const float v = par[(int64_t)f * p.per_flow + 2 * half + q];
@@ -935,7 +964,7 @@ __global__ void __launch_bounds__(256) k_flow_fwd_seg(FlowP p) {
     if (threadIdx.x < 4) an[p.F * 4 + threadIdx.x] = par[p.P_flow + threadIdx.x];
   }
   __syncthreads();
-  const float* ans = sp + p.F * 2 * FLOW_TAB_FWD;
+  const float* ans = sp + p.F * FLOW_TAB_FWD;
   const float* lin = ans + p.F * 4;
   const int64_t r0 = (int64_t)blockIdx.x * p.chunk, r1 = r0 + p.chunk < p.N ? r0 + p.chunk : p.N;
   const bool save = p.zin != nullptr;
@@ -958,25 +987,24 @@ __global__ void __launch_bounds__(256) k_flow_fwd_seg(FlowP p) {
     }
     if (!ok[0]) return false;
     // one coupling + ActNorm; zm: the masked coordinate (feeds the MLPs, passes through), zu: the transformed one
-    auto couple = [&](uint32_t ts, uint32_t tt, float& zm, float& zu, float am, float bm, float au, float bu, float4* r, bool st,
-                      bool m_first) {
-      const uint32_t js = seg_find4(ts, zm), jt = seg_find4(tt, zm);
-      const float2 cs = lds_f32x2(ts + 128 + 2 * js), ct = lds_f32x2(tt + 128 + 2 * jt);      // (slope, intercept) of the segment
-      const float s_ = tanh_seg(fmaf(cs.x, zm, cs.y)), t_ = tanh_seg(fmaf(ct.x, zm, ct.y));      // finite or NaN
+    auto couple = [&](uint32_t tb, float& zm, float& zu, float am, float bm, float au, float bu, float4* r, bool st, bool m_first) {
+      const uint32_t J4 = seg_find4(tb, zm);
+      const float4 cf = lds_f32x4(tb + FLOW_TAB_SEG * 4 + 4 * J4);      // (slope_s, slope_t, intercept_s, intercept_t) of the segment
+      const float s_ = tanh_seg(fmaf(cf.x, zm, cf.z)), t_ = tanh_seg(fmaf(cf.y, zm, cf.w));      // finite or NaN
       if (st) *r = m_first ? make_float4(zm, zu, s_, t_) : make_float4(zu, zm, s_, t_);
       zu = fmaf(fmaf(zu, exp_seg(s_), t_), au, bu);
       zm = fmaf(zm, am, bm);
     };
 #pragma unroll 1
     for (int f = 0; f < p.F; f++) {
-      const uint32_t ts = (uint32_t)__cvta_generic_to_shared(sp + f * 2 * FLOW_TAB_FWD), tt = ts + FLOW_TAB_FWD * 4;
+      const uint32_t tb = (uint32_t)__cvta_generic_to_shared(sp + f * FLOW_TAB_FWD);
       const float4 an = *reinterpret_cast<const float4*>(ans + f * 4);      // exp(s0), exp(s1), t0, t1
       if (p.fc.masks[f * 2] != 0) {          // component 0 is the masked one
 #pragma unroll
-        for (int q = 0; q < P; q++) couple(ts, tt, z0[q], z1[q], an.x, an.z, an.y, an.w, rec[q], save && ok[q], true);
+        for (int q = 0; q < P; q++) couple(tb, z0[q], z1[q], an.x, an.z, an.y, an.w, rec[q], save && ok[q], true);
       } else {
 #pragma unroll
-        for (int q = 0; q < P; q++) couple(ts, tt, z1[q], z0[q], an.y, an.w, an.x, an.z, rec[q], save && ok[q], false);
+        for (int q = 0; q < P; q++) couple(tb, z1[q], z0[q], an.y, an.w, an.x, an.z, rec[q], save && ok[q], false);
       }
 #pragma unroll
       for (int q = 0; q < P; q++) rec[q] += p.N;
@@ -1027,7 +1055,7 @@ __device__ __forceinline__ float warp_reduce_scatter(float* v, int lane) {
 // warp sums ITS 32 columns after each flow (warp reduce-scatter, 32 rows at a time) and parks the 138 sums in an L2-resident
 // scratch.  One block barrier after the last flow, then the warps' sums are added in a fixed order and converted into the
 // gradients of all flows at once.
-// Shared memory: tables [F][2][FLOW_TAB] | exp(an_s) [F][4] | 64 floats | staged records [2][P][T][4] | histogram [132][T]
+// Shared memory: tables [F][FLOW_TAB] | exp(an_s) [F][4] | 64 floats | staged records [2][P][T][4] | histogram [132][T]
 // (afterwards: summed rows [F][FLOW_SEG_RS]) | running gradient [2][chunk] (DZS)
 constexpr int FLOW_SEG_RS = 144;      // scratch floats per (flow, warp): 132 histogram rows | 6 scalar sums | pad
 template <bool DZS>
@@ -1042,7 +1070,7 @@ __global__ void __launch_bounds__(FLOW_BWD_T, 1) k_flow_bwd_seg(FlowP p) {
   const int m = p.m, half = 4 * m + m + 2;
   const int64_t r0 = (int64_t)blockIdx.x * p.chunk, r1 = r0 + p.chunk < p.N ? r0 + p.chunk : p.N;
   float* tabs = sp;
-  float* eas = tabs + p.F * 2 * FLOW_TAB;
+  float* eas = tabs + p.F * FLOW_TAB;
   float* red2 = eas + p.F * 4;
   float* stage = red2 + 64;
   float* hist = stage + 2 * P * T * 4;
@@ -1052,8 +1080,8 @@ __global__ void __launch_bounds__(FLOW_BWD_T, 1) k_flow_bwd_seg(FlowP p) {
     // further back in the stream only (the tables and the parameters of this step), dX is read after the wait
 #pragma unroll 4
     for (int i = 0; i < FLOW_SEG_ROWS; i++) hist[i * T + tid] = 0.f;
-    const float* tg = p.tab + (int64_t)o * p.F * 2 * FLOW_TAB;
-    for (int i = tid; i < p.F * 2 * FLOW_TAB; i += T) tabs[i] = tg[i];
+    const float* tg = p.tab + (int64_t)o * p.F * FLOW_TAB;
+    for (int i = tid; i < p.F * (FLOW_TAB / 4); i += T) reinterpret_cast<float4*>(tabs)[i] = reinterpret_cast<const float4*>(tg)[i];
     for (int i = tid; i < p.F * 4; i += T) {
       const int f = i >> 2, c = i & 3;
       eas[i] = c < C ? expf(par[(int64_t)f * p.per_flow + 2 * half + c]) : 0.f;
@@ -1102,7 +1130,7 @@ __global__ void __launch_bounds__(FLOW_BWD_T, 1) k_flow_bwd_seg(FlowP p) {
   for (int f = p.F - 1; f >= 0; f--) {
     const bool m0 = p.fc.masks[f * 2] != 0;
     const int cmi = m0 ? 0 : 1, cui = 1 - cmi;
-    const uint32_t ts = (uint32_t)__cvta_generic_to_shared(tabs + f * 2 * FLOW_TAB), tt = ts + FLOW_TAB * 4;
+    const uint32_t tb = (uint32_t)__cvta_generic_to_shared(tabs + f * FLOW_TAB);
     const float ea_m = eas[f * 4 + cmi], ea_u = eas[f * 4 + cui];
     float* dzm_p = dzg + cmi * dz_cs + wbase * dz_ps;
     float* dzu_p = dzg + cui * dz_cs + wbase * dz_ps;
@@ -1140,8 +1168,11 @@ __global__ void __launch_bounds__(FLOW_BWD_T, 1) k_flow_bwd_seg(FlowP p) {
         sas_m = fmaf(dzm * zm, ea_m, sas_m); sat_m += dzm;
         sas_u = fmaf(dzu * fmaf(zu, e, t), ea_u, sas_u); sat_u += dzu;
         sb2s += g_s; sb2t += g_t;
-        const uint32_t j_s = seg_find4(ts, zm), j_t = seg_find4(tt, zm);
-        const float Ss = lds_f32(ts + 128 + 2 * j_s), St = lds_f32(tt + 128 + 2 * j_t);      // slopes of the segments
+        const uint32_t J4 = seg_find4(tb, zm);                                    // merged segment (x 4)
+        const float2 sl = lds_f32x2(tb + FLOW_TAB_SEG * 4 + 4 * J4);              // slopes of the segment, both nets
+        const uint32_t jj = lds_u32(tb + FLOW_TAB_JJ * 4 + J4);                   // 4 j_s | 4 j_t << 16
+        const uint32_t j_s = jj & 0xffffu, j_t = jj >> 16;
+        const float Ss = sl.x, St = sl.y;
         if (ok[q]) {
           dzm_p[li * dz_ps] = fmaf(dzm, ea_m, fmaf(g_s, Ss, g_t * St));
           dzu_p[li * dz_ps] = dzp * e;
@@ -1267,7 +1298,7 @@ __global__ void __launch_bounds__(FLOW_BWD_T, 1) k_flow_bwd_seg(FlowP p) {
     int info = -1;
     if (k < m) {
       w1 = wn[k * 2 + cmi]; b1 = wn[2 * m + k]; w2 = wn[2 * m + m + cui * m + k];
-      info = reinterpret_cast<const int*>(tabs + pr * FLOW_TAB)[FLOW_TAB_FWD + k];
+      info = reinterpret_cast<const int*>(tabs + f * FLOW_TAB)[FLOW_TAB_INFO + net * 32 + k];
     }
     const float2 h = *reinterpret_cast<const float2*>(hr + 2 * lane);          // segment `lane`
     const float2 e = *reinterpret_cast<const float2*>(hr + 64);                // segment 32
@@ -1458,7 +1489,7 @@ static FlowP make_p(const awb_prior* h, const float* params, const awb_grid_spec
 // operations; the tables reassociate the sums (differences at the 1e-7 level, tests/test_gpu_flow.py).
 static size_t flow_seg_bwd_smem(const awb_prior* h, int T, int64_t chunk_in_smem) {
   const size_t hist = (size_t)FLOW_SEG_ROWS * T, rows = (size_t)h->lay.F * FLOW_SEG_RS;      // the region is reused for the summed rows
-  return sizeof(float) * ((size_t)h->lay.F * (2 * FLOW_TAB + 4) + 64 + 2 * (size_t)FLOW_PB * T * 4 + (hist > rows ? hist : rows) +
+  return sizeof(float) * ((size_t)h->lay.F * (FLOW_TAB + 4) + 64 + 2 * (size_t)FLOW_PB * T * 4 + (hist > rows ? hist : rows) +
                           2 * (size_t)chunk_in_smem);
 }
 bool flow_seg_capable(const awb_prior* h) {
@@ -1473,7 +1504,7 @@ int64_t flow_seg_scratch_floats(const awb_prior* h, int S) {
   return flow_seg_capable(h) ? (int64_t)S * h->desc.n_objects * h->lay.F * 8 * FLOW_SEG_RS : 0;
 }
 int64_t flow_tab_floats(const awb_prior* h) {
-  return flow_seg_capable(h) ? (int64_t)h->desc.n_objects * h->lay.F * 2 * FLOW_TAB : 0;
+  return flow_seg_capable(h) ? (int64_t)h->desc.n_objects * h->lay.F * FLOW_TAB : 0;
 }
 
 int flow_forward(const awb_prior* h, const float* params, const awb_grid_spec* g, const Workspace& ws,
@@ -1488,7 +1519,8 @@ int flow_forward(const awb_prior* h, const float* params, const awb_grid_spec* g
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
   FlowGeo geo;
-  geo.T = 128;
+  const bool seg = flow_seg_path(h) && p.tab;
+  geo.T = seg ? 256 : 128;        // segment kernel: the per-CTA table staging is amortised over twice the pixels
   int64_t per_sm = (p.N * h->desc.n_objects + sms - 1) / sms;
   int k = (int)((per_sm + FLOW_P * geo.T / 2) / (FLOW_P * geo.T));
   if (k < 1) k = 1;
@@ -1504,9 +1536,9 @@ int flow_forward(const awb_prior* h, const float* params, const awb_grid_spec* g
   p.rounds1 = (int)((geo.chunk - (int64_t)geo.R * FLOW_P * geo.T + geo.T - 1) / geo.T);
   size_t smem = sizeof(float) * ((size_t)h->lay.F * (h->lay.C == 2 ? FlowPack<2>::flow_stride(h->lay.m) : FlowPack<3>::flow_stride(h->lay.m)) + 2 * h->lay.C);
   dim3 grid(geo.S, h->desc.n_objects);
-  if (flow_seg_path(h) && p.tab) {
-    smem = sizeof(float) * ((size_t)h->lay.F * (2 * FLOW_TAB_FWD + 4) + 4);
-    AWB_LAUNCH(PK_FLOW_FWD, st, k_flow_tables<<<dim3(2 * h->lay.F, h->desc.n_objects), 32, 0, st>>>(p));
+  if (seg) {
+    smem = sizeof(float) * ((size_t)h->lay.F * (FLOW_TAB_FWD + 4) + 4);
+    AWB_LAUNCH(PK_FLOW_FWD, st, k_flow_tables<<<dim3(h->lay.F, h->desc.n_objects), 64, 0, st>>>(p));
     AWB_CUDA(cudaFuncSetAttribute(k_flow_fwd_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AWB_LAUNCH(PK_FLOW_FWD, st, k_flow_fwd_seg<<<grid, geo.T, smem, st>>>(p));
   } else if (h->lay.C == 2) {
