@@ -924,6 +924,26 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
   asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
   return v;
 }
+// the same for PP pixels at once, breadth first (step k of every pixel before step k + 1 of any): the PP dependent chains
+// of loads overlap instead of running one after the other
+template <int PP>
+__device__ __forceinline__ void seg_find4_multi(uint32_t tab, const float* z, uint32_t* o) {
+  const float g31 = lds_f32(tab + 31 * 4), g63 = lds_f32(tab + 63 * 4);
+  uint32_t top[PP];
+#pragma unroll
+  for (int q = 0; q < PP; q++) { o[q] = g31 < z[q] ? 128u : 0u; top[q] = g63 < z[q] ? 4u : 0u; }
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    const uint32_t off = (15u >> k) * 4u, inc = 64u >> k;      // (15, 64), (7, 32), (3, 16), (1, 8), (0, 4)
+    float v[PP];
+#pragma unroll
+    for (int q = 0; q < PP; q++) v[q] = lds_f32(tab + o[q] + off);
+#pragma unroll
+    for (int q = 0; q < PP; q++) o[q] += v[q] < z[q] ? inc : 0u;
+  }
+#pragma unroll
+  for (int q = 0; q < PP; q++) o[q] += top[q];
+}
 __device__ __forceinline__ uint32_t seg_find4(uint32_t tab, float z) {
   uint32_t o = lds_f32(tab + 31 * 4) < z ? 128u : 0u;
   const uint32_t top = lds_f32(tab + 63 * 4) < z ? 4u : 0u;
@@ -986,26 +1006,27 @@ __global__ void __launch_bounds__(256) k_flow_fwd_seg(FlowP p) {
       rec[q] = reinterpret_cast<float4*>(p.zin) + ((int64_t)o * p.F * p.N + n[q]);
     }
     if (!ok[0]) return false;
-    // one coupling + ActNorm; zm: the masked coordinate (feeds the MLPs, passes through), zu: the transformed one
-    auto couple = [&](uint32_t tb, float& zm, float& zu, float am, float bm, float au, float bu, float4* r, bool st, bool m_first) {
-      const uint32_t J4 = seg_find4(tb, zm);
-      const float4 cf = lds_f32x4(tb + FLOW_TAB_SEG * 4 + 4 * J4);      // (slope_s, slope_t, intercept_s, intercept_t) of the segment
-      const float s_ = tanh_seg(fmaf(cf.x, zm, cf.z)), t_ = tanh_seg(fmaf(cf.y, zm, cf.w));      // finite or NaN
-      if (st) *r = m_first ? make_float4(zm, zu, s_, t_) : make_float4(zu, zm, s_, t_);
-      zu = fmaf(fmaf(zu, exp_seg(s_), t_), au, bu);
-      zm = fmaf(zm, am, bm);
+    // one coupling + ActNorm for the P pixels; zm: the masked coordinate (feeds the MLPs, passes through), zu: the transformed one
+    auto couple = [&](uint32_t tb, float* zm, float* zu, float am, float bm, float au, float bu, bool m_first) {
+      uint32_t J4[P];
+      seg_find4_multi<P>(tb, zm, J4);
+      float4 cf[P];
+#pragma unroll
+      for (int q = 0; q < P; q++) cf[q] = lds_f32x4(tb + FLOW_TAB_SEG * 4 + 4 * J4[q]);      // (slope_s, slope_t, intercept_s, intercept_t)
+#pragma unroll
+      for (int q = 0; q < P; q++) {
+        const float s_ = tanh_seg(fmaf(cf[q].x, zm[q], cf[q].z)), t_ = tanh_seg(fmaf(cf[q].y, zm[q], cf[q].w));      // finite or NaN
+        if (save && ok[q]) *rec[q] = m_first ? make_float4(zm[q], zu[q], s_, t_) : make_float4(zu[q], zm[q], s_, t_);
+        zu[q] = fmaf(fmaf(zu[q], exp_seg(s_), t_), au, bu);
+        zm[q] = fmaf(zm[q], am, bm);
+      }
     };
 #pragma unroll 1
     for (int f = 0; f < p.F; f++) {
       const uint32_t tb = (uint32_t)__cvta_generic_to_shared(sp + f * FLOW_TAB_FWD);
       const float4 an = *reinterpret_cast<const float4*>(ans + f * 4);      // exp(s0), exp(s1), t0, t1
-      if (p.fc.masks[f * 2] != 0) {          // component 0 is the masked one
-#pragma unroll
-        for (int q = 0; q < P; q++) couple(tb, z0[q], z1[q], an.x, an.z, an.y, an.w, rec[q], save && ok[q], true);
-      } else {
-#pragma unroll
-        for (int q = 0; q < P; q++) couple(tb, z1[q], z0[q], an.y, an.w, an.x, an.z, rec[q], save && ok[q], false);
-      }
+      if (p.fc.masks[f * 2] != 0) couple(tb, z0, z1, an.x, an.z, an.y, an.w, true);          // component 0 is the masked one
+      else couple(tb, z1, z0, an.y, an.w, an.x, an.z, false);
 #pragma unroll
       for (int q = 0; q < P; q++) rec[q] += p.N;
     }
@@ -1146,39 +1167,48 @@ __global__ void __launch_bounds__(FLOW_BWD_T, 1) k_flow_bwd_seg(FlowP p) {
     auto round = [&](auto p_c, auto all_c, int i0, const float* src, const float4* reg) {
       constexpr int PP = decltype(p_c)::value;
       constexpr bool ALL = decltype(all_c)::value;      // every slot of the round holds a pixel for every lane: no predicates
+      // breadth first over the PP pixels of the round (loads, then every step of the search for all of them, ...): their
+      // dependent chains overlap
       bool ok[PP];
-      float gs[PP], gt[PP], zmv[PP];
-      uint32_t js[PP], jt[PP];          // 4 x segment index
+      int li[PP];
+      float zm[PP], zu[PP], sv[PP], tv[PP], dzm[PP], dzu[PP];
 #pragma unroll
       for (int q = 0; q < PP; q++) {
-        const int li = (i0 + q) * 32 + lane;
-        ok[q] = ALL || li < wlen;
+        li[q] = (i0 + q) * 32 + lane;
+        ok[q] = ALL || li[q] < wlen;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        float dzm = 0.f, dzu = 0.f;
+        dzm[q] = 0.f; dzu[q] = 0.f;
         if (reg) a = *reg;
         else if (src) { if (ok[q]) a = *reinterpret_cast<const float4*>(src + (q * T + tid) * 4); }
-        else if (ok[q]) a = *reinterpret_cast<const float4*>(zrec_w + (uint32_t)(li * RW));
-        if (ok[q]) { dzm = dzm_p[li * dz_ps]; dzu = dzu_p[li * dz_ps]; }
-        const float zm = m0 ? a.x : a.y, zu = m0 ? a.y : a.x, s = a.z, t = a.w;
-        const float dzp = dzu * ea_u;
-        const float e = exp_seg(s);                      // s = tanh(.), the same function as the forward
-        const float dsv = dzp * zu * e;
-        const float g_s = dsv * (1.f - s * s);           // d tanh(a) / da = 1 - tanh^2
-        const float g_t = dzp * (1.f - t * t);
-        sas_m = fmaf(dzm * zm, ea_m, sas_m); sat_m += dzm;
-        sas_u = fmaf(dzu * fmaf(zu, e, t), ea_u, sas_u); sat_u += dzu;
-        sb2s += g_s; sb2t += g_t;
-        const uint32_t J4 = seg_find4(tb, zm);                                    // merged segment (x 4)
-        const float2 sl = lds_f32x2(tb + FLOW_TAB_SEG * 4 + 4 * J4);              // slopes of the segment, both nets
-        const uint32_t jj = lds_u32(tb + FLOW_TAB_JJ * 4 + J4);                   // 4 j_s | 4 j_t << 16
-        const uint32_t j_s = jj & 0xffffu, j_t = jj >> 16;
-        const float Ss = sl.x, St = sl.y;
+        else if (ok[q]) a = *reinterpret_cast<const float4*>(zrec_w + (uint32_t)(li[q] * RW));
+        if (ok[q]) { dzm[q] = dzm_p[li[q] * dz_ps]; dzu[q] = dzu_p[li[q] * dz_ps]; }
+        zm[q] = m0 ? a.x : a.y; zu[q] = m0 ? a.y : a.x; sv[q] = a.z; tv[q] = a.w;
+      }
+      uint32_t J4[PP], js[PP], jt[PP];
+      seg_find4_multi<PP>(tb, zm, J4);                                                  // merged segment (x 4)
+      float2 sl[PP];
+#pragma unroll
+      for (int q = 0; q < PP; q++) {
+        sl[q] = lds_f32x2(tb + FLOW_TAB_SEG * 4 + 4 * J4[q]);                           // slopes of the segment, both nets
+        const uint32_t jj = lds_u32(tb + FLOW_TAB_JJ * 4 + J4[q]);                      // 4 j_s | 4 j_t << 16
+        js[q] = jj & 0xffffu; jt[q] = jj >> 16;
+      }
+      float gs[PP], gt[PP];
+#pragma unroll
+      for (int q = 0; q < PP; q++) {
+        const float dzp = dzu[q] * ea_u;
+        const float e = exp_seg(sv[q]);                  // s = tanh(.), the same function as the forward
+        const float dsv = dzp * zu[q] * e;
+        gs[q] = dsv * (1.f - sv[q] * sv[q]);             // d tanh(a) / da = 1 - tanh^2
+        gt[q] = dzp * (1.f - tv[q] * tv[q]);
+        sas_m = fmaf(dzm[q] * zm[q], ea_m, sas_m); sat_m += dzm[q];
+        sas_u = fmaf(dzu[q] * fmaf(zu[q], e, tv[q]), ea_u, sas_u); sat_u += dzu[q];
+        sb2s += gs[q]; sb2t += gt[q];
         if (ok[q]) {
-          dzm_p[li * dz_ps] = fmaf(dzm, ea_m, fmaf(g_s, Ss, g_t * St));
-          dzu_p[li * dz_ps] = dzp * e;
-          lo_s = min(lo_s, j_s); hi_s = max(hi_s, j_s); lo_t = min(lo_t, j_t); hi_t = max(hi_t, j_t);
+          dzm_p[li[q] * dz_ps] = fmaf(dzm[q], ea_m, fmaf(gs[q], sl[q].x, gt[q] * sl[q].y));
+          dzu_p[li[q] * dz_ps] = dzp * e;
+          lo_s = min(lo_s, js[q]); hi_s = max(hi_s, js[q]); lo_t = min(lo_t, jt[q]); hi_t = max(hi_t, jt[q]);
         }
-        gs[q] = g_s; gt[q] = g_t; zmv[q] = zm; js[q] = j_s; jt[q] = j_t;
       }
 #pragma unroll
       for (int q = 0; q < PP; q++) {
@@ -1186,9 +1216,9 @@ __global__ void __launch_bounds__(FLOW_BWD_T, 1) k_flow_bwd_seg(FlowP p) {
         float* ht = hmine + (66 + (jt[q] >> 1)) * T;
         if (ok[q]) {
           hs[0] += gs[q];
-          hs[T] = fmaf(gs[q], zmv[q], hs[T]);
+          hs[T] = fmaf(gs[q], zm[q], hs[T]);
           ht[0] += gt[q];
-          ht[T] = fmaf(gt[q], zmv[q], ht[T]);
+          ht[T] = fmaf(gt[q], zm[q], ht[T]);
         }
       }
     };
