@@ -26,8 +26,11 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 template <bool BORDER>
 __device__ __forceinline__ int rmap(int i, int n) { return BORDER ? reflect101(i, n) : i; }
 __device__ __forceinline__ int to_u8(float v) {            // (image * 255).astype(np.uint8)
-  int q = __float2int_rz(v * 255.0f);
-  return q < 0 ? 0 : (q > 255 ? 255 : q);
+  // truncation with saturation to [0, 255] in one conversion (NaN -> 0), as the numpy cast does for in-range values;
+  // out-of-range inputs clamp (the reference's frames are in [0, 1])
+  uint32_t q;
+  asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(q) : "f"(v * 255.0f));
+  return (int)q;
 }
 
 // ---- _process_image: tile 64 x 16 outputs (4 per thread), 68 x 20 uint8 inputs per channel in shared memory, separable
@@ -201,6 +204,20 @@ __device__ __forceinline__ void neighbours(uint32_t w, int* p) {
   p[6] = r & 255; p[7] = (r >> 8) & 255;
 }
 
+// the 4 byte windows (x-1, x, x+1, x+2) of a lane's 4 pixels, for 3-tap filters as one dp4a each (4th coefficient 0)
+__device__ __forceinline__ void windows3(uint32_t w, uint32_t* win) {
+  const uint32_t l = __shfl_up_sync(0xffffffffu, w, 1), r = __shfl_down_sync(0xffffffffu, w, 1);
+  win[0] = __byte_perm(l, w, 0x6543);
+  win[1] = w;
+  win[2] = __byte_perm(w, r, 0x4321);
+  win[3] = __byte_perm(w, r, 0x5432);
+}
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b_signed, int c) {      // unsigned bytes x signed bytes + c
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b_signed), "r"(c));
+  return d;
+}
+
 // _process_image: grid (windows, bands / 4, frames * 3); a warp = one band of R rows of one channel
 __global__ void __launch_bounds__(128) k_image_process_stream(const float* __restrict__ img, float* __restrict__ out, int H, int W,
                                                               int R, int bgr) {
@@ -231,10 +248,15 @@ __global__ void __launch_bounds__(128) k_image_process_stream(const float* __res
 #pragma unroll
     for (int k = 0; k + 1 < DEPTH; k++) raw[k] = raw[k + 1];
     raw[DEPTH - 1] = load_raw4(src + (int64_t)reflect1(v + DEPTH, H) * W, xv, W);
-    int p[8], h[4];
-    neighbours(w, p);
-#pragma unroll
-    for (int i = 0; i < 4; i++) h[i] = p[i] + 4 * p[i + 1] + 6 * p[i + 2] + 4 * p[i + 3] + p[i + 4];      // [1 4 6 4 1], exact
+    // [1 4 6 4 1], exact: four taps as one dp4a on the byte window (x-2 .. x+1) of the pixel, the fifth added
+    int h[4];
+    {
+      const uint32_t l = __shfl_up_sync(0xffffffffu, w, 1), r = __shfl_down_sync(0xffffffffu, w, 1);
+      h[0] = (int)__dp4a(__byte_perm(l, w, 0x5432), 0x04060401u, (w >> 16) & 255u);
+      h[1] = (int)__dp4a(__byte_perm(l, w, 0x6543), 0x04060401u, w >> 24);
+      h[2] = (int)__dp4a(w, 0x04060401u, r & 255u);
+      h[3] = (int)__dp4a(__byte_perm(w, r, 0x4321), 0x04060401u, (r >> 8) & 255u);
+    }
     const int y = v - 2;
     if (y >= yb && store) {
       float o[4];
@@ -265,15 +287,15 @@ __global__ void __launch_bounds__(128, 4) k_image_edge_stream(const float* __res
   const bool store = lane >= 1 && lane <= 30 && xv < W;
   const int y_end = yb + R < H ? yb + R : H;
   const double k0 = 0.375, k1 = 0.25, k2 = 0.0625;
-  // rings, newest last.  A: [1 2 1]-filtered source rows (3 channels), G: gray rows with their x-1 / x+4 neighbours,
+  // rings, newest last.  A: [1 2 1]-filtered source rows (3 channels), G: gray rows as 3-pixel windows,
   // D: row-filtered float64 gradient rows
   int ra[2][3][4];
-  int rg[2][6];
+  uint32_t rg[2][4];
   double rd[4][4];
 #pragma unroll
   for (int k = 0; k < 2; k++) {
 #pragma unroll
-    for (int i = 0; i < 6; i++) rg[k][i] = 0;
+    for (int i = 0; i < 4; i++) rg[k][i] = 0u;
 #pragma unroll
     for (int cc = 0; cc < 3; cc++) { ra[k][cc][0] = ra[k][cc][1] = ra[k][cc][2] = ra[k][cc][3] = 0; }
   }
@@ -301,14 +323,14 @@ __global__ void __launch_bounds__(128, 4) k_image_edge_stream(const float* __res
         raw[DEPTH - 1][cc] = load_raw4(src + cc * hw + ro, xv, W);
       }
     }
-    // stage 1: GaussianBlur 3x3 per channel (rows of [1 2 1] now, columns from the ring), RGB2GRAY
+    // stage 1: GaussianBlur 3x3 per channel (rows of [1 2 1] now -- one dp4a per pixel --, columns from the ring), RGB2GRAY
     int ha[3][4];
 #pragma unroll
     for (int cc = 0; cc < 3; cc++) {
-      int p[8];
-      neighbours(w[cc], p);
+      uint32_t win[4];
+      windows3(w[cc], win);
 #pragma unroll
-      for (int i = 0; i < 4; i++) ha[cc][i] = p[i + 1] + 2 * p[i + 2] + p[i + 3];
+      for (int i = 0; i < 4; i++) ha[cc][i] = (int)__dp4a(win[i], 0x00010201u, 0u);
     }
     uint32_t gw = 0;
 #pragma unroll
@@ -323,28 +345,22 @@ __global__ void __launch_bounds__(128, 4) k_image_edge_stream(const float* __res
 #pragma unroll
       for (int i = 0; i < 4; i++) { ra[0][cc][i] = ra[1][cc][i]; ra[1][cc][i] = ha[cc][i]; }
     }
-    // gray row v-1 with its neighbours: g[0] = x-1, g[1..4] = x .. x+3, g[5] = x+4
-    int g[6];
-    {
-      int p[8];
-      neighbours(gw, p);
-#pragma unroll
-      for (int i = 0; i < 6; i++) g[i] = p[i + 1];
-    }
-    // stage 2: Sobel on gray rows v-3, v-2, v-1 -> gradient row v-2
+    // gray row v-1 as windows (x-1, x, x+1) per pixel
+    uint32_t g[4];
+    windows3(gw, g);
+    // stage 2: Sobel on gray rows v-3, v-2, v-1 -> gradient row v-2; five dp4a per pixel:
+    //   gx = top . (-1, 0, 1) + mid . (-2, 0, 2) + bottom . (-1, 0, 1),  gy = bottom . (1, 2, 1) - top . (1, 2, 1)
     uint32_t dw = 0;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const int a = rg[0][i], b = rg[0][i + 1], cq = rg[0][i + 2];
-      const int d = rg[1][i], fq = rg[1][i + 2];
-      const int gq = g[i], hq = g[i + 1], kq = g[i + 2];
-      int gx = (cq + 2 * fq + kq) - (a + 2 * d + gq), gy = (gq + 2 * hq + kq) - (a + 2 * b + cq);
+      int gx = dp4a_us(rg[0][i], 0x000100FFu, dp4a_us(rg[1][i], 0x000200FEu, dp4a_us(g[i], 0x000100FFu, 0)));
+      int gy = dp4a_us(g[i], 0x00010201u, dp4a_us(rg[0][i], 0x00FFFEFFu, 0));
       gx = gx < 0 ? -gx : gx; gy = gy < 0 ? -gy : gy;
       const int sm = (gx > 255 ? 255 : gx) + (gy > 255 ? 255 : gy);
       dw |= (uint32_t)(sm / 2 + ((sm & 1) & ((sm / 2) & 1))) << (8 * i);      // addWeighted(.5, .5): round half to even
     }
 #pragma unroll
-    for (int i = 0; i < 6; i++) { rg[0][i] = rg[1][i]; rg[1][i] = g[i]; }
+    for (int i = 0; i < 4; i++) { rg[0][i] = rg[1][i]; rg[1][i] = g[i]; }
     // stage 3: float64 GaussianBlur 5x5 of gradient / 255: row v-2 filtered now, columns from the ring -> output row v-4
     double hd[4];
     {
