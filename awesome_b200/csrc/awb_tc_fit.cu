@@ -168,7 +168,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
   uint8_t* stx = simg + IMG;                      // TX[2]
   uint8_t* szero = stx + 2 * TX_B;
   float* xchg = reinterpret_cast<float*>(szero + ZERO_B);          // [NCG][128]
-  float* xchg2 = xchg + NCG * 128;                                  // [NCG-1][128][3]
   uint64_t* bars = reinterpret_cast<uint64_t*>(szero + ZERO_B + XCHG_B + XCHG2_B);
   uint64_t* bar_e2m = bars;        // epilogue -> issuer (one arrival per epilogue warp)
   uint64_t* bar_m2e = bars + 1;    // tcgen05.commit -> epilogue
@@ -236,7 +235,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
   auto T_DW = [](int i) { return (uint32_t)(144 * i); };                       // i = 1..L
   auto T_PB = [](int i) { return (uint32_t)(144 * (L + 1) + 16 * (i - 1)); };  // i = 1..L
   constexpr uint32_t T_GIN = 144 * (L + 1) + 16 * L, T_GO = T_GIN + 16;
-  static_assert(T_GO + 16 <= 512, "TMEM budget");
+  constexpr uint32_t T_DX = T_GO + 16;      // flow priors: delta_0 * W_in = gradient reaching the coordinates through the input layer
+  static_assert(T_DX + 16 <= 512, "TMEM budget");
 
   auto tile_ptr = [&](int t) { return tiles + t * TILE_B; };       // t < L: ZT[t]; L: ZL; L+1: DT
   auto dbuf = [&](int i) { return tile_ptr(((L - i) & 1) ? L : L + 1); };      // delta_i lives in DT / ZL alternately
@@ -286,6 +286,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
         for (int k = 0; k < 8; k++)
           tc::umma_f16_lh(tbase + dcol, a0.lo + k * (256 / 16), a0.hi, b0.lo + k * (256 / 16), b0.hi, idesc,
                           (acc || k > 0) ? 1u : 0u);
+      };
+      // coordinate gradient through the input layer (flow priors): DXIN[128 x 16] = delta_0[128 x 144] * WIN[144 x 16] --
+      // A like every K-major delta tile (18th chunk -> zero chunk), B = the WIN bytes read MN-major (N chunk 1 = zero chunk)
+      auto mma_dx = [&](uint32_t a) {
+        const uint32_t idesc = tc::make_idesc(128, 16, 0, 1);
+        const tc::DescLH a0 = tc::make_desc_lh(a, 2048, 128), a8 = tc::make_desc_lh(a + 8 * 4096, zero_a - (a + 8 * 4096), 128);
+        const tc::DescLH b0 = tc::make_desc_lh(a_win, 128, zero_a - a_win);
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          tc::umma_f16_lh(tbase + T_DX, a0.lo + k * (4096 / 16), a0.hi, b0.lo + k * (256 / 16), b0.hi, idesc, k > 0);
+        tc::umma_f16_lh(tbase + T_DX, a8.lo, a8.hi, b0.lo + 8 * (256 / 16), b0.hi, idesc, 1);
       };
       // input layer of a tile: ACC = TX[128x16] * WIN^T   (both operands: one stored K chunk + the zero chunk)
       const tc::DescLH in_b = tc::make_desc_lh(a_win, zero_a - a_win, 128);
@@ -347,6 +358,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
             mma_px(T_PB(i), zprev, d + 16 * 2048, 2048, 16, acc);                 // wgrad_i rows 128,129 (transposed)
             dbg();
           } else {
+            if constexpr (DX) mma_dx(t_addr(dbuf(0)));                            // 9 x 8 cycles: ahead of both commits
             if (more) {                                                           // next tile's input layer first:
               mma_input(a_txn);                                                   // its epilogue does not wait for
               dbg();
@@ -385,6 +397,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
     if (p.amax) { const float am = p.amax[o]; S = (am > 0.f && isfinite(am)) ? exp2f(rintf(log2f(64.f / am))) : 1.f; }
     constexpr bool has_dx = DX;
     float adx0 = 0.f, adx1 = 0.f, adx2 = 0.f;     // last group: d loss / d (x, y, t) of this row (scaled by S)
+    // the input-layer part of it comes from the tensor pipe one round trip later: the row's sums and pixel wait for it
+    float pdx0 = 0.f, pdx1 = 0.f, pdx2 = 0.f;
+    int64_t pn = -1;
+    auto flush_dx = [&]() {        // last group, after a wait on bar_m2e that covers the tile's DXIN contraction
+      float g[4];
+      tc::tmem_ld4(tlane + T_DX, g);
+      tc::tmem_ld_wait();
+      if (pn >= 0) {
+        const float inv = 1.f / S;
+        *reinterpret_cast<float4*>(p.dX + ((int64_t)o * p.N + pn) * 4) =
+            make_float4((pdx0 + g[0]) * inv, (pdx1 + g[1]) * inv, C > 2 ? (pdx2 + g[2]) * inv : 0.f, 0.f);
+      }
+    };
     float v[48];
     const float* w = wo + 48 * cg;
 
@@ -467,6 +492,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
         tc::mbar_wait(bar_m2e, ph); ph ^= 1;
         tc::fence_after_sync();
         AWB_TR();
+        if (has_dx && fit && last && s == 1 && it > 0) flush_dx();      // previous tile's coordinate gradient
         load_acc(tlane + T_ACC);
         AWB_TR();
         uint8_t* dst = tile_ptr(s - 1) + ch0 * 2048 + row * 16;
@@ -610,7 +636,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
         if (last && has_dx) { adx0 += v[34]; adx1 += v[35]; if (C > 2) adx2 += v[36]; }   // skip-connection columns of dZA
         uint8_t* dst = dbuf(i - 1) + ch0 * 2048 + row * 16;
         float d128 = 0.f, d129 = 0.f;
-        uint32_t d0w[24];            // delta_0 words, kept for the input-layer coordinate gradient
 #pragma unroll
         for (int c = 0; c < 6; c++) {
           if (c < nch) {
@@ -622,7 +647,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
               d129 = (mk[16] >> 16) ? v[33] : 0.f;
             }
             st16(dst + c * 2048, w0, w1, w2, w3);
-            if (i == 1) { d0w[4 * c] = w0; d0w[4 * c + 1] = w1; d0w[4 * c + 2] = w2; d0w[4 * c + 3] = w3; }
           }
         }
         if (i == 1 && more) write_tx((it + 1) & 1, x0n, x1n, x2n);   // next tile's input operand rides this round trip
@@ -644,36 +668,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
           }
           accC[i - 1] += warp_reduce_scatter16(cv, lane);
         }
-        if (i == 1 && has_dx) {
-          // d x += delta_0 * W_in (K = 130 split over the three column groups of the row; W_in rows from the fp16 image)
-          const uint8_t* win = simg + L * W_B;     // [144 rows j][8 halfs]: (w_x, w_y, [w_t,] bias, 0..)
-          float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-#pragma unroll
-          for (int c = 0; c < 6; c++) {
-            if (c < nch) {
-#pragma unroll
-              for (int k = 0; k < 4; k++) {
-                const int j = (ch0 + c) * 8 + 2 * k;
-                const uint2 wa = *reinterpret_cast<const uint2*>(win + j * 16);
-                const uint2 wb = *reinterpret_cast<const uint2*>(win + (j + 1) * 16);
-                const float da = half_lo(d0w[4 * c + k]), db = half_hi(d0w[4 * c + k]);
-                g0 = fmaf(da, half_lo(wa.x), g0); g1 = fmaf(da, half_hi(wa.x), g1);
-                g0 = fmaf(db, half_lo(wb.x), g0); g1 = fmaf(db, half_hi(wb.x), g1);
-                if (C > 2) { g2 = fmaf(da, half_lo(wa.y), g2); g2 = fmaf(db, half_lo(wb.y), g2); }
-              }
-            }
-          }
-          if (!last) { float* xs = xchg2 + (cg * 128 + row) * 3; xs[0] = g0; xs[1] = g1; xs[2] = g2; }
-          asm volatile("bar.sync %0, 96;" ::"r"(1 + q) : "memory");
-          if (last && live) {
-            const float inv = 1.f / S;
-            const float* xa = xchg2 + row * 3;
-            const float* xb = xchg2 + (128 + row) * 3;
-            *reinterpret_cast<float4*>(p.dX + ((int64_t)o * p.N + n) * 4) =
-                make_float4((adx0 + g0 + xa[0] + xb[0]) * inv, (adx1 + g1 + xa[1] + xb[1]) * inv,
-                            C > 2 ? (adx2 + g2 + xa[2] + xb[2]) * inv : 0.f, 0.f);
-          }
-        }
+        if (i == 1 && has_dx && last) { pdx0 = adx0; pdx1 = adx1; pdx2 = adx2; pn = live ? n : -1; }
       }
     }
 
@@ -681,6 +676,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
     tc::mbar_wait(bar_m2e, ph); ph ^= 1;
     tc::fence_after_sync();
     AWB_TR();
+    if (has_dx && fit && last && n_my > 0) flush_dx();              // the last tile's coordinate gradient
     if (trace && warp == 0 && lane == 0) trace[123] = clock64();    // tile loop done
 
     // =========================================================== per-CTA partial write-out
