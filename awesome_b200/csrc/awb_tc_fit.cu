@@ -492,7 +492,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
         tc::mbar_wait(bar_m2e, ph); ph ^= 1;
         tc::fence_after_sync();
         AWB_TR();
-        if (has_dx && fit && last && s == 1 && it > 0) flush_dx();      // previous tile's coordinate gradient
         load_acc(tlane + T_ACC);
         AWB_TR();
         uint8_t* dst = tile_ptr(s - 1) + ch0 * 2048 + row * 16;
@@ -603,6 +602,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_icnn_fit_tc(TcP p) {
         s_so0 += dys * x0; s_so1 += dys * x1;
         if (C > 2) s_so2 += dys * x2;
       } else if (last) {
+        if (has_dx && it > 0) flush_dx();      // previous tile's coordinate gradient (its contraction finished rounds ago)
         // corner of dW_L: delta_L[128..129] x ZT[L-1][128..133], and d w_o[128], [129]
         float c6[6], cv[16];
         chunk16_f32(tile_ptr(L - 1), c6);
