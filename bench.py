@@ -280,10 +280,11 @@ def sustained_leg(fitter, pool, dev, gpu_index: int, G: int, seconds: float = 10
 
 def frames_per_s_leg(A, dev, rank: int, world: int, G: int, precision: str, barrier, n_frames: int = 60, n_segments: int = 8):
     """The second half of BASELINE's metric, MEASURED: wall-clock frames/s of fitting the whole synthetic 60-frame 640x480
-    sequence (configs[1]) with ``awesome_b200.fit_sequence_sharded`` -- 8 fixed segments over the ranks, 4000 cold / 400 warm
-    steps, G frames per fused launch, CUDA-graph step loops, no-foreground skip, IoU check + retry, every frame's unaries
-    copied from pinned host memory, masks / states / IoUs gathered on every rank at the end.  Time = barrier to barrier,
-    max over ranks.  ``digest`` hashes every fitted state: it is the same for any number of GPUs."""
+    sequence (configs[1]) with ``awesome_b200.fit_sequence_sharded`` -- 8 fixed segments over the ranks, inside a segment
+    the reference's chain (4000 steps cold for its first frame, 400 warm for every following one; G = 1 frame per launch),
+    native step loops, no-foreground skip, IoU check + retry, every frame's unaries copied from pinned host memory, masks /
+    states / IoUs gathered on every rank at the end.  Time = barrier to barrier, max over ranks.  ``digest`` hashes every
+    fitted state: it is the same for any number of GPUs."""
     import hashlib
     import torch
     import torch.distributed as dist
@@ -315,7 +316,7 @@ def frames_per_s_leg(A, dev, rank: int, world: int, G: int, precision: str, barr
             h.update(res[i]["state"].numpy().tobytes())
     fitted = [r for r in res.values() if not r["skipped"]]
     return {"value": n_frames / wall, "unit": "frames/s", "measured": True, "frames": n_frames, "wall_s": wall,
-            "segments": n_segments, "frames_per_launch": G, "schedule": "4000 steps cold (first group of a segment) / 400 warm, Adam 1e-3",
+            "segments": n_segments, "frames_per_launch": G, "schedule": "4000 steps cold (first frame of a segment) / 400 warm (every following frame), Adam 1e-3",
             "steps_total_per_rank_max": max(sum(4000 if k == 0 else 400 for k in range((len(sg) + G - 1) // G))
                                             for sg in segs) * len(A.segments_of_rank(len(segs), 0, world)),
             "mean_iou": sum(r["iou"] for r in fitted) / max(1, len(fitted)), "min_iou": min(r["iou"] for r in fitted),
@@ -672,7 +673,7 @@ def main():
     frames_leg = None
     if not args.no_frames:
         fitter.set_target_pool(None)
-        frames_leg = frames_per_s_leg(A, dev, rank, world, G, args.precision, barrier)
+        frames_leg = frames_per_s_leg(A, dev, rank, world, 1, args.precision, barrier)      # the warm-start chain: one frame per launch
 
     # ---- configs[4]: joint UNet + prior step with its gradient all-reduce (every rank takes part)
     joint = None
