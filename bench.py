@@ -456,6 +456,16 @@ def secondary_workloads(A, dev, unaries640):
     ms = _time_fitter(f, 20)
     out["c3_multi_object_8x640x480"] = {"ms_per_step": ms, "pixel_samples_per_s": 8 * N_PIX / ms * 1e3}
     del f, multi
+    # configs[4], prior side only: the (x, y, t) RealNVP(18 flows) o ICNN prior of the spatio-temporal configs fitted on a batch of
+    # 2 frames (the prefit / pretrain step of path_connected_net.py:511-728 with cached unaries; the joint step is `joint_unet_prior`)
+    st = A.real_nvp_path_connected_net(channels=3, hidden_units=32, flow_n_flows=18, flow_output_fn="tanh", norm="minmax",
+                                       convex_net_hidden_units=130, convex_net_hidden_layers=2, precision="f16").to(dev)
+    grid3 = A.GridSpecHost("linspace", 2, H, W, t0=0.0, t_step=1.0 / 199)
+    tg3 = torch.stack([unaries640, torch.roll(unaries640, shifts=(5, 9), dims=(0, 1))])
+    f = st.make_fitter(grid3, tg3, A.LossConfig("mse"), opt, steps_per_graph=10)
+    ms = _time_fitter(f, 30)
+    out["c4_spatio_temporal_prior_2x640x480"] = {"ms_per_step": ms, "pixel_samples_per_s": 2 * N_PIX / ms * 1e3}
+    del f, st
     torch.cuda.empty_cache()
     out["n4_image_preprocess_640x480"] = image_preprocess_throughput(A, dev)
     return out
