@@ -264,7 +264,7 @@ int awb_prior_set_flow_eval(awb_handle h, int32_t mode) {
   if (!h) { set_error("null argument"); return AWB_ERR_INVALID; }
   if (h->desc.kind != AWB_KIND_FLOW_ICNN) { set_error("not a flow prior"); return AWB_ERR_INVALID; }
   if (mode < 0 || mode > 2) { set_error("flow_eval must be 0 (auto), 1 (unit loops) or 2 (segment tables), got %d", mode); return AWB_ERR_INVALID; }
-  if (mode == 2 && !flow_seg_capable(h)) { set_error("segment tables need C = 2 and m <= 32"); return AWB_ERR_UNSUPPORTED; }
+  if (mode == 2 && !flow_seg_capable(h) && !flow_seg3_capable(h)) { set_error("segment tables need m <= 32"); return AWB_ERR_UNSUPPORTED; }
   h->flow_eval = mode;
   return AWB_OK;
 }

@@ -193,6 +193,49 @@ struct FlowGeo { int S, T, R; int64_t chunk; };
 template <int C> struct FlowSave { static constexpr int RW = C == 2 ? 4 : 8; };
 int flow_save_floats(int C) { return C == 2 ? 4 : 8; }
 
+constexpr int FLOW_TAB3 = 584;     // C = 3 forward tables, see k_flow_tables3
+// number of merged breakpoints below z (0 .. 64) TIMES 4: lower bound over gamma[0..62] in six dependent steps, gamma[63] on
+// its own.  `tab`: shared-space address of the table (ld.shared with an immediate offset per step: load, compare,
+// predicated add).
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float2 lds_f32x2(uint32_t a) { float2 v; asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+// the same for PP pixels at once, breadth first (step k of every pixel before step k + 1 of any): the PP dependent chains
+// of loads overlap instead of running one after the other
+template <int PP>
+__device__ __forceinline__ void seg_find4_multi(uint32_t tab, const float* z, uint32_t* o) {
+  const float g31 = lds_f32(tab + 31 * 4), g63 = lds_f32(tab + 63 * 4);
+  uint32_t top[PP];
+#pragma unroll
+  for (int q = 0; q < PP; q++) { o[q] = g31 < z[q] ? 128u : 0u; top[q] = g63 < z[q] ? 4u : 0u; }
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    const uint32_t off = (15u >> k) * 4u, inc = 64u >> k;      // (15, 64), (7, 32), (3, 16), (1, 8), (0, 4)
+    float v[PP];
+#pragma unroll
+    for (int q = 0; q < PP; q++) v[q] = lds_f32(tab + o[q] + off);
+#pragma unroll
+    for (int q = 0; q < PP; q++) o[q] += v[q] < z[q] ? inc : 0u;
+  }
+#pragma unroll
+  for (int q = 0; q < PP; q++) o[q] += top[q];
+}
+__device__ __forceinline__ uint32_t seg_find4(uint32_t tab, float z) {
+  uint32_t o = lds_f32(tab + 31 * 4) < z ? 128u : 0u;
+  const uint32_t top = lds_f32(tab + 63 * 4) < z ? 4u : 0u;
+  o += lds_f32(tab + o + 15 * 4) < z ? 64u : 0u;
+  o += lds_f32(tab + o + 7 * 4) < z ? 32u : 0u;
+  o += lds_f32(tab + o + 3 * 4) < z ? 16u : 0u;
+  o += lds_f32(tab + o + 1 * 4) < z ? 8u : 0u;
+  o += lds_f32(tab + o) < z ? 4u : 0u;
+  return o + top;
+}
+
 constexpr int FLOW_P = 4;          // forward: pixels per thread and round: every weight record (2-3 LDS.128) feeds 4 pixels
 constexpr int FLOW_PB = 4;         // backward: same, bounded by the 128 accumulator registers beside them
 constexpr int FLOW_RED_FLOATS = 16 * 128 + 16 * 16;   // one reduction scratch: 16 warps x (128 accumulator sums + 16 scalar sums)
@@ -208,6 +251,19 @@ __global__ void __launch_bounds__(256) k_flow_fwd(FlowP p) {
   stage_flow_packed<C>(par, p.F, m, p.per_flow, sp, p.fc, /*exp_actnorm=*/true);
   float* lin = sp + p.F * FS;
   if (threadIdx.x < 2 * C) lin[threadIdx.x] = par[p.P_flow + threadIdx.x];
+  // C = 3 on the tensor path: segment tables of the flows with one masked coordinate behind the weights (k_flow_tables3)
+  const bool seg3 = C == 3 && p.tab != nullptr;
+  float* tab3 = lin + 2 * C + 2;          // 16-byte aligned: F * FS and 2 C + 2 are multiples of 4 floats
+  if (seg3) {
+    const float* tg = p.tab + (int64_t)o * p.F * FLOW_TAB3;
+    for (int i = threadIdx.x; i < p.F * (FLOW_TAB3 / 4); i += blockDim.x) {
+      const int f = i / (FLOW_TAB3 / 4);
+      int mbf = 0;
+#pragma unroll
+      for (int c = 0; c < C; c++) mbf |= p.fc.masks[f * C + c] != 0 ? 1 << c : 0;
+      if (__popc(mbf) == 1) reinterpret_cast<float4*>(tab3)[i] = reinterpret_cast<const float4*>(tg)[i];
+    }
+  }
   __syncthreads();
   const int T = blockDim.x;
   const int64_t r0 = (int64_t)blockIdx.x * p.chunk, r1 = r0 + p.chunk < p.N ? r0 + p.chunk : p.N;
@@ -243,9 +299,31 @@ __global__ void __launch_bounds__(256) k_flow_fwd(FlowP p) {
 #pragma unroll
         for (int c = 0; c < C; c++) { so[q][c] = tail[c]; to[q][c] = tail[C + c]; }
       }
+      if (C == 3 && seg3 && (mb == 1 || mb == 2 || mb == 4)) {
+        // one masked coordinate: both MLPs are piecewise linear in it -- one search over the merged breakpoints and one FMA
+        // per net and output instead of the unit loop (same pre-activation outputs up to the order of the sums)
+        const int cm = mb == 1 ? 0 : (mb == 2 ? 1 : 2), ua = cm == 0 ? 1 : 0, ub = cm == 2 ? 1 : 2;
+        const uint32_t tb = (uint32_t)__cvta_generic_to_shared(tab3 + f * FLOW_TAB3);
+        float zm[P];
+        uint32_t J4[P];
+#pragma unroll
+        for (int q = 0; q < P; q++) zm[q] = cm == 0 ? z[q][0] : (cm == 1 ? z[q][1] : z[q][C - 1]);
+        seg_find4_multi<P>(tb, zm, J4);
+#pragma unroll
+        for (int q = 0; q < P; q++) {
+          const float4 sl = lds_f32x4(tb + 256 + 8 * J4[q]), ic = lds_f32x4(tb + 256 + 8 * J4[q] + 16);
+          const float sa = fmaf(sl.x, zm[q], ic.x), sb_ = fmaf(sl.y, zm[q], ic.y), ta = fmaf(sl.z, zm[q], ic.z), tb_ = fmaf(sl.w, zm[q], ic.w);
+#pragma unroll
+          for (int c = 0; c < C; c++) {
+            if (c == ua) { so[q][c] = sa; to[q][c] = ta; }
+            if (c == ub) { so[q][c] = sb_; to[q][c] = tb_; }
+          }
+        }
+      } else {
 #define AWB_CALL(MB) coupling_mlp_fwd<C, MB, P>(wf, m, z, b, so, to)
-      AWB_FLOW_DISPATCH(C, mb, AWB_CALL);
+        AWB_FLOW_DISPATCH(C, mb, AWB_CALL);
 #undef AWB_CALL
+      }
 #pragma unroll
       for (int q = 0; q < P; q++) {
         float sv[2] = {0.f, 0.f}, tv[2] = {0.f, 0.f}, zi[3] = {0.f, 0.f, 0.f};
@@ -913,46 +991,87 @@ __global__ void __launch_bounds__(64) k_flow_tables(FlowP p) {
   }
 }
 
-// number of merged breakpoints below z (0 .. 64) TIMES 4: lower bound over gamma[0..62] in six dependent steps, gamma[63] on
-// its own.  `tab`: shared-space address of the table (ld.shared with an immediate offset per step: load, compare,
-// predicated add).
-__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ float2 lds_f32x2(uint32_t a) { float2 v; asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
-__device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
-  float4 v;
-  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
-  return v;
-}
-// the same for PP pixels at once, breadth first (step k of every pixel before step k + 1 of any): the PP dependent chains
-// of loads overlap instead of running one after the other
-template <int PP>
-__device__ __forceinline__ void seg_find4_multi(uint32_t tab, const float* z, uint32_t* o) {
-  const float g31 = lds_f32(tab + 31 * 4), g63 = lds_f32(tab + 63 * 4);
-  uint32_t top[PP];
+// C = 3: the flows that mask ONE coordinate (three of the six mask patterns of net_factory.py:86-99) feed one scalar into
+// their MLPs as well; each net has two outputs (the two transformed coordinates a < b).  Forward only -- the backward of
+// C = 3 priors keeps the unit loops (its per-thread histogram would need 264 rows).  Table of one flow, FLOW_TAB3 floats:
+//   [0, 64)     gamma, merged and sorted as for C = 2
+//   [64, 584)   per merged segment J = 0 .. 64: (slope_sa, slope_sb, slope_ta, slope_tb, icpt_sa, icpt_sb, icpt_ta, icpt_tb)
+// Flows with two masked coordinates leave their table untouched (never read).
+__global__ void __launch_bounds__(64) k_flow_tables3(FlowP p) {
+  const unsigned full = 0xffffffffu;
+  const int f = blockIdx.x, o = blockIdx.y, lane = threadIdx.x & 31, net = threadIdx.x >> 5;
+  int mb = 0;
 #pragma unroll
-  for (int q = 0; q < PP; q++) { o[q] = g31 < z[q] ? 128u : 0u; top[q] = g63 < z[q] ? 4u : 0u; }
+  for (int c = 0; c < 3; c++) mb |= p.fc.masks[f * 3 + c] != 0 ? 1 << c : 0;
+  if (__popc(mb) != 1) return;
+  const int cm = __ffs(mb) - 1, ua = cm == 0 ? 1 : 0, ub = cm == 2 ? 1 : 2;
+  const int m = p.m, half = 6 * m + m + 3;
+  const float* wn = p.params + (int64_t)o * p.P + p.off_flow + (int64_t)f * p.per_flow + net * half;
+  __shared__ float sb[2][32], sS[2][2][33], sI[2][2][33];
+  __shared__ int flag[64];
+  float w = 0.f, b = 0.f, va = 0.f, vb = 0.f;
+  if (lane < m) { w = wn[lane * 3 + cm]; b = wn[3 * m + lane]; va = wn[3 * m + m + ua * m + lane]; vb = wn[3 * m + m + ub * m + lane]; }
+  const float c0a = wn[3 * m + m + 3 * m + ua], c0b = wn[3 * m + m + 3 * m + ub];
+  float beta = INFINITY;
+  int type = 0;
+  if (w > 0.f) { beta = -b / w; }
+  else if (w < 0.f) { beta = -b / w; type = 1; }
+  else if (b > 0.f) { type = 1; }
+  if (!(beta == beta)) beta = INFINITY;
+  if (lane >= m) { type = 0; va = 0.f; vb = 0.f; }
+  float kb = beta;
+  int ki = lane;
 #pragma unroll
-  for (int k = 0; k < 5; k++) {
-    const uint32_t off = (15u >> k) * 4u, inc = 64u >> k;      // (15, 64), (7, 32), (3, 16), (1, 8), (0, 4)
-    float v[PP];
+  for (int k2 = 2; k2 <= 32; k2 <<= 1) {
 #pragma unroll
-    for (int q = 0; q < PP; q++) v[q] = lds_f32(tab + o[q] + off);
-#pragma unroll
-    for (int q = 0; q < PP; q++) o[q] += v[q] < z[q] ? inc : 0u;
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      const float ob = __shfl_xor_sync(full, kb, j);
+      const int oi = __shfl_xor_sync(full, ki, j);
+      const bool asc = (lane & k2) == 0, lower = (lane & j) == 0;
+      const bool other_less = ob < kb || (ob == kb && oi < ki);
+      if ((lower == asc) ? other_less : !other_less) { kb = ob; ki = oi; }
+    }
   }
+  const float ws_ = __shfl_sync(full, w, ki), bs_ = __shfl_sync(full, b, ki);
+  const float vas = __shfl_sync(full, va, ki), vbs = __shfl_sync(full, vb, ki);
+  const int ts_ = __shfl_sync(full, type, ki);
 #pragma unroll
-  for (int q = 0; q < PP; q++) o[q] += top[q];
-}
-__device__ __forceinline__ uint32_t seg_find4(uint32_t tab, float z) {
-  uint32_t o = lds_f32(tab + 31 * 4) < z ? 128u : 0u;
-  const uint32_t top = lds_f32(tab + 63 * 4) < z ? 4u : 0u;
-  o += lds_f32(tab + o + 15 * 4) < z ? 64u : 0u;
-  o += lds_f32(tab + o + 7 * 4) < z ? 32u : 0u;
-  o += lds_f32(tab + o + 3 * 4) < z ? 16u : 0u;
-  o += lds_f32(tab + o + 1 * 4) < z ? 8u : 0u;
-  o += lds_f32(tab + o) < z ? 4u : 0u;
-  return o + top;
+  for (int u = 0; u < 2; u++) {
+    const double v = u == 0 ? (double)vas : (double)vbs;
+    const double a = v * (double)ws_, d = v * (double)bs_;
+    double pa = ts_ == 0 ? a : 0.0, pd = ts_ == 0 ? d : 0.0, na = ts_ == 1 ? a : 0.0, nd = ts_ == 1 ? d : 0.0;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const double xa = __shfl_up_sync(full, pa, off), xd = __shfl_up_sync(full, pd, off);
+      const double ya = __shfl_down_sync(full, na, off), yd = __shfl_down_sync(full, nd, off);
+      if (lane >= off) { pa += xa; pd += xd; }
+      if (lane + off < 32) { na += ya; nd += yd; }
+    }
+    double ea = __shfl_up_sync(full, pa, 1), ed = __shfl_up_sync(full, pd, 1);
+    if (lane == 0) { ea = 0.0; ed = 0.0; }
+    const double c0 = u == 0 ? (double)c0a : (double)c0b;
+    sS[net][u][lane] = (float)(ea + na);
+    sI[net][u][lane] = (float)(c0 + ed + nd);
+    if (lane == 31) { sS[net][u][32] = (float)pa; sI[net][u][32] = (float)(c0 + pd); }
+  }
+  sb[net][lane] = kb;
+  __syncthreads();
+  float* tab = p.tab + ((int64_t)o * p.F + f) * FLOW_TAB3;
+  int cnt = 0;
+#pragma unroll 8
+  for (int i = 0; i < 32; i++) cnt += net == 0 ? (sb[1][i] < kb ? 1 : 0) : (sb[0][i] <= kb ? 1 : 0);
+  const int pos = lane + cnt;
+  tab[pos] = kb;
+  flag[pos] = net;
+  __syncthreads();
+  for (int J = threadIdx.x; J <= 64; J += 64) {
+    int js = 0;
+    for (int i = 0; i < J; i++) js += flag[i] == 0 ? 1 : 0;
+    const int jt = J - js;
+    float4* e = reinterpret_cast<float4*>(tab + 64 + 8 * J);
+    e[0] = make_float4(sS[0][0][js], sS[0][1][js], sS[1][0][jt], sS[1][1][jt]);
+    e[1] = make_float4(sI[0][0][js], sI[0][1][js], sI[1][0][jt], sI[1][1][jt]);
+  }
 }
 
 // tanh / exp of the segment kernels: ex2.approx.ftz / rcp.approx.ftz without the denormal fix-ups of __expf / __fdividef
@@ -1533,7 +1652,14 @@ bool flow_seg_path(const awb_prior* h) {
 int64_t flow_seg_scratch_floats(const awb_prior* h, int S) {
   return flow_seg_capable(h) ? (int64_t)S * h->desc.n_objects * h->lay.F * 8 * FLOW_SEG_RS : 0;
 }
+// C = 3: forward tables for the flows with one masked coordinate (the backward keeps the unit loops)
+bool flow_seg3_capable(const awb_prior* h) { return h->desc.kind == AWB_KIND_FLOW_ICNN && h->lay.C == 3 && h->lay.m <= 32; }
+bool flow_seg3_path(const awb_prior* h) {
+  if (!flow_seg3_capable(h) || h->flow_eval == 1 || !h->desc.flow_tanh || h->fc.out_scale != 1.f) return false;
+  return h->flow_eval == 2 || h->desc.precision == AWB_PREC_F16;
+}
 int64_t flow_tab_floats(const awb_prior* h) {
+  if (flow_seg3_capable(h)) return (int64_t)h->desc.n_objects * h->lay.F * FLOW_TAB3;
   return flow_seg_capable(h) ? (int64_t)h->desc.n_objects * h->lay.F * FLOW_TAB : 0;
 }
 
@@ -1550,7 +1676,9 @@ int flow_forward(const awb_prior* h, const float* params, const awb_grid_spec* g
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
   FlowGeo geo;
   const bool seg = flow_seg_path(h) && p.tab;
-  geo.T = seg ? 256 : 128;        // segment kernel: the per-CTA table staging is amortised over twice the pixels
+  const bool seg3 = flow_seg3_path(h) && p.tab;
+  if (h->lay.C == 3 && !seg3) p.tab = nullptr;      // k_flow_fwd<3> takes a non-null table pointer as "tables are built"
+  geo.T = (seg || seg3) ? 256 : 128;        // segment kernels: the per-CTA table staging is amortised over twice the pixels
   int64_t per_sm = (p.N * h->desc.n_objects + sms - 1) / sms;
   int k = (int)((per_sm + FLOW_P * geo.T / 2) / (FLOW_P * geo.T));
   if (k < 1) k = 1;
@@ -1575,6 +1703,10 @@ int flow_forward(const awb_prior* h, const float* params, const awb_grid_spec* g
     AWB_CUDA(cudaFuncSetAttribute(k_flow_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AWB_LAUNCH(PK_FLOW_FWD, st, k_flow_fwd<2><<<grid, geo.T, smem, st>>>(p));
   } else {
+    if (seg3) {
+      smem += sizeof(float) * (2 + (size_t)h->lay.F * FLOW_TAB3);
+      AWB_LAUNCH(PK_FLOW_FWD, st, k_flow_tables3<<<dim3(h->lay.F, h->desc.n_objects), 64, 0, st>>>(p));
+    }
     AWB_CUDA(cudaFuncSetAttribute(k_flow_fwd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AWB_LAUNCH(PK_FLOW_FWD, st, k_flow_fwd<3><<<grid, geo.T, smem, st>>>(p));
   }

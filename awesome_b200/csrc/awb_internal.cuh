@@ -202,6 +202,7 @@ int flow_backward(const awb_prior* h, const float* params, const awb_grid_spec* 
 int flow_save_floats(int C);                                     // floats saved per pixel and flow by the training forward
 bool flow_seg_capable(const awb_prior* h);                        // C = 2, m <= 32: segment-table kernels exist (awb_flow.cu)
 bool flow_seg_path(const awb_prior* h);                           // ... and are the ones this handle runs
+bool flow_seg3_capable(const awb_prior* h);                       // C = 3: forward tables for the one-masked-coordinate flows
 int64_t flow_tab_floats(const awb_prior* h);                      // size of Workspace.flowtab
 int64_t flow_seg_scratch_floats(const awb_prior* h, int S);       // size of Workspace.flowseg
 bool flow_bwd_dz_in_smem(const awb_prior* h, int64_t N);         // the backward keeps its running gradient on the SM
