@@ -302,23 +302,25 @@ __global__ void __launch_bounds__(256) k_flow_fwd(FlowP p) {
       if (C == 3 && seg3 && (mb == 1 || mb == 2 || mb == 4)) {
         // one masked coordinate: both MLPs are piecewise linear in it -- one search over the merged breakpoints and one FMA
         // per net and output instead of the unit loop (same pre-activation outputs up to the order of the sums)
-        const int cm = mb == 1 ? 0 : (mb == 2 ? 1 : 2), ua = cm == 0 ? 1 : 0, ub = cm == 2 ? 1 : 2;
         const uint32_t tb = (uint32_t)__cvta_generic_to_shared(tab3 + f * FLOW_TAB3);
-        float zm[P];
-        uint32_t J4[P];
+        auto seg_couple = [&](auto cm_c) {
+          constexpr int cm = decltype(cm_c)::value < C ? decltype(cm_c)::value : 0;
+          constexpr int ua = cm == 0 ? 1 : 0, ub = cm == C - 1 ? C - 2 : C - 1;
+          float zm[P];
+          uint32_t J4[P];
 #pragma unroll
-        for (int q = 0; q < P; q++) zm[q] = cm == 0 ? z[q][0] : (cm == 1 ? z[q][1] : z[q][C - 1]);
-        seg_find4_multi<P>(tb, zm, J4);
+          for (int q = 0; q < P; q++) zm[q] = z[q][cm];
+          seg_find4_multi<P>(tb, zm, J4);
 #pragma unroll
-        for (int q = 0; q < P; q++) {
-          const float4 sl = lds_f32x4(tb + 256 + 8 * J4[q]), ic = lds_f32x4(tb + 256 + 8 * J4[q] + 16);
-          const float sa = fmaf(sl.x, zm[q], ic.x), sb_ = fmaf(sl.y, zm[q], ic.y), ta = fmaf(sl.z, zm[q], ic.z), tb_ = fmaf(sl.w, zm[q], ic.w);
-#pragma unroll
-          for (int c = 0; c < C; c++) {
-            if (c == ua) { so[q][c] = sa; to[q][c] = ta; }
-            if (c == ub) { so[q][c] = sb_; to[q][c] = tb_; }
+          for (int q = 0; q < P; q++) {
+            const float4 sl = lds_f32x4(tb + 256 + 8 * J4[q]), ic = lds_f32x4(tb + 256 + 8 * J4[q] + 16);
+            so[q][ua] = fmaf(sl.x, zm[q], ic.x); so[q][ub] = fmaf(sl.y, zm[q], ic.y);
+            to[q][ua] = fmaf(sl.z, zm[q], ic.z); to[q][ub] = fmaf(sl.w, zm[q], ic.w);
           }
-        }
+        };
+        if (mb == 1) seg_couple(std::integral_constant<int, 0>{});
+        else if (mb == 2) seg_couple(std::integral_constant<int, 1>{});
+        else seg_couple(std::integral_constant<int, 2>{});
       } else {
 #define AWB_CALL(MB) coupling_mlp_fwd<C, MB, P>(wf, m, z, b, so, to)
         AWB_FLOW_DISPATCH(C, mb, AWB_CALL);
