@@ -143,7 +143,7 @@ int awb_prior_set_flow_output_scale(awb_handle h, float scale);
 
 /* How the coupling MLPs s, t = MLP([C, m, C]) of a RealNVP prior are evaluated (net_factory.py:101-113):
  *   1  unit loops: sum_k W2[k] relu(W1[k] z + b1[k]) in the reference's order of operations;
- *   2  segment tables (C = 2 and m <= 32 only): with two coordinates every coupling feeds ONE scalar into its MLPs, which
+ *   2  segment tables (m <= 32; C = 2: forward and backward, C = 3: forward of the flows that mask one coordinate): with two coordinates every coupling feeds ONE scalar into its MLPs, which
  *      are then piecewise linear with m breakpoints; the breakpoints of both nets are sorted and merged once per forward and
  *      each pixel costs one 7-step search and one FMA per net (backward: 4 histogram updates instead of 4 m masked sums).  Same function, the
  *      sums reassociated: outputs agree with mode 1 to ~1e-6, a hidden unit that is active nowhere still gets an exactly
